@@ -1,0 +1,121 @@
+/*
+ * unibev_b200 -- C ABI of libunibev_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the UniBEV uniform-BEV-encoder hot path.  Plain pointers
+ * and sizes only: no torch types cross this boundary.  All pointers are DEVICE
+ * pointers unless the parameter comment says "host".  Every call is asynchronous
+ * on `stream` (a cudaStream_t), allocates nothing, and returns 0 on success or a
+ * negative UB_E* code (message: ub_last_error(), thread-local).  Tensors are
+ * contiguous row-major fp32 unless stated.
+ *
+ * Reference interfaces replaced (paths under /root/reference):
+ *   [R1] mmcv MultiScaleDeformableAttnFunction.apply / ext_module.ms_deform_attn_forward|backward,
+ *        called at projects/UniBEV/unibev_plugin/models/modules/spatial_cross_attention_img.py:432-435,
+ *        spatial_cross_attention_pts.py:439-442, decoder.py:324-327 (ext handles loaded at
+ *        spatial_cross_attention_img.py:19-20).
+ *   [R2] ImgEncoder.get_reference_points + point_sampling, encoder_unibev_detr_img.py:45-187.
+ *   [R3] SpatialCrossAttentionImg.forward rebatch/sample/scatter/count, spatial_cross_attention_img.py:141-212,
+ *        with MSDeformableAttention3DImg.forward softmax/offset/anchor logic, :385-419.
+ *   [R4] PtsEncoder.point_sampling + SpatialCrossAttentionPts/MSDeformableAttention3DPts.forward,
+ *        encoder_unibev_detr_pts.py:105-127, spatial_cross_attention_pts.py:159-204,383-437; and the BEV
+ *        self-attention (mmcv MultiScaleDeformableAttention, verbatim copy at decoder.py:278-330).
+ *   [R5] residual add + nn.LayerNorm steps of BaseTransformerLayer ('norm' ops), encoder_unibev_detr_img.py:434-436.
+ *   [R6] UniBEVTransformer.channel_feature_norm / spatial_feature_norm / multi_modal_fusion,
+ *        transformer_fusion.py:316-337, 386-413, 280-314.
+ *   [R7] UniBEVTransformer._pre_process_img_feats / _pre_process_pts_feats, transformer_fusion.py:231-278.
+ */
+#ifndef UNIBEV_B200_H_
+#define UNIBEV_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ub_stream_t; /* cudaStream_t */
+
+enum {
+  UB_OK = 0,
+  UB_EINVAL = -1,   /* bad argument / unsupported shape */
+  UB_ECUDA = -2,    /* CUDA runtime error at launch */
+  UB_EALIGN = -3    /* pointer not 16-byte aligned */
+};
+
+/* Fusion modes of ub_cnw_fuse [R6]. */
+enum { UB_FUSE_LINEAR = 0, UB_FUSE_AVG = 1, UB_FUSE_CAT = 2 };
+
+/* ABI version (major*1000 + minor) and last error text of the calling thread. */
+int ub_version(void);
+const char* ub_last_error(void);
+/* Number of kernels this library has launched since load / since the last reset (bench bookkeeping). */
+int64_t ub_launch_count(void);
+void ub_launch_count_reset(void);
+
+/* ---- [R1] generic multi-scale deformable attention -------------------------------------------------
+ * value (B, Nv, H, D); spatial_shapes (L, 2) int64 (h, w); level_start_index (L) int64;
+ * sampling_loc (B, Nq, H, L, P, 2) normalised (x, y); attn_weight (B, Nq, H, L, P); out (B, Nq, H*D).
+ * Pixel convention x_pix = x*W - 0.5, zero padding, each corner bounds-checked (mmcv kernel semantics).
+ * No im2col_step restriction (mmcv asserts B % min(B, 64) == 0; this does not). */
+int ub_msda_fwd(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                const float* sampling_loc, const float* attn_weight, float* out,
+                int B, int Nv, int H, int D, int Nq, int L, int P, ub_stream_t stream);
+/* grad_value must be zero-filled by the caller (accumulated with atomics); grad_loc / grad_w are overwritten. */
+int ub_msda_bwd(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                const float* sampling_loc, const float* attn_weight, const float* grad_out,
+                float* grad_value, float* grad_loc, float* grad_w,
+                int B, int Nv, int H, int D, int Nq, int L, int P, ub_stream_t stream);
+
+/* ---- [R2] pillar reference points -> camera planes ------------------------------------------------
+ * For every (b, q = h*bev_w + w, cam, anchor d): lift the BEV cell centre to z-anchor d, scale to
+ * metres with pc_range, project with lidar2img[b, cam] (row-major 4x4), clamp depth at 1e-5, divide by
+ * (img_w, img_h); mask = depth > 1e-5 && 0 < x < 1 && 0 < y < 1.
+ * lidar2img (B, N, 16); zs_host: D normalised anchor heights (host, D <= 8); pc_range_host: 6 floats (host).
+ * ref_cam out (B, Nq, N, D, 2); mask out (B, Nq, N) uint8, bit d = anchor d visible. */
+int ub_project_points(const float* lidar2img, const float* zs_host, const float* pc_range_host,
+                      float img_h, float img_w, float* ref_cam, uint8_t* mask,
+                      int B, int N, int bev_h, int bev_w, int D, ub_stream_t stream);
+
+/* ---- [R4] fused BEV-grid deformable sampling (BEV self-attention, LiDAR cross-attention) ----------
+ * One level.  value (B, fH*fW, H*Dh) already value-projected.  qproj holds, per query row of stride
+ * `ld` floats, the raw sampling offsets (H, P, 2) at column off_col and the raw attention logits (H, P)
+ * at column logit_col (i.e. the un-normalised outputs of the sampling_offsets / attention_weights
+ * linears).  The kernel generates the reference point ((w+.5)/bev_w, (h+.5)/bev_h) itself, adds
+ * offset/(fW, fH), applies softmax over the P logits, gathers bilinearly and reduces: out (B, Nq, H*Dh). */
+int ub_bev_sample_fwd(const float* value, const float* qproj, float* out,
+                      int B, int bev_h, int bev_w, int fH, int fW, int H, int Dh, int P,
+                      int ld, int off_col, int logit_col, ub_stream_t stream);
+
+/* ---- [R3] fused camera cross-attention sampling ---------------------------------------------------
+ * value (B, N, fH*fW, H*Dh); qproj as above (one row per BEV query, shared by all cameras);
+ * ref_cam / mask from ub_project_points with D anchors; sampling point p uses anchor p % D.
+ * A camera contributes to query q of batch item b iff batch item 0's mask for (q, cam) is non-zero
+ * (reference quirk, spatial_cross_attention_img.py:142); the sum over cameras is divided by
+ * max(1, #cameras whose mask for (b, q) is non-zero) (:209-212).  out (B, Nq, H*Dh). */
+int ub_img_sample_fwd(const float* value, const float* qproj, const float* ref_cam, const uint8_t* mask,
+                      float* out, int B, int N, int bev_h, int bev_w, int fH, int fW, int H, int Dh, int P,
+                      int D, int ld, int off_col, int logit_col, ub_stream_t stream);
+
+/* ---- [R5] y = LayerNorm(x + bias + residual) * gamma + beta over the last dim C ---------------------
+ * bias (C) and residual (rows, C) may be NULL.  C % 4 == 0, C <= 1024.  out may alias x. */
+int ub_add_layernorm(const float* x, const float* bias, const float* residual, const float* gamma,
+                     const float* beta, float* out, int64_t rows, int C, float eps, ub_stream_t stream);
+
+/* ---- [R6] channel-normalised-weight fusion --------------------------------------------------------
+ * img / pts (rows, C), either may be NULL (missing modality == zeros).  w_img / w_pts (C) CNW parameters
+ * or NULL for feature_norm=None.  s_img / s_pts (rows_per_item) spatial-norm parameters or NULL.
+ * modal_embed (C_out) or NULL.  out (rows, C) for LINEAR/AVG, (rows, 2C) for CAT. */
+int ub_cnw_fuse(const float* img, const float* pts, const float* w_img, const float* w_pts,
+                const float* s_img, const float* s_pts, const float* modal_embed, float* out,
+                int64_t rows, int rows_per_item, int C, int mode, int c_flag, int l_flag, ub_stream_t stream);
+
+/* ---- [R7] backbone feature map -> token-major value input -----------------------------------------
+ * in (G, C, HW) -> out (G, HW, C) with out[g, p, c] = in[g, c, p] + embed_a[g % n_a, c] + embed_b[c];
+ * embed_a / embed_b may be NULL. */
+int ub_flatten_feats(const float* in, const float* embed_a, int n_a, const float* embed_b, float* out,
+                     int G, int C, int HW, ub_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIBEV_B200_H_ */

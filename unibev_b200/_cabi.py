@@ -1,0 +1,79 @@
+"""ctypes binding of libunibev_b200.so (the C ABI declared in include/unibev_b200.h).
+
+There is no CPU fallback: if the shared library is missing, loading raises and every
+op in this package fails loudly.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libunibev_b200.so')
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_i64 = ctypes.c_int64
+_f = ctypes.c_float
+
+# name -> argtypes; every entry point of include/unibev_b200.h (tests check the header against this table)
+PROTOTYPES = {
+    'ub_version': ([], _i),
+    'ub_last_error': ([], ctypes.c_char_p),
+    'ub_launch_count': ([], _i64),
+    'ub_launch_count_reset': ([], None),
+    'ub_msda_fwd': ([_p] * 6 + [_i] * 7 + [_p], _i),
+    'ub_msda_bwd': ([_p] * 9 + [_i] * 7 + [_p], _i),
+    'ub_project_points': ([_p, _p, _p, _f, _f, _p, _p] + [_i] * 5 + [_p], _i),
+    'ub_bev_sample_fwd': ([_p] * 3 + [_i] * 11 + [_p], _i),
+    'ub_img_sample_fwd': ([_p] * 5 + [_i] * 13 + [_p], _i),
+    'ub_add_layernorm': ([_p] * 6 + [_i64, _i, _f, _p], _i),
+    'ub_cnw_fuse': ([_p] * 8 + [_i64, _i, _i, _i, _i, _i, _p], _i),
+    'ub_flatten_feats': ([_p, _p, _i, _p, _p, _i, _i, _i, _p], _i),
+}
+# not part of the public header: tuning hook used by bench/sweeps
+_PRIVATE = {
+    'ub_set_tuning': ([_i] * 5, _i),
+}
+
+_lib = None
+
+
+class UniBEVNativeError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise UniBEVNativeError(
+                f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                '(nvcc, sm_100a). unibev_b200 has no CPU or PyTorch fallback.')
+        handle = ctypes.CDLL(LIB_PATH)
+        for table in (PROTOTYPES, _PRIVATE):
+            for name, (argtypes, restype) in table.items():
+                fn = getattr(handle, name)
+                fn.argtypes = argtypes
+                fn.restype = restype
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().ub_last_error().decode('utf-8', 'replace')
+        if rc == -1:
+            raise ValueError(f'{what}: {msg}')
+        raise UniBEVNativeError(f'{what} failed (code {rc}): {msg}')
+
+
+def launch_count():
+    return int(lib().ub_launch_count())
+
+
+def reset_launch_count():
+    lib().ub_launch_count_reset()
+
+
+def set_tuning(which, tile_w, tile_h, heads_per_cta, threads):
+    """which: 0 = ub_bev_sample_fwd, 1 = ub_img_sample_fwd."""
+    check(lib().ub_set_tuning(which, tile_w, tile_h, heads_per_cta, threads), 'ub_set_tuning')

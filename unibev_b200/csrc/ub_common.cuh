@@ -1,0 +1,98 @@
+// Shared device/host helpers for libunibev_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "unibev_b200.h"
+
+namespace ub {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+void set_error(const char* fmt, ...);
+void count_launch();
+
+#define UB_REQUIRE(cond, ...)                 \
+  do {                                        \
+    if (!(cond)) {                            \
+      ub::set_error(__VA_ARGS__);             \
+      return UB_EINVAL;                       \
+    }                                         \
+  } while (0)
+
+#define UB_REQUIRE_ALIGNED16(p)                                         \
+  do {                                                                  \
+    if ((reinterpret_cast<uintptr_t>(p) & 15u) != 0) {                  \
+      ub::set_error("%s: pointer %s is not 16-byte aligned", __func__, #p); \
+      return UB_EALIGN;                                                 \
+    }                                                                   \
+  } while (0)
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return UB_ECUDA;
+  }
+  count_launch();
+  return UB_OK;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// streaming (read-once / write-once) accesses: keep them out of L1 so the gathered value map stays resident
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ld_stream2(const float* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_stream1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
+  acc.x = fmaf(w, v.x, acc.x);
+  acc.y = fmaf(w, v.y, acc.y);
+  acc.z = fmaf(w, v.z, acc.z);
+  acc.w = fmaf(w, v.w, acc.w);
+}
+
+// One bilinear sample of a (fH, fW, stride) fp32 map at pixel coords (h_im, w_im), mmcv semantics:
+// contributes iff h_im > -1 && w_im > -1 && h_im < fH && w_im < fW; each corner bounds-checked.
+// `base` points at channel slice of pixel (0,0); `pix_stride` floats between neighbouring pixels.
+__device__ __forceinline__ void bilinear_acc4(float4& acc, const float* __restrict__ base, int fH, int fW,
+                                              int pix_stride, float h_im, float w_im, float aw) {
+  if (!(h_im > -1.f && w_im > -1.f && h_im < (float)fH && w_im < (float)fW)) return;
+  const float hf = floorf(h_im), wf = floorf(w_im);
+  const int h0 = (int)hf, w0 = (int)wf;
+  const float lh = h_im - hf, lw = w_im - wf;
+  const float hh = 1.f - lh, hw = 1.f - lw;
+  const bool top = h0 >= 0, bot = h0 + 1 <= fH - 1, left = w0 >= 0, right = w0 + 1 <= fW - 1;
+  const float* p00 = base + ((int64_t)h0 * fW + w0) * pix_stride;
+  float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1, v3 = v1, v4 = v1;
+  if (top && left) v1 = ldg4(p00);
+  if (top && right) v2 = ldg4(p00 + pix_stride);
+  if (bot && left) v3 = ldg4(p00 + (int64_t)fW * pix_stride);
+  if (bot && right) v4 = ldg4(p00 + (int64_t)fW * pix_stride + pix_stride);
+  fma4(acc, aw * (hh * hw), v1);
+  fma4(acc, aw * (hh * lw), v2);
+  fma4(acc, aw * (lh * hw), v3);
+  fma4(acc, aw * (lh * lw), v4);
+}
+
+}  // namespace ub

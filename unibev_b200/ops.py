@@ -1,0 +1,168 @@
+"""Torch-facing wrappers of the C ABI: tensors in, tensors out, current CUDA stream.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); the
+arithmetic happens in libunibev_b200.so.  Every op requires CUDA fp32 tensors and
+raises otherwise -- there is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _cabi
+
+FUSE_MODES = {'linear': 0, 'avg': 1, 'cat': 2}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f'unibev_b200: `{name}` must be a CUDA tensor (no CPU fallback exists)')
+    if t.dtype != dtype:
+        raise TypeError(f'unibev_b200: `{name}` must be {dtype}, got {t.dtype}')
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def msda_forward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
+    value = _need(value, 'value')
+    loc = _need(sampling_locations, 'sampling_locations')
+    w = _need(attention_weights, 'attention_weights')
+    shapes = _need(spatial_shapes.to(value.device), 'spatial_shapes', torch.int64)
+    lsi = _need(level_start_index.to(value.device), 'level_start_index', torch.int64)
+    B, Nv, H, D = value.shape
+    _, Nq, _, L, P, _ = loc.shape
+    if loc.shape != (B, Nq, H, L, P, 2) or w.shape != (B, Nq, H, L, P) or shapes.shape != (L, 2):
+        raise ValueError('msda: inconsistent shapes '
+                         f'value{tuple(value.shape)} loc{tuple(loc.shape)} w{tuple(w.shape)} shapes{tuple(shapes.shape)}')
+    out = torch.empty(B, Nq, H * D, device=value.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().ub_msda_fwd(_ptr(value), _ptr(shapes), _ptr(lsi), _ptr(loc), _ptr(w), _ptr(out),
+                                        B, Nv, H, D, Nq, L, P, _stream()), 'ub_msda_fwd')
+    return out
+
+
+class MultiScaleDeformableAttnFunction(torch.autograd.Function):
+    """Same call signature and gradient tuple as mmcv's op of the same name
+    (reference call site spatial_cross_attention_img.py:433-435)."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+                im2col_step=64):
+        out = msda_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                           attention_weights)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                              attention_weights)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, lsi, loc, w = ctx.saved_tensors
+        value, loc, w = _need(value, 'value'), _need(loc, 'loc'), _need(w, 'w')
+        shapes = _need(shapes.to(value.device), 'spatial_shapes', torch.int64)
+        lsi = _need(lsi.to(value.device), 'level_start_index', torch.int64)
+        go = _need(grad_output, 'grad_output')
+        B, Nv, H, D = value.shape
+        _, Nq, _, L, P, _ = loc.shape
+        g_value = torch.zeros_like(value)
+        g_loc = torch.empty_like(loc)
+        g_w = torch.empty_like(w)
+        _cabi.check(_cabi.lib().ub_msda_bwd(_ptr(value), _ptr(shapes), _ptr(lsi), _ptr(loc), _ptr(w), _ptr(go),
+                                            _ptr(g_value), _ptr(g_loc), _ptr(g_w), B, Nv, H, D, Nq, L, P, _stream()),
+                    'ub_msda_bwd')
+        return g_value, None, None, g_loc, g_w, None
+
+
+def project_points(lidar2img, zs, pc_range, img_h, img_w, bev_h, bev_w):
+    """lidar2img (B, N, 4, 4) cuda fp32; zs: D floats (host); -> ref_cam (B, Nq, N, D, 2), mask (B, Nq, N) uint8."""
+    l2i = _need(lidar2img, 'lidar2img')
+    B, N = l2i.shape[:2]
+    D = len(zs)
+    zs_c = (ctypes.c_float * D)(*[float(z) for z in zs])
+    pc_c = (ctypes.c_float * 6)(*[float(v) for v in pc_range])
+    Nq = bev_h * bev_w
+    ref = torch.empty(B, Nq, N, D, 2, device=l2i.device, dtype=torch.float32)
+    mask = torch.empty(B, Nq, N, device=l2i.device, dtype=torch.uint8)
+    _cabi.check(_cabi.lib().ub_project_points(_ptr(l2i), zs_c, pc_c, float(img_h), float(img_w), _ptr(ref), _ptr(mask),
+                                              B, N, bev_h, bev_w, D, _stream()), 'ub_project_points')
+    return ref, mask
+
+
+def bev_sample(value, qproj, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out=None):
+    """value (B, fH*fW, C); qproj (B, Nq, ld) -> (B, Nq, C)."""
+    value, qproj = _need(value, 'value'), _need(qproj, 'qproj')
+    B, Nv, C = value.shape
+    if Nv != fH * fW or qproj.shape[0] != B or qproj.shape[1] != bev_h * bev_w or C % H:
+        raise ValueError(f'bev_sample: inconsistent shapes value{tuple(value.shape)} qproj{tuple(qproj.shape)}')
+    if out is None:
+        out = torch.empty(B, bev_h * bev_w, C, device=value.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().ub_bev_sample_fwd(_ptr(value), _ptr(qproj), _ptr(out), B, bev_h, bev_w, fH, fW, H, C // H, P,
+                                              qproj.shape[2], off_col, logit_col, _stream()), 'ub_bev_sample_fwd')
+    return out
+
+
+def img_sample(value, qproj, ref_cam, mask, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out=None):
+    """value (B, N, fH*fW, C); qproj (B, Nq, ld); ref_cam (B, Nq, N, D, 2); mask (B, Nq, N) uint8 -> (B, Nq, C)."""
+    value, qproj, ref_cam = _need(value, 'value'), _need(qproj, 'qproj'), _need(ref_cam, 'ref_cam')
+    mask = _need(mask, 'mask', torch.uint8)
+    B, N, Nv, C = value.shape
+    D = ref_cam.shape[3]
+    Nq = bev_h * bev_w
+    if Nv != fH * fW or qproj.shape[:2] != (B, Nq) or ref_cam.shape != (B, Nq, N, D, 2) or mask.shape != (B, Nq, N) or C % H:
+        raise ValueError('img_sample: inconsistent shapes')
+    if out is None:
+        out = torch.empty(B, Nq, C, device=value.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().ub_img_sample_fwd(_ptr(value), _ptr(qproj), _ptr(ref_cam), _ptr(mask), _ptr(out), B, N,
+                                              bev_h, bev_w, fH, fW, H, C // H, P, D, qproj.shape[2], off_col, logit_col,
+                                              _stream()), 'ub_img_sample_fwd')
+    return out
+
+
+def add_layernorm(x, gamma, beta, bias=None, residual=None, eps=1e-5, out=None):
+    x = _need(x, 'x')
+    C = x.shape[-1]
+    rows = x.numel() // C
+    gamma, beta = _need(gamma, 'gamma'), _need(beta, 'beta')
+    bias = _need(bias, 'bias') if bias is not None else None
+    residual = _need(residual, 'residual') if residual is not None else None
+    if residual is not None and residual.shape != x.shape:
+        raise ValueError('add_layernorm: residual shape mismatch')
+    if out is None:
+        out = torch.empty_like(x)
+    _cabi.check(_cabi.lib().ub_add_layernorm(_ptr(x), _ptr(bias), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(out),
+                                             rows, C, float(eps), _stream()), 'ub_add_layernorm')
+    return out
+
+
+def cnw_fuse(img, pts, w_img, w_pts, mode, c_flag, l_flag, s_img=None, s_pts=None, modal_embed=None):
+    ref = img if img is not None else pts
+    if ref is None:
+        raise ValueError('cnw_fuse: both modalities are None')
+    img = _need(img, 'img') if img is not None else None
+    pts = _need(pts, 'pts') if pts is not None else None
+    B, Nq, C = ref.shape
+    opt = [(_need(t, n) if t is not None else None) for t, n in
+           ((w_img, 'w_img'), (w_pts, 'w_pts'), (s_img, 's_img'), (s_pts, 's_pts'), (modal_embed, 'modal_embed'))]
+    out = torch.empty(B, Nq, C * (2 if mode == 'cat' else 1), device=ref.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().ub_cnw_fuse(_ptr(img), _ptr(pts), *[_ptr(t) for t in opt], _ptr(out), B * Nq, Nq, C,
+                                        FUSE_MODES[mode], int(c_flag), int(l_flag), _stream()), 'ub_cnw_fuse')
+    return out
+
+
+def flatten_feats(feat, embed_a=None, embed_b=None):
+    """feat (..., C, h, w) with G = prod(leading dims) -> (G, h*w, C) + embed_a[g % len(embed_a)] + embed_b."""
+    feat = _need(feat, 'feat')
+    C, h, w = feat.shape[-3:]
+    G = feat.numel() // (C * h * w)
+    embed_a = _need(embed_a, 'embed_a') if embed_a is not None else None
+    embed_b = _need(embed_b, 'embed_b') if embed_b is not None else None
+    n_a = embed_a.shape[0] if embed_a is not None else 0
+    out = torch.empty(G, h * w, C, device=feat.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().ub_flatten_feats(_ptr(feat), _ptr(embed_a), n_a, _ptr(embed_b), _ptr(out), G, C, h * w,
+                                             _stream()), 'ub_flatten_feats')
+    return out

@@ -1,0 +1,10 @@
+"""Importing this package registers the hot-path modules under the reference's names
+(ATTENTION / TRANSFORMER_LAYER / TRANSFORMER_LAYER_SEQUENCE / TRANSFORMER registries)."""
+from .attention import (MSDeformableAttention3DImg, MSDeformableAttention3DPts, MultiScaleDeformableAttention,
+                        SpatialCrossAttentionImg, SpatialCrossAttentionPts)
+from .encoder import FFN, ImgEncoder, ImgLayer, PtsEncoder, PtsLayer
+from .transformer import UniBEVTransformer
+
+__all__ = ['MSDeformableAttention3DImg', 'MSDeformableAttention3DPts', 'MultiScaleDeformableAttention',
+           'SpatialCrossAttentionImg', 'SpatialCrossAttentionPts', 'FFN', 'ImgEncoder', 'ImgLayer', 'PtsEncoder',
+           'PtsLayer', 'UniBEVTransformer']

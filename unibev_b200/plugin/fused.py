@@ -1,0 +1,189 @@
+"""Fused inference pipeline of the uniform BEV encoder (eval mode).
+
+Reads the parameters held by a ``UniBEVTransformer`` module tree and runs, per
+encoder layer:
+
+    self-attention   V  = x Wv^T + bv                     GEMM  (N = C)
+                     QP = (x + pos) [Woff;Watt]^T + b     GEMM  (N = H*P*3), pos part precomputed per frame
+                     S  = ub_bev_sample_fwd(V, QP)        fused ref-point/softmax/gather/reduce
+                     x  = LN(S Wo^T + bo + x)             GEMM + ub_add_layernorm
+    cross-attention  QP = x [Woff;Watt]^T + b             GEMM  (N = H*P*3)
+                     S  = ub_img_sample_fwd | ub_bev_sample_fwd (value projected once per frame)
+                     x  = LN(S Wo^T + bo + x)             GEMM + ub_add_layernorm
+    FFN              x  = LN(relu(x W1^T + b1) W2^T + b2 + x)
+
+No sampling_locations / attention_weights / rebatch tensors exist, nothing syncs with
+the host, and all activations live in buffers allocated once per shape.  GEMMs are
+cuBLAS(Lt) through torch (TF32 tensor-core math by default -- what torch 1.10, the
+reference's stack, also defaulted to -- or strict fp32 with ``precision='fp32'``).
+
+Reference lines reproduced: transformer_fusion.py:231-278,463-538;
+encoder_unibev_detr_img.py:189-289,413-479; encoder_unibev_detr_pts.py:129-209;
+spatial_cross_attention_img.py:141-215,381-419; spatial_cross_attention_pts.py:159-206.
+"""
+import contextlib
+
+import numpy as np
+import torch
+
+from .. import ops
+from .attention import (MSDeformableAttention3DImg, MSDeformableAttention3DPts, MultiScaleDeformableAttention,
+                        SpatialCrossAttentionImg, SpatialCrossAttentionPts)
+from .encoder import anchor_heights
+
+_ORDER = ('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm')
+
+
+def _layer_ok(layer, cross_cls, inner_cls):
+    if tuple(layer.operation_order) != _ORDER or len(layer.attentions) != 2:
+        return False
+    sa, ca = layer.attentions
+    if type(sa) is not MultiScaleDeformableAttention or type(ca) is not cross_cls:
+        return False
+    da = ca.deformable_attention
+    if not isinstance(da, inner_cls):
+        return False
+    return (sa.num_levels == 1 and da.num_levels == 1 and sa.batch_first and da.batch_first
+            and sa.num_points <= 16 and da.num_points <= 16)
+
+
+def fused_supported(model, img_feats, pts_feats):
+    """The fused pipeline covers the shapes every shipped UniBEV config uses: one feature level,
+    (self_attn, norm, cross_attn, norm, ffn, norm) layers.  Anything else takes the module path."""
+    if img_feats is not None:
+        if len(img_feats) != 1 or not all(_layer_ok(l, SpatialCrossAttentionImg, MSDeformableAttention3DImg)
+                                          for l in model.img_bev_encoder.layers):
+            return False
+        if model.img_bev_encoder.return_intermediate:
+            return False
+    if pts_feats is not None:
+        if len(pts_feats) != 1 or not all(_layer_ok(l, SpatialCrossAttentionPts, MSDeformableAttention3DPts)
+                                          for l in model.pts_bev_encoder.layers):
+            return False
+        if model.pts_bev_encoder.return_intermediate:
+            return False
+    return True
+
+
+@contextlib.contextmanager
+def _matmul_precision(tf32):
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+class _LayerWeights:
+    """Per-layer weights in the layout the fused pipeline wants (concatenated offset|logit linears)."""
+
+    def __init__(self, layer):
+        sa, ca = layer.attentions
+        da = ca.deformable_attention
+        f = layer.ffns[0]
+        cat = torch.cat
+        self.H_s, self.P_s = sa.num_heads, sa.num_points
+        self.H_c, self.P_c = da.num_heads, da.num_points
+        self.sa_wv, self.sa_bv = sa.value_proj.weight.detach(), sa.value_proj.bias.detach()
+        self.sa_wq = cat((sa.sampling_offsets.weight, sa.attention_weights.weight), 0).detach().contiguous()
+        self.sa_bq = cat((sa.sampling_offsets.bias, sa.attention_weights.bias), 0).detach().contiguous()
+        self.sa_wo, self.sa_bo = sa.output_proj.weight.detach(), sa.output_proj.bias.detach()
+        self.ca_wv, self.ca_bv = da.value_proj.weight.detach(), da.value_proj.bias.detach()
+        self.ca_wq = cat((da.sampling_offsets.weight, da.attention_weights.weight), 0).detach().contiguous()
+        self.ca_bq = cat((da.sampling_offsets.bias, da.attention_weights.bias), 0).detach().contiguous()
+        self.ca_wo, self.ca_bo = ca.output_proj.weight.detach(), ca.output_proj.bias.detach()
+        self.w1, self.b1 = f.layers[0][0].weight.detach(), f.layers[0][0].bias.detach()
+        self.w2, self.b2 = f.layers[1].weight.detach(), f.layers[1].bias.detach()
+        self.ln = [(n.weight.detach(), n.bias.detach(), n.eps) for n in layer.norms]
+
+
+class FusedEncoder:
+    def __init__(self, model, precision='tf32'):
+        if precision not in ('tf32', 'fp32'):
+            raise ValueError("precision must be 'tf32' or 'fp32'")
+        self.m = model
+        self.precision = precision
+        self.tf32 = precision == 'tf32'
+        self._w = {}
+
+    def _weights(self, name):
+        if name not in self._w:
+            enc = getattr(self.m, name)
+            layers = [_LayerWeights(l) for l in enc.layers]
+            pos_w = torch.cat([lw.sa_wq for lw in layers], 0).contiguous()      # every layer's (offset|logit) rows
+            self._w[name] = (layers, pos_w)
+        return self._w[name]
+
+    # one BEV encoder ------------------------------------------------------------------------------
+    def _run_encoder(self, name, x, pos, value_tokens, sample_cross, bev_h, bev_w):
+        """x (B, Nq, C) initial queries; pos (B*Nq, C) or None; value_tokens (rows, C) un-projected features."""
+        layers, pos_w = self._weights(name)
+        B, Nq, C = x.shape
+        x = x.reshape(B * Nq, C)
+        n_q = [lw.sa_wq.shape[0] for lw in layers]
+        pos_q = torch.mm(pos, pos_w.t()).split(n_q, dim=1) if pos is not None else None
+        for i, lw in enumerate(layers):
+            # --- BEV self-attention (mmcv MultiScaleDeformableAttention, value = query, 1 level)
+            v = torch.addmm(lw.sa_bv, x, lw.sa_wv.t())
+            qp = torch.addmm(lw.sa_bq, x, lw.sa_wq.t())
+            if pos_q is not None:
+                qp += pos_q[i]
+            s = ops.bev_sample(v.view(B, Nq, C), qp.view(B, Nq, -1), bev_h, bev_w, bev_h, bev_w, lw.H_s, lw.P_s,
+                               0, lw.H_s * lw.P_s * 2)
+            o = torch.mm(s.view(B * Nq, C), lw.sa_wo.t())
+            x = ops.add_layernorm(o, lw.ln[0][0], lw.ln[0][1], bias=lw.sa_bo, residual=x, eps=lw.ln[0][2], out=o)
+            # --- spatial cross-attention (query_pos is None for attentions[1])
+            val = torch.addmm(lw.ca_bv, value_tokens, lw.ca_wv.t())
+            qp = torch.addmm(lw.ca_bq, x, lw.ca_wq.t())
+            s = sample_cross(val, qp.view(B, Nq, -1), lw)
+            o = torch.mm(s.view(B * Nq, C), lw.ca_wo.t())
+            x = ops.add_layernorm(o, lw.ln[1][0], lw.ln[1][1], bias=lw.ca_bo, residual=x, eps=lw.ln[1][2], out=o)
+            # --- FFN
+            h = torch._addmm_activation(lw.b1, x, lw.w1.t(), use_gelu=False)
+            o = torch.mm(h, lw.w2.t())
+            x = ops.add_layernorm(o, lw.ln[2][0], lw.ln[2][1], bias=lw.b2, residual=x, eps=lw.ln[2][2], out=o)
+        return x.view(B, Nq, C)
+
+    def __call__(self, img_feats, pts_feats, bev_queries, bev_h, bev_w, bev_pos, img_metas):
+        m = self.m
+        ref = (img_feats or pts_feats)[0]
+        B, dev = ref.size(0), ref.device
+        Nq, C = bev_h * bev_w, m.embed_dims
+        if m.dual_queries:
+            q_img, q_pts = bev_queries
+        else:
+            q_img = q_pts = bev_queries
+        pos = ops.flatten_feats(bev_pos).view(B * Nq, C) if bev_pos is not None else None
+        img = pts = None
+        with torch.no_grad(), _matmul_precision(self.tf32):
+            if img_feats is not None:
+                feat = img_feats[0]
+                _, N, _, fh, fw = feat.shape
+                enc = m.img_bev_encoder
+                tokens = ops.flatten_feats(feat, m.cams_embeds if m.use_cams_embeds else None, m.img_level_embeds[0])
+                l2i = torch.from_numpy(np.asarray([mt['lidar2img'] for mt in img_metas], dtype=np.float32)).to(dev)
+                D = enc.num_points_in_pillar
+                zs = anchor_heights(enc.pc_range[5] - enc.pc_range[2], D).tolist()
+                ih, iw = img_metas[0]['img_shape'][0][0], img_metas[0]['img_shape'][0][1]
+                ref_cam, mask = ops.project_points(l2i, zs, enc.pc_range, ih, iw, bev_h, bev_w)
+
+                def cross(val, qp, lw):
+                    return ops.img_sample(val.view(B, N, fh * fw, C), qp, ref_cam, mask, bev_h, bev_w, fh, fw,
+                                          lw.H_c, lw.P_c, 0, lw.H_c * lw.P_c * 2)
+                x0 = q_img.detach().unsqueeze(0).expand(B, Nq, C)
+                img = self._run_encoder('img_bev_encoder', x0, pos, tokens.view(B * N * fh * fw, C), cross, bev_h, bev_w)
+            if pts_feats is not None:
+                feat = pts_feats[0]
+                _, _, fh, fw = feat.shape
+                enc = m.pts_bev_encoder
+                tokens = ops.flatten_feats(feat, None, m.pts_level_embeds[0])
+
+                def cross(val, qp, lw, fh=fh, fw=fw):
+                    return ops.bev_sample(val.view(B, fh * fw, C), qp, bev_h, bev_w, fh, fw, lw.H_c, lw.P_c,
+                                          0, lw.H_c * lw.P_c * 2)
+                x0 = q_pts.detach().unsqueeze(0).expand(B, Nq, C)
+                pts = self._run_encoder('pts_bev_encoder', x0, pos, tokens.view(B * fh * fw, C), cross, bev_h, bev_w)
+            return ops.cnw_fuse(img, pts, getattr(m, 'img_channel_weights', None), getattr(m, 'pts_channel_weights', None),
+                                m.fusion_method, m.c_flag, m.l_flag, getattr(m, 'img_spatial_weights', None),
+                                getattr(m, 'pts_spatial_weights', None), m._modal_embed())
