@@ -55,23 +55,15 @@ def main():
         'pts_cross': (0, lambda i: ops.bev_sample(v_pts[i % R], qp_pts, 200, 200, 180, 180, H, 8, 0, 128, out=out), 104.9e6),
         'img_cross': (1, lambda i: ops.img_sample(v_img[i % R], qp_img, ref_cam, mask, 200, 200, 29, 50, H, 8, 0, 128, out=out), 82.5e6),
     }
-    tiles = [(16, 8), (8, 8), (16, 16), (32, 8), (8, 4), (200, 1), (25, 5), (20, 10)]
     results = []
     for name, (which, fn, nbytes) in runs.items():
-        for (tw, th), hpc, threads in itertools.product(tiles, (0, 1, 2), (128, 256, 512, 1024)):
-            if tw * th * 8 < threads and hpc:       # fewer (q) items than groups
-                continue
-            _cabi.set_tuning(which, tw, th, hpc, threads)
+        for tw in (2, 4, 8, 16, 32, 64):
+            _cabi.set_tuning(which, tw, 64 // tw, 0, 256)
             us = timeit(fn)
-            results.append((name, tw, th, hpc, threads, us, nbytes / us / 1e3))
-    _cabi.set_tuning(0, 16, 8, 0, 256)
-    _cabi.set_tuning(1, 16, 8, 0, 256)
-    for name in runs:
-        best = sorted((r for r in results if r[0] == name), key=lambda r: r[5])
-        print(f'== {name}: best 8 of {len(best)}')
-        for r in best[:8]:
-            print('   tile %dx%d heads/cta %d threads %d : %.1f us  (%.0f GB/s algorithmic)' % r[1:])
-        print('   worst: tile %dx%d heads/cta %d threads %d : %.1f us' % best[-1][1:6])
+            results.append((name, tw, 64 // tw, us, nbytes / us / 1e3))
+            print('%-10s tile %2dx%-2d : %7.1f us  (%.0f GB/s algorithmic)' % results[-1], flush=True)
+    _cabi.set_tuning(0, 8, 8, 0, 256)
+    _cabi.set_tuning(1, 8, 8, 0, 256)
     os.makedirs('gpurun_out', exist_ok=True)
     json.dump(results, open('gpurun_out/sweep_sampling.json', 'w'))
 
