@@ -57,13 +57,13 @@ def main():
     }
     results = []
     for name, (which, fn, nbytes) in runs.items():
-        for tw in (2, 4, 8, 16, 32, 64):
-            _cabi.set_tuning(which, tw, 64 // tw, 0, 256)
+        for tw, cps in [(8, 0), (8, 2), (8, 3), (8, 5), (8, 6), (4, 0), (16, 0), (32, 0)]:
+            _cabi.set_tuning(which, tw, cps)
             us = timeit(fn)
-            results.append((name, tw, 64 // tw, us, nbytes / us / 1e3))
-            print('%-10s tile %2dx%-2d : %7.1f us  (%.0f GB/s algorithmic)' % results[-1], flush=True)
-    _cabi.set_tuning(0, 8, 8, 0, 256)
-    _cabi.set_tuning(1, 8, 8, 0, 256)
+            results.append((name, tw, 64 // tw, cps, us, nbytes / us / 1e3))
+            print('%-10s tile %2dx%-2d ctas/SM %d : %7.1f us  (%.0f GB/s algorithmic)' % results[-1], flush=True)
+    _cabi.set_tuning(0)
+    _cabi.set_tuning(1)
     os.makedirs('gpurun_out', exist_ok=True)
     json.dump(results, open('gpurun_out/sweep_sampling.json', 'w'))
 

@@ -31,7 +31,7 @@ PROTOTYPES = {
 }
 # not part of the public header: tuning hook used by bench/sweeps
 _PRIVATE = {
-    'ub_set_tuning': ([_i] * 5, _i),
+    'ub_set_tuning': ([_i] * 3, _i),
 }
 
 _lib = None
@@ -74,6 +74,6 @@ def reset_launch_count():
     lib().ub_launch_count_reset()
 
 
-def set_tuning(which, tile_w, tile_h, heads_per_cta, threads):
-    """which: 0 = ub_bev_sample_fwd, 1 = ub_img_sample_fwd."""
-    check(lib().ub_set_tuning(which, tile_w, tile_h, heads_per_cta, threads), 'ub_set_tuning')
+def set_tuning(which, tile_w=8, ctas_per_sm=0):
+    """which: 0 = ub_bev_sample_fwd, 1 = ub_img_sample_fwd; tile = tile_w x 64/tile_w queries."""
+    check(lib().ub_set_tuning(which, tile_w, ctas_per_sm), 'ub_set_tuning')

@@ -1,0 +1,104 @@
+"""Frame pipeline: streams nuScenes samples through ``UniBEVTransformer.encode`` from HOST buffers.
+
+The reference moves every batch host->device synchronously (``MMDataParallel.scatter``, test_UniBEV.py:214-217) and
+copies ``lidar2img`` inside the encoder on every forward (encoder_unibev_detr_img.py:115-124).  Here each frame
+owns one of ``depth`` slots (pinned host staging + device buffers + a pinned host result) and three streams work
+on different frames at once:
+
+    copy-in stream   H2D of the frame's feature tensors and calibration
+    compute stream   the fused encoder (libunibev_b200 kernels + GEMMs)
+    copy-out stream  D2H of fused_bev_embed into the slot's pinned result
+
+so PCIe traffic of frame i+1 / i-1 overlaps the kernels of frame i.  Samples are independent (no collective).
+"""
+import numpy as np
+import torch
+
+
+class _Slot:
+    def __init__(self, img_shape, pts_shape, n_cams, out_shape, dev):
+        f32 = torch.float32
+        self.img_host = torch.empty(img_shape, dtype=f32).pin_memory() if img_shape else None
+        self.pts_host = torch.empty(pts_shape, dtype=f32).pin_memory() if pts_shape else None
+        self.img_dev = torch.empty(img_shape, dtype=f32, device=dev) if img_shape else None
+        self.pts_dev = torch.empty(pts_shape, dtype=f32, device=dev) if pts_shape else None
+        B = (img_shape or pts_shape)[0]
+        self.l2i_host = torch.empty(B, n_cams, 4, 4, dtype=f32).pin_memory() if img_shape else None
+        self.l2i_dev = torch.empty(B, n_cams, 4, 4, dtype=f32, device=dev) if img_shape else None
+        self.out_host = torch.empty(out_shape, dtype=f32).pin_memory()
+        self.copied_in = torch.cuda.Event()
+        self.computed = torch.cuda.Event()
+        self.copied_out = torch.cuda.Event()
+        self.busy = False
+
+
+class FramePipeline:
+    """``submit`` enqueues one batch of samples and returns a ticket; ``result(ticket)`` blocks until that batch's
+    fused_bev_embed is in pinned host memory and returns it (valid until the slot is reused ``depth`` submits later)."""
+
+    def __init__(self, model, bev_queries, bev_h, bev_w, bev_pos=None, img_shape=None, pts_shape=None,
+                 img_hw=None, depth=2, device=None):
+        if img_shape is None and pts_shape is None:
+            raise ValueError('at least one of img_shape / pts_shape is required')
+        self.model = model
+        self.dev = torch.device(device if device is not None else torch.cuda.current_device())
+        self.bev_h, self.bev_w, self.img_hw = bev_h, bev_w, img_hw
+        to = lambda t: t.to(self.dev) if t is not None else None   # noqa: E731
+        self.bev_queries = [to(q) for q in bev_queries] if isinstance(bev_queries, (list, tuple)) else to(bev_queries)
+        self.bev_pos = to(bev_pos)
+        B = (img_shape or pts_shape)[0]
+        n_cams = img_shape[1] if img_shape else 0
+        out_shape = (B, bev_h * bev_w, model.embed_dims * model.scale_factor)
+        self.slots = [_Slot(img_shape, pts_shape, n_cams, out_shape, self.dev) for _ in range(depth)]
+        self.s_in, self.s_compute, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
+        self.n_submitted = 0
+        self.h2d_bytes = sum(t.numel() * 4 for t in (self.slots[0].img_host, self.slots[0].pts_host,
+                                                      self.slots[0].l2i_host) if t is not None)
+        self.d2h_bytes = self.slots[0].out_host.numel() * 4
+
+    def submit(self, img_feat=None, pts_feat=None, img_metas=None):
+        """img_feat (B, N, C, h, w) / pts_feat (B, C, h, w): HOST tensors (pinned or not); img_metas: the reference's
+        list[dict] with 'lidar2img' (and 'img_shape' unless ``img_hw`` was given)."""
+        ticket = self.n_submitted
+        slot = self.slots[ticket % len(self.slots)]
+        if slot.busy:
+            slot.copied_out.synchronize()       # its previous result must have left the device
+        slot.busy = True
+        img_hw = self.img_hw
+        with torch.cuda.stream(self.s_in):
+            if slot.img_dev is not None:
+                src = img_feat if img_feat.is_pinned() else slot.img_host.copy_(img_feat)
+                slot.img_dev.copy_(src, non_blocking=True)
+                slot.l2i_host.copy_(torch.from_numpy(np.asarray([m['lidar2img'] for m in img_metas], dtype=np.float32)))
+                slot.l2i_dev.copy_(slot.l2i_host, non_blocking=True)
+                if img_hw is None:
+                    img_hw = tuple(img_metas[0]['img_shape'][0][:2])
+            if slot.pts_dev is not None:
+                src = pts_feat if pts_feat.is_pinned() else slot.pts_host.copy_(pts_feat)
+                slot.pts_dev.copy_(src, non_blocking=True)
+            slot.copied_in.record(self.s_in)
+        with torch.cuda.stream(self.s_compute), torch.no_grad():
+            self.s_compute.wait_event(slot.copied_in)
+            out = self.model.encode([slot.img_dev] if slot.img_dev is not None else None,
+                                    [slot.pts_dev] if slot.pts_dev is not None else None,
+                                    self.bev_queries, self.bev_h, self.bev_w, bev_pos=self.bev_pos,
+                                    img_metas=img_metas, lidar2img=slot.l2i_dev, img_shape=img_hw)
+            slot.computed.record(self.s_compute)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(slot.computed)
+            slot.out_host.copy_(out, non_blocking=True)
+            out.record_stream(self.s_out)
+            slot.copied_out.record(self.s_out)
+        self.n_submitted += 1
+        return ticket
+
+    def result(self, ticket):
+        if ticket < self.n_submitted - len(self.slots) or ticket >= self.n_submitted:
+            raise ValueError(f'ticket {ticket} is no longer (or not yet) held by a slot')
+        slot = self.slots[ticket % len(self.slots)]
+        slot.copied_out.synchronize()
+        return slot.out_host
+
+    def drain(self):
+        for s in (self.s_in, self.s_compute, self.s_out):
+            s.synchronize()

@@ -43,8 +43,10 @@ def _layer_ok(layer, cross_cls, inner_cls):
     da = ca.deformable_attention
     if not isinstance(da, inner_cls):
         return False
+    head_dims_ok = all(m.embed_dims // m.num_heads in (8, 16, 32, 64) and m.embed_dims % m.num_heads == 0
+                       for m in (sa, da))
     return (sa.num_levels == 1 and da.num_levels == 1 and sa.batch_first and da.batch_first
-            and sa.num_points <= 16 and da.num_points <= 16)
+            and sa.num_points <= 16 and da.num_points <= 16 and head_dims_ok)
 
 
 def fused_supported(model, img_feats, pts_feats):
@@ -145,7 +147,11 @@ class FusedEncoder:
             x = ops.add_layernorm(o, lw.ln[2][0], lw.ln[2][1], bias=lw.b2, residual=x, eps=lw.ln[2][2], out=o)
         return x.view(B, Nq, C)
 
-    def __call__(self, img_feats, pts_feats, bev_queries, bev_h, bev_w, bev_pos, img_metas):
+    def __call__(self, img_feats, pts_feats, bev_queries, bev_h, bev_w, bev_pos, img_metas, lidar2img=None,
+                 img_shape=None):
+        """``lidar2img`` (B, N, 4, 4) fp32 already on the device and ``img_shape`` (h, w) replace the per-call
+        host->device copy of ``img_metas[i]['lidar2img']`` (encoder_unibev_detr_img.py:115-124) when the caller
+        stages calibration itself (``unibev_b200.pipeline.FramePipeline``)."""
         m = self.m
         ref = (img_feats or pts_feats)[0]
         B, dev = ref.size(0), ref.device
@@ -162,10 +168,14 @@ class FusedEncoder:
                 _, N, _, fh, fw = feat.shape
                 enc = m.img_bev_encoder
                 tokens = ops.flatten_feats(feat, m.cams_embeds if m.use_cams_embeds else None, m.img_level_embeds[0])
-                l2i = torch.from_numpy(np.asarray([mt['lidar2img'] for mt in img_metas], dtype=np.float32)).to(dev)
+                if lidar2img is not None:
+                    l2i = lidar2img
+                    ih, iw = img_shape
+                else:
+                    l2i = torch.from_numpy(np.asarray([mt['lidar2img'] for mt in img_metas], dtype=np.float32)).to(dev)
+                    ih, iw = img_metas[0]['img_shape'][0][0], img_metas[0]['img_shape'][0][1]
                 D = enc.num_points_in_pillar
                 zs = anchor_heights(enc.pc_range[5] - enc.pc_range[2], D).tolist()
-                ih, iw = img_metas[0]['img_shape'][0][0], img_metas[0]['img_shape'][0][1]
                 ref_cam, mask = ops.project_points(l2i, zs, enc.pc_range, ih, iw, bev_h, bev_w)
 
                 def cross(val, qp, lw):

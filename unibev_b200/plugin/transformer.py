@@ -247,7 +247,7 @@ class UniBEVTransformer(nn.Module):
             if self._fused is None or self._fused.precision != self.fused_precision:
                 self._fused = FusedEncoder(self, self.fused_precision)
             return self._fused(img_mlvl_feats, pts_mlvl_feats, bev_queries, bev_h, bev_w, bev_pos,
-                               kwargs.get('img_metas'))
+                               kwargs.get('img_metas'), kwargs.get('lidar2img'), kwargs.get('img_shape'))
         img, pts = self._encode_modules(img_mlvl_feats, pts_mlvl_feats, bev_queries, bev_h, bev_w, bev_pos, **kwargs)
         if grad:
             return self._fuse_modules(img, pts)
