@@ -313,11 +313,15 @@ def main():
     roofline = None
     if dominant:
         k = kernels[dominant]
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(dominant) if B == 1 else None
+        except OSError:
+            traffic = None
         roofline = {'bound': 'hbm', 'kernel': {'bev_self': 'bev_sample_kernel (BEV self-attn, P=4)',
                                                'pts_cross': 'bev_sample_kernel (LiDAR cross-attn, P=8)',
                                                'img_cross': 'img_sample_kernel (camera cross-attn, P=8)'}[dominant],
                     'achieved': k['achieved_gbs'], 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
-                    'frac': k['frac'], 'traffic': None, 'avg_us': k['avg_us'], 'alg_bytes_per_launch': k['alg_bytes']}
+                    'frac': k['frac'], 'traffic': traffic, 'avg_us': k['avg_us'], 'alg_bytes_per_launch': k['alg_bytes']}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -92,3 +92,25 @@ def test_dropflags_fixtures_cover_both_branches():
     f1 = load_golden('encoder_half_lc_cnw_dropflags')[0]['flags'].tolist()
     f2 = load_golden('encoder_half_lc_cnw_dropdict')[0]['flags'].tolist()
     assert sorted([tuple(f1), tuple(f2)]) == [(0, 1), (1, 0)] or {tuple(f1), tuple(f2)} <= {(0, 1), (1, 0)}
+
+
+def test_c_oracle_matches_kat_and_torch_oracle():
+    """The plain-C restatement of mmcv's CUDA-kernel semantics (oracle/msda_core.c) against the transformers-made
+    known-answer vectors, and against the grid_sample oracle on adversarial coordinates (outside, on borders,
+    exactly on pixel centres, huge magnitudes from z < eps projections, NaN-free)."""
+    from oracle import c_msda
+    a, _ = load_golden('msda_core')
+    shapes = [tuple(int(v) for v in r) for r in a['shapes']]
+    got = c_msda.msda_forward(a['value'].numpy(), shapes, a['loc'].numpy(), a['w'].numpy())
+    np.testing.assert_allclose(got, a['out'].numpy(), rtol=1e-5, atol=2e-6)
+    g = torch.Generator().manual_seed(11)
+    shapes = [(5, 7), (3, 2)]
+    B, H, D, Nq, P = 2, 3, 4, 40, 4
+    value = torch.randn(B, sum(h * w for h, w in shapes), H, D, generator=g)
+    loc = torch.rand(B, Nq, H, len(shapes), P, 2, generator=g) * 1.6 - 0.3
+    loc[0, :6] = torch.tensor([0.0, 1.0, 0.5, -1e7, 1e7, 0.1])[:, None, None, None, None]      # borders / blow-ups
+    loc[1, :5, :, 0] = (torch.arange(5)[:, None, None, None] + 0.5) / 7.0                        # exact pixel centres
+    w = torch.rand(B, Nq, H, len(shapes), P, generator=g)
+    want = ms.msda_core(value, shapes, loc, w)
+    got = c_msda.msda_forward(value.numpy(), shapes, loc.numpy(), w.numpy())
+    np.testing.assert_allclose(got, want.numpy(), rtol=1e-5, atol=2e-6)
