@@ -39,7 +39,8 @@ enum {
   UB_OK = 0,
   UB_EINVAL = -1,   /* bad argument / unsupported shape */
   UB_ECUDA = -2,    /* CUDA runtime error at launch */
-  UB_EALIGN = -3    /* pointer not 16-byte aligned */
+  UB_EALIGN = -3,   /* pointer not 16-byte aligned */
+  UB_EUNSUPPORTED = -4 /* valid arguments, but this entry point has no kernel for the shape: use the generic one */
 };
 
 /* Fusion modes of ub_cnw_fuse [R6]. */
@@ -95,6 +96,33 @@ int ub_bev_sample_fwd(const float* value, const float* qproj, float* out,
 int ub_img_sample_fwd(const float* value, const float* qproj, const float* ref_cam, const uint8_t* mask,
                       float* out, int B, int N, int bev_h, int bev_w, int fH, int fW, int H, int Dh, int P,
                       int D, int ld, int off_col, int logit_col, ub_stream_t stream);
+
+/* ---- [R4]/[R3] window-staged fast path (fp16-staged values, fp32 accumulation) ------------------------
+ * Same arithmetic as ub_bev_sample_fwd / ub_img_sample_fwd, but the value map is read from fp16 head-major
+ * planes staged in shared memory by TMA, and the bilinear x attention weights are rounded to fp16 before the
+ * fp32-accumulated multiply-add (error well below that of a TF32 projection GEMM).  Head dim 32
+ * and 4 or 8 points only: other shapes return UB_EUNSUPPORTED and the caller uses the fp32 entry points.
+ *
+ * ub_value_to_half: value (G*Nv, H*Dh) fp32 token-major  ->  value16 (G, H, Nv, Dh) fp16 (saturating). */
+int ub_value_to_half(const float* value, void* value16, int G, int Nv, int H, int Dh, ub_stream_t stream);
+/* value16 (B, H, fH*fW, 32) fp16; qproj / out as in ub_bev_sample_fwd (ld, off_col, logit_col multiples of 4). */
+int ub_bev_sample_win_fwd(const void* value16, const float* qproj, float* out,
+                          int B, int bev_h, int bev_w, int fH, int fW, int H, int Dh, int P,
+                          int ld, int off_col, int logit_col, ub_stream_t stream);
+/* Halo (value-map pixels) the BEV windows extend beyond the tile's reference points; 0 = default (P + 1).
+ * Samples outside the window are still exact (slow path), so this is a performance knob only. */
+int ub_set_window_halo(int halo);
+/* mask (B, Nq, N) from ub_project_points -> hit_idx (N, Nq) int32: the queries batch item 0 sees in camera n,
+ * ascending (spatial_cross_attention_img.py:141-152); hit_cnt (N) int32; inv_cnt (B, Nq) = 1 / max(1, #cameras
+ * whose mask for (b, q) is non-zero) (:209-212). */
+int ub_build_hits(const uint8_t* mask, int* hit_idx, int* hit_cnt, float* inv_cnt, int B, int N, int Nq,
+                  ub_stream_t stream);
+/* value16 (B, N, H, fH*fW, 32) fp16; out (B, Nq, H*32) is zero-filled by the call, then accumulated with
+ * red.global.add (sums over more than two cameras are order-dependent in the last bit). */
+int ub_img_sample_win_fwd(const void* value16, const float* qproj, const float* ref_cam, const int* hit_idx,
+                          const int* hit_cnt, const float* inv_cnt, float* out, int B, int N, int bev_h, int bev_w,
+                          int fH, int fW, int H, int Dh, int P, int D, int ld, int off_col, int logit_col,
+                          ub_stream_t stream);
 
 /* ---- [R5] y = LayerNorm(x + bias + residual) * gamma + beta over the last dim C ---------------------
  * bias (C) and residual (rows, C) may be NULL.  C % 4 == 0, C <= 1024.  out may alias x. */

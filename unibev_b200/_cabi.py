@@ -25,6 +25,11 @@ PROTOTYPES = {
     'ub_project_points': ([_p, _p, _p, _f, _f, _p, _p] + [_i] * 5 + [_p], _i),
     'ub_bev_sample_fwd': ([_p] * 3 + [_i] * 11 + [_p], _i),
     'ub_img_sample_fwd': ([_p] * 5 + [_i] * 13 + [_p], _i),
+    'ub_value_to_half': ([_p, _p] + [_i] * 4 + [_p], _i),
+    'ub_bev_sample_win_fwd': ([_p] * 3 + [_i] * 11 + [_p], _i),
+    'ub_set_window_halo': ([_i], _i),
+    'ub_build_hits': ([_p] * 4 + [_i] * 3 + [_p], _i),
+    'ub_img_sample_win_fwd': ([_p] * 7 + [_i] * 13 + [_p], _i),
     'ub_add_layernorm': ([_p] * 6 + [_i64, _i, _f, _p], _i),
     'ub_cnw_fuse': ([_p] * 8 + [_i64, _i, _i, _i, _i, _i, _p], _i),
     'ub_flatten_feats': ([_p, _p, _i, _p, _p, _i, _i, _i, _p], _i),
@@ -58,11 +63,20 @@ def lib():
     return _lib
 
 
+UB_EUNSUPPORTED = -4
+
+
+class UnsupportedShape(UniBEVNativeError):
+    """The specialised entry point has no kernel for this shape; callers switch to the generic one."""
+
+
 def check(rc, what):
     if rc != 0:
         msg = lib().ub_last_error().decode('utf-8', 'replace')
         if rc == -1:
             raise ValueError(f'{what}: {msg}')
+        if rc == UB_EUNSUPPORTED:
+            raise UnsupportedShape(f'{what}: {msg}')
         raise UniBEVNativeError(f'{what} failed (code {rc}): {msg}')
 
 

@@ -123,6 +123,68 @@ def img_sample(value, qproj, ref_cam, mask, bev_h, bev_w, fH, fW, H, P, off_col,
     return out
 
 
+def value_to_half(value, G, Nv, H, out=None):
+    """value (G*Nv, C) fp32 token-major -> (G, H, Nv, C // H) fp16 head-major planes for the window kernels."""
+    value = _need(value, 'value')
+    C = value.shape[-1]
+    if value.numel() != G * Nv * C or C % H or (C // H) % 8:
+        raise ValueError(f'value_to_half: inconsistent shapes value{tuple(value.shape)} G={G} Nv={Nv} H={H}')
+    if out is None:
+        out = torch.empty(G, H, Nv, C // H, device=value.device, dtype=torch.float16)
+    _cabi.check(_cabi.lib().ub_value_to_half(_ptr(value), _ptr(out), G, Nv, H, C // H, _stream()), 'ub_value_to_half')
+    return out
+
+
+def window_supported(Dh, P):
+    """Shapes the window-staged (fp16) sampling kernels are built for."""
+    return Dh == 32 and P in (4, 8)
+
+
+def bev_sample_win(value16, qproj, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out=None):
+    """value16 (B, H, fH*fW, 32) fp16 from value_to_half; qproj (B, Nq, ld) -> (B, Nq, H*32) fp32."""
+    value16, qproj = _need(value16, 'value16', torch.float16), _need(qproj, 'qproj')
+    B, Hh, Nv, Dh = value16.shape
+    if Hh != H or Nv != fH * fW or qproj.shape[0] != B or qproj.shape[1] != bev_h * bev_w:
+        raise ValueError(f'bev_sample_win: inconsistent shapes value16{tuple(value16.shape)} qproj{tuple(qproj.shape)}')
+    if out is None:
+        out = torch.empty(B, bev_h * bev_w, H * Dh, device=qproj.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().ub_bev_sample_win_fwd(_ptr(value16), _ptr(qproj), _ptr(out), B, bev_h, bev_w, fH, fW, H, Dh,
+                                                  P, qproj.shape[2], off_col, logit_col, _stream()),
+                'ub_bev_sample_win_fwd')
+    return out
+
+
+def build_hits(mask):
+    """mask (B, Nq, N) uint8 -> hit_idx (N, Nq) int32, hit_cnt (N) int32, inv_cnt (B, Nq) fp32 (all on the device)."""
+    mask = _need(mask, 'mask', torch.uint8)
+    B, Nq, N = mask.shape
+    hit_idx = torch.empty(N, Nq, device=mask.device, dtype=torch.int32)
+    hit_cnt = torch.empty(N, device=mask.device, dtype=torch.int32)
+    inv_cnt = torch.empty(B, Nq, device=mask.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().ub_build_hits(_ptr(mask), _ptr(hit_idx), _ptr(hit_cnt), _ptr(inv_cnt), B, N, Nq, _stream()),
+                'ub_build_hits')
+    return hit_idx, hit_cnt, inv_cnt
+
+
+def img_sample_win(value16, qproj, ref_cam, hits, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out=None):
+    """value16 (B, N, H, fH*fW, 32) fp16; hits = build_hits(mask); -> (B, Nq, H*32) fp32."""
+    value16, qproj, ref_cam = _need(value16, 'value16', torch.float16), _need(qproj, 'qproj'), _need(ref_cam, 'ref_cam')
+    hit_idx, hit_cnt, inv_cnt = hits
+    B, N, Hh, Nv, Dh = value16.shape
+    D = ref_cam.shape[3]
+    Nq = bev_h * bev_w
+    if (Hh != H or Nv != fH * fW or qproj.shape[:2] != (B, Nq) or ref_cam.shape != (B, Nq, N, D, 2)
+            or hit_idx.shape != (N, Nq) or inv_cnt.shape != (B, Nq)):
+        raise ValueError('img_sample_win: inconsistent shapes')
+    if out is None:
+        out = torch.empty(B, Nq, H * Dh, device=qproj.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().ub_img_sample_win_fwd(_ptr(value16), _ptr(qproj), _ptr(ref_cam), _ptr(hit_idx), _ptr(hit_cnt),
+                                                  _ptr(inv_cnt), _ptr(out), B, N, bev_h, bev_w, fH, fW, H, Dh, P, D,
+                                                  qproj.shape[2], off_col, logit_col, _stream()),
+                'ub_img_sample_win_fwd')
+    return out
+
+
 def add_layernorm(x, gamma, beta, bias=None, residual=None, eps=1e-5, out=None):
     x = _need(x, 'x')
     C = x.shape[-1]

@@ -14,8 +14,13 @@ encoder layer:
 
 No sampling_locations / attention_weights / rebatch tensors exist, nothing syncs with
 the host, and all activations live in buffers allocated once per shape.  GEMMs are
-cuBLAS(Lt) through torch (TF32 tensor-core math by default -- what torch 1.10, the
-reference's stack, also defaulted to -- or strict fp32 with ``precision='fp32'``).
+cuBLAS(Lt) through torch.  Two precision classes:
+
+* ``precision='tf32'`` (default): TF32 tensor-core GEMMs -- what torch 1.10, the reference's
+  stack, also defaulted to -- and the window-staged sampling kernels (``ub_*_sample_win_fwd``:
+  value maps staged as fp16 planes by TMA, fp32 accumulation) where the shape is covered
+  (head dim 32, 4 / 8 points); their rounding error is a fraction of the TF32 GEMMs'.
+* ``precision='fp32'``: strict fp32 GEMMs and the fp32 sampling kernels.
 
 Reference lines reproduced: transformer_fusion.py:231-278,463-538;
 encoder_unibev_detr_img.py:189-289,413-479; encoder_unibev_detr_pts.py:129-209;
@@ -26,7 +31,7 @@ import contextlib
 import numpy as np
 import torch
 
-from .. import ops
+from .. import _cabi, ops
 from .attention import (MSDeformableAttention3DImg, MSDeformableAttention3DPts, MultiScaleDeformableAttention,
                         SpatialCrossAttentionImg, SpatialCrossAttentionPts)
 from .encoder import anchor_heights
@@ -107,6 +112,7 @@ class FusedEncoder:
         self.m = model
         self.precision = precision
         self.tf32 = precision == 'tf32'
+        self.fast_sampling = self.tf32      # window-staged fp16 sampling kernels where the shape is covered
         self._w = {}
 
     def _weights(self, name):
@@ -116,6 +122,17 @@ class FusedEncoder:
             pos_w = torch.cat([lw.sa_wq for lw in layers], 0).contiguous()      # every layer's (offset|logit) rows
             self._w[name] = (layers, pos_w)
         return self._w[name]
+
+    def _bev_sample(self, val, qp, B, bev_h, bev_w, fh, fw, H, P):
+        """val (B*fh*fw, C) projected value rows -> sampled (B, Nq, C); window kernels when the shape is covered."""
+        C = val.shape[-1]
+        if self.fast_sampling and ops.window_supported(C // H, P) and qp.shape[2] % 4 == 0:
+            try:
+                return ops.bev_sample_win(ops.value_to_half(val, B, fh * fw, H), qp, bev_h, bev_w, fh, fw, H, P,
+                                          0, H * P * 2)
+            except _cabi.UnsupportedShape:
+                pass
+        return ops.bev_sample(val.view(B, fh * fw, C), qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2)
 
     # one BEV encoder ------------------------------------------------------------------------------
     def _run_encoder(self, name, x, pos, value_tokens, sample_cross, bev_h, bev_w):
@@ -131,8 +148,7 @@ class FusedEncoder:
             qp = torch.addmm(lw.sa_bq, x, lw.sa_wq.t())
             if pos_q is not None:
                 qp += pos_q[i]
-            s = ops.bev_sample(v.view(B, Nq, C), qp.view(B, Nq, -1), bev_h, bev_w, bev_h, bev_w, lw.H_s, lw.P_s,
-                               0, lw.H_s * lw.P_s * 2)
+            s = self._bev_sample(v, qp.view(B, Nq, -1), B, bev_h, bev_w, bev_h, bev_w, lw.H_s, lw.P_s)
             o = torch.mm(s.view(B * Nq, C), lw.sa_wo.t())
             x = ops.add_layernorm(o, lw.ln[0][0], lw.ln[0][1], bias=lw.sa_bo, residual=x, eps=lw.ln[0][2], out=o)
             # --- spatial cross-attention (query_pos is None for attentions[1])
@@ -177,8 +193,16 @@ class FusedEncoder:
                 D = enc.num_points_in_pillar
                 zs = anchor_heights(enc.pc_range[5] - enc.pc_range[2], D).tolist()
                 ref_cam, mask = ops.project_points(l2i, zs, enc.pc_range, ih, iw, bev_h, bev_w)
+                hits = []
 
                 def cross(val, qp, lw):
+                    if (self.fast_sampling and ops.window_supported(C // lw.H_c, lw.P_c)
+                            and (fh + 2) * (fw + 2) * 64 <= 150 * 1024):
+                        if not hits:
+                            hits.append(ops.build_hits(mask))
+                        v16 = ops.value_to_half(val, B * N, fh * fw, lw.H_c).view(B, N, lw.H_c, fh * fw, -1)
+                        return ops.img_sample_win(v16, qp, ref_cam, hits[0], bev_h, bev_w, fh, fw, lw.H_c, lw.P_c,
+                                                  0, lw.H_c * lw.P_c * 2)
                     return ops.img_sample(val.view(B, N, fh * fw, C), qp, ref_cam, mask, bev_h, bev_w, fh, fw,
                                           lw.H_c, lw.P_c, 0, lw.H_c * lw.P_c * 2)
                 x0 = q_img.detach().unsqueeze(0).expand(B, Nq, C)
@@ -190,8 +214,7 @@ class FusedEncoder:
                 tokens = ops.flatten_feats(feat, None, m.pts_level_embeds[0])
 
                 def cross(val, qp, lw, fh=fh, fw=fw):
-                    return ops.bev_sample(val.view(B, fh * fw, C), qp, bev_h, bev_w, fh, fw, lw.H_c, lw.P_c,
-                                          0, lw.H_c * lw.P_c * 2)
+                    return self._bev_sample(val, qp, B, bev_h, bev_w, fh, fw, lw.H_c, lw.P_c)
                 x0 = q_pts.detach().unsqueeze(0).expand(B, Nq, C)
                 pts = self._run_encoder('pts_bev_encoder', x0, pos, tokens.view(B * fh * fw, C), cross, bev_h, bev_w)
             return ops.cnw_fuse(img, pts, getattr(m, 'img_channel_weights', None), getattr(m, 'pts_channel_weights', None),
