@@ -12,22 +12,26 @@
 // tile of queries can reach is brought into shared memory by one TMA box copy per (tile, head) -- no demand
 // misses, zero padding outside the map for free (TMA fills out-of-bounds box elements with zeros).
 //
-// Work unit (BEV mode) = 16 x 16 BEV queries x one head.  512 threads:
-//   phase 1  one thread per SAMPLE (query, point): offsets / logits come from a TMA-staged tile of the fused
-//            offset|logit GEMM output; softmax across the P adjacent lanes; the sample becomes a descriptor in
-//            shared memory: a 16-bit pixel index into the window and two half2 words
-//            {w_top, w_bottom} x {left, right} (attention weight folded in).
-//   phase 2  8 lanes per ITEM (query, head): lanes 0-3 own the left pixel, 4-7 the right one, 8 channels each;
-//            per point 1 LDS.32 (weights) + 2 LDS.128 (top / bottom pixel pair) + 16 mixed-precision FMAs
-//            (fma.rn.f32.f16: fp16 value x fp16 weight accumulated in fp32); the halves are combined with four
-//            shuffles and written as one 128-byte row.
+// Worker warp w of a CTA (16 per CTA, one CTA per SM) owns 16 items (query, head) of the current unit:
+//   P1  one lane per SAMPLE (query, point): offsets / logits (the warp's TMA-staged row of the fused
+//       offset|logit GEMM output in BEV mode, register-prefetched direct loads in camera mode), softmax across the
+//       P adjacent lanes, then a descriptor in the warp's shared-memory slice: a 16-bit pixel index into the
+//       window and two half2 words {w_top, w_bottom} x {left, right} (attention weight folded in).
+//   P2  8 lanes per ITEM: lanes 0-3 own the left pixel, 4-7 the right one, 8 channels each; per point 1 LDS.32
+//       (weights) + 2 LDS.128 (top / bottom pixel pair) + 16 mixed-precision FMAs (fma.rn.f32.f16: fp16 value x
+//       fp16 weight, fp32 accumulation); the halves are combined with four shuffles and written as one 128-byte
+//       row.
+// There is no CTA-wide barrier in the loop: windows are handed over through full / empty mbarriers, so the warps
+// drift apart and descriptor building (ALU / SFU bound) of some overlaps the gather (shared-memory bound) of
+// others, while the next window streams in behind both (double-buffered in BEV mode).
+//
+// BEV mode: unit = 16 x 16 BEV queries x one head, handed out by a scheduler warp (atomic counter, re-armed by the
+// last CTA) that also streams the windows.
 // Samples whose 2 x 2 footprint is not inside the staged window (offsets larger than the halo) take a slow,
 // exact path straight from global memory (fp32 weights), so any offsets are handled; the halo is a tuning knob.
-// Windows are double-buffered (the next unit's window streams in during the current unit), units are handed
-// out by an atomic counter that the last CTA resets.
 //
-// Camera mode: a unit is 256 hits of one camera x one head; the whole (camera, head) plane plus a one-pixel zero
-// halo is the window (loaded when the CTA's contiguous unit range crosses into a new plane); contributions are
+// Camera mode: unit = 256 hits of one camera x one head; the whole (camera, head) plane plus a one-pixel zero
+// halo is the window (reloaded when the CTA's contiguous unit range crosses into a new plane); contributions are
 // pre-scaled by 1/count and accumulated with red.global.add.v4.f32 into a zero-filled output.
 #include <cuda_fp16.h>
 
@@ -35,10 +39,12 @@
 
 namespace ub {
 
-constexpr int kWinThreads = 512;
-constexpr int kTQ = 16;                  // BEV tile: 16 x 16 queries
-constexpr int kUnitItems = kTQ * kTQ;    // items (query, head) per unit
-constexpr int kGroups = kWinThreads / 8; // 8-lane groups per CTA
+constexpr int kWorkerWarps = 16;                           // one query row / 16 hits of the unit each
+constexpr int kWarpItems = 16;                             // items (query, head) per worker warp and unit
+constexpr int kBevThreads = (kWorkerWarps + 1) * 32;       // + the scheduler warp
+constexpr int kImgThreads = kWorkerWarps * 32;
+constexpr int kTQ = 16;                                    // BEV tile: 16 x 16 queries
+constexpr int kUnitItems = kWorkerWarps * kWarpItems;      // items per unit
 
 static int g_bev_halo = 0;  // 0 = default (P + 1)
 
@@ -71,27 +77,68 @@ __global__ void __launch_bounds__(256) value_to_half_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------------------------
 // shared pieces of the two sampling kernels
 
+// Per-warp descriptor buffer of the warp's 16 items: weight pairs (item stride padded by two words so the four
+// items a warp reads in one instruction fall into different banks), then 16-bit window pixel indices.
+template <int PP>
+struct Desc {
+  static constexpr int w_stride = PP * 2 + 2;  // words per item
+  static constexpr int w_bytes = kWarpItems * w_stride * 4;
+  static constexpr int idx_bytes = kWarpItems * PP * 2;
+  static constexpr int bytes = w_bytes + idx_bytes;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// softmax weight of this lane's logit across the PP adjacent lanes of its item
 template <int PP>
 __device__ __forceinline__ float softmax_pp(float logit, bool ok) {
   float mx = logit;
 #pragma unroll
   for (int o = PP / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  const float e = ok ? __expf(logit - mx) : 0.f;
+  const float e = ok ? ex2_approx((logit - mx) * 1.4426950408889634f) : 0.f;
   float sum = e;
 #pragma unroll
   for (int o = PP / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  return ok ? __fdividef(e, sum) : 0.f;
-}
-
-// word index of a sample's {left, right} weight pair; the XOR spreads the four items of a warp over the banks
-template <int PP>
-__device__ __forceinline__ int w_word(int item, int p) {
-  return (item * PP + (PP == 8 ? (p ^ ((item >> 1) & 1)) : p)) * 2;
+  return ok ? e * rcp_approx(sum) : 0.f;
 }
 
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   const __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// One sample -> descriptor (branch-free).  (h_im, w_im): pixel coordinates in the value map; aw: attention weight
+// (already scaled); window origin (wy0, wx0) / size (WW, WH) in value-map pixels.  Returns true when the sample
+// touches the map but its 2 x 2 footprint is not inside the window ("far").
+template <int PP>
+__device__ __forceinline__ bool store_desc(uint32_t sm_w, uint32_t sm_idx, int item, int p, bool ok, float h_im,
+                                           float w_im, float aw, int fH, int fW, int wy0, int wx0, int WW, int WH) {
+  const bool inmap = ok & (h_im > -1.f) & (w_im > -1.f) & (h_im < (float)fH) & (w_im < (float)fW);
+  const int y0 = __float2int_rd(h_im), x0 = __float2int_rd(w_im);   // saturating: wild coordinates are harmless
+  const float lh = h_im - (float)y0, lw = w_im - (float)x0;
+  const int yy = y0 - wy0, xx = x0 - wx0;
+  const bool inwin = ((unsigned)xx < (unsigned)(WW - 1)) & ((unsigned)yy < (unsigned)(WH - 1));
+  const bool use = inmap & inwin;
+  const float a2 = use ? aw : 0.f;
+  const float wb = a2 * lh, wt = a2 - wb;
+  const float wbr = wb * lw, wtr = wt * lw;
+  const uint32_t wl = pack_h2(wt - wtr, wb - wbr), wr = pack_h2(wtr, wbr);
+  const uint32_t idx = use ? (uint32_t)(yy * WW + xx) : 0u;
+  asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sm_w + (uint32_t)(item * Desc<PP>::w_stride + p * 2) * 4u), "r"(wl),
+               "r"(wr)
+               : "memory");
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(sm_idx + (uint32_t)(item * PP + p) * 2u), "h"((unsigned short)idx)
+               : "memory");
+  return inmap & !inwin;
 }
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -153,24 +200,27 @@ __device__ __forceinline__ void red_add4(float* p, const float4& v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// Phase 2 of one unit: group `grp` (8 lanes) reduces items grp, grp + 64, grp + 128, grp + 192, two at a time.
-// s_w / s_idx: descriptor arrays (shared-space byte addresses); win: window base + sub * 16; row_b: bytes per
-// window row.  emit(item, lane_acc) receives this lane's four output channels (item, cq * 8 + half * 4 ...).
-template <int PP, typename Emit>
-__device__ __forceinline__ void gather_unit(uint32_t s_w, uint32_t s_idx, uint32_t win, uint32_t row_b, int grp, int half,
-                                            Emit emit) {
+// The gather of one warp's 16 items: lane group `grp` (8 lanes) reduces items grp, grp + 4, grp + 8, grp + 12, two
+// at a time.  sm_w / sm_idx: the warp's descriptor arrays (shared-space byte addresses); win: window base
+// + sub * 16; ROWB > 0: bytes per window row known at compile time (immediate offset of the bottom-row load).
+// emit(item, o) receives this lane's four output channels (channel cq * 8 + half * 4 ...).
+template <int PP, int ROWB, typename Emit>
+__device__ __forceinline__ void gather_warp(uint32_t sm_w, uint32_t sm_idx, uint32_t win, uint32_t row_rt, int grp,
+                                            int half, Emit emit) {
+  const uint32_t row_b = ROWB > 0 ? (uint32_t)ROWB : row_rt;
 #pragma unroll 1
-  for (int k = 0; k < kUnitItems / kGroups; k += 2) {
-    const int item[2] = {grp + k * kGroups, grp + (k + 1) * kGroups};
-    uint32_t ix[2][4];
+  for (int k = 0; k < 4; k += 2) {
+    const int item[2] = {grp + k * 4, grp + (k + 1) * 4};
+    uint32_t ix[2][4], wa[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
+      wa[j] = sm_w + (uint32_t)(item[j] * Desc<PP>::w_stride + half) * 4u;
       if (PP == 8) {
-        const uint4 t = lds128(s_idx + item[j] * 16);
+        const uint4 t = lds128(sm_idx + item[j] * 16);
         ix[j][0] = t.x, ix[j][1] = t.y, ix[j][2] = t.z, ix[j][3] = t.w;
       } else {
         uint32_t a, b;
-        asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(s_idx + item[j] * 8));
+        asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(sm_idx + item[j] * 8));
         ix[j][0] = a, ix[j][1] = b, ix[j][2] = 0, ix[j][3] = 0;
       }
     }
@@ -188,7 +238,7 @@ __device__ __forceinline__ void gather_unit(uint32_t s_w, uint32_t s_idx, uint32
         const uint32_t word = ix[j][p >> 1];
         const uint32_t id = (p & 1) ? (word >> 16) : (word & 0xffffu);
         const uint32_t a = win + id * 64u;
-        w[j] = lds32(s_w + (uint32_t)(w_word<PP>(item[j], p) + half) * 4u);
+        w[j] = lds32(wa[j] + p * 8);
         top[j] = lds128(a);
         bot[j] = lds128(a + row_b);
       }
@@ -201,17 +251,15 @@ __device__ __forceinline__ void gather_unit(uint32_t s_w, uint32_t s_idx, uint32
     // combine the left / right pixel halves: after the exchange half 0 owns channels +0..3, half 1 channels +4..7
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
+      const float s0 = half ? acc[j][0] : acc[j][4], s1 = half ? acc[j][1] : acc[j][5];
+      const float s2 = half ? acc[j][2] : acc[j][6], s3 = half ? acc[j][3] : acc[j][7];
+      const float r0 = __shfl_xor_sync(0xffffffffu, s0, 4), r1 = __shfl_xor_sync(0xffffffffu, s1, 4);
+      const float r2 = __shfl_xor_sync(0xffffffffu, s2, 4), r3 = __shfl_xor_sync(0xffffffffu, s3, 4);
       float4 o;
-      {
-        const float s0 = half ? acc[j][0] : acc[j][4], s1 = half ? acc[j][1] : acc[j][5];
-        const float s2 = half ? acc[j][2] : acc[j][6], s3 = half ? acc[j][3] : acc[j][7];
-        const float r0 = __shfl_xor_sync(0xffffffffu, s0, 4), r1 = __shfl_xor_sync(0xffffffffu, s1, 4);
-        const float r2 = __shfl_xor_sync(0xffffffffu, s2, 4), r3 = __shfl_xor_sync(0xffffffffu, s3, 4);
-        o.x = (half ? acc[j][4] : acc[j][0]) + r0;
-        o.y = (half ? acc[j][5] : acc[j][1]) + r1;
-        o.z = (half ? acc[j][6] : acc[j][2]) + r2;
-        o.w = (half ? acc[j][7] : acc[j][3]) + r3;
-      }
+      o.x = (half ? acc[j][4] : acc[j][0]) + r0;
+      o.y = (half ? acc[j][5] : acc[j][1]) + r1;
+      o.z = (half ? acc[j][6] : acc[j][2]) + r2;
+      o.w = (half ? acc[j][7] : acc[j][3]) + r3;
       emit(item[j], o);
     }
   }
@@ -229,154 +277,161 @@ struct BevWinArgs {
   float sx, sy;
 };
 
-template <int PP>
-struct BevSmem {
-  static constexpr int n_samples = kUnitItems * PP;
-  static constexpr int off_bytes = n_samples * 8, lg_bytes = n_samples * 4;
-  static constexpr int w_bytes = n_samples * 8, idx_bytes = n_samples * 2;
-  static size_t total(int win_bytes) { return (size_t)2 * win_bytes + off_bytes + lg_bytes + w_bytes + idx_bytes; }
+struct __align__(16) UnitInfo {
+  int u, b, h, tx0, ty0, wx0, wy0, pad;
 };
 
 template <int PP>
-__global__ void __launch_bounds__(kWinThreads, 1)
+struct BevSmem {
+  static constexpr int slice_off_bytes = kWarpItems * PP * 8, slice_lg_bytes = kWarpItems * PP * 4;
+  static constexpr int slice_bytes = slice_off_bytes + slice_lg_bytes;      // one query row of the offset|logit tile
+  static constexpr int warp_bytes = slice_bytes + ((Desc<PP>::bytes + 127) & ~127);
+  static size_t total(int win_bytes) { return (size_t)2 * win_bytes + (size_t)kWorkerWarps * warp_bytes; }
+};
+
+// Worker warp w owns query row ty0 + w of the unit's 16 x 16 tile.  Its loop per unit k:
+//   P1  descriptors of its 128 / 64 samples from its TMA-staged slice of the offset|logit rows (own mbarrier)
+//   --  issue the slice of unit k + 1 (the buffer is free), slow path for far samples
+//   P2  wait for window k (full[k & 1]), gather its 16 items, arrive on empty[k & 1]
+// No CTA-wide barrier: the warps drift apart, so some build descriptors (ALU / SFU) while others gather (LDS).
+// The scheduler warp hands out units (atomic counter), publishes them two units ahead through a 4-slot ring and
+// streams window k into buffer k & 1 as soon as every worker has released it (unit k - 2).
+template <int PP, int ROWB>
+__global__ void __launch_bounds__(kBevThreads, 1)
     bev_sample_win_kernel(const BevWinArgs a, const __grid_constant__ CUtensorMap map_val,
                           const __grid_constant__ CUtensorMap map_off, const __grid_constant__ CUtensorMap map_lg) {
   using S = BevSmem<PP>;
-  constexpr int SPT = S::n_samples / kWinThreads;
+  using D = Desc<PP>;
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t s_bar[3];  // window buffers 0 / 1, offset|logit tile
-  __shared__ int s_unit[2];
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2], s_unit[4], s_qp[kWorkerWarps];
+  __shared__ UnitInfo s_ring[4];
 
   const int win_bytes = (a.WW * a.WH * 64 + 127) & ~127;
-  unsigned char* p_off = smem + 2 * (size_t)win_bytes;
-  unsigned char* p_lg = p_off + S::off_bytes;
-  unsigned char* p_w = p_lg + S::lg_bytes;
-  unsigned char* p_idx = p_w + S::w_bytes;
-  const uint32_t sm_win = smem_u32(smem), sm_off = smem_u32(p_off), sm_lg = smem_u32(p_lg);
-  const uint32_t sm_w = smem_u32(p_w), sm_idx = smem_u32(p_idx);
-  const uint32_t bar_win0 = smem_u32(&s_bar[0]), bar_qp = smem_u32(&s_bar[2]);
-
-  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t sm_win = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Nq = a.bev_h * a.bev_w, C = a.H * 32;
-  const int n_tiles = a.tiles_x * a.tiles_y;
-  const uint32_t qp_bytes = S::off_bytes + S::lg_bytes;
-  const uint32_t box_bytes = (uint32_t)(a.WW * a.WH * 64);
-
-  struct Unit {
-    int b, h, tx0, ty0, wx0, wy0;
-  };
-  auto decode = [&](int u) {
-    Unit w;
-    w.h = u % a.H;
-    const int t = (u / a.H) % n_tiles;
-    w.b = u / (a.H * n_tiles);
-    w.tx0 = (t % a.tiles_x) * kTQ, w.ty0 = (t / a.tiles_x) * kTQ;
-    w.wx0 = (int)floorf(((float)w.tx0 + 0.5f) * a.sx - 0.5f) - a.R;
-    w.wy0 = (int)floorf(((float)w.ty0 + 0.5f) * a.sy - 0.5f) - a.R;
-    return w;
-  };
-  auto issue_window = [&](int u, int buf) {  // one thread
-    const Unit w = decode(u);
-    const uint32_t bar = bar_win0 + 8u * buf;
-    mbar_arrive_expect_tx(bar, box_bytes);
-    tma_load_4d(sm_win + (uint32_t)buf * win_bytes, &map_val, bar, 0, w.wx0, w.wy0, w.b * a.H + w.h);
-  };
-  auto issue_qproj = [&](int u) {  // one thread
-    const Unit w = decode(u);
-    mbar_arrive_expect_tx(bar_qp, qp_bytes);
-    tma_load_4d(sm_off, &map_off, bar_qp, a.off_col + w.h * PP * 2, w.tx0, w.ty0, w.b);
-    tma_load_4d(sm_lg, &map_lg, bar_qp, a.logit_col + w.h * PP, w.tx0, w.ty0, w.b);
-  };
 
   if (tid == 0) {
-    mbar_init(bar_win0, 1);
-    mbar_init(bar_win0 + 8, 1);
-    mbar_init(bar_qp, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&s_full[i]), 1), mbar_init(smem_u32(&s_empty[i]), kWorkerWarps);
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s_unit[i]), 1);
+    for (int i = 0; i < kWorkerWarps; ++i) mbar_init(smem_u32(&s_qp[i]), 1);
     mbar_init_fence();
-    tma_prefetch_desc(&map_val);
-    tma_prefetch_desc(&map_off);
-    tma_prefetch_desc(&map_lg);
-    const int u0 = atomicAdd(&a.counters[0], 1);
-    const int u1 = atomicAdd(&a.counters[0], 1);
-    s_unit[0] = u0, s_unit[1] = u1;
-    if (u0 < a.n_units) issue_qproj(u0), issue_window(u0, 0);
-    if (u1 < a.n_units) issue_window(u1, 1);
   }
   __syncthreads();
 
-  const int grp = tid >> 3, sub = tid & 7, half = sub >> 2, cq = sub & 3;
+  if (warp == kWorkerWarps) {
+    // ---------------- scheduler warp (one lane)
+    if (lane != 0) return;
+    tma_prefetch_desc(&map_val);
+    const int n_tiles = a.tiles_x * a.tiles_y;
+    for (int k = 0;; ++k) {
+      const int u = atomicAdd(&a.counters[0], 1);
+      UnitInfo w;
+      w.pad = 0;
+      if (u >= a.n_units) {
+        w.u = -1, w.b = w.h = w.tx0 = w.ty0 = w.wx0 = w.wy0 = 0;
+      } else {
+        w.u = u;
+        w.h = u % a.H;
+        const int t = (u / a.H) % n_tiles;
+        w.b = u / (a.H * n_tiles);
+        w.tx0 = (t % a.tiles_x) * kTQ, w.ty0 = (t / a.tiles_x) * kTQ;
+        w.wx0 = (int)floorf(((float)w.tx0 + 0.5f) * a.sx - 0.5f) - a.R;
+        w.wy0 = (int)floorf(((float)w.ty0 + 0.5f) * a.sy - 0.5f) - a.R;
+      }
+      // ring slot k & 3 held unit k - 4, which every worker released before window k - 2 was issued
+      s_ring[k & 3] = w;
+      mbar_arrive(smem_u32(&s_unit[k & 3]));
+      if (w.u < 0) break;
+      if (k >= 2) mbar_wait(smem_u32(&s_empty[k & 1]), (uint32_t)(((k >> 1) - 1) & 1));
+      const uint32_t bar = smem_u32(&s_full[k & 1]);
+      mbar_arrive_expect_tx(bar, (uint32_t)(a.WW * a.WH * 64));
+      tma_load_4d(sm_win + (uint32_t)(k & 1) * win_bytes, &map_val, bar, 0, w.wx0, w.wy0, w.b * a.H + w.h);
+    }
+    // the last CTA to leave re-arms the unit counter for the next launch
+    __threadfence();
+    const int done = atomicAdd(&a.counters[1], 1);
+    if (done == (int)gridDim.x - 1) {
+      a.counters[0] = 0;
+      a.counters[1] = 0;
+      __threadfence();
+    }
+    return;
+  }
 
-  for (int it = 0;; ++it) {
-    const int cur = it & 1;
-    const int u = s_unit[cur];
-    if (u >= a.n_units) break;
-    int u_fetch = 0;
-    if (tid == 0) u_fetch = atomicAdd(&a.counters[0], 1);  // consumed at the end of the iteration
-    const Unit w = decode(u);
+  // ---------------- worker warps
+  const uint32_t sm_slice = sm_win + 2u * win_bytes + (uint32_t)warp * S::warp_bytes;  // {offsets, logits}
+  const uint32_t sm_w = sm_slice + S::slice_bytes, sm_idx = sm_w + D::w_bytes;
+  const uint32_t bar_qp = smem_u32(&s_qp[warp]);
+  constexpr int R1 = kWarpItems * PP / 32;   // samples per lane
+  constexpr int item_step = 32 / PP;         // items between a lane's consecutive samples
+  const int p = lane % PP, it0 = lane / PP;
+  const int grp = lane >> 3, sub = lane & 7, half = sub >> 2, cq = sub & 3;
 
-    // ---- phase 1
-    mbar_wait(bar_qp, (uint32_t)(it & 1));
-    float far_h[SPT], far_w[SPT], far_a[SPT];
+  auto issue_slice = [&](const UnitInfo& w) {  // lane 0: this warp's query row of the offset|logit tile
+    mbar_arrive_expect_tx(bar_qp, (uint32_t)S::slice_bytes);
+    tma_load_4d(sm_slice, &map_off, bar_qp, a.off_col + w.h * PP * 2, w.tx0, w.ty0 + warp, w.b);
+    tma_load_4d(sm_slice + S::slice_off_bytes, &map_lg, bar_qp, a.logit_col + w.h * PP, w.tx0, w.ty0 + warp, w.b);
+  };
+
+  mbar_wait(smem_u32(&s_unit[0]), 0u);
+  UnitInfo w = s_ring[0];
+  if (w.u >= 0 && lane == 0) issue_slice(w);
+
+  for (int k = 0; w.u >= 0; ++k) {
+    const int qy = w.ty0 + warp;
+    const bool row_ok = qy < a.bev_h;
+    const float hbase = (float)qy + 0.5f;
+    // ---- P1
+    mbar_wait(bar_qp, (uint32_t)(k & 1));
+    float far_h[R1], far_w[R1], far_a[R1];
     unsigned far_bits = 0;
 #pragma unroll
-    for (int r = 0; r < SPT; ++r) {
-      const int s = r * kWinThreads + tid;
-      const int p = s % PP, item = s / PP;
-      const int qx = w.tx0 + (item & (kTQ - 1)), qy = w.ty0 + (item >> 4);
-      const bool ok = qx < a.bev_w && qy < a.bev_h;
+    for (int r = 0; r < R1; ++r) {
+      const int item = r * item_step + it0;
+      const int qx = w.tx0 + item;
+      const bool ok = row_ok & (qx < a.bev_w);
+      const int sl = r * 32 + lane;
       float ox, oy, lg;
-      asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(ox), "=f"(oy) : "r"(sm_off + (uint32_t)s * 8u));
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lg) : "r"(sm_lg + (uint32_t)s * 4u));
+      asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(ox), "=f"(oy) : "r"(sm_slice + (uint32_t)sl * 8u));
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lg) : "r"(sm_slice + S::slice_off_bytes + (uint32_t)sl * 4u));
       const float aw = softmax_pp<PP>(ok ? lg : 0.f, ok);
       // pixel = ((q + .5) / bev + off / f) * f - .5  ==  (q + .5) * (f / bev) + off - .5
-      const float h_im = fmaf((float)qy + 0.5f, a.sy, oy - 0.5f), w_im = fmaf((float)qx + 0.5f, a.sx, ox - 0.5f);
-      uint32_t wl = 0u, wr = 0u, idx = 0u;
+      const float h_im = fmaf(hbase, a.sy, oy - 0.5f), w_im = fmaf((float)qx + 0.5f, a.sx, ox - 0.5f);
       far_h[r] = h_im, far_w[r] = w_im, far_a[r] = aw;
-      if (ok && h_im > -1.f && w_im > -1.f && h_im < (float)a.fH && w_im < (float)a.fW) {
-        const float hf = floorf(h_im), wf = floorf(w_im);
-        const float lh = h_im - hf, lw = w_im - wf;
-        const int yy = (int)hf - w.wy0, xx = (int)wf - w.wx0;
-        if (xx >= 0 && xx < a.WW - 1 && yy >= 0 && yy < a.WH - 1) {
-          const float wt = aw * (1.f - lh), wb = aw * lh;
-          wl = pack_h2(wt * (1.f - lw), wb * (1.f - lw));
-          wr = pack_h2(wt * lw, wb * lw);
-          idx = (uint32_t)(yy * a.WW + xx);
-        } else {
-          far_bits |= 1u << r;
-        }
-      }
-      asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sm_w + (uint32_t)w_word<PP>(item, p) * 4u), "r"(wl), "r"(wr)
-                   : "memory");
-      asm volatile("st.shared.u16 [%0], %1;" ::"r"(sm_idx + (uint32_t)s * 2u), "h"((unsigned short)idx) : "memory");
+      if (store_desc<PP>(sm_w, sm_idx, item, p, ok, h_im, w_im, aw, a.fH, a.fW, w.wy0, w.wx0, a.WW, a.WH))
+        far_bits |= 1u << r;
     }
-    const int n_far = __syncthreads_count(far_bits != 0u);
-    // the offset|logit tile is free again: stream in the next unit's
-    if (tid == 0) {
-      const int un = s_unit[cur ^ 1];
-      if (un < a.n_units) issue_qproj(un);
-    }
+    const bool any_far = __any_sync(0xffffffffu, far_bits != 0u);
+    __syncwarp();   // descriptor stores visible to the whole warp
+    // ---- the slice buffer is free: stream in the next unit's row
+    mbar_wait(smem_u32(&s_unit[(k + 1) & 3]), (uint32_t)(((k + 1) >> 2) & 1));
+    const UnitInfo wn = s_ring[(k + 1) & 3];
+    if (wn.u >= 0 && lane == 0) issue_slice(wn);
 
     // ---- slow path for samples outside the staged window (exact: fp32 weights, per-corner bounds checks)
-    if (n_far > 0) {
+    if (any_far) {
+      if (row_ok) {
 #pragma unroll
-      for (int k = 0; k < kUnitItems * 8 / kWinThreads; ++k) {
-        const int e = k * kWinThreads + tid, item = e >> 3, c4 = e & 7;
-        const int qx = w.tx0 + (item & (kTQ - 1)), qy = w.ty0 + (item >> 4);
-        if (qx < a.bev_w && qy < a.bev_h)
-          *reinterpret_cast<float4*>(a.out + ((int64_t)w.b * Nq + qy * a.bev_w + qx) * C + w.h * 32 + c4 * 4) =
-              make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = lane; e < kWarpItems * 8; e += 32) {
+          const int item = e >> 3, c4 = e & 7;
+          if (w.tx0 + item < a.bev_w)
+            *reinterpret_cast<float4*>(a.out + ((int64_t)w.b * Nq + qy * a.bev_w + w.tx0 + item) * C + w.h * 32 + c4 * 4) =
+                make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
-      __syncthreads();
+      __syncwarp();
       const __half* plane = a.value16 + (int64_t)(w.b * a.H + w.h) * a.fH * a.fW * 32;
 #pragma unroll
-      for (int r = 0; r < SPT; ++r) {
+      for (int r = 0; r < R1; ++r) {
         unsigned m = __ballot_sync(0xffffffffu, (far_bits >> r) & 1u);
         while (m) {
           const int src = __ffs(m) - 1;
           m &= m - 1;
-          const float h_im = __shfl_sync(0xffffffffu, far_h[r], src), w_im = __shfl_sync(0xffffffffu, far_w[r], src);
+          const float h_im = __shfl_sync(0xffffffffu, far_h[r], src);
+          const float w_im = __shfl_sync(0xffffffffu, far_w[r], src);
           const float aw = __shfl_sync(0xffffffffu, far_a[r], src);
-          const int item = (r * kWinThreads + (tid & ~31) + src) / PP;
+          const int item = r * item_step + src / PP;
           const int corner = lane >> 3, c4 = lane & 7, dy = corner >> 1, dx = corner & 1;
           const float hf = floorf(h_im), wf = floorf(w_im);
           const float lh = h_im - hf, lw = w_im - wf;
@@ -394,41 +449,29 @@ __global__ void __launch_bounds__(kWinThreads, 1)
             v.x += __shfl_xor_sync(0xffffffffu, v.x, o), v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
             v.z += __shfl_xor_sync(0xffffffffu, v.z, o), v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
           }
-          const int qx = w.tx0 + (item & (kTQ - 1)), qy = w.ty0 + (item >> 4);
-          if (lane < 8) red_add4(a.out + ((int64_t)w.b * Nq + qy * a.bev_w + qx) * C + w.h * 32 + c4 * 4, v);
+          if (lane < 8)
+            red_add4(a.out + ((int64_t)w.b * Nq + qy * a.bev_w + w.tx0 + item) * C + w.h * 32 + c4 * 4, v);
         }
       }
+      __syncwarp();
     }
 
-    // ---- phase 2
-    mbar_wait(bar_win0 + 8u * cur, (uint32_t)((it >> 1) & 1));
-    gather_unit<PP>(sm_w, sm_idx, sm_win + (uint32_t)cur * win_bytes + sub * 16u, (uint32_t)a.WW * 64u, grp, half,
-                    [&](int item, const float4& o) {
-                      const int qx = w.tx0 + (item & (kTQ - 1)), qy = w.ty0 + (item >> 4);
-                      if (qx < a.bev_w && qy < a.bev_h) {
-                        float* dst = a.out + ((int64_t)w.b * Nq + qy * a.bev_w + qx) * C + w.h * 32 + cq * 8 + half * 4;
-                        if (n_far > 0)
-                          red_add4(dst, o);
-                        else
-                          st_stream4(dst, o);
-                      }
-                    });
-    __syncthreads();  // window buffer `cur` and the descriptors are free
-    if (tid == 0) {
-      s_unit[cur] = u_fetch;
-      if (u_fetch < a.n_units) issue_window(u_fetch, cur);
-    }
-  }
-
-  // the last CTA to leave re-arms the unit counter for the next launch
-  if (tid == 0) {
-    __threadfence();
-    const int done = atomicAdd(&a.counters[1], 1);
-    if (done == (int)gridDim.x - 1) {
-      a.counters[0] = 0;
-      a.counters[1] = 0;
-      __threadfence();
-    }
+    // ---- P2
+    mbar_wait(smem_u32(&s_full[k & 1]), (uint32_t)((k >> 1) & 1));
+    gather_warp<PP, ROWB>(sm_w, sm_idx, sm_win + (uint32_t)(k & 1) * win_bytes + sub * 16u, (uint32_t)a.WW * 64u, grp,
+                          half, [&](int item, const float4& o) {
+                            const int qx = w.tx0 + item;
+                            if (row_ok && qx < a.bev_w) {
+                              float* dst = a.out + ((int64_t)w.b * Nq + qy * a.bev_w + qx) * C + w.h * 32 + cq * 8 + half * 4;
+                              if (any_far)
+                                red_add4(dst, o);
+                              else
+                                st_stream4(dst, o);
+                            }
+                          });
+    __syncwarp();   // every lane is done with the window and the descriptors
+    if (lane == 0) mbar_arrive(smem_u32(&s_empty[k & 1]));
+    w = wn;
   }
 }
 
@@ -468,11 +511,13 @@ __global__ void __launch_bounds__(1024) build_hits_kernel(const uint8_t* __restr
       __syncthreads();
     }
     if (tid == 0) hit_cnt[n] = s_base;
-  }
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < (int64_t)B * Nq; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = 0;
-    for (int n = 0; n < N; ++n) c += mask[i * N + n] != 0 ? 1 : 0;
-    inv_cnt[i] = 1.f / (float)max(c, 1);
+  } else {
+    const int64_t nb = gridDim.x - N;
+    for (int64_t i = (int64_t)(blockIdx.x - N) * blockDim.x + tid; i < (int64_t)B * Nq; i += nb * blockDim.x) {
+      int c = 0;
+      for (int n = 0; n < N; ++n) c += mask[i * N + n] != 0 ? 1 : 0;
+      inv_cnt[i] = 1.f / (float)max(c, 1);
+    }
   }
 }
 
@@ -489,30 +534,39 @@ struct ImgWinArgs {
 };
 
 template <int PP>
-__global__ void __launch_bounds__(kWinThreads, 1)
+struct ImgSmem {
+  static constexpr int warp_bytes = (Desc<PP>::bytes + kWarpItems * 4 + 127) & ~127;
+  static size_t total(int win_bytes) { return (size_t)win_bytes + (size_t)kWorkerWarps * warp_bytes; }
+};
+
+// Camera mode.  Units (b, camera, head, chunk of 256 hits) in a contiguous range per CTA; warp w owns hits
+// chunk * 256 + 16 w .. + 15.  Per unit and warp: descriptors from registers prefetched during the previous gather
+// (hit index -> offsets / logits / projected anchor / 1/count straight from global memory), then the gather.
+// The only CTA-wide barrier is at a plane change (the window is reloaded once every warp has left the old plane).
+template <int PP, int ROWB>
+__global__ void __launch_bounds__(kImgThreads, 1)
     img_sample_win_kernel(const ImgWinArgs a, const __grid_constant__ CUtensorMap map_val) {
-  constexpr int n_samples = kUnitItems * PP, SPT = n_samples / kWinThreads;
+  using D = Desc<PP>;
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_q[kUnitItems];
 
   const int win_bytes = (a.WW * a.WH * 64 + 127) & ~127;
-  unsigned char* p_w = smem + win_bytes;
-  unsigned char* p_idx = p_w + n_samples * 8;
-  const uint32_t sm_win = smem_u32(smem), sm_w = smem_u32(p_w), sm_idx = smem_u32(p_idx), bar = smem_u32(&s_bar);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sm_win = smem_u32(smem), bar = smem_u32(&s_bar);
+  const uint32_t sm_w = sm_win + (uint32_t)win_bytes + (uint32_t)warp * ImgSmem<PP>::warp_bytes, sm_idx = sm_w + D::w_bytes;
+  const uint32_t sm_q = sm_idx + D::idx_bytes;   // query index per item
   const int C = a.H * 32;
 
   // units: (b, camera, head, chunk of 256 hits), contiguous range per CTA
   int chunks_tot = 0;
-  for (int n = 0; n < a.N; ++n) chunks_tot += (a.hit_cnt[n] + kUnitItems - 1) / kUnitItems;
+  for (int n = 0; n < a.N; ++n) chunks_tot += (__ldg(a.hit_cnt + n) + kUnitItems - 1) / kUnitItems;
   const int per_b = chunks_tot * a.H, total = per_b * a.B;
   const int per = total / gridDim.x, rem = total % gridDim.x;
-  int u = blockIdx.x * per + min((int)blockIdx.x, rem);
-  const int u_end = u + per + ((int)blockIdx.x < rem ? 1 : 0);
+  const int u_beg = blockIdx.x * per + min((int)blockIdx.x, rem);
+  const int u_end = u_beg + per + ((int)blockIdx.x < rem ? 1 : 0);
 
   struct Unit {
-    int b, n, h, chunk, cnt;
+    int b, n, h, chunk, cnt, plane;
   };
   auto decode = [&](int uu) {
     Unit w;
@@ -520,99 +574,101 @@ __global__ void __launch_bounds__(kWinThreads, 1)
     int r = uu % per_b;
     w.n = 0, w.cnt = 0, w.h = 0, w.chunk = 0;
     for (int n = 0; n < a.N; ++n) {
-      const int cnt = a.hit_cnt[n], ch = (cnt + kUnitItems - 1) / kUnitItems;
+      const int cnt = __ldg(a.hit_cnt + n), ch = (cnt + kUnitItems - 1) / kUnitItems;
       if (r < ch * a.H) {
         w.n = n, w.cnt = cnt, w.h = r / ch, w.chunk = r % ch;
         break;
       }
       r -= ch * a.H;
     }
+    w.plane = (w.b * a.N + w.n) * a.H + w.h;
     return w;
   };
 
+  if (u_beg >= u_end) return;   // uniform per CTA
+  Unit w = decode(u_beg);
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_init_fence();
     tma_prefetch_desc(&map_val);
+    mbar_arrive_expect_tx(bar, (uint32_t)(a.WW * a.WH * 64));
+    tma_load_4d(sm_win, &map_val, bar, 0, -1, -1, w.plane);
   }
   __syncthreads();
-  if (u >= u_end) return;
 
-  float ox[SPT], oy[SPT], lg[SPT], rx[SPT], ry[SPT], ic[SPT];
-  int qq[SPT];
-  auto prefetch = [&](const Unit& w) {
+  constexpr int R1 = kWarpItems * PP / 32;   // samples per lane
+  constexpr int item_step = 32 / PP;
+  const int p = lane % PP, it0 = lane / PP;
+  const int grp = lane >> 3, sub = lane & 7, half = sub >> 2, cq = sub & 3;
+
+  float ox[R1], oy[R1], lg[R1], rx[R1], ry[R1], ic[R1];
+  int qq[R1];
+  auto prefetch = [&](const Unit& wu) {
 #pragma unroll
-    for (int r = 0; r < SPT; ++r) {
-      const int s = r * kWinThreads + tid;
-      const int p = s % PP, item = s / PP;
-      const int ord = w.chunk * kUnitItems + item;
-      ox[r] = 0.f, oy[r] = 0.f, lg[r] = 0.f, rx[r] = 0.f, ry[r] = 0.f, ic[r] = 0.f, qq[r] = -1;
-      if (ord < w.cnt && p < a.P) {
-        const int q = __ldg(a.hit_idx + (int64_t)w.n * a.Nq + ord);
-        const int64_t bq = (int64_t)w.b * a.Nq + q;
+    for (int r = 0; r < R1; ++r) {
+      const int ord = wu.chunk * kUnitItems + warp * kWarpItems + r * item_step + it0;
+      qq[r] = ord < wu.cnt ? __ldg(a.hit_idx + (int64_t)wu.n * a.Nq + ord) : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      ox[r] = 0.f, oy[r] = 0.f, lg[r] = 0.f, rx[r] = 0.f, ry[r] = 0.f, ic[r] = 0.f;
+      if (qq[r] >= 0) {
+        const int64_t bq = (int64_t)wu.b * a.Nq + qq[r];
         const float* rowp = a.qproj + bq * a.ld;
-        const float2 t = ld_stream2(rowp + a.off_col + (w.h * a.P + p) * 2);
+        const float2 t = ld_stream2(rowp + a.off_col + (wu.h * PP + p) * 2);
         ox[r] = t.x, oy[r] = t.y;
-        lg[r] = ld_stream1(rowp + a.logit_col + w.h * a.P + p);
-        const float2 rc = __ldg(reinterpret_cast<const float2*>(a.ref_cam) + (bq * a.N + w.n) * a.D + (p % a.D));
+        lg[r] = ld_stream1(rowp + a.logit_col + wu.h * PP + p);
+        const float2 rc = __ldg(reinterpret_cast<const float2*>(a.ref_cam) + (bq * a.N + wu.n) * a.D + (p % a.D));
         rx[r] = rc.x, ry[r] = rc.y;
         ic[r] = __ldg(a.inv_cnt + bq);
-        qq[r] = q;
       }
     }
   };
-
-  const int grp = tid >> 3, sub = tid & 7, half = sub >> 2, cq = sub & 3;
-  Unit w = decode(u);
   prefetch(w);
-  int loaded = -1, n_loads = 0;
 
-  for (; u < u_end; ++u) {
-    const int plane = (w.b * a.N + w.n) * a.H + w.h;
-    const bool reload = plane != loaded;
-    if (reload && tid == 0) {  // every thread passed the barrier that ended the previous phase 2
-      mbar_arrive_expect_tx(bar, (uint32_t)(a.WW * a.WH * 64));
-      tma_load_4d(sm_win, &map_val, bar, 0, -1, -1, plane);
-    }
-    loaded = plane;
-    // ---- phase 1
+  int loaded = w.plane, n_waited = 0;
+  bool fresh = true;
+  for (int u = u_beg; u < u_end; ++u) {
+    // ---- P1 from the prefetched registers
 #pragma unroll
-    for (int r = 0; r < SPT; ++r) {
-      const int s = r * kWinThreads + tid;
-      const int p = s % PP, item = s / PP;
+    for (int r = 0; r < R1; ++r) {
+      const int item = r * item_step + it0;
       const bool ok = qq[r] >= 0;
       const float aw = softmax_pp<PP>(lg[r], ok) * ic[r];
       const float h_im = fmaf(ry[r], (float)a.fH, oy[r] - 0.5f), w_im = fmaf(rx[r], (float)a.fW, ox[r] - 0.5f);
-      uint32_t wl = 0u, wr = 0u, idx = 0u;
-      if (ok && h_im > -1.f && w_im > -1.f && h_im < (float)a.fH && w_im < (float)a.fW) {
-        const float hf = floorf(h_im), wf = floorf(w_im);
-        const float lh = h_im - hf, lw = w_im - wf;
-        const float wt = aw * (1.f - lh), wb = aw * lh;
-        wl = pack_h2(wt * (1.f - lw), wb * (1.f - lw));
-        wr = pack_h2(wt * lw, wb * lw);
-        idx = (uint32_t)(((int)hf + 1) * a.WW + (int)wf + 1);  // window origin is pixel (-1, -1)
-      }
-      asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sm_w + (uint32_t)w_word<PP>(item, p) * 4u), "r"(wl), "r"(wr)
-                   : "memory");
-      asm volatile("st.shared.u16 [%0], %1;" ::"r"(sm_idx + (uint32_t)s * 2u), "h"((unsigned short)idx) : "memory");
-      if (p == 0) s_q[item] = qq[r];
+      // the window is the whole plane plus a one-pixel zero halo (origin (-1, -1)): nothing is ever far
+      store_desc<PP>(sm_w, sm_idx, item, p, ok, h_im, w_im, aw, a.fH, a.fW, -1, -1, a.WW, a.WH);
+      if (p == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(sm_q + (uint32_t)item * 4u), "r"(qq[r]) : "memory");
     }
-    __syncthreads();
+    __syncwarp();
     const Unit w_cur = w;
     if (u + 1 < u_end) {
       w = decode(u + 1);
       prefetch(w);
     }
-    // ---- phase 2
-    if (reload) {
-      mbar_wait(bar, (uint32_t)(n_loads & 1));
-      ++n_loads;
+    // ---- P2
+    if (fresh) {
+      mbar_wait(bar, (uint32_t)(n_waited & 1));
+      ++n_waited;
+      fresh = false;
     }
-    gather_unit<PP>(sm_w, sm_idx, sm_win + sub * 16u, (uint32_t)a.WW * 64u, grp, half, [&](int item, const float4& o) {
-      const int q = s_q[item];
-      if (q >= 0) red_add4(a.out + ((int64_t)w_cur.b * a.Nq + q) * C + w_cur.h * 32 + cq * 8 + half * 4, o);
-    });
-    __syncthreads();
+    gather_warp<PP, ROWB>(sm_w, sm_idx, sm_win + sub * 16u, (uint32_t)a.WW * 64u, grp, half,
+                          [&](int item, const float4& o) {
+                            int q;
+                            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(q) : "r"(sm_q + (uint32_t)item * 4u));
+                            if (q >= 0)
+                              red_add4(a.out + ((int64_t)w_cur.b * a.Nq + q) * C + w_cur.h * 32 + cq * 8 + half * 4, o);
+                          });
+    __syncwarp();
+    if (u + 1 < u_end && w.plane != loaded) {   // uniform per CTA: every warp leaves the old plane, then reload
+      __syncthreads();
+      if (tid == 0) {
+        mbar_arrive_expect_tx(bar, (uint32_t)(a.WW * a.WH * 64));
+        tma_load_4d(sm_win, &map_val, bar, 0, -1, -1, w.plane);
+      }
+      loaded = w.plane;
+      fresh = true;
+    }
   }
 }
 
@@ -639,13 +695,38 @@ static int set_smem(K kernel, size_t smem, const char* fn) {
   return UB_OK;
 }
 
-constexpr size_t kSmemBudget = 220 * 1024;
+constexpr size_t kSmemBudget = 232448 - 1024 - 64;  // 227 KB per CTA minus the static part
+
+template <int PP, int ROWB>
+static int launch_bev_win_v(BevWinArgs& a, const CUtensorMap& mv, const CUtensorMap& mo, const CUtensorMap& ml,
+                            size_t smem, cudaStream_t s) {
+  const char* fn = "ub_bev_sample_win_fwd";
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (int rc = set_smem(bev_sample_win_kernel<PP, ROWB>, smem, fn)) return rc;
+    configured = smem;
+  }
+  const int grid = a.n_units < kNumSMs ? a.n_units : kNumSMs;
+  bev_sample_win_kernel<PP, ROWB><<<grid, kBevThreads, smem, s>>>(a, mv, mo, ml);
+  return check_launch(fn);
+}
 
 template <int PP>
 static int launch_bev_win(BevWinArgs& a, const void* value16, const float* qproj, int ld, cudaStream_t s) {
   const char* fn = "ub_bev_sample_win_fwd";
-  // shrink the halo until two windows fit (samples beyond it stay exact through the slow path)
+  // preferred row pitch with a compile-time kernel variant; otherwise shrink the halo until two windows fit
+  // (samples beyond it stay exact through the slow path)
+  constexpr int kPrefWW = PP == 8 ? 36 : 28;
   auto smem_for = [&]() { return BevSmem<PP>::total((a.WW * a.WH * 64 + 127) & ~127); };
+  bool fixed = false;
+  if (a.WW <= kPrefWW) {
+    const int keep = a.WW;
+    a.WW = kPrefWW;
+    if (smem_for() <= kSmemBudget)
+      fixed = true;
+    else
+      a.WW = keep;
+  }
   while (smem_for() > kSmemBudget && a.R > 1) --a.R, a.WW -= 2, a.WH -= 2;
   const size_t smem = smem_for();
   if (smem > kSmemBudget) {
@@ -664,7 +745,7 @@ static int launch_bev_win(BevWinArgs& a, const void* value16, const float* qproj
   {
     const uint64_t dims[4] = {(uint64_t)ld, (uint64_t)a.bev_w, (uint64_t)a.bev_h, (uint64_t)a.B};
     const uint64_t str[3] = {(uint64_t)ld * 4, (uint64_t)a.bev_w * ld * 4, (uint64_t)a.bev_h * a.bev_w * ld * 4};
-    const uint32_t box_o[4] = {2 * PP, kTQ, kTQ, 1}, box_l[4] = {PP, kTQ, kTQ, 1};
+    const uint32_t box_o[4] = {2 * PP, kTQ, 1, 1}, box_l[4] = {PP, kTQ, 1, 1};  // one query row per worker warp
     if (int rc = make_tensor_map(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, qproj, dims, str, box_o,
                                  CU_TENSOR_MAP_SWIZZLE_NONE))
       return rc;
@@ -672,18 +753,24 @@ static int launch_bev_win(BevWinArgs& a, const void* value16, const float* qproj
                                  CU_TENSOR_MAP_SWIZZLE_NONE))
       return rc;
   }
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (int rc = set_smem(bev_sample_win_kernel<PP>, smem, fn)) return rc;
-    configured = smem;
-  }
   a.counters = counter_slot();
   if (!a.counters) {
     set_error("%s: cannot allocate the unit counters", fn);
     return UB_ECUDA;
   }
-  const int grid = a.n_units < kNumSMs ? a.n_units : kNumSMs;
-  bev_sample_win_kernel<PP><<<grid, kWinThreads, smem, s>>>(a, mv, mo, ml);
+  if (fixed) return launch_bev_win_v<PP, kPrefWW * 64>(a, mv, mo, ml, smem, s);
+  return launch_bev_win_v<PP, 0>(a, mv, mo, ml, smem, s);
+}
+
+template <int PP, int ROWB>
+static int launch_img_win_v(ImgWinArgs& a, const CUtensorMap& mv, size_t smem, cudaStream_t s) {
+  const char* fn = "ub_img_sample_win_fwd";
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (int rc = set_smem(img_sample_win_kernel<PP, ROWB>, smem, fn)) return rc;
+    configured = smem;
+  }
+  img_sample_win_kernel<PP, ROWB><<<kNumSMs, kImgThreads, smem, s>>>(a, mv);
   return check_launch(fn);
 }
 
@@ -691,7 +778,7 @@ template <int PP>
 static int launch_img_win(ImgWinArgs& a, const void* value16, cudaStream_t s) {
   const char* fn = "ub_img_sample_win_fwd";
   const int win_bytes = (a.WW * a.WH * 64 + 127) & ~127;
-  const size_t smem = (size_t)win_bytes + kUnitItems * PP * 10;
+  const size_t smem = ImgSmem<PP>::total(win_bytes);
   if (smem > kSmemBudget) {
     set_error("%s: plane %d x %d needs %zu bytes of shared memory", fn, a.fH, a.fW, smem);
     return UB_EUNSUPPORTED;
@@ -703,17 +790,12 @@ static int launch_img_win(ImgWinArgs& a, const void* value16, cudaStream_t s) {
   if (int rc = make_tensor_map(&mv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, value16, dims, str, box,
                                CU_TENSOR_MAP_SWIZZLE_NONE))
     return rc;
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (int rc = set_smem(img_sample_win_kernel<PP>, smem, fn)) return rc;
-    configured = smem;
-  }
   if (cudaMemsetAsync(a.out, 0, (size_t)a.B * a.Nq * a.H * 32 * sizeof(float), s) != cudaSuccess) {
     set_error("%s: cudaMemsetAsync failed", fn);
     return UB_ECUDA;
   }
-  img_sample_win_kernel<PP><<<kNumSMs, kWinThreads, smem, s>>>(a, mv);
-  return check_launch(fn);
+  if (a.WW == 52) return launch_img_win_v<PP, 52 * 64>(a, mv, smem, s);  // nuScenes 1600 x 928 / 32 -> 50 + 2
+  return launch_img_win_v<PP, 0>(a, mv, smem, s);
 }
 
 }  // namespace ub
@@ -776,10 +858,9 @@ extern "C" int ub_build_hits(const uint8_t* mask, int* hit_idx, int* hit_cnt, fl
                              ub_stream_t stream) {
   UB_REQUIRE(mask && hit_idx && hit_cnt && inv_cnt, "ub_build_hits: null pointer");
   UB_REQUIRE(B > 0 && N > 0 && N <= 32 && Nq > 0, "ub_build_hits: bad dimension (B=%d N=%d Nq=%d)", B, N, Nq);
-  int blocks = (int)(((int64_t)B * Nq + 1023) / 1024);
-  if (blocks < N) blocks = N;
-  if (blocks > kNumSMs) blocks = kNumSMs;
-  build_hits_kernel<<<blocks, 1024, 0, (cudaStream_t)stream>>>(mask, hit_idx, hit_cnt, inv_cnt, B, N, Nq);
+  int extra = (int)(((int64_t)B * Nq + 1023) / 1024);
+  if (extra > kNumSMs) extra = kNumSMs;
+  build_hits_kernel<<<N + extra, 1024, 0, (cudaStream_t)stream>>>(mask, hit_idx, hit_cnt, inv_cnt, B, N, Nq);
   return check_launch("ub_build_hits");
 }
 
