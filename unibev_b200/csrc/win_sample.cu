@@ -98,30 +98,36 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
-// softmax weight of this lane's logit across the PP adjacent lanes of its item
-template <int PP>
-__device__ __forceinline__ float softmax_pp(float logit, bool ok) {
-  float mx = logit;
-#pragma unroll
-  for (int o = PP / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  const float e = ok ? ex2_approx((logit - mx) * 1.4426950408889634f) : 0.f;
-  float sum = e;
-#pragma unroll
-  for (int o = PP / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  return ok ? e * rcp_approx(sum) : 0.f;
-}
-
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   const __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// One sample -> descriptor (branch-free).  (h_im, w_im): pixel coordinates in the value map; aw: attention weight
-// (already scaled); window origin (wy0, wx0) / size (WW, WH) in value-map pixels.  Returns true when the sample
-// touches the map but its 2 x 2 footprint is not inside the window ("far").
-template <int PP>
-__device__ __forceinline__ bool store_desc(uint32_t sm_w, uint32_t sm_idx, int item, int p, bool ok, float h_im,
-                                           float w_im, float aw, int fH, int fW, int wy0, int wx0, int WW, int WH) {
+// P1 works with two lanes per item, each owning PPL = P / 2 consecutive sampling points.
+// Softmax over the item's P logits: in-lane over the PPL own ones, one shuffle with the partner lane.
+template <int PPL>
+__device__ __forceinline__ void softmax_pair(const float (&lg)[PPL], bool ok, float scale, float (&aw)[PPL]) {
+  float mx = lg[0];
+#pragma unroll
+  for (int i = 1; i < PPL; ++i) mx = fmaxf(mx, lg[i]);
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) {
+    aw[i] = ex2_approx((lg[i] - mx) * 1.4426950408889634f);
+    sum += aw[i];
+  }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  const float inv = ok ? rcp_approx(sum) * scale : 0.f;
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) aw[i] *= inv;
+}
+
+// One sample -> descriptor words (branch-free).  (h_im, w_im): pixel coordinates in the value map; aw: attention
+// weight (already scaled, 0 for an invalid item); window origin (wy0, wx0) / size (WW, WH) in value-map pixels.
+// Returns true when the sample touches the map but its 2 x 2 footprint is not inside the window ("far").
+__device__ __forceinline__ bool make_desc(bool ok, float h_im, float w_im, float aw, int fH, int fW, int wy0, int wx0,
+                                          int WW, int WH, uint32_t& wl, uint32_t& wr, uint32_t& idx) {
   const bool inmap = ok & (h_im > -1.f) & (w_im > -1.f) & (h_im < (float)fH) & (w_im < (float)fW);
   const int y0 = __float2int_rd(h_im), x0 = __float2int_rd(w_im);   // saturating: wild coordinates are harmless
   const float lh = h_im - (float)y0, lw = w_im - (float)x0;
@@ -131,14 +137,26 @@ __device__ __forceinline__ bool store_desc(uint32_t sm_w, uint32_t sm_idx, int i
   const float a2 = use ? aw : 0.f;
   const float wb = a2 * lh, wt = a2 - wb;
   const float wbr = wb * lw, wtr = wt * lw;
-  const uint32_t wl = pack_h2(wt - wtr, wb - wbr), wr = pack_h2(wtr, wbr);
-  const uint32_t idx = use ? (uint32_t)(yy * WW + xx) : 0u;
-  asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sm_w + (uint32_t)(item * Desc<PP>::w_stride + p * 2) * 4u), "r"(wl),
-               "r"(wr)
-               : "memory");
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(sm_idx + (uint32_t)(item * PP + p) * 2u), "h"((unsigned short)idx)
-               : "memory");
+  wl = pack_h2(wt - wtr, wb - wbr), wr = pack_h2(wtr, wbr);
+  idx = use ? (uint32_t)(yy * WW + xx) : 0u;
   return inmap & !inwin;
+}
+
+// the lane's PPL descriptors -> the warp's descriptor arrays (weight pairs at item stride Desc::w_stride, indices)
+template <int PP>
+__device__ __forceinline__ void store_descs(uint32_t sm_w, uint32_t sm_idx, int item, int p0, const uint32_t (&wl)[PP / 2],
+                                            const uint32_t (&wr)[PP / 2], const uint32_t (&idx)[PP / 2]) {
+  constexpr int PPL = PP / 2;
+  const uint32_t wa = sm_w + (uint32_t)(item * Desc<PP>::w_stride + p0 * 2) * 4u;
+#pragma unroll
+  for (int i = 0; i < PPL; ++i)
+    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(wa + i * 8), "r"(wl[i]), "r"(wr[i]) : "memory");
+  const uint32_t ia = sm_idx + (uint32_t)(item * PP + p0) * 2u;
+  if (PPL == 4)
+    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(ia), "r"(idx[0] | (idx[1] << 16)), "r"(idx[2] | (idx[PPL - 1] << 16))
+                 : "memory");
+  else
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(ia), "r"(idx[0] | (idx[1] << 16)) : "memory");
 }
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -363,9 +381,8 @@ __global__ void __launch_bounds__(kBevThreads, 1)
   const uint32_t sm_slice = sm_win + 2u * win_bytes + (uint32_t)warp * S::warp_bytes;  // {offsets, logits}
   const uint32_t sm_w = sm_slice + S::slice_bytes, sm_idx = sm_w + D::w_bytes;
   const uint32_t bar_qp = smem_u32(&s_qp[warp]);
-  constexpr int R1 = kWarpItems * PP / 32;   // samples per lane
-  constexpr int item_step = 32 / PP;         // items between a lane's consecutive samples
-  const int p = lane % PP, it0 = lane / PP;
+  constexpr int PPL = PP / 2;                // sampling points per lane in P1 (two lanes per item)
+  const int item_l = lane >> 1, p0 = (lane & 1) * PPL;
   const int grp = lane >> 3, sub = lane & 7, half = sub >> 2, cq = sub & 3;
 
   auto issue_slice = [&](const UnitInfo& w) {  // lane 0: this warp's query row of the offset|logit tile
@@ -384,23 +401,36 @@ __global__ void __launch_bounds__(kBevThreads, 1)
     const float hbase = (float)qy + 0.5f;
     // ---- P1
     mbar_wait(bar_qp, (uint32_t)(k & 1));
-    float far_h[R1], far_w[R1], far_a[R1];
-    unsigned far_bits = 0;
+    const int qx1 = w.tx0 + item_l;
+    const bool ok = row_ok & (qx1 < a.bev_w);
+    float off[PPL * 2], lg[PPL], far_h[PPL], far_w[PPL], far_a[PPL];
+    {
+      const uint32_t oa = sm_slice + (uint32_t)(item_l * PP + p0) * 8u;
+      const uint32_t la = sm_slice + S::slice_off_bytes + (uint32_t)(item_l * PP + p0) * 4u;
 #pragma unroll
-    for (int r = 0; r < R1; ++r) {
-      const int item = r * item_step + it0;
-      const int qx = w.tx0 + item;
-      const bool ok = row_ok & (qx < a.bev_w);
-      const int sl = r * 32 + lane;
-      float ox, oy, lg;
-      asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(ox), "=f"(oy) : "r"(sm_slice + (uint32_t)sl * 8u));
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lg) : "r"(sm_slice + S::slice_off_bytes + (uint32_t)sl * 4u));
-      const float aw = softmax_pp<PP>(ok ? lg : 0.f, ok);
+      for (int i = 0; i < PPL / 2; ++i)
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(off[4 * i]), "=f"(off[4 * i + 1]), "=f"(off[4 * i + 2]), "=f"(off[4 * i + 3])
+                     : "r"(oa + i * 16));
+      if (PPL == 4)
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(lg[0]), "=f"(lg[1]), "=f"(lg[2]), "=f"(lg[PPL - 1]) : "r"(la));
+      else
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(lg[0]), "=f"(lg[1]) : "r"(la));
+    }
+    softmax_pair<PPL>(lg, ok, 1.f, far_a);
+    unsigned far_bits = 0;
+    {
       // pixel = ((q + .5) / bev + off / f) * f - .5  ==  (q + .5) * (f / bev) + off - .5
-      const float h_im = fmaf(hbase, a.sy, oy - 0.5f), w_im = fmaf((float)qx + 0.5f, a.sx, ox - 0.5f);
-      far_h[r] = h_im, far_w[r] = w_im, far_a[r] = aw;
-      if (store_desc<PP>(sm_w, sm_idx, item, p, ok, h_im, w_im, aw, a.fH, a.fW, w.wy0, w.wx0, a.WW, a.WH))
-        far_bits |= 1u << r;
+      const float wbase = (float)qx1 + 0.5f;
+      uint32_t wl[PPL], wr[PPL], idx[PPL];
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) {
+        far_w[i] = fmaf(wbase, a.sx, off[2 * i] - 0.5f);
+        far_h[i] = fmaf(hbase, a.sy, off[2 * i + 1] - 0.5f);
+        if (make_desc(ok, far_h[i], far_w[i], far_a[i], a.fH, a.fW, w.wy0, w.wx0, a.WW, a.WH, wl[i], wr[i], idx[i]))
+          far_bits |= 1u << i;
+      }
+      store_descs<PP>(sm_w, sm_idx, item_l, p0, wl, wr, idx);
     }
     const bool any_far = __any_sync(0xffffffffu, far_bits != 0u);
     __syncwarp();   // descriptor stores visible to the whole warp
@@ -423,7 +453,7 @@ __global__ void __launch_bounds__(kBevThreads, 1)
       __syncwarp();
       const __half* plane = a.value16 + (int64_t)(w.b * a.H + w.h) * a.fH * a.fW * 32;
 #pragma unroll
-      for (int r = 0; r < R1; ++r) {
+      for (int r = 0; r < PPL; ++r) {
         unsigned m = __ballot_sync(0xffffffffu, (far_bits >> r) & 1u);
         while (m) {
           const int src = __ffs(m) - 1;
@@ -431,7 +461,7 @@ __global__ void __launch_bounds__(kBevThreads, 1)
           const float h_im = __shfl_sync(0xffffffffu, far_h[r], src);
           const float w_im = __shfl_sync(0xffffffffu, far_w[r], src);
           const float aw = __shfl_sync(0xffffffffu, far_a[r], src);
-          const int item = r * item_step + src / PP;
+          const int item = src >> 1;
           const int corner = lane >> 3, c4 = lane & 7, dy = corner >> 1, dx = corner & 1;
           const float hf = floorf(h_im), wf = floorf(w_im);
           const float lh = h_im - hf, lw = w_im - wf;
@@ -596,32 +626,41 @@ __global__ void __launch_bounds__(kImgThreads, 1)
   }
   __syncthreads();
 
-  constexpr int R1 = kWarpItems * PP / 32;   // samples per lane
-  constexpr int item_step = 32 / PP;
-  const int p = lane % PP, it0 = lane / PP;
+  constexpr int PPL = PP / 2;                // sampling points per lane in P1 (two lanes per item)
+  const int item_l = lane >> 1, p0 = (lane & 1) * PPL;
   const int grp = lane >> 3, sub = lane & 7, half = sub >> 2, cq = sub & 3;
-
-  float ox[R1], oy[R1], lg[R1], rx[R1], ry[R1], ic[R1];
-  int qq[R1];
+  float off[PPL * 2], lg[PPL], ref[PPL * 2], ic;
+  int qq;
   auto prefetch = [&](const Unit& wu) {
+    const int ord = wu.chunk * kUnitItems + warp * kWarpItems + item_l;
+    qq = ord < wu.cnt ? __ldg(a.hit_idx + (int64_t)wu.n * a.Nq + ord) : -1;
+    ic = 0.f;
 #pragma unroll
-    for (int r = 0; r < R1; ++r) {
-      const int ord = wu.chunk * kUnitItems + warp * kWarpItems + r * item_step + it0;
-      qq[r] = ord < wu.cnt ? __ldg(a.hit_idx + (int64_t)wu.n * a.Nq + ord) : -1;
-    }
+    for (int i = 0; i < PPL; ++i) off[2 * i] = 0.f, off[2 * i + 1] = 0.f, lg[i] = 0.f, ref[2 * i] = 0.f, ref[2 * i + 1] = 0.f;
+    if (qq >= 0) {
+      const int64_t bq = (int64_t)wu.b * a.Nq + qq;
+      const float* rowp = a.qproj + bq * a.ld;
+      const float4* op = reinterpret_cast<const float4*>(rowp + a.off_col + (wu.h * PP + p0) * 2);
 #pragma unroll
-    for (int r = 0; r < R1; ++r) {
-      ox[r] = 0.f, oy[r] = 0.f, lg[r] = 0.f, rx[r] = 0.f, ry[r] = 0.f, ic[r] = 0.f;
-      if (qq[r] >= 0) {
-        const int64_t bq = (int64_t)wu.b * a.Nq + qq[r];
-        const float* rowp = a.qproj + bq * a.ld;
-        const float2 t = ld_stream2(rowp + a.off_col + (wu.h * PP + p) * 2);
-        ox[r] = t.x, oy[r] = t.y;
-        lg[r] = ld_stream1(rowp + a.logit_col + wu.h * PP + p);
-        const float2 rc = __ldg(reinterpret_cast<const float2*>(a.ref_cam) + (bq * a.N + wu.n) * a.D + (p % a.D));
-        rx[r] = rc.x, ry[r] = rc.y;
-        ic[r] = __ldg(a.inv_cnt + bq);
+      for (int i = 0; i < PPL / 2; ++i) {
+        const float4 t = ld_stream4(reinterpret_cast<const float*>(op + i));
+        off[4 * i] = t.x, off[4 * i + 1] = t.y, off[4 * i + 2] = t.z, off[4 * i + 3] = t.w;
       }
+      const float* lp = rowp + a.logit_col + wu.h * PP + p0;
+      if (PPL == 4) {
+        const float4 t = ld_stream4(lp);
+        lg[0] = t.x, lg[1] = t.y, lg[2] = t.z, lg[PPL - 1] = t.w;
+      } else {
+        const float2 t = ld_stream2(lp);
+        lg[0] = t.x, lg[1] = t.y;
+      }
+      const float2* rp = reinterpret_cast<const float2*>(a.ref_cam) + (bq * a.N + wu.n) * a.D;
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) {
+        const float2 t = __ldg(rp + (p0 + i) % a.D);
+        ref[2 * i] = t.x, ref[2 * i + 1] = t.y;
+      }
+      ic = __ldg(a.inv_cnt + bq);
     }
   };
   prefetch(w);
@@ -630,15 +669,20 @@ __global__ void __launch_bounds__(kImgThreads, 1)
   bool fresh = true;
   for (int u = u_beg; u < u_end; ++u) {
     // ---- P1 from the prefetched registers
+    {
+      const bool ok = qq >= 0;
+      float aw[PPL];
+      softmax_pair<PPL>(lg, ok, ic, aw);
+      uint32_t wl[PPL], wr[PPL], idx[PPL];
 #pragma unroll
-    for (int r = 0; r < R1; ++r) {
-      const int item = r * item_step + it0;
-      const bool ok = qq[r] >= 0;
-      const float aw = softmax_pp<PP>(lg[r], ok) * ic[r];
-      const float h_im = fmaf(ry[r], (float)a.fH, oy[r] - 0.5f), w_im = fmaf(rx[r], (float)a.fW, ox[r] - 0.5f);
-      // the window is the whole plane plus a one-pixel zero halo (origin (-1, -1)): nothing is ever far
-      store_desc<PP>(sm_w, sm_idx, item, p, ok, h_im, w_im, aw, a.fH, a.fW, -1, -1, a.WW, a.WH);
-      if (p == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(sm_q + (uint32_t)item * 4u), "r"(qq[r]) : "memory");
+      for (int i = 0; i < PPL; ++i) {
+        const float w_im = fmaf(ref[2 * i], (float)a.fW, off[2 * i] - 0.5f);
+        const float h_im = fmaf(ref[2 * i + 1], (float)a.fH, off[2 * i + 1] - 0.5f);
+        // the window is the whole plane plus a one-pixel zero halo (origin (-1, -1)): nothing is ever far
+        make_desc(ok, h_im, w_im, aw[i], a.fH, a.fW, -1, -1, a.WW, a.WH, wl[i], wr[i], idx[i]);
+      }
+      store_descs<PP>(sm_w, sm_idx, item_l, p0, wl, wr, idx);
+      if (p0 == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(sm_q + (uint32_t)item_l * 4u), "r"(qq) : "memory");
     }
     __syncwarp();
     const Unit w_cur = w;
@@ -879,7 +923,8 @@ extern "C" int ub_img_sample_win_fwd(const void* value16, const float* qproj, co
   UB_REQUIRE_ALIGNED16(out);
   UB_REQUIRE((reinterpret_cast<uintptr_t>(ref_cam) & 7u) == 0 && (reinterpret_cast<uintptr_t>(qproj) & 7u) == 0,
              "%s: ref_cam / qproj not 8-byte aligned", fn);
-  if (Dh != 32 || (P != 4 && P != 8) || ld % 2 != 0 || off_col % 2 != 0 || fW + 2 > 256 || fH + 2 > 256 ||
+  if (Dh != 32 || (P != 4 && P != 8) || ld % 4 != 0 || off_col % 4 != 0 || logit_col % 4 != 0 ||
+      (reinterpret_cast<uintptr_t>(qproj) & 15u) != 0 || fW + 2 > 256 || fH + 2 > 256 ||
       (int64_t)(fH + 2) * (fW + 2) > 65535 || (int64_t)B * N * H > (1 << 20)) {
     set_error("%s: shape not covered by the window kernels (Dh=%d P=%d fH=%d fW=%d)", fn, Dh, P, fH, fW);
     return UB_EUNSUPPORTED;
