@@ -124,6 +124,21 @@ int ub_img_sample_win_fwd(const void* value16, const float* qproj, const float* 
                           int fH, int fW, int H, int Dh, int P, int D, int ld, int off_col, int logit_col,
                           ub_stream_t stream);
 
+/* ---- [R5] dense projection on the tcgen05 tensor cores with fused epilogue -------------------------
+ * acc = A (M, K) @ W (N, K)^T, TF32 inputs, fp32 accumulation (the nn.Linear layers of the encoder:
+ * value_proj / sampling_offsets|attention_weights / output_proj / FFN, e.g. spatial_cross_attention_img.py:381-389,
+ * :212-215, and mmcv FFN).  A and W contiguous row-major fp32.
+ *   flags bit 0: ReLU.  flags bit 1: LayerNorm over the N outputs of (acc + bias + residual) with gamma / beta / eps
+ *   (N <= 256) -- the 'norm' step that follows every attention / FFN, encoder_unibev_detr_img.py:434-436.
+ *   residual (M, N) row stride ldr, or NULL.  out (M, N) row stride ldc.
+ *   planes != NULL: instead of `out`, write fp16(acc + bias) head-major (M / Nv, N / 32, Nv, 32), the value-map
+ *   layout of ub_bev_sample_win_fwd / ub_img_sample_win_fwd (no ReLU / residual / LayerNorm).
+ * K % 32 == 0, N % 32 == 0 and (N <= 256 or N % 256 == 0), else UB_EUNSUPPORTED. */
+enum { UB_LIN_RELU = 1, UB_LIN_LAYERNORM = 2 };
+int ub_linear_tf32(const float* A, const float* W, const float* bias, const float* residual, int ldr,
+                   const float* gamma, const float* beta, float eps, float* out, int ldc, void* planes, int Nv,
+                   int M, int N, int K, int flags, ub_stream_t stream);
+
 /* ---- [R5] y = LayerNorm(x + bias + residual) * gamma + beta over the last dim C ---------------------
  * bias (C) and residual (rows, C) may be NULL.  C % 4 == 0, C <= 1024.  out may alias x. */
 int ub_add_layernorm(const float* x, const float* bias, const float* residual, const float* gamma,

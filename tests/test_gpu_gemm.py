@@ -1,0 +1,87 @@
+"""GPU parity of ub_linear_tf32 (tcgen05 GEMM with fused epilogues) against torch.
+
+Two kinds of checks: (1) inputs that are exactly representable in TF32 (multiples of 1/8 in a small range), so
+the tensor-core product must equal the fp32 reference up to accumulation order -- this pins the operand layouts,
+descriptors and every epilogue exactly; (2) Gaussian inputs with the stated TF32 tolerance (inputs are reduced to
+10 mantissa bits: |err| <~ 2^-10 * sqrt(K) * |a||w|)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from unibev_b200 import ops as _ops
+    return _ops
+
+
+def _exact(shape, g, scale=8):
+    return torch.randint(-16, 17, shape, generator=g).float() / scale
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 256, 256), (1000, 256, 256), (40000, 256, 256), (333, 96, 256),
+                                   (700, 192, 256), (513, 512, 256), (260, 256, 512), (129, 128, 128), (64, 32, 32)])
+@pytest.mark.parametrize('relu', [False, True])
+def test_linear_plain_exact(ops, M, N, K, relu):
+    g = torch.Generator().manual_seed(M + N + K)
+    x, w, b = _exact((M, K), g), _exact((N, K), g), _exact((N,), g)
+    want = F.linear(x.double(), w.double(), b.double())
+    want = (want.relu() if relu else want).float()
+    got = ops.linear_tf32(x.cuda(), w.cuda(), b.cuda(), relu=relu).cpu()
+    torch.testing.assert_close(got, want, rtol=0, atol=1e-4)
+
+
+def test_linear_residual_and_strided_out(ops):
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 777, 96, 256
+    x, w, b, r = _exact((M, K), g), _exact((N, K), g), _exact((N,), g), _exact((M, N), g)
+    want = (F.linear(x.double(), w.double(), b.double()) + r.double()).float()
+    got = ops.linear_tf32(x.cuda(), w.cuda(), b.cuda(), residual=r.cuda()).cpu()
+    torch.testing.assert_close(got, want, rtol=0, atol=1e-4)
+    got2 = ops.linear_tf32(x.cuda(), w.cuda(), None).cpu()
+    torch.testing.assert_close(got2, F.linear(x, w), rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize('M,N,K', [(1000, 256, 256), (40000, 256, 512), (200, 128, 128), (131, 32, 64)])
+def test_linear_layernorm_exact_inputs(ops, M, N, K):
+    g = torch.Generator().manual_seed(N + K)
+    x, w, b, r = _exact((M, K), g), _exact((N, K), g, 64), _exact((N,), g), _exact((M, N), g)
+    gam, bet = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    pre = F.linear(x.double(), w.double(), b.double()) + r.double()
+    want = F.layer_norm(pre, (N,), gam.double(), bet.double(), 1e-5).float()
+    got = ops.linear_tf32(x.cuda(), w.cuda(), b.cuda(), residual=r.cuda(), ln=(gam.cuda(), bet.cuda(), 1e-5)).cpu()
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('G,Nv', [(1, 1000), (6, 1450), (2, 333)])
+def test_linear_half_planes(ops, G, Nv):
+    g = torch.Generator().manual_seed(Nv)
+    N, K = 256, 256
+    x, w, b = _exact((G * Nv, K), g), _exact((N, K), g, 64), _exact((N,), g)
+    want = F.linear(x, w, b).view(G, Nv, 8, 32).permute(0, 2, 1, 3).half()
+    got = ops.linear_tf32(x.cuda(), w.cuda(), b.cuda(), planes_nv=Nv).cpu()
+    assert got.shape == (G, 8, Nv, 32)
+    torch.testing.assert_close(got.float(), want.float(), rtol=1e-3, atol=1e-3)
+    same = ops.value_to_half(F.linear(x, w, b).cuda(), G, Nv, 8).cpu()
+    assert (got.float() - same.float()).abs().max() <= 1e-3 * want.float().abs().max()
+
+
+def test_linear_tf32_tolerance_gaussian(ops):
+    g = torch.Generator().manual_seed(0)
+    M, N, K = 4096, 256, 256
+    x, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    want = F.linear(x.double(), w.double(), b.double()).float()
+    got = ops.linear_tf32(x.cuda(), w.cuda(), b.cuda()).cpu()
+    err = (got - want).abs()
+    assert float(err.max()) < 8e-3 and float(err.mean()) < 1.5e-3, (float(err.max()), float(err.mean()))
+
+
+def test_linear_rejects_uncovered_shapes(ops):
+    from unibev_b200 import _cabi
+    with pytest.raises(_cabi.UnsupportedShape):
+        ops.linear_tf32(torch.zeros(10, 30, device='cuda'), torch.zeros(32, 30, device='cuda'))
+    with pytest.raises(_cabi.UnsupportedShape):
+        ops.linear_tf32(torch.zeros(10, 32, device='cuda'), torch.zeros(40, 32, device='cuda'))

@@ -185,6 +185,46 @@ def img_sample_win(value16, qproj, ref_cam, hits, bev_h, bev_w, fH, fW, H, P, of
     return out
 
 
+def linear_tf32(x, weight, bias=None, residual=None, relu=False, ln=None, out=None, planes_nv=None):
+    """x (M, K) @ weight (N, K)^T on the tcgen05 tensor cores (TF32) with the epilogue fused:
+    + bias, + residual (M, N), ReLU, LayerNorm (ln = (gamma, beta, eps)); ``planes_nv`` = rows per value map:
+    return fp16 head-major planes (M // planes_nv, N // 32, planes_nv, 32) instead of an fp32 (M, N) matrix."""
+    x, weight = _need(x, 'x'), _need(weight, 'weight')
+    M, K = x.shape
+    N = weight.shape[0]
+    if weight.shape[1] != K:
+        raise ValueError(f'linear_tf32: x{tuple(x.shape)} vs weight{tuple(weight.shape)}')
+    bias = _need(bias, 'bias') if bias is not None else None
+    flags = (1 if relu else 0) | (2 if ln is not None else 0)
+    gamma = beta = None
+    eps = 0.0
+    if ln is not None:
+        gamma, beta, eps = _need(ln[0], 'gamma'), _need(ln[1], 'beta'), float(ln[2])
+    ldr = 0
+    if residual is not None:
+        residual = _need(residual, 'residual')
+        if residual.shape != (M, N):
+            raise ValueError('linear_tf32: residual shape mismatch')
+        ldr = N
+    planes = None
+    if planes_nv is not None:
+        if M % planes_nv or N % 32:
+            raise ValueError('linear_tf32: planes need M % Nv == 0 and N % 32 == 0')
+        planes = out if out is not None else torch.empty(M // planes_nv, N // 32, planes_nv, 32, device=x.device,
+                                                         dtype=torch.float16)
+        res = planes
+        out_ptr, ldc = None, 0
+    else:
+        if out is None:
+            out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        res = out
+        out_ptr, ldc = _ptr(out), out.stride(0)
+    _cabi.check(_cabi.lib().ub_linear_tf32(_ptr(x), _ptr(weight), _ptr(bias), _ptr(residual), ldr, _ptr(gamma), _ptr(beta),
+                                           eps, out_ptr, ldc, _ptr(planes), planes_nv or 0, M, N, K, flags, _stream()),
+                'ub_linear_tf32')
+    return res
+
+
 def add_layernorm(x, gamma, beta, bias=None, residual=None, eps=1e-5, out=None):
     x = _need(x, 'x')
     C = x.shape[-1]
