@@ -61,13 +61,21 @@ def test_fused_path_is_taken_and_native():
     a, p = load_golden('encoder_half_lc_cnw_linear')
     cfg, img, pts, q, bev_h, bev_w = encoder_half_inputs(a)
     m = _build(cfg, p).eval()
-    _cabi.reset_launch_count()
-    with torch.no_grad():
-        m.encode(_cuda(img), _cuda(pts), _cuda(q), bev_h, bev_w, bev_pos=a['bev_pos'].cuda(), img_metas=metas_from(a))
-    assert m._fused is not None
     layers = cfg['img_encoder']['num_layers']
-    # per encoder: flatten + layers*(2 samples + 3 LN); + bev_pos flatten + project + fuse
-    assert _cabi.launch_count() == 2 * (1 + layers * 5) + 3
+    counts = {}
+    for prec in ('fp32', 'tf32'):
+        m.fused_precision = prec
+        _cabi.reset_launch_count()
+        with torch.no_grad():
+            m.encode(_cuda(img), _cuda(pts), _cuda(q), bev_h, bev_w, bev_pos=a['bev_pos'].cuda(),
+                     img_metas=metas_from(a))
+        assert m._fused is not None
+        counts[prec] = _cabi.launch_count()
+    # fp32: per encoder flatten + layers*(2 samples + 3 LN); + bev_pos flatten + project + fuse (GEMMs: cuBLAS)
+    assert counts['fp32'] == 2 * (1 + layers * 5) + 3
+    # tf32: the LayerNorms ride in the tcgen05 GEMM epilogues and the covered projections are native as well
+    # (this fixture: head dim 8 -> fp32 sampling kernels; N = 48 offset|logit rows of the self-attention -> cuBLAS)
+    assert counts['tf32'] == 2 * (1 + layers * 7) + 3
 
 
 def test_module_path_backward_matches_oracle_autograd():

@@ -85,3 +85,26 @@ def test_linear_rejects_uncovered_shapes(ops):
         ops.linear_tf32(torch.zeros(10, 30, device='cuda'), torch.zeros(32, 30, device='cuda'))
     with pytest.raises(_cabi.UnsupportedShape):
         ops.linear_tf32(torch.zeros(10, 32, device='cuda'), torch.zeros(40, 32, device='cuda'))
+
+
+@pytest.mark.parametrize('cs', [1, 2, 4])
+def test_linear_cluster_sizes_agree(ops, cs):
+    """The cluster size (TMA multicast of the weight tile) is a performance knob: results must not depend on it."""
+    from unibev_b200 import _cabi
+    g = torch.Generator().manual_seed(11)
+    _cabi.check(_cabi.lib().ub_set_gemm_cluster(cs), 'ub_set_gemm_cluster')
+    try:
+        for M, N, K in ((40000, 256, 256), (1000, 96, 256), (650, 512, 256), (129, 256, 512), (5000, 192, 256)):
+            x, w, b, r = _exact((M, K), g), _exact((N, K), g, 64), _exact((N,), g), _exact((M, N), g)
+            want = F.linear(x.double(), w.double(), b.double()).float()
+            got = ops.linear_tf32(x.cuda(), w.cuda(), b.cuda()).cpu()
+            torch.testing.assert_close(got, want, rtol=0, atol=1e-4)
+            if N <= 256:
+                gam, bet = torch.randn(N, generator=g), torch.randn(N, generator=g)
+                want = F.layer_norm(F.linear(x.double(), w.double(), b.double()) + r.double(), (N,), gam.double(),
+                                    bet.double(), 1e-5).float()
+                got = ops.linear_tf32(x.cuda(), w.cuda(), b.cuda(), residual=r.cuda(),
+                                      ln=(gam.cuda(), bet.cuda(), 1e-5)).cpu()
+                torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+    finally:
+        _cabi.lib().ub_set_gemm_cluster(4)

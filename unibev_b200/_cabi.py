@@ -38,6 +38,8 @@ PROTOTYPES = {
 # not part of the public header: tuning hook used by bench/sweeps
 _PRIVATE = {
     'ub_set_tuning': ([_i] * 3, _i),
+    'ub_set_gemm_cluster': ([_i], _i),
+    'ub_set_gemm_trace': ([_p], _i),
 }
 
 _lib = None

@@ -26,21 +26,38 @@
 
 namespace ub {
 
-constexpr int kGemmThreads = 256;
-constexpr int kBM = 128, kBK = 32, kStages = 3;
-constexpr int kEpiWarps = 4, kChunk = 32;          // epilogue column chunk
+constexpr int kGemmThreads = 384;                 // 4 control warps + 8 epilogue warps
+constexpr int kBM = 128, kBK = 32, kMaxStages = 8;
+constexpr int kEpiWarps = 8, kChunk = 32;          // epilogue warps (two per TMEM lane quarter), column chunk
 constexpr int kStageBuf = kChunk * 32 * 4;         // one warp's 32 rows x 32 columns staging buffer (4 KB)
 
 struct GemmArgs {
   const float* bias;    // (N) or null
   const float* gamma;   // (N) layernorm
   const float* beta;
+  const float* A;         // (M, K) contiguous (L2 prefetch; the k-blocks themselves come through the tensor map)
+  const float* residual;  // (M, N) row stride ldr, or null
+  float* out;           // (M, N) row stride ldc (unused with planes)
+  int ldr, ldc;
   __half* planes;       // fp16 head-major output or null
   int Nv, H;            // planes: rows per plane group, heads (= N / 32)
   int M, N, K, BN, n_tiles_m, n_tiles_n;
   float eps;
-  int relu, ln, has_res;
+  int relu, ln;
+  int SA, SW;           // ring depths (A k-blocks, W k-blocks)
+  int cs;               // CTAs per cluster: they work on `cs` consecutive row tiles and share W by TMA multicast
+  unsigned long long* trace;   // optional per-CTA event timestamps (tools/trace_gemm.py), else null
 };
+
+// trace slots per CTA: [0] start, [1 + 32 r + i]: role r (0 producer, 1 mma, 2 epilogue warp 0), event i
+constexpr int kTraceSlots = 128;
+__device__ __forceinline__ void trace_event(const GemmArgs& a, int role, int i) {
+  if (a.trace && i < 40) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[(size_t)blockIdx.x * kTraceSlots + 1 + role * 40 + i] = t;
+  }
+}
 
 // ---- tcgen05 wrappers -------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -67,6 +84,29 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// the same arrive delivered to the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void mma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                      uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, "
+      "%5}], [%2], %3;" ::"r"(dst),
+      "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// contiguous global bytes -> L2 (no destination): turns the strided k-block reads of a tile into one sequential
+// DRAM stream issued well ahead of the TMA loads
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // 32 consecutive fp32 columns of this thread's TMEM lane
@@ -114,29 +154,39 @@ __device__ __forceinline__ uint32_t swz(uint32_t base, int row, int j) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Shared-memory rings: the A k-blocks come from DRAM (about 1.5 us away under load), so their ring is deep; the W
+// k-blocks are re-read from L2 by every tile and need only a shallow ring.  Each ring has its own producer lane.
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
-    gemm_tf32_kernel(const GemmArgs a, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r) {
+    gemm_tf32_kernel(const GemmArgs a, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_tfull[2], s_tempty[2], s_res[kEpiWarps][2];
+  __shared__ __align__(8) uint64_t s_fa[kMaxStages], s_ea[kMaxStages], s_fw[kMaxStages], s_ew[kMaxStages], s_tfull[2],
+      s_tempty[2];
   __shared__ uint32_t s_tmem;
+  __shared__ float2 s_stat[2][kBM];   // LayerNorm partial (sum, sum of squares) of the two column halves
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t stage_bytes = (uint32_t)(kBM * 128 + a.BN * 128);
-  const uint32_t sm_base = smem_u32(smem);
-  const uint32_t sm_stage_buf = sm_base + kStages * stage_bytes;                 // [4 warps][2] x 4 KB
-  float* s_par = reinterpret_cast<float*>(smem + kStages * stage_bytes + kEpiWarps * 2 * kStageBuf);  // bias|gamma|beta
-  const int n_tiles = a.n_tiles_m * a.n_tiles_n;
+  const int SA = a.SA, SW = a.SW;
+  const uint32_t a_bytes = kBM * 128, w_bytes = (uint32_t)a.BN * 128;
+  const uint32_t sm_a = smem_u32(smem), sm_w = sm_a + (uint32_t)SA * a_bytes;
+  const uint32_t sm_stage_buf = sm_w + (uint32_t)SW * w_bytes;                  // [8 warps] x 4 KB
+  float* s_par = reinterpret_cast<float*>(smem + (size_t)SA * a_bytes + (size_t)SW * w_bytes + kEpiWarps * kStageBuf);
   const int k_blocks = a.K / kBK;
+  // Work = groups of `cs` consecutive row tiles of one column tile; cluster c takes groups c, c + n_clusters, ...
+  // and CTA rank r of the cluster the r-th row tile of the group (possibly past M: loads zero-fill, nothing is stored).
+  const int cs = a.cs, rank = (int)blockIdx.x % cs, cluster_id = (int)blockIdx.x / cs, n_clusters = (int)gridDim.x / cs;
+  const int groups_m = (a.n_tiles_m + cs - 1) / cs, n_groups = groups_m * a.n_tiles_n;
+  const uint16_t cta_mask = (uint16_t)((1u << cs) - 1u);
+  const uint32_t w_slice_rows = (uint32_t)(a.BN / cs), w_slice_bytes = w_slice_rows * 128u;
 
   for (int i = tid; i < a.N; i += kGemmThreads) {
     s_par[i] = a.bias ? a.bias[i] : 0.f;
     if (a.ln) s_par[a.N + i] = a.gamma[i], s_par[2 * a.N + i] = a.beta[i];
   }
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) mbar_init(smem_u32(&s_full[i]), 1), mbar_init(smem_u32(&s_empty[i]), 1);
+    for (int i = 0; i < SA; ++i) mbar_init(smem_u32(&s_fa[i]), 1), mbar_init(smem_u32(&s_ea[i]), 1);
+    for (int i = 0; i < SW; ++i) mbar_init(smem_u32(&s_fw[i]), 1), mbar_init(smem_u32(&s_ew[i]), cs);
     for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&s_tfull[i]), 1), mbar_init(smem_u32(&s_tempty[i]), kEpiWarps);
-    for (int i = 0; i < kEpiWarps; ++i) mbar_init(smem_u32(&s_res[i][0]), 1), mbar_init(smem_u32(&s_res[i][1]), 1);
     mbar_init_fence();
   }
   if (warp == 2) {
@@ -145,26 +195,63 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // every CTA's barriers exist before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
+  if (a.trace && tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[(size_t)blockIdx.x * kTraceSlots] = t;
+  }
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ A producer (+ L2 prefetch two tiles ahead)
     if (lane == 0) {
       tma_prefetch_desc(&map_a);
+      auto prefetch_tile = [&](int g) {   // the A rows (contiguous: lda == K) and the residual rows of group g
+        if (g >= n_groups) return;
+        const int m0 = ((g % groups_m) * cs + rank) * kBM, n0 = (g / groups_m) * a.BN;
+        if (m0 >= a.M) return;
+        const int rows = min(kBM, a.M - m0);
+        if (g / groups_m == 0 || a.n_tiles_n == 1) bulk_prefetch_l2(a.A + (size_t)m0 * a.K, (uint32_t)(rows * a.K * 4));
+        if (a.residual && a.ldr == a.BN) bulk_prefetch_l2(a.residual + (size_t)m0 * a.ldr + n0, (uint32_t)(rows * a.ldr * 4));
+      };
+      prefetch_tile(cluster_id);
+      prefetch_tile(cluster_id + n_clusters);
+      int stage = 0, ev = 0;
+      uint32_t phase = 0;
+      for (int g = cluster_id; g < n_groups; g += n_clusters) {
+        const int m0 = ((g % groups_m) * cs + rank) * kBM;
+        prefetch_tile(g + 2 * n_clusters);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(smem_u32(&s_ea[stage]), phase ^ 1u);
+          const uint32_t bar = smem_u32(&s_fa[stage]);
+          mbar_arrive_expect_tx(bar, a_bytes);
+          tma_load_2d(sm_a + (uint32_t)stage * a_bytes, &map_a, bar, kb * kBK, m0);
+          trace_event(a, 0, ev++);
+          if (++stage == SA) stage = 0, phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ W producer
+    if (lane == 0) {
       tma_prefetch_desc(&map_w);
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int m0 = (t / a.n_tiles_n) * kBM, n0 = (t % a.n_tiles_n) * a.BN;
+      for (int g = cluster_id; g < n_groups; g += n_clusters) {
+        const int n0 = (g / groups_m) * a.BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(smem_u32(&s_empty[stage]), phase ^ 1u);
-          const uint32_t bar = smem_u32(&s_full[stage]);
-          const uint32_t dst = sm_base + (uint32_t)stage * stage_bytes;
-          mbar_arrive_expect_tx(bar, stage_bytes);
-          tma_load_2d(dst, &map_a, bar, kb * kBK, m0);
-          tma_load_2d(dst + kBM * 128, &map_w, bar, kb * kBK, n0);
-          if (++stage == kStages) stage = 0, phase ^= 1u;
+          mbar_wait(smem_u32(&s_ew[stage]), phase ^ 1u);   // every CTA of the cluster has consumed the slot
+          const uint32_t bar = smem_u32(&s_fw[stage]);
+          const uint32_t dst = sm_w + (uint32_t)stage * w_bytes;
+          mbar_arrive_expect_tx(bar, w_bytes);             // all `cs` slices of the W k-block
+          if (cs == 1)
+            tma_load_2d(dst, &map_w, bar, kb * kBK, n0);
+          else
+            tma_load_2d_multicast(dst + (uint32_t)rank * w_slice_bytes, &map_w, bar, kb * kBK, n0 + rank * (int)w_slice_rows,
+                                  cta_mask);
+          if (++stage == SW) stage = 0, phase ^= 1u;
         }
       }
     }
@@ -172,74 +259,121 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(a.BN);
-      int stage = 0;
-      uint32_t phase = 0;
+      int sa = 0, sw = 0, ev = 0;
+      uint32_t pa = 0, pw = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      for (int g = cluster_id; g < n_groups; g += n_clusters, ++it) {
         const int acc = it & 1;
         mbar_wait(smem_u32(&s_tempty[acc]), (uint32_t)(((it >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(smem_u32(&s_full[stage]), phase);
+          mbar_wait(smem_u32(&s_fw[sw]), pw);
+          mbar_wait(smem_u32(&s_fa[sa]), pa);
+          trace_event(a, 1, ev++);
           tc_fence_after();
-          const uint32_t sa = sm_base + (uint32_t)stage * stage_bytes;
-          const uint64_t adesc = smem_desc_k128(sa), bdesc = smem_desc_k128(sa + kBM * 128);
+          const uint64_t adesc = smem_desc_k128(sm_a + (uint32_t)sa * a_bytes);
+          const uint64_t bdesc = smem_desc_k128(sm_w + (uint32_t)sw * w_bytes);
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k)   // 8 tf32 = 32 bytes per MMA along K: advance the start address
             mma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-          mma_commit(smem_u32(&s_empty[stage]));
-          if (++stage == kStages) stage = 0, phase ^= 1u;
+          mma_commit(smem_u32(&s_ea[sa]));
+          if (cs == 1)
+            mma_commit(smem_u32(&s_ew[sw]));
+          else
+            mma_commit_multicast(smem_u32(&s_ew[sw]), cta_mask);   // the W slot is shared: release it everywhere
+          if (++sa == SA) sa = 0, pa ^= 1u;
+          if (++sw == SW) sw = 0, pw ^= 1u;
         }
         mma_commit(smem_u32(&s_tfull[acc]));
       }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 4;
-    const uint32_t buf0 = sm_stage_buf + (uint32_t)ew * 2 * kStageBuf;
-    const uint32_t bar_res0 = smem_u32(&s_res[ew][0]);
+    // Thread = one row of the tile (its TMEM lane); the two warps of a lane quarter split the 32-column chunks.
+    // Rows meet global memory through one 128-byte-swizzled 4 KB buffer per warp: coalesced 16-byte accesses on
+    // the global side (4 rows x 128 B per instruction), whole rows on the thread side, __syncwarp in between.
+    const int ew = warp - 4, q = ew & 3, hsel = ew >> 2;
+    const uint32_t buf = sm_stage_buf + (uint32_t)ew * kStageBuf;
     const int n_chunks = a.BN / kChunk;
-    uint32_t res_uses = 0;   // completed waits on the residual barriers: parity of buffer b = (uses of b) & 1
+    const int c_beg = hsel ? (n_chunks + 1) / 2 : 0, c_end = hsel ? n_chunks : (n_chunks + 1) / 2;
+    const int crow = lane >> 3, ccol = lane & 7;              // coalesced side: rows crow + 4 i, 16-byte column ccol
     int it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    for (int g = cluster_id; g < n_groups; g += n_clusters, ++it) {
       const int acc = it & 1;
-      const int m0 = (t / a.n_tiles_n) * kBM, n0 = (t % a.n_tiles_n) * a.BN;
-      const int row0 = m0 + ew * 32;                        // this warp's 32 rows
-      const uint32_t tbase = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(ew * 32) << 16);
-      const bool rows_live = row0 < a.M;                    // warp-uniform: rows beyond M are never loaded / stored
-      // residual chunks 0 / 1 stream in while the accumulator is still being computed
-      if (a.has_res && lane == 0 && rows_live) {
-        bulk_wait_read<0>();                                // the previous tile's stores have left the buffers
-        for (int c = 0; c < 2 && c < n_chunks; ++c) {
-          mbar_arrive_expect_tx(bar_res0 + 8u * c, kStageBuf);
-          tma_load_2d(buf0 + (uint32_t)c * kStageBuf, &map_r, bar_res0 + 8u * c, n0 + c * kChunk, row0);
+      const int m0 = ((g % groups_m) * cs + rank) * kBM, n0 = (g / groups_m) * a.BN;
+      const int row0 = m0 + q * 32;                           // this warp's 32 rows
+      const uint32_t tbase = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
+      const bool rows_live = row0 < a.M;                      // warp-uniform (and equal for both warps of the quarter)
+
+      float4 rr[8];                                           // residual chunk in flight (coalesced layout)
+      auto load_res = [&](int c) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = row0 + crow + 4 * i;
+          rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < a.M) rr[i] = ld_stream4(a.residual + (size_t)row * a.ldr + n0 + c * kChunk + ccol * 4);
         }
-      }
+      };
+      auto add_res = [&](float (&f)[32]) {                    // registers -> swizzled buffer -> this thread's row
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(swz(buf, crow + 4 * i, ccol)), "f"(rr[i].x), "f"(rr[i].y),
+                       "f"(rr[i].z), "f"(rr[i].w)
+                       : "memory");
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 r;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(swz(buf, lane, j)));
+          f[4 * j] += r.x, f[4 * j + 1] += r.y, f[4 * j + 2] += r.z, f[4 * j + 3] += r.w;
+        }
+        __syncwarp();
+      };
+      auto store_rows = [&](int c, const float (&f)[32]) {    // this thread's row chunk -> global (coalesced)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(swz(buf, lane, j)), "f"(f[4 * j]), "f"(f[4 * j + 1]),
+                       "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                       : "memory");
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = row0 + crow + 4 * i;
+          float4 o;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                       : "r"(swz(buf, crow + 4 * i, ccol)));
+          if (row < a.M) st_stream4(a.out + (size_t)row * a.ldc + n0 + c * kChunk + ccol * 4, o);
+        }
+        __syncwarp();
+      };
+      auto params4 = [&](const float* p, int j) {             // 16-byte broadcast read of bias / gamma / beta
+        return *reinterpret_cast<const float4*>(p + 4 * j);
+      };
+
+      if (a.residual && rows_live && c_beg < c_end) load_res(c_beg);   // in flight while the accumulator is computed
       mbar_wait(smem_u32(&s_tfull[acc]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
+      if (ew == 0 && lane == 0) trace_event(a, 2, 2 * it);
 
       float sum = 0.f, sumsq = 0.f;
       // ---- pass A: acc + bias (+ residual); LayerNorm: statistics, row parked back in TMEM
       //              otherwise: activation and store
-      for (int c = 0; c < n_chunks; ++c) {
-        const int b = c & 1;
-        const uint32_t buf = buf0 + (uint32_t)b * kStageBuf;
+      for (int c = c_beg; c < c_end; ++c) {
         uint32_t v[32];
         tmem_ld32(tbase + (uint32_t)(c * kChunk), v);
         if (!rows_live) continue;
         float f[32];
+        const float* bias = s_par + n0 + c * kChunk;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + s_par[n0 + c * kChunk + j];
-        if (a.has_res) {
-          mbar_wait(bar_res0 + 8u * b, (res_uses >> b) & 1u);
-          res_uses ^= 1u << b;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 r;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(swz(buf, lane, j)));
-            f[4 * j] += r.x, f[4 * j + 1] += r.y, f[4 * j + 2] += r.z, f[4 * j + 3] += r.w;
-          }
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = params4(bias, j);
+          f[4 * j] = __uint_as_float(v[4 * j]) + b4.x, f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z, f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+        }
+        if (a.residual) {
+          add_res(f);                                         // consumes rr
+          if (c + 1 < c_end) load_res(c + 1);                 // next chunk's loads fly during this chunk's tail
         }
         if (a.ln) {
 #pragma unroll
@@ -249,17 +383,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             v[j] = __float_as_uint(f[j]);
           }
           tmem_st32(tbase + (uint32_t)(c * kChunk), v);
-          __syncwarp();
-          if (a.has_res && lane == 0 && c + 2 < n_chunks) {   // the buffer is free: next residual chunk
-            mbar_arrive_expect_tx(bar_res0 + 8u * b, kStageBuf);
-            tma_load_2d(buf, &map_r, bar_res0 + 8u * b, n0 + (c + 2) * kChunk, row0);
-          }
         } else if (a.planes) {
           // fp16 head-major planes: chunk c of the row is head (n0 / 32 + c) of token (row % Nv) in group row / Nv
           const int row = row0 + lane;
           if (row < a.M) {
-            const int g = row / a.Nv, tok = row - g * a.Nv;
-            uint4* dst = reinterpret_cast<uint4*>(a.planes + (((int64_t)g * a.H + (n0 / kChunk + c)) * a.Nv + tok) * 32);
+            const int gi = row / a.Nv, tok = row - gi * a.Nv;
+            uint4* dst = reinterpret_cast<uint4*>(a.planes + (((int64_t)gi * a.H + (n0 / kChunk + c)) * a.Nv + tok) * 32);
             const float lim = 65504.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -275,71 +404,53 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             }
           }
         } else {
-          if (!a.has_res) {                                   // the buffer may still feed an earlier store
-            if (lane == 0) bulk_wait_read<1>();
-            __syncwarp();
-          }
+          if (a.relu) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            if (a.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(swz(buf, lane, j)), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
-                         : "memory");
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&map_c, buf, n0 + c * kChunk, row0);
-            bulk_commit();
-            if (a.has_res && c + 2 < n_chunks) {              // reuse the buffer once the store has read it
-              bulk_wait_read<0>();
-              mbar_arrive_expect_tx(bar_res0 + 8u * b, kStageBuf);
-              tma_load_2d(buf, &map_r, bar_res0 + 8u * b, n0 + (c + 2) * kChunk, row0);
-            }
-          }
+          store_rows(c, f);
         }
       }
-      // ---- pass B (LayerNorm): normalise the parked row, store
-      if (a.ln && rows_live) {
-        const float inv_n = 1.f / (float)a.BN;
-        const float mean = sum * inv_n;
-        const float rstd = rsqrtf(fmaxf(sumsq * inv_n - mean * mean, 0.f) + a.eps);
-        const float* gam = s_par + a.N + n0;
-        const float* bet = s_par + 2 * a.N + n0;
-        for (int c = 0; c < n_chunks; ++c) {
-          const uint32_t buf = buf0 + (uint32_t)(c & 1) * kStageBuf;
-          uint32_t v[32];
-          tmem_ld32(tbase + (uint32_t)(c * kChunk), v);
-          if (lane == 0) bulk_wait_read<1>();                 // the store issued two chunks ago has read this buffer
-          __syncwarp();
+      // ---- pass B (LayerNorm): the two warps of the quarter exchange their partial statistics, then each
+      //      normalises and stores its chunks of the parked row
+      if (a.ln) {
+        s_stat[hsel][q * 32 + lane] = make_float2(sum, sumsq);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const float2 other = s_stat[hsel ^ 1][q * 32 + lane];
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // s_stat is reused by the next tile
+        if (rows_live) {
+          const float inv_n = 1.f / (float)a.BN;
+          const float mean = (sum + other.x) * inv_n;
+          const float rstd = rsqrtf(fmaxf((sumsq + other.y) * inv_n - mean * mean, 0.f) + a.eps);
+          for (int c = c_beg; c < c_end; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tbase + (uint32_t)(c * kChunk), v);
+            float f[32];
+            const float* gam = s_par + a.N + n0 + c * kChunk;
+            const float* bet = s_par + 2 * a.N + n0 + c * kChunk;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o;
-            o.x = (__uint_as_float(v[4 * j]) - mean) * rstd * gam[c * kChunk + 4 * j] + bet[c * kChunk + 4 * j];
-            o.y = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * gam[c * kChunk + 4 * j + 1] + bet[c * kChunk + 4 * j + 1];
-            o.z = (__uint_as_float(v[4 * j + 2]) - mean) * rstd * gam[c * kChunk + 4 * j + 2] + bet[c * kChunk + 4 * j + 2];
-            o.w = (__uint_as_float(v[4 * j + 3]) - mean) * rstd * gam[c * kChunk + 4 * j + 3] + bet[c * kChunk + 4 * j + 3];
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(swz(buf, lane, j)), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
-                         : "memory");
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&map_c, buf, n0 + c * kChunk, row0);
-            bulk_commit();
+            for (int j = 0; j < 8; ++j) {
+              const float4 g4 = params4(gam, j), b4 = params4(bet, j);
+              f[4 * j] = (__uint_as_float(v[4 * j]) - mean) * rstd * g4.x + b4.x;
+              f[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * g4.y + b4.y;
+              f[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) - mean) * rstd * g4.z + b4.z;
+              f[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) - mean) * rstd * g4.w + b4.w;
+            }
+            store_rows(c, f);
           }
         }
       }
       // the accumulator is drained
       tc_fence_before();
       __syncwarp();
+      if (ew == 0 && lane == 0) trace_event(a, 2, 2 * it + 1);
       if (lane == 0) mbar_arrive(smem_u32(&s_tempty[acc]));
     }
-    if (lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -349,6 +460,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 }  // namespace ub
 
 using namespace ub;
+
+static int g_gemm_cluster = 4;
+static unsigned long long* g_gemm_trace = nullptr;
+// debugging aid (tools/trace_gemm.py): device buffer of 148 x 128 u64 that the next launches fill with timestamps
+extern "C" int ub_set_gemm_trace(void* buf) {
+  g_gemm_trace = reinterpret_cast<unsigned long long*>(buf);
+  return UB_OK;
+}
+// CTAs per cluster of ub_linear_tf32 (1, 2 or 4): a performance knob, results do not depend on it
+extern "C" int ub_set_gemm_cluster(int cs) {
+  UB_REQUIRE(cs == 1 || cs == 2 || cs == 4, "ub_set_gemm_cluster: cluster size must be 1, 2 or 4");
+  g_gemm_cluster = cs;
+  return UB_OK;
+}
 
 // out = epilogue(A (M, K) @ W (N, K)^T).  flags: bit 0 relu, bit 1 layernorm (needs residual-or-not, gamma, beta,
 // N <= 256).  planes != NULL: fp16 head-major output (G = M / Nv groups, H = N / 32 heads), `out` ignored.
@@ -373,8 +498,13 @@ extern "C" int ub_linear_tf32(const float* A, const float* W, const float* bias,
   a.Nv = Nv, a.H = N / 32;
   a.M = M, a.N = N, a.K = K, a.BN = N > 256 ? 256 : N;
   a.n_tiles_m = (M + kBM - 1) / kBM, a.n_tiles_n = N / a.BN;
-  a.eps = eps, a.relu = relu, a.ln = ln, a.has_res = residual != nullptr;
-  CUtensorMap ma, mw, mc, mr;
+  a.eps = eps, a.relu = relu, a.ln = ln;
+  a.A = A, a.residual = residual, a.out = out, a.ldr = ldr, a.ldc = ldc;
+  // cluster size: the W tile is split into `cs` slices of whole 8-row swizzle groups
+  a.trace = g_gemm_trace;
+  a.cs = g_gemm_cluster;
+  while (a.cs > 1 && ((a.BN / a.cs) % 8 != 0 || a.BN % a.cs != 0 || a.n_tiles_m < a.cs)) a.cs >>= 1;
+  CUtensorMap ma, mw;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)K * 4};
     const uint32_t box[2] = {kBK, kBM};
@@ -383,27 +513,21 @@ extern "C" int ub_linear_tf32(const float* A, const float* W, const float* bias,
   }
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)K * 4};
-    const uint32_t box[2] = {kBK, (uint32_t)a.BN};
+    const uint32_t box[2] = {kBK, (uint32_t)(a.BN / a.cs)};
     if (int rc = make_tensor_map(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, W, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return rc;
   }
-  const uint32_t cbox[2] = {kChunk, 32};
-  if (out) {
-    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, str[1] = {(uint64_t)ldc * 4};
-    if (int rc = make_tensor_map(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, str, cbox, CU_TENSOR_MAP_SWIZZLE_128B))
-      return rc;
-  } else {
-    mc = ma;
+  // ring depths: W shallow, A as deep as the 227 KB of shared memory allow (up to 8)
+  const size_t fixed = kEpiWarps * kStageBuf + (size_t)3 * N * sizeof(float);
+  a.SW = a.BN > 128 ? 3 : 4;
+  const size_t budget = 232448 - 3072 - 1024;   // minus static shared memory and slack
+  a.SA = (int)((budget - fixed - (size_t)a.SW * a.BN * 128) / (kBM * 128));
+  if (a.SA > kMaxStages) a.SA = kMaxStages;
+  if (a.SA < 2) {
+    set_error("%s: no room for the operand rings (N=%d)", fn, N);
+    return UB_EUNSUPPORTED;
   }
-  if (residual) {
-    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, str[1] = {(uint64_t)ldr * 4};
-    if (int rc = make_tensor_map(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, residual, dims, str, cbox,
-                                 CU_TENSOR_MAP_SWIZZLE_128B))
-      return rc;
-  } else {
-    mr = ma;
-  }
-  const size_t smem = (size_t)kStages * (kBM * 128 + a.BN * 128) + kEpiWarps * 2 * kStageBuf + (size_t)3 * N * sizeof(float);
+  const size_t smem = (size_t)a.SA * kBM * 128 + (size_t)a.SW * a.BN * 128 + fixed;
   static size_t configured = 0;
   if (smem > configured) {
     if (cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -413,8 +537,33 @@ extern "C" int ub_linear_tf32(const float* A, const float* W, const float* bias,
     }
     configured = smem;
   }
-  const int n_tiles = a.n_tiles_m * a.n_tiles_n;
-  const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-  gemm_tf32_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(a, ma, mw, mc, mr);
+  const int n_groups = ((a.n_tiles_m + a.cs - 1) / a.cs) * a.n_tiles_n;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = a.cs, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  // persistent grid: as many clusters as can be resident at once (one CTA per SM; clusters do not span GPCs)
+  static int max_clusters[5] = {0, 0, 0, 0, 0};
+  static size_t max_clusters_smem[5] = {0, 0, 0, 0, 0};
+  if (max_clusters[a.cs] == 0 || max_clusters_smem[a.cs] != smem) {
+    cfg.gridDim = dim3(kNumSMs / a.cs * a.cs);
+    int n = 0;
+    if (a.cs == 1 || cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = a.cs == 1 ? kNumSMs : (kNumSMs / a.cs) * 3 / 4;
+    }
+    max_clusters[a.cs] = n, max_clusters_smem[a.cs] = smem;
+  }
+  int clusters = max_clusters[a.cs];
+  if (clusters > n_groups) clusters = n_groups;
+  cfg.gridDim = dim3(clusters * a.cs);
+  if (cudaLaunchKernelEx(&cfg, gemm_tf32_kernel, a, ma, mw) != cudaSuccess) {
+    set_error("%s: launch failed: %s", fn, cudaGetErrorString(cudaGetLastError()));
+    return UB_ECUDA;
+  }
   return check_launch(fn);
 }

@@ -202,10 +202,11 @@ def linear_tf32(x, weight, bias=None, residual=None, relu=False, ln=None, out=No
         gamma, beta, eps = _need(ln[0], 'gamma'), _need(ln[1], 'beta'), float(ln[2])
     ldr = 0
     if residual is not None:
-        residual = _need(residual, 'residual')
         if residual.shape != (M, N):
             raise ValueError('linear_tf32: residual shape mismatch')
-        ldr = N
+        if not (residual.is_cuda and residual.dtype == torch.float32 and residual.stride(1) == 1):
+            residual = _need(residual, 'residual')
+        ldr = residual.stride(0)
     planes = None
     if planes_nv is not None:
         if M % planes_nv or N % 32:
@@ -217,6 +218,8 @@ def linear_tf32(x, weight, bias=None, residual=None, relu=False, ln=None, out=No
     else:
         if out is None:
             out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        elif out.shape != (M, N) or out.stride(1) != 1 or out.dtype != torch.float32 or not out.is_cuda:
+            raise ValueError('linear_tf32: `out` must be an fp32 CUDA (M, N) matrix with unit column stride')
         res = out
         out_ptr, ldc = _ptr(out), out.stride(0)
     _cabi.check(_cabi.lib().ub_linear_tf32(_ptr(x), _ptr(weight), _ptr(bias), _ptr(residual), ldr, _ptr(gamma), _ptr(beta),

@@ -113,6 +113,7 @@ class FusedEncoder:
         self.precision = precision
         self.tf32 = precision == 'tf32'
         self.fast_sampling = self.tf32      # window-staged fp16 sampling kernels where the shape is covered
+        self.tc_gemm = self.tf32            # hand-written tcgen05 GEMM with fused epilogues where the shape is covered
         self._w = {}
 
     def _weights(self, name):
@@ -123,44 +124,83 @@ class FusedEncoder:
             self._w[name] = (layers, pos_w)
         return self._w[name]
 
-    def _bev_sample(self, val, qp, B, bev_h, bev_w, fh, fw, H, P):
-        """val (B*fh*fw, C) projected value rows -> sampled (B, Nq, C); window kernels when the shape is covered."""
-        C = val.shape[-1]
-        if self.fast_sampling and ops.window_supported(C // H, P) and qp.shape[2] % 4 == 0:
+    # dense projections ------------------------------------------------------------------------------
+    def _lin(self, x, w, b, residual=None, relu=False, ln=None, out=None):
+        """epilogue(x @ w^T): the tcgen05 GEMM with the epilogue fused (precision='tf32'), else cuBLAS + one
+        elementwise kernel.  ln = (gamma, beta, eps)."""
+        if self.tc_gemm:
             try:
-                return ops.bev_sample_win(ops.value_to_half(val, B, fh * fw, H), qp, bev_h, bev_w, fh, fw, H, P,
-                                          0, H * P * 2)
+                return ops.linear_tf32(x, w, b, residual=residual, relu=relu, ln=ln, out=out)
             except _cabi.UnsupportedShape:
                 pass
-        return ops.bev_sample(val.view(B, fh * fw, C), qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2)
+        if ln is not None:
+            o = torch.mm(x, w.t())
+            return ops.add_layernorm(o, ln[0], ln[1], bias=b, residual=residual, eps=ln[2], out=o)
+        if relu:
+            o = torch._addmm_activation(b, x, w.t(), use_gelu=False)
+        else:
+            o = torch.addmm(b, x, w.t()) if b is not None else torch.mm(x, w.t())
+        if residual is not None:
+            o += residual
+        if out is not None:
+            out.copy_(o)
+            return out
+        return o
+
+    def _project_value(self, tokens, w, b, G, Nv, H, P):
+        """value_proj of `tokens` (G*Nv, C) -> (fp16 head-major planes for the window kernels or None, fp32 rows or
+        None).  With the tcgen05 GEMM the planes come straight out of the epilogue."""
+        C = w.shape[0]
+        if self.fast_sampling and ops.window_supported(C // H, P):
+            if self.tc_gemm:
+                try:
+                    return ops.linear_tf32(tokens, w, b, planes_nv=Nv), None
+                except _cabi.UnsupportedShape:
+                    pass
+            rows = torch.addmm(b, tokens, w.t())
+            return ops.value_to_half(rows, G, Nv, H), rows
+        return None, torch.addmm(b, tokens, w.t())
+
+    def _bev_sample(self, tokens, w, b, qp, B, bev_h, bev_w, fh, fw, H, P):
+        """value_proj + BEV-grid sampling: tokens (B*fh*fw, C) un-projected -> sampled (B, Nq, C)."""
+        C = w.shape[0]
+        planes, rows = self._project_value(tokens, w, b, B, fh * fw, H, P)
+        if planes is not None and qp.shape[2] % 4 == 0:
+            try:
+                return ops.bev_sample_win(planes, qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2)
+            except _cabi.UnsupportedShape:
+                pass
+        if rows is None:
+            rows = torch.addmm(b, tokens, w.t())
+        return ops.bev_sample(rows.view(B, fh * fw, C), qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2)
 
     # one BEV encoder ------------------------------------------------------------------------------
     def _run_encoder(self, name, x, pos, value_tokens, sample_cross, bev_h, bev_w):
-        """x (B, Nq, C) initial queries; pos (B*Nq, C) or None; value_tokens (rows, C) un-projected features."""
+        """x (B, Nq, C) initial queries; pos (B*Nq, C) or None; value_tokens (rows, C) un-projected features;
+        sample_cross(lw, value_tokens, qp) -> sampled (B, Nq, C)."""
         layers, pos_w = self._weights(name)
         B, Nq, C = x.shape
-        x = x.reshape(B * Nq, C)
-        n_q = [lw.sa_wq.shape[0] for lw in layers]
-        pos_q = torch.mm(pos, pos_w.t()).split(n_q, dim=1) if pos is not None else None
+        x = x.reshape(B * Nq, C).contiguous()
+        pos_q = None
+        if pos is not None:
+            # positional part of every layer's self-attention offset|logit rows, once per frame
+            n_q = [lw.sa_wq.shape[0] for lw in layers]
+            buf = torch.empty(B * Nq, sum(n_q), device=x.device, dtype=torch.float32)
+            pos_q = buf.split(n_q, dim=1)
+            for lw, dst in zip(layers, pos_q):
+                self._lin(pos, lw.sa_wq, None, out=dst)
         for i, lw in enumerate(layers):
             # --- BEV self-attention (mmcv MultiScaleDeformableAttention, value = query, 1 level)
-            v = torch.addmm(lw.sa_bv, x, lw.sa_wv.t())
-            qp = torch.addmm(lw.sa_bq, x, lw.sa_wq.t())
-            if pos_q is not None:
-                qp += pos_q[i]
-            s = self._bev_sample(v, qp.view(B, Nq, -1), B, bev_h, bev_w, bev_h, bev_w, lw.H_s, lw.P_s)
-            o = torch.mm(s.view(B * Nq, C), lw.sa_wo.t())
-            x = ops.add_layernorm(o, lw.ln[0][0], lw.ln[0][1], bias=lw.sa_bo, residual=x, eps=lw.ln[0][2], out=o)
+            qp = self._lin(x, lw.sa_wq, lw.sa_bq, residual=pos_q[i] if pos_q is not None else None)
+            s = self._bev_sample(x, lw.sa_wv, lw.sa_bv, qp.view(B, Nq, -1), B, bev_h, bev_w, bev_h, bev_w, lw.H_s, lw.P_s)
+            x = self._lin(s.view(B * Nq, C), lw.sa_wo, lw.sa_bo, residual=x, ln=lw.ln[0])
             # --- spatial cross-attention (query_pos is None for attentions[1])
-            val = torch.addmm(lw.ca_bv, value_tokens, lw.ca_wv.t())
-            qp = torch.addmm(lw.ca_bq, x, lw.ca_wq.t())
-            s = sample_cross(val, qp.view(B, Nq, -1), lw)
-            o = torch.mm(s.view(B * Nq, C), lw.ca_wo.t())
-            x = ops.add_layernorm(o, lw.ln[1][0], lw.ln[1][1], bias=lw.ca_bo, residual=x, eps=lw.ln[1][2], out=o)
+            qp = self._lin(x, lw.ca_wq, lw.ca_bq)
+            s = sample_cross(lw, value_tokens, qp.view(B, Nq, -1))
+            x = self._lin(s.view(B * Nq, C), lw.ca_wo, lw.ca_bo, residual=x, ln=lw.ln[1])
             # --- FFN
-            h = torch._addmm_activation(lw.b1, x, lw.w1.t(), use_gelu=False)
-            o = torch.mm(h, lw.w2.t())
-            x = ops.add_layernorm(o, lw.ln[2][0], lw.ln[2][1], bias=lw.b2, residual=x, eps=lw.ln[2][2], out=o)
+            h = self._lin(x, lw.w1, lw.b1, relu=True)
+            x = self._lin(h, lw.w2, lw.b2, residual=x, ln=lw.ln[2])
         return x.view(B, Nq, C)
 
     def __call__(self, img_feats, pts_feats, bev_queries, bev_h, bev_w, bev_pos, img_metas, lidar2img=None,
@@ -195,15 +235,19 @@ class FusedEncoder:
                 ref_cam, mask = ops.project_points(l2i, zs, enc.pc_range, ih, iw, bev_h, bev_w)
                 hits = []
 
-                def cross(val, qp, lw):
-                    if (self.fast_sampling and ops.window_supported(C // lw.H_c, lw.P_c)
-                            and (fh + 2) * (fw + 2) * 64 <= 150 * 1024):
+                def cross(lw, tokens, qp):
+                    planes, rows = self._project_value(tokens, lw.ca_wv, lw.ca_bv, B * N, fh * fw, lw.H_c, lw.P_c)
+                    if planes is not None and (fh + 2) * (fw + 2) * 64 <= 150 * 1024 and qp.shape[2] % 4 == 0:
                         if not hits:
                             hits.append(ops.build_hits(mask))
-                        v16 = ops.value_to_half(val, B * N, fh * fw, lw.H_c).view(B, N, lw.H_c, fh * fw, -1)
-                        return ops.img_sample_win(v16, qp, ref_cam, hits[0], bev_h, bev_w, fh, fw, lw.H_c, lw.P_c,
-                                                  0, lw.H_c * lw.P_c * 2)
-                    return ops.img_sample(val.view(B, N, fh * fw, C), qp, ref_cam, mask, bev_h, bev_w, fh, fw,
+                        try:
+                            return ops.img_sample_win(planes.view(B, N, lw.H_c, fh * fw, -1), qp, ref_cam, hits[0], bev_h,
+                                                      bev_w, fh, fw, lw.H_c, lw.P_c, 0, lw.H_c * lw.P_c * 2)
+                        except _cabi.UnsupportedShape:
+                            pass
+                    if rows is None:
+                        rows = torch.addmm(lw.ca_bv, tokens, lw.ca_wv.t())
+                    return ops.img_sample(rows.view(B, N, fh * fw, C), qp, ref_cam, mask, bev_h, bev_w, fh, fw,
                                           lw.H_c, lw.P_c, 0, lw.H_c * lw.P_c * 2)
                 x0 = q_img.detach().unsqueeze(0).expand(B, Nq, C)
                 img = self._run_encoder('img_bev_encoder', x0, pos, tokens.view(B * N * fh * fw, C), cross, bev_h, bev_w)
@@ -213,8 +257,8 @@ class FusedEncoder:
                 enc = m.pts_bev_encoder
                 tokens = ops.flatten_feats(feat, None, m.pts_level_embeds[0])
 
-                def cross(val, qp, lw, fh=fh, fw=fw):
-                    return self._bev_sample(val, qp, B, bev_h, bev_w, fh, fw, lw.H_c, lw.P_c)
+                def cross(lw, tokens, qp, fh=fh, fw=fw):
+                    return self._bev_sample(tokens, lw.ca_wv, lw.ca_bv, qp, B, bev_h, bev_w, fh, fw, lw.H_c, lw.P_c)
                 x0 = q_pts.detach().unsqueeze(0).expand(B, Nq, C)
                 pts = self._run_encoder('pts_bev_encoder', x0, pos, tokens.view(B * fh * fw, C), cross, bev_h, bev_w)
             return ops.cnw_fuse(img, pts, getattr(m, 'img_channel_weights', None), getattr(m, 'pts_channel_weights', None),
