@@ -41,7 +41,8 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=1, help='frames per GPU per step')
+    ap.add_argument('--batch', type=int, default=4, help='frames per GPU per step (BASELINE configs[3]: 32 frames over 8 GPUs)')
+    ap.add_argument('--no-graphs', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
     ap.add_argument('--precision', default='tf32', choices=['tf32', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-budget-s', type=float, default=20.0)
@@ -59,7 +60,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -185,6 +186,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
 
     B = args.batch
+    use_graphs = not args.no_graphs
     model, cfg = synth.build_model(WORKLOAD)
     model = model.to(dev).eval()
     model.fused_precision = args.precision
@@ -192,11 +194,15 @@ def main():
     dev_sets = [dict(s, img_feats=[s['img_feats'][0].to(dev)], pts_feats=[s['pts_feats'][0].to(dev)],
                      bev_pos=s['bev_pos'].to(dev)) for s in host_sets]
     bev_q = host_sets[0]['bev_queries'].to(dev)
+    import numpy as np
+    img_hw = tuple(host_sets[0]['img_metas'][0]['img_shape'][0][:2])
+    for s in dev_sets:
+        s['lidar2img'] = torch.from_numpy(np.asarray([m['lidar2img'] for m in s['img_metas']], dtype=np.float32)).to(dev)
 
-    def step(s):
+    def eager_step(s):
         with torch.no_grad():
             return model.encode(s['img_feats'], s['pts_feats'], bev_q, s['bev_h'], s['bev_w'], bev_pos=s['bev_pos'],
-                                img_metas=s['img_metas'])
+                                img_metas=s['img_metas'], lidar2img=s['lidar2img'], img_shape=img_hw)
 
     def barrier():
         if world > 1:
@@ -218,24 +224,39 @@ def main():
         barrier()
         return float(ms.item())
 
+    # kernels libunibev_b200 launches per step (counted on an eager step; graph replays launch the same kernels
+    # without passing through the C ABI's counter)
+    eager_step(dev_sets[0])
+    torch.cuda.synchronize()
+    _cabi.reset_launch_count()
+    eager_step(dev_sets[0])
+    torch.cuda.synchronize()
+    launches_per_step = _cabi.launch_count()
+
     # ---- device-resident throughput ---------------------------------------------------------------------
+    from unibev_b200.pipeline import FramePipeline, GraphedEncoder
+    if use_graphs:   # one captured graph per input set: a step = one cudaGraphLaunch over inputs resident in HBM
+        graphed = [GraphedEncoder(model, s['img_feats'][0], s['pts_feats'][0], bev_q, s['bev_h'], s['bev_w'],
+                                  bev_pos=s['bev_pos'], lidar2img=s['lidar2img'], img_hw=img_hw) for s in dev_sets]
+        step = lambda i: graphed[i % N_INPUT_SETS].replay()     # noqa: E731
+    else:
+        step = lambda i: eager_step(dev_sets[i % N_INPUT_SETS])  # noqa: E731
     for i in range(max(args.warmup, 3)):
-        step(dev_sets[i % N_INPUT_SETS])
-    with ClockSampler(local) as clk:
-        _cabi.reset_launch_count()
-        ms_total = timed(lambda i: step(dev_sets[i % N_INPUT_SETS]), args.steps)
-        launches = _cabi.launch_count()
+        step(i)
+    clk = ClockSampler(local)
+    clk.__enter__()
+    ms_total = timed(step, args.steps)
+    launches = launches_per_step * args.steps
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total / 1e3)
 
     # ---- end to end through the public streaming API with pinned HOST buffers -------------------------------
     # every step: H2D of that step's feature tensors + calibration, encode, D2H of fused_bev_embed into pinned
     # host memory; FramePipeline overlaps the copies of neighbouring steps with the kernels (3 streams, 2 slots)
-    from unibev_b200.pipeline import FramePipeline
     h0 = host_sets[0]
     pipe = FramePipeline(model, bev_q, h0['bev_h'], h0['bev_w'], bev_pos=dev_sets[0]['bev_pos'],
                          img_shape=tuple(h0['img_feats'][0].shape), pts_shape=tuple(h0['pts_feats'][0].shape),
-                         img_hw=tuple(h0['img_metas'][0]['img_shape'][0][:2]), depth=2, device=dev)
+                         img_hw=img_hw, depth=2, device=dev, graphs=use_graphs)
 
     def e2e_run(steps):
         barrier()
@@ -264,15 +285,22 @@ def main():
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
 
-    # ---- per-kernel CUDA-event timing of the sampling kernels (instrumented pass, same rotating inputs) ----
+    # ---- per-kernel CUDA-event timing (instrumented eager pass over the same rotating inputs) ---------------
     records = {}
-    real = {n: getattr(ops, n) for n in ('bev_sample', 'img_sample')}
+    op_names = ('bev_sample', 'img_sample', 'bev_sample_win', 'img_sample_win', 'linear_tf32', 'linear_f16',
+                'add_layernorm', 'value_to_half', 'flatten_feats', 'cnw_fuse', 'build_hits', 'project_points')
+    real = {n: getattr(ops, n) for n in op_names}
 
     def wrap(name):
         def inner(*a, **k):
-            P = a[7] if name == 'bev_sample' else a[9]
-            fH = a[4] if name == 'bev_sample' else a[6]
-            key = 'img_cross' if name == 'img_sample' else ('bev_self' if (P == 4 and fH == a[2]) else 'pts_cross')
+            if name in ('bev_sample', 'bev_sample_win'):
+                key = 'bev_self' if (a[7] == 4 and a[4] == a[2]) else 'pts_cross'
+            elif name in ('img_sample', 'img_sample_win'):
+                key = 'img_cross'
+            else:
+                key = name
+            if key in ('bev_self', 'pts_cross', 'img_cross'):
+                real[name](*a, **k)      # queued first, so the timed launch below never waits for the host
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             r = real[name](*a, **k)
@@ -280,16 +308,16 @@ def main():
             records.setdefault(key, []).append((e0, e1))
             return r
         return inner
-    import unibev_b200.plugin.fused as fused_mod
     for n in real:
-        setattr(fused_mod.ops, n, wrap(n))
+        setattr(ops, n, wrap(n))
     try:
-        for i in range(min(args.steps, 10)):
-            step(dev_sets[i % N_INPUT_SETS])
+        for i in range(min(args.steps, 8)):
+            eager_step(dev_sets[i % N_INPUT_SETS])
         torch.cuda.synchronize()
     finally:
         for n, f in real.items():
-            setattr(fused_mod.ops, n, f)
+            setattr(ops, n, f)
+    clk.__exit__(None, None, None)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -298,17 +326,22 @@ def main():
     peak, peak_src = (peaks['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)') if 'hbm_gbs' in peaks else (6650.0, 'fallback (B200_PROFILING.md)')
     Nq, C, H = 40000, 256, 8
     pairs = int(_hit_pairs(dev_sets[0]['img_metas'], ops, dev))
-    # algorithmic bytes per launch: value map read once + raw offset/logit rows + output rows
-    # (+ projected anchors of the hit (camera, query) pairs and the visibility bytes for the camera kernel), fp32
+    # algorithmic bytes per launch (fixed since round 1): fp32 value map read once + raw offset/logit rows
+    # + fp32 output rows (+ projected anchors of the hit (camera, query) pairs and the visibility bytes for the
+    # camera kernel)
     alg = {'bev_self': algorithmic_bytes('self', B, C, H, Nq, Nq, 4),
            'pts_cross': algorithmic_bytes('pts', B, C, H, Nq, 180 * 180, 8),
            'img_cross': algorithmic_bytes('img', B, C, H, Nq, 6 * 1450, 8) + B * (pairs * 4 * 2 * 4 + 2 * Nq * 6)}
-    kernels = {}
+    kernels, other = {}, {}
+    frames_timed = min(args.steps, 8)
     for key, evs in records.items():
         us = [a.elapsed_time(b) * 1e3 for a, b in evs]
         mean_us = sum(us) / len(us)
-        kernels[key] = {'launches': len(us), 'avg_us': mean_us, 'alg_bytes': alg[key],
-                        'achieved_gbs': alg[key] / mean_us / 1e3, 'frac': alg[key] / mean_us / 1e3 / peak}
+        if key in alg:
+            kernels[key] = {'launches': len(us), 'avg_us': mean_us, 'alg_bytes': alg[key],
+                            'achieved_gbs': alg[key] / mean_us / 1e3, 'frac': alg[key] / mean_us / 1e3 / peak}
+        else:
+            other[key] = {'launches_per_step': len(us) / frames_timed, 'avg_us': mean_us}
     dominant = max(kernels, key=lambda k: kernels[k]['avg_us'] * kernels[k]['launches']) if kernels else None
     roofline = None
     if dominant:
@@ -317,9 +350,9 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(dominant) if B == 1 else None
         except OSError:
             traffic = None
-        roofline = {'bound': 'hbm', 'kernel': {'bev_self': 'bev_sample_kernel (BEV self-attn, P=4)',
-                                               'pts_cross': 'bev_sample_kernel (LiDAR cross-attn, P=8)',
-                                               'img_cross': 'img_sample_kernel (camera cross-attn, P=8)'}[dominant],
+        roofline = {'bound': 'hbm', 'kernel': {'bev_self': 'bev_sample_win_kernel (BEV self-attn, P=4)',
+                                               'pts_cross': 'bev_sample_win_kernel (LiDAR cross-attn, P=8)',
+                                               'img_cross': 'img_sample_win_kernel (camera cross-attn, P=8)'}[dominant],
                     'achieved': k['achieved_gbs'], 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
                     'frac': k['frac'], 'traffic': traffic, 'avg_us': k['avg_us'], 'alg_bytes_per_launch': k['alg_bytes']}
 
@@ -332,14 +365,17 @@ def main():
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'tf32' if args.precision == 'tf32' else 'f32', 'data': 'synthetic',
-                'config': {'workload': f'{WORKLOAD} inference, batch {B} per GPU, {world} GPU(s), batch-sharded, no collective',
+                'config': {'workload': f'{WORKLOAD} inference, {B} frames per GPU per step, {world} GPU(s), batch-sharded, '
+                                       'no collective (BASELINE configs[3]: 32 frames over 8 GPUs = 4 per GPU; --batch 1 = configs[2])',
                            'frames_per_step': world * B, 'bev': '200x200', 'embed_dims': 256, 'layers': 3,
                            'l2_policy': f'rotating over {N_INPUT_SETS} input sets (> L2) + >1 GB of intermediates per frame',
-                           'gemm_math': args.precision, 'sampling_math': 'fp32'},
+                           'gemm_math': 'tcgen05 TF32 / fp16 operands, fp32 accumulate' if args.precision == 'tf32' else 'fp32',
+                           'sampling_math': 'fp16-staged value maps and weights, fp32 accumulate' if args.precision == 'tf32' else 'fp32',
+                           'cuda_graphs': use_graphs},
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': e2e_ms / args.steps},
                 'gpu_launches': launches, 'clocks': clk.summary(), 'roofline': roofline, 'kernels': kernels,
-                'cpu_baseline': cpu}
+                'other_kernels': other, 'cpu_baseline': cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -112,6 +112,9 @@ int ub_bev_sample_win_fwd(const void* value16, const float* qproj, float* out,
 /* Halo (value-map pixels) the BEV windows extend beyond the tile's reference points; 0 = default (P + 1).
  * Samples outside the window are still exact (slow path), so this is a performance knob only. */
 int ub_set_window_halo(int halo);
+/* on != 0: ub_bev_sample_win_fwd rounds its outputs to the nearest TF32 value (10 mantissa bits).  For callers that
+ * feed them to a TF32 tensor-core projection (ub_linear_tf32), whose operand fetch truncates instead. */
+int ub_set_window_round_tf32(int on);
 /* mask (B, Nq, N) from ub_project_points -> hit_idx (N, Nq) int32: the queries batch item 0 sees in camera n,
  * ascending (spatial_cross_attention_img.py:141-152); hit_cnt (N) int32; inv_cnt (B, Nq) = 1 / max(1, #cameras
  * whose mask for (b, q) is non-zero) (:209-212). */
@@ -139,10 +142,24 @@ int ub_linear_tf32(const float* A, const float* W, const float* bias, const floa
                    const float* gamma, const float* beta, float eps, float* out, int ldc, void* planes, int Nv,
                    int M, int N, int K, int flags, ub_stream_t stream);
 
+/* ub_linear_tf32 that also writes an fp16 copy `out16` (row stride ldc16) of the result rows. */
+int ub_linear_tf32_dual(const float* A, const float* W, const float* bias, const float* residual, int ldr,
+                        const float* gamma, const float* beta, float eps, float* out, int ldc, void* out16, int ldc16,
+                        int M, int N, int K, int flags, ub_stream_t stream);
+/* The same projection with fp16 operands A16 (M, K) / W16 (N, K) (the significand of TF32 in half the bytes; the
+ * weight tile then stays resident in shared memory) and, optionally, an fp16 copy `out16` (row stride ldc16) of
+ * the result next to / instead of the fp32 `out`: the A operand of the next projection.  K % 64 == 0. */
+int ub_linear_f16(const void* A16, const void* W16, const float* bias, const float* residual, int ldr,
+                  const float* gamma, const float* beta, float eps, float* out, int ldc, void* out16, int ldc16,
+                  void* planes, int Nv, int M, int N, int K, int flags, ub_stream_t stream);
+
 /* ---- [R5] y = LayerNorm(x + bias + residual) * gamma + beta over the last dim C ---------------------
  * bias (C) and residual (rows, C) may be NULL.  C % 4 == 0, C <= 1024.  out may alias x. */
 int ub_add_layernorm(const float* x, const float* bias, const float* residual, const float* gamma,
                      const float* beta, float* out, int64_t rows, int C, float eps, ub_stream_t stream);
+/* The same, additionally writing an fp16 copy `out16` (rows, C) of the result (may be NULL). */
+int ub_add_layernorm16(const float* x, const float* bias, const float* residual, const float* gamma,
+                       const float* beta, float* out, void* out16, int64_t rows, int C, float eps, ub_stream_t stream);
 
 /* ---- [R6] channel-normalised-weight fusion --------------------------------------------------------
  * img / pts (rows, C), either may be NULL (missing modality == zeros).  w_img / w_pts (C) CNW parameters

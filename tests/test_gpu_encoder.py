@@ -14,7 +14,9 @@ pytestmark = pytest.mark.gpu
 # Stated tolerances (BASELINE.json north_star: encoder BEV-feature output within rtol 1e-3 of the reference).
 # Outputs are post-LayerNorm, O(1); atol covers elements near zero.
 TOL_FP32 = dict(rtol=1e-3, atol=1e-4)      # fp32 GEMMs: same arithmetic as the reference up to summation order
-TOL_TF32 = dict(rtol=1e-3, atol=4e-3)      # TF32 tensor-core GEMMs (torch 1.10's own default on Ampere+)
+TOL_TF32 = dict(rtol=1e-3, atol=5e-3)      # TF32-class path: tensor-core GEMMs (TF32 / fp16 operands, fp32 accumulate; the
+                                           # activation operand of kind::tf32 is truncated, weights are pre-rounded) and
+                                           # fp16-staged sampling; torch 1.10, the reference's stack, defaulted to TF32 too
 
 
 def _build(cfg, params):
@@ -73,9 +75,10 @@ def test_fused_path_is_taken_and_native():
         counts[prec] = _cabi.launch_count()
     # fp32: per encoder flatten + layers*(2 samples + 3 LN); + bev_pos flatten + project + fuse (GEMMs: cuBLAS)
     assert counts['fp32'] == 2 * (1 + layers * 5) + 3
-    # tf32: the LayerNorms ride in the tcgen05 GEMM epilogues and the covered projections are native as well
-    # (this fixture: head dim 8 -> fp32 sampling kernels; N = 48 offset|logit rows of the self-attention -> cuBLAS)
-    assert counts['tf32'] == 2 * (1 + layers * 7) + 3
+    # tf32: the covered projections run on the tcgen05 GEMM as well: per layer output_proj x 2, cross offset|logit
+    # rows, FFN x 2 (this fixture: head dim 8 -> fp32 sampling kernels, value_proj feeds them through cuBLAS;
+    # N = 48 offset|logit rows of the self-attention -> cuBLAS)
+    assert counts['tf32'] == counts['fp32'] + 2 * layers * 5
 
 
 def test_module_path_backward_matches_oracle_autograd():

@@ -108,3 +108,47 @@ def test_linear_cluster_sizes_agree(ops, cs):
                 torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
     finally:
         _cabi.lib().ub_set_gemm_cluster(4)
+
+
+# ---- fp16-operand variant (resident weight tile, optional fp16 copy of the result) ----------------------------
+
+@pytest.mark.parametrize('M,N,K', [(1000, 256, 256), (40000, 256, 256), (333, 96, 256), (700, 192, 256),
+                                   (260, 256, 512), (129, 128, 128), (5000, 512, 256), (64, 32, 64)])
+def test_linear_f16_plain_exact(ops, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    x, w, b = _exact((M, K), g), _exact((N, K), g), _exact((N,), g)
+    want = F.linear(x.double(), w.double(), b.double()).relu().float()
+    got, got16 = ops.linear_f16(x.half().cuda(), w.half().cuda(), b.cuda(), relu=True, f16_out=True)
+    torch.testing.assert_close(got.cpu(), want, rtol=0, atol=1e-4)
+    torch.testing.assert_close(got16.cpu().float(), want.half().float(), rtol=1e-3, atol=1e-3)
+    only16 = ops.linear_f16(x.half().cuda(), w.half().cuda(), b.cuda(), relu=True, fp32_out=False, f16_out=True)
+    assert only16[0] is None and torch.equal(only16[1].cpu(), got16.cpu())
+
+
+@pytest.mark.parametrize('M,N,K', [(1000, 256, 256), (40000, 256, 512), (200, 128, 128)])
+def test_linear_f16_layernorm(ops, M, N, K):
+    g = torch.Generator().manual_seed(N + K + 1)
+    x, w, b, r = _exact((M, K), g), _exact((N, K), g, 64), _exact((N,), g), _exact((M, N), g)
+    gam, bet = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    pre = F.linear(x.double(), w.double(), b.double()) + r.double()
+    want = F.layer_norm(pre, (N,), gam.double(), bet.double(), 1e-5).float()
+    got, got16 = ops.linear_f16(x.half().cuda(), w.half().cuda(), b.cuda(), residual=r.cuda(),
+                                ln=(gam.cuda(), bet.cuda(), 1e-5), f16_out=True)
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(got16.cpu().float(), want, rtol=2e-3, atol=2e-3)
+
+
+def test_linear_f16_planes_and_strided_outputs(ops):
+    g = torch.Generator().manual_seed(5)
+    G, Nv, N, K = 3, 450, 256, 256
+    x, w, b = _exact((G * Nv, K), g), _exact((N, K), g, 64), _exact((N,), g)
+    want = F.linear(x, w, b).view(G, Nv, 8, 32).permute(0, 2, 1, 3).half()
+    got = ops.linear_f16(x.half().cuda(), w.half().cuda(), b.cuda(), planes_nv=Nv).cpu()
+    torch.testing.assert_close(got.float(), want.float(), rtol=1e-3, atol=1e-3)
+    # two column halves of a wider output (how the 512-wide FFN hidden layer is produced)
+    w2, b2 = _exact((512, K), g, 64), _exact((512,), g)
+    buf = torch.empty(G * Nv, 512, device='cuda', dtype=torch.float16)
+    for h in range(2):
+        ops.linear_f16(x.half().cuda(), w2[h * 256:(h + 1) * 256].half().cuda(), b2[h * 256:(h + 1) * 256].cuda(),
+                       relu=True, fp32_out=False, out16=buf[:, h * 256:(h + 1) * 256])
+    torch.testing.assert_close(buf.cpu().float(), F.linear(x, w2, b2).relu().half().float(), rtol=1e-3, atol=1e-3)

@@ -22,6 +22,7 @@ def timeit(fn, iters=20):
     tot = 0.0
     for i in range(iters):
         flush_buf.zero_()
+        flush_sink = flush_buf[:160 << 20].sum()      # leave L2 full of CLEAN lines: evictions cost nothing
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
@@ -72,5 +73,27 @@ def main():
                 print('%-20s cuBLAS + value_to_half %7.1f us | fused planes %7.1f us' % ('', t_cublas + t_c, t_p), flush=True)
 
 
+def main_f16():
+    dev = 'cuda'
+    M = 40000
+    r = torch.randn(M, 256, device=dev)
+    g, bt = torch.randn(256, device=dev), torch.randn(256, device=dev)
+    for name, N, K in (('f16 256x256', 256, 256), ('f16 qp 96', 96, 256), ('f16 qp 192', 192, 256), ('f16 K512', 256, 512)):
+        a = torch.randn(M, K, device=dev).half()
+        w = (torch.randn(N, K, device=dev) / 16).half()
+        b = torch.randn(N, device=dev)
+        out = torch.empty(M, N, device=dev)
+        o16 = torch.empty(M, N, device=dev, dtype=torch.float16)
+        t_plain = timeit(lambda: ops.linear_f16(a, w, b, out=out))
+        t_16 = timeit(lambda: ops.linear_f16(a, w, b, fp32_out=False, out16=o16))
+        line = '%-14s fp32 out %6.1f us | fp16 out %6.1f us' % (name, t_plain, t_16)
+        if N == 256:
+            t_ln = timeit(lambda: ops.linear_f16(a, w, b, residual=r, ln=(g, bt, 1e-5), out=out, out16=o16))
+            t_pl = timeit(lambda: ops.linear_f16(a, w, b, planes_nv=M))
+            line += ' | LN + both outputs %6.1f us | planes %6.1f us' % (t_ln, t_pl)
+        print(line, flush=True)
+
+
 if __name__ == '__main__':
+    main_f16()
     main()

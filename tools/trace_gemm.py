@@ -23,14 +23,21 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     _cabi.lib().ub_set_gemm_cluster(cs)
 
+    x16, w16 = x.half(), w.half()
+
     def run():
         if mode == 'ln':
             return ops.linear_tf32(x, w, b, residual=r, ln=(g, g, 1e-5))
+        if mode == 'f16':
+            return ops.linear_f16(x16, w16, b)
+        if mode == 'f16ln':
+            return ops.linear_f16(x16, w16, b, residual=r, ln=(g, g, 1e-5), f16_out=True)
         return ops.linear_tf32(x, w, b)
     for _ in range(3):
         run()
     trace = torch.zeros(148 * 128, dtype=torch.int64, device=dev)
     flush.zero_()
+    sink = flush[:160 << 20].sum()
     torch.cuda.synchronize()
     _cabi.lib().ub_set_gemm_trace(ctypes.c_void_p(trace.data_ptr()))
     run()

@@ -28,10 +28,14 @@ PROTOTYPES = {
     'ub_value_to_half': ([_p, _p] + [_i] * 4 + [_p], _i),
     'ub_bev_sample_win_fwd': ([_p] * 3 + [_i] * 11 + [_p], _i),
     'ub_set_window_halo': ([_i], _i),
+    'ub_set_window_round_tf32': ([_i], _i),
     'ub_build_hits': ([_p] * 4 + [_i] * 3 + [_p], _i),
     'ub_img_sample_win_fwd': ([_p] * 7 + [_i] * 13 + [_p], _i),
     'ub_linear_tf32': ([_p] * 4 + [_i, _p, _p, _f, _p, _i, _p] + [_i] * 5 + [_p], _i),
+    'ub_linear_tf32_dual': ([_p] * 4 + [_i, _p, _p, _f, _p, _i, _p] + [_i] * 5 + [_p], _i),
+    'ub_linear_f16': ([_p] * 4 + [_i, _p, _p, _f, _p, _i, _p, _i, _p] + [_i] * 5 + [_p], _i),
     'ub_add_layernorm': ([_p] * 6 + [_i64, _i, _f, _p], _i),
+    'ub_add_layernorm16': ([_p] * 7 + [_i64, _i, _f, _p], _i),
     'ub_cnw_fuse': ([_p] * 8 + [_i64, _i, _i, _i, _i, _i, _p], _i),
     'ub_flatten_feats': ([_p, _p, _i, _p, _p, _i, _i, _i, _p], _i),
 }

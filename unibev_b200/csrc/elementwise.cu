@@ -1,5 +1,7 @@
 // Bandwidth-bound glue of the BEV encoder: residual+LayerNorm [R5], CNW fusion [R6], feature flatten [R7].
 // Each is one pass: 128-bit accesses along the channel dim, no intermediate tensors.
+#include <cuda_fp16.h>
+
 #include "ub_common.cuh"
 
 namespace ub {
@@ -10,7 +12,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
                                                             const float* __restrict__ res,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float* __restrict__ out,
-                                                            int64_t rows, int C, float eps) {
+                                                            uint2* __restrict__ out16, int64_t rows, int C, float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const float inv_c = 1.f / (float)C;
@@ -60,6 +62,14 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
         o.z = (v[k].z - mean) * rstd * g.z + bt.z;
         o.w = (v[k].w - mean) * rstd * g.w + bt.w;
         st_stream4(out + r * C + c, o);
+        if (out16) {   // fp16 copy of the row: the A operand of the projections that read it next
+          const float lim = 65504.f;
+          const __half2 h0 = __floats2half2_rn(fminf(fmaxf(o.x, -lim), lim), fminf(fmaxf(o.y, -lim), lim));
+          const __half2 h1 = __floats2half2_rn(fminf(fmaxf(o.z, -lim), lim), fminf(fmaxf(o.w, -lim), lim));
+          uint2 p;
+          p.x = *reinterpret_cast<const uint32_t*>(&h0), p.y = *reinterpret_cast<const uint32_t*>(&h1);
+          out16[(r * C + c) >> 2] = p;
+        }
       }
     }
   }
@@ -180,7 +190,14 @@ using namespace ub;
 
 extern "C" int ub_add_layernorm(const float* x, const float* bias, const float* residual, const float* gamma,
                                 const float* beta, float* out, int64_t rows, int C, float eps, ub_stream_t stream) {
+  return ub_add_layernorm16(x, bias, residual, gamma, beta, out, nullptr, rows, C, eps, stream);
+}
+
+extern "C" int ub_add_layernorm16(const float* x, const float* bias, const float* residual, const float* gamma,
+                                  const float* beta, float* out, void* out16, int64_t rows, int C, float eps,
+                                  ub_stream_t stream) {
   UB_REQUIRE(x && gamma && beta && out, "ub_add_layernorm: null pointer");
+  UB_REQUIRE((reinterpret_cast<uintptr_t>(out16) & 7u) == 0, "ub_add_layernorm: out16 not 8-byte aligned");
   UB_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= 1024, "ub_add_layernorm: need rows>0, C%%4==0, C<=1024 (C=%d)", C);
   UB_REQUIRE_ALIGNED16(x);
   UB_REQUIRE_ALIGNED16(out);
@@ -192,7 +209,7 @@ extern "C" int ub_add_layernorm(const float* x, const float* bias, const float* 
   if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
   cudaStream_t s = (cudaStream_t)stream;
   const int nv = (C + 127) / 128;
-#define UB_LN(NV) add_layernorm_kernel<NV><<<(int)blocks, 256, 0, s>>>(x, bias, residual, gamma, beta, out, rows, C, eps)
+#define UB_LN(NV) add_layernorm_kernel<NV><<<(int)blocks, 256, 0, s>>>(x, bias, residual, gamma, beta, out, reinterpret_cast<uint2*>(out16), rows, C, eps)
   if (nv <= 1) UB_LN(1);
   else if (nv <= 2) UB_LN(2);
   else if (nv <= 4) UB_LN(4);

@@ -26,10 +26,10 @@
 
 namespace ub {
 
-constexpr int kGemmThreads = 384;                 // 4 control warps + 8 epilogue warps
-constexpr int kBM = 128, kBK = 32, kMaxStages = 8;
-constexpr int kEpiWarps = 8, kChunk = 32;          // epilogue warps (two per TMEM lane quarter), column chunk
-constexpr int kStageBuf = kChunk * 32 * 4;         // one warp's 32 rows x 32 columns staging buffer (4 KB)
+constexpr int kGemmThreads = 640;                 // 4 control warps + 16 epilogue warps
+constexpr int kBM = 128, kMaxStages = 8;
+constexpr int kEpiWarps = 16, kChunk = 16;         // epilogue warps (four per TMEM lane quarter), column chunk
+constexpr int kStageBuf = kChunk * 32 * 4;         // one warp's 32 rows x 16 columns staging buffer (2 KB)
 
 struct GemmArgs {
   const float* bias;    // (N) or null
@@ -45,6 +45,12 @@ struct GemmArgs {
   float eps;
   int relu, ln;
   int SA, SW;           // ring depths (A k-blocks, W k-blocks)
+  int f16;              // operands are fp16 (kind::f16, 64-element k-blocks) instead of fp32 / TF32 (32-element k-blocks)
+  int kb_elems;         // elements per k-block: one 128-byte swizzled row
+  int balanced;         // contiguous, equally sized row range per CTA (see the kernel)
+  int w_res;            // the whole W tile stays resident in the W ring (loaded once per CTA)
+  __half* out16;        // optional fp16 copy of the result rows (row stride ldc16), the next GEMM's A operand
+  int ldc16;
   int cs;               // CTAs per cluster: they work on `cs` consecutive row tiles and share W by TMA multicast
   unsigned long long* trace;   // optional per-CTA event timestamps (tools/trace_gemm.py), else null
 };
@@ -71,6 +77,20 @@ __device__ __forceinline__ uint64_t smem_desc_k128(uint32_t saddr) {
 // D (fp32) += A (tf32, K-major) * B (tf32, K-major), M = 128
 __device__ __forceinline__ uint32_t idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+// D (fp32) += A (fp16, K-major) * B (fp16, K-major), M = 128
+__device__ __forceinline__ uint32_t idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
 }
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -148,9 +168,29 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// 16-byte chunk j of row `row` in a 128-byte-swizzled buffer whose rows are 128 bytes
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::"r"(v[0]),
+      "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// 16-byte chunk j (0..3) of row `row` (0..31) in a warp's staging buffer: rows of 64 bytes, chunks XOR-swizzled so
+// that both the thread-per-row side and the coalesced side (8 rows x 64 B per instruction) are bank-conflict free
 __device__ __forceinline__ uint32_t swz(uint32_t base, int row, int j) {
-  return base + (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
+  return base + (uint32_t)row * 64u + (uint32_t)((j ^ ((row >> 1) & 3)) << 4);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -163,21 +203,39 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   __shared__ __align__(8) uint64_t s_fa[kMaxStages], s_ea[kMaxStages], s_fw[kMaxStages], s_ew[kMaxStages], s_tfull[2],
       s_tempty[2];
   __shared__ uint32_t s_tmem;
-  __shared__ float2 s_stat[2][kBM];   // LayerNorm partial (sum, sum of squares) of the two column halves
+  __shared__ float2 s_stat[4][kBM];   // LayerNorm partial (sum, sum of squares) per epilogue warp of a lane quarter
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int SA = a.SA, SW = a.SW;
   const uint32_t a_bytes = kBM * 128, w_bytes = (uint32_t)a.BN * 128;
   const uint32_t sm_a = smem_u32(smem), sm_w = sm_a + (uint32_t)SA * a_bytes;
-  const uint32_t sm_stage_buf = sm_w + (uint32_t)SW * w_bytes;                  // [8 warps] x 4 KB
+  const uint32_t sm_stage_buf = sm_w + (uint32_t)SW * w_bytes;                  // [16 warps] x 2 KB
   float* s_par = reinterpret_cast<float*>(smem + (size_t)SA * a_bytes + (size_t)SW * w_bytes + kEpiWarps * kStageBuf);
-  const int k_blocks = a.K / kBK;
+  const int k_blocks = a.K / a.kb_elems;
   // Work = groups of `cs` consecutive row tiles of one column tile; cluster c takes groups c, c + n_clusters, ...
   // and CTA rank r of the cluster the r-th row tile of the group (possibly past M: loads zero-fill, nothing is stored).
   const int cs = a.cs, rank = (int)blockIdx.x % cs, cluster_id = (int)blockIdx.x / cs, n_clusters = (int)gridDim.x / cs;
   const int groups_m = (a.n_tiles_m + cs - 1) / cs, n_groups = groups_m * a.n_tiles_n;
   const uint16_t cta_mask = (uint16_t)((1u << cs) - 1u);
   const uint32_t w_slice_rows = (uint32_t)(a.BN / cs), w_slice_bytes = w_slice_rows * 128u;
+  // Balanced mode (one column tile, no clusters): every CTA owns a contiguous range of M / grid rows and walks it
+  // in 128-row tiles; the last tile of a range is partial (its extra rows belong to the next CTA and are computed
+  // but not stored), so all CTAs carry the same load instead of 2 or 3 whole tiles.
+  int r_beg = 0, r_end = a.M, n_iter;
+  if (a.balanced) {
+    const int base = a.M / (int)gridDim.x, rem = a.M % (int)gridDim.x;
+    r_beg = (int)blockIdx.x * base + min((int)blockIdx.x, rem);
+    r_end = r_beg + base + ((int)blockIdx.x < rem ? 1 : 0);
+    n_iter = (r_end - r_beg + kBM - 1) / kBM;
+  } else {
+    n_iter = cluster_id < n_groups ? (n_groups - cluster_id + n_clusters - 1) / n_clusters : 0;
+  }
+  auto tile_m0 = [&](int i) {
+    if (a.balanced) return r_beg + i * kBM;
+    const int g = cluster_id + i * n_clusters;
+    return ((g % groups_m) * cs + rank) * kBM;
+  };
+  auto tile_n0 = [&](int i) { return a.balanced ? 0 : ((cluster_id + i * n_clusters) / groups_m) * a.BN; };
 
   for (int i = tid; i < a.N; i += kGemmThreads) {
     s_par[i] = a.bias ? a.bias[i] : 0.f;
@@ -208,26 +266,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // ------------------------------------------------------------------ A producer (+ L2 prefetch two tiles ahead)
     if (lane == 0) {
       tma_prefetch_desc(&map_a);
-      auto prefetch_tile = [&](int g) {   // the A rows (contiguous: lda == K) and the residual rows of group g
-        if (g >= n_groups) return;
-        const int m0 = ((g % groups_m) * cs + rank) * kBM, n0 = (g / groups_m) * a.BN;
-        if (m0 >= a.M) return;
-        const int rows = min(kBM, a.M - m0);
-        if (g / groups_m == 0 || a.n_tiles_n == 1) bulk_prefetch_l2(a.A + (size_t)m0 * a.K, (uint32_t)(rows * a.K * 4));
+      auto prefetch_tile = [&](int i) {   // the residual rows of tile i -> L2, ahead of the epilogue that reads them
+        if (i >= n_iter) return;
+        const int m0 = tile_m0(i), n0 = tile_n0(i);
+        if (m0 >= r_end) return;
+        const int rows = min(kBM, r_end - m0);
         if (a.residual && a.ldr == a.BN) bulk_prefetch_l2(a.residual + (size_t)m0 * a.ldr + n0, (uint32_t)(rows * a.ldr * 4));
       };
-      prefetch_tile(cluster_id);
-      prefetch_tile(cluster_id + n_clusters);
+      prefetch_tile(0);
       int stage = 0, ev = 0;
       uint32_t phase = 0;
-      for (int g = cluster_id; g < n_groups; g += n_clusters) {
-        const int m0 = ((g % groups_m) * cs + rank) * kBM;
-        prefetch_tile(g + 2 * n_clusters);
+      for (int i = 0; i < n_iter; ++i) {
+        const int m0 = tile_m0(i);
+        prefetch_tile(i + 1);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(smem_u32(&s_ea[stage]), phase ^ 1u);
           const uint32_t bar = smem_u32(&s_fa[stage]);
           mbar_arrive_expect_tx(bar, a_bytes);
-          tma_load_2d(sm_a + (uint32_t)stage * a_bytes, &map_a, bar, kb * kBK, m0);
+          tma_load_2d(sm_a + (uint32_t)stage * a_bytes, &map_a, bar, kb * a.kb_elems, m0);
           trace_event(a, 0, ev++);
           if (++stage == SA) stage = 0, phase ^= 1u;
         }
@@ -237,121 +293,156 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // ------------------------------------------------------------------ W producer
     if (lane == 0) {
       tma_prefetch_desc(&map_w);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int g = cluster_id; g < n_groups; g += n_clusters) {
-        const int n0 = (g / groups_m) * a.BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(smem_u32(&s_ew[stage]), phase ^ 1u);   // every CTA of the cluster has consumed the slot
-          const uint32_t bar = smem_u32(&s_fw[stage]);
-          const uint32_t dst = sm_w + (uint32_t)stage * w_bytes;
-          mbar_arrive_expect_tx(bar, w_bytes);             // all `cs` slices of the W k-block
-          if (cs == 1)
-            tma_load_2d(dst, &map_w, bar, kb * kBK, n0);
-          else
-            tma_load_2d_multicast(dst + (uint32_t)rank * w_slice_bytes, &map_w, bar, kb * kBK, n0 + rank * (int)w_slice_rows,
-                                  cta_mask);
-          if (++stage == SW) stage = 0, phase ^= 1u;
+      if (a.w_res) {
+        // the whole W tile (all k-blocks) fits: load it once, it is never released
+        if (n_iter > 0)
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            const uint32_t bar = smem_u32(&s_fw[kb]);
+            mbar_arrive_expect_tx(bar, w_bytes);
+            tma_load_2d(sm_w + (uint32_t)kb * w_bytes, &map_w, bar, kb * a.kb_elems, 0);
+          }
+      } else {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int i = 0; i < n_iter; ++i) {
+          const int n0 = tile_n0(i);
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(smem_u32(&s_ew[stage]), phase ^ 1u);   // every CTA of the cluster has consumed the slot
+            const uint32_t bar = smem_u32(&s_fw[stage]);
+            const uint32_t dst = sm_w + (uint32_t)stage * w_bytes;
+            mbar_arrive_expect_tx(bar, w_bytes);             // all `cs` slices of the W k-block
+            if (cs == 1)
+              tma_load_2d(dst, &map_w, bar, kb * a.kb_elems, n0);
+            else
+              tma_load_2d_multicast(dst + (uint32_t)rank * w_slice_bytes, &map_w, bar, kb * a.kb_elems,
+                                    n0 + rank * (int)w_slice_rows, cta_mask);
+            if (++stage == SW) stage = 0, phase ^= 1u;
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(a.BN);
+      const uint32_t idesc = a.f16 ? idesc_f16(a.BN) : idesc_tf32(a.BN);
       int sa = 0, sw = 0, ev = 0;
       uint32_t pa = 0, pw = 0;
-      int it = 0;
-      for (int g = cluster_id; g < n_groups; g += n_clusters, ++it) {
+      for (int it = 0; it < n_iter; ++it) {
         const int acc = it & 1;
         mbar_wait(smem_u32(&s_tempty[acc]), (uint32_t)(((it >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
         for (int kb = 0; kb < k_blocks; ++kb) {
+          if (a.w_res) sw = kb, pw = 0;                     // resident: slot kb, its only phase
           mbar_wait(smem_u32(&s_fw[sw]), pw);
           mbar_wait(smem_u32(&s_fa[sa]), pa);
           trace_event(a, 1, ev++);
           tc_fence_after();
           const uint64_t adesc = smem_desc_k128(sm_a + (uint32_t)sa * a_bytes);
           const uint64_t bdesc = smem_desc_k128(sm_w + (uint32_t)sw * w_bytes);
+          // 8 tf32 / 16 fp16 = 32 bytes per MMA along K: advance the descriptors' start address by 32 B
+          if (a.f16) {
 #pragma unroll
-          for (int k = 0; k < kBK / 8; ++k)   // 8 tf32 = 32 bytes per MMA along K: advance the start address
-            mma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              mma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
           mma_commit(smem_u32(&s_ea[sa]));
-          if (cs == 1)
-            mma_commit(smem_u32(&s_ew[sw]));
-          else
-            mma_commit_multicast(smem_u32(&s_ew[sw]), cta_mask);   // the W slot is shared: release it everywhere
           if (++sa == SA) sa = 0, pa ^= 1u;
-          if (++sw == SW) sw = 0, pw ^= 1u;
+          if (!a.w_res) {
+            if (cs == 1)
+              mma_commit(smem_u32(&s_ew[sw]));
+            else
+              mma_commit_multicast(smem_u32(&s_ew[sw]), cta_mask);   // the W slot is shared: release it everywhere
+            if (++sw == SW) sw = 0, pw ^= 1u;
+          }
         }
         mma_commit(smem_u32(&s_tfull[acc]));
       }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    // Thread = one row of the tile (its TMEM lane); the two warps of a lane quarter split the 32-column chunks.
-    // Rows meet global memory through one 128-byte-swizzled 4 KB buffer per warp: coalesced 16-byte accesses on
-    // the global side (4 rows x 128 B per instruction), whole rows on the thread side, __syncwarp in between.
-    const int ew = warp - 4, q = ew & 3, hsel = ew >> 2;
+    // Thread = one row of the tile (its TMEM lane); the four warps of a lane quarter take the 16-column chunks
+    // round-robin.  Rows meet global memory through one swizzled 2 KB buffer per warp: coalesced 16-byte accesses
+    // on the global side (8 rows x 64 B per instruction), whole rows on the thread side, __syncwarp in between.
+    const int ew = warp - 4, q = ew & 3, part = ew >> 2;
     const uint32_t buf = sm_stage_buf + (uint32_t)ew * kStageBuf;
     const int n_chunks = a.BN / kChunk;
-    const int c_beg = hsel ? (n_chunks + 1) / 2 : 0, c_end = hsel ? n_chunks : (n_chunks + 1) / 2;
-    const int crow = lane >> 3, ccol = lane & 7;              // coalesced side: rows crow + 4 i, 16-byte column ccol
-    int it = 0;
-    for (int g = cluster_id; g < n_groups; g += n_clusters, ++it) {
+    const int crow = lane >> 2, ccol = lane & 3;              // coalesced side: rows crow + 8 i, 16-byte column ccol
+    for (int it = 0; it < n_iter; ++it) {
       const int acc = it & 1;
-      const int m0 = ((g % groups_m) * cs + rank) * kBM, n0 = (g / groups_m) * a.BN;
+      const int m0 = tile_m0(it), n0 = tile_n0(it);
       const int row0 = m0 + q * 32;                           // this warp's 32 rows
       const uint32_t tbase = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
-      const bool rows_live = row0 < a.M;                      // warp-uniform (and equal for both warps of the quarter)
+      const bool rows_live = row0 < r_end;                      // warp-uniform (and equal for the warps of the quarter)
 
-      float4 rr[8];                                           // residual chunk in flight (coalesced layout)
+      float4 rr[4];                                           // residual chunk in flight (coalesced layout)
       auto load_res = [&](int c) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = row0 + crow + 4 * i;
+        for (int i = 0; i < 4; ++i) {
+          const int row = row0 + crow + 8 * i;
           rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row < a.M) rr[i] = ld_stream4(a.residual + (size_t)row * a.ldr + n0 + c * kChunk + ccol * 4);
+          if (row < r_end) rr[i] = ld_stream4(a.residual + (size_t)row * a.ldr + n0 + c * kChunk + ccol * 4);
         }
       };
-      auto add_res = [&](float (&f)[32]) {                    // registers -> swizzled buffer -> this thread's row
+      auto add_res = [&](float (&f)[16]) {                    // registers -> swizzled buffer -> this thread's row
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(swz(buf, crow + 4 * i, ccol)), "f"(rr[i].x), "f"(rr[i].y),
+        for (int i = 0; i < 4; ++i)
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(swz(buf, crow + 8 * i, ccol)), "f"(rr[i].x), "f"(rr[i].y),
                        "f"(rr[i].z), "f"(rr[i].w)
                        : "memory");
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           float4 r;
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(swz(buf, lane, j)));
           f[4 * j] += r.x, f[4 * j + 1] += r.y, f[4 * j + 2] += r.z, f[4 * j + 3] += r.w;
         }
         __syncwarp();
       };
-      auto store_rows = [&](int c, const float (&f)[32]) {    // this thread's row chunk -> global (coalesced)
+      auto store_rows = [&](int c, const float (&f)[16]) {    // this thread's row chunk -> global
+        if (a.out) {                                          // fp32 rows, coalesced through the buffer
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(swz(buf, lane, j)), "f"(f[4 * j]), "f"(f[4 * j + 1]),
-                       "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
-                       : "memory");
-        __syncwarp();
+          for (int j = 0; j < 4; ++j)
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(swz(buf, lane, j)), "f"(f[4 * j]), "f"(f[4 * j + 1]),
+                         "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                         : "memory");
+          __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = row0 + crow + 4 * i;
-          float4 o;
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
-                       : "r"(swz(buf, crow + 4 * i, ccol)));
-          if (row < a.M) st_stream4(a.out + (size_t)row * a.ldc + n0 + c * kChunk + ccol * 4, o);
+          for (int i = 0; i < 4; ++i) {
+            const int row = row0 + crow + 8 * i;
+            float4 o;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                         : "r"(swz(buf, crow + 8 * i, ccol)));
+            if (row < r_end) st_stream4(a.out + (size_t)row * a.ldc + n0 + c * kChunk + ccol * 4, o);
+          }
+          __syncwarp();
         }
-        __syncwarp();
+        if (a.out16 && row0 + lane < r_end) {                   // fp16 copy: 32 bytes of this thread's row
+          uint4* dst = reinterpret_cast<uint4*>(a.out16 + (size_t)(row0 + lane) * a.ldc16 + n0 + c * kChunk);
+          const float lim = 65504.f;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint4 o;
+            uint32_t* ow = &o.x;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __half2 h = __floats2half2_rn(fminf(fmaxf(f[8 * j + 2 * e], -lim), lim),
+                                                  fminf(fmaxf(f[8 * j + 2 * e + 1], -lim), lim));
+              ow[e] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            dst[j] = o;
+          }
+        }
       };
       auto params4 = [&](const float* p, int j) {             // 16-byte broadcast read of bias / gamma / beta
         return *reinterpret_cast<const float4*>(p + 4 * j);
       };
 
-      if (a.residual && rows_live && c_beg < c_end) load_res(c_beg);   // in flight while the accumulator is computed
+      if (a.residual && rows_live && part < n_chunks) load_res(part);   // in flight while the accumulator is computed
       mbar_wait(smem_u32(&s_tfull[acc]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       if (ew == 0 && lane == 0) trace_event(a, 2, 2 * it);
@@ -359,39 +450,41 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       float sum = 0.f, sumsq = 0.f;
       // ---- pass A: acc + bias (+ residual); LayerNorm: statistics, row parked back in TMEM
       //              otherwise: activation and store
-      for (int c = c_beg; c < c_end; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tbase + (uint32_t)(c * kChunk), v);
+      for (int c = part; c < n_chunks; c += 4) {
+        uint32_t v[16];
+        tmem_ld16(tbase + (uint32_t)(c * kChunk), v);
         if (!rows_live) continue;
-        float f[32];
+        float f[16];
         const float* bias = s_par + n0 + c * kChunk;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           const float4 b4 = params4(bias, j);
           f[4 * j] = __uint_as_float(v[4 * j]) + b4.x, f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
           f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z, f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
         }
         if (a.residual) {
           add_res(f);                                         // consumes rr
-          if (c + 1 < c_end) load_res(c + 1);                 // next chunk's loads fly during this chunk's tail
+          if (c + 4 < n_chunks) load_res(c + 4);              // the next chunk's loads fly during this chunk's tail
         }
         if (a.ln) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < 16; ++j) {
             sum += f[j];
             sumsq = fmaf(f[j], f[j], sumsq);
             v[j] = __float_as_uint(f[j]);
           }
-          tmem_st32(tbase + (uint32_t)(c * kChunk), v);
+          tmem_st16(tbase + (uint32_t)(c * kChunk), v);
         } else if (a.planes) {
-          // fp16 head-major planes: chunk c of the row is head (n0 / 32 + c) of token (row % Nv) in group row / Nv
+          // fp16 head-major planes: chunk c of the row is half (c & 1) of head (n0 / 32 + c / 2) of token (row % Nv)
+          // in group row / Nv
           const int row = row0 + lane;
-          if (row < a.M) {
+          if (row < r_end) {
             const int gi = row / a.Nv, tok = row - gi * a.Nv;
-            uint4* dst = reinterpret_cast<uint4*>(a.planes + (((int64_t)gi * a.H + (n0 / kChunk + c)) * a.Nv + tok) * 32);
+            uint4* dst = reinterpret_cast<uint4*>(a.planes + (((int64_t)gi * a.H + (n0 / 32 + (c >> 1))) * a.Nv + tok) * 32 +
+                                                  (c & 1) * 16);
             const float lim = 65504.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
               uint4 o;
               uint32_t* ow = &o.x;
 #pragma unroll
@@ -406,30 +499,35 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         } else {
           if (a.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
           }
           store_rows(c, f);
         }
       }
-      // ---- pass B (LayerNorm): the two warps of the quarter exchange their partial statistics, then each
+      // ---- pass B (LayerNorm): the four warps of the quarter exchange their partial statistics, then each
       //      normalises and stores its chunks of the parked row
       if (a.ln) {
-        s_stat[hsel][q * 32 + lane] = make_float2(sum, sumsq);
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-        const float2 other = s_stat[hsel ^ 1][q * 32 + lane];
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // s_stat is reused by the next tile
+        s_stat[part][q * 32 + lane] = make_float2(sum, sumsq);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+        float tsum = 0.f, tsq = 0.f;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float2 o = s_stat[p][q * 32 + lane];
+          tsum += o.x, tsq += o.y;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");   // s_stat is reused by the next tile
         if (rows_live) {
           const float inv_n = 1.f / (float)a.BN;
-          const float mean = (sum + other.x) * inv_n;
-          const float rstd = rsqrtf(fmaxf((sumsq + other.y) * inv_n - mean * mean, 0.f) + a.eps);
-          for (int c = c_beg; c < c_end; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tbase + (uint32_t)(c * kChunk), v);
-            float f[32];
+          const float mean = tsum * inv_n;
+          const float rstd = rsqrtf(fmaxf(tsq * inv_n - mean * mean, 0.f) + a.eps);
+          for (int c = part; c < n_chunks; c += 4) {
+            uint32_t v[16];
+            tmem_ld16(tbase + (uint32_t)(c * kChunk), v);
+            float f[16];
             const float* gam = s_par + a.N + n0 + c * kChunk;
             const float* bet = s_par + 2 * a.N + n0 + c * kChunk;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               const float4 g4 = params4(gam, j), b4 = params4(bet, j);
               f[4 * j] = (__uint_as_float(v[4 * j]) - mean) * rstd * g4.x + b4.x;
               f[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * g4.y + b4.y;
@@ -475,20 +573,21 @@ extern "C" int ub_set_gemm_cluster(int cs) {
   return UB_OK;
 }
 
-// out = epilogue(A (M, K) @ W (N, K)^T).  flags: bit 0 relu, bit 1 layernorm (needs residual-or-not, gamma, beta,
-// N <= 256).  planes != NULL: fp16 head-major output (G = M / Nv groups, H = N / 32 heads), `out` ignored.
-extern "C" int ub_linear_tf32(const float* A, const float* W, const float* bias, const float* residual, int ldr,
-                              const float* gamma, const float* beta, float eps, float* out, int ldc, void* planes,
-                              int Nv, int M, int N, int K, int flags, ub_stream_t stream) {
-  const char* fn = "ub_linear_tf32";
+// Shared launcher.  f16 = 0: A / W fp32 (TF32 MMA);  f16 = 1: A / W fp16.
+static int launch_linear(const char* fn, int f16, const void* A, const void* W, const float* bias, const float* residual,
+                         int ldr, const float* gamma, const float* beta, float eps, float* out, int ldc, void* out16,
+                         int ldc16, void* planes, int Nv, int M, int N, int K, int flags, ub_stream_t stream) {
   const int relu = flags & 1, ln = (flags >> 1) & 1;
-  UB_REQUIRE(A && W && (out || planes), "%s: null pointer", fn);
+  const int kb_elems = f16 ? 64 : 32, esize = f16 ? 2 : 4;
+  UB_REQUIRE(A && W && (out || out16 || planes), "%s: null pointer", fn);
   UB_REQUIRE(M > 0 && N > 0 && K > 0, "%s: non-positive dimension", fn);
   UB_REQUIRE(!ln || (gamma && beta), "%s: layernorm needs gamma and beta", fn);
   UB_REQUIRE_ALIGNED16(A);
   UB_REQUIRE_ALIGNED16(W);
-  if (K % kBK != 0 || N % 32 != 0 || (N > 256 && N % 256 != 0) || (ln && N > 256) || (planes && (ln || relu || residual)) ||
-      (planes && (Nv <= 0 || M % Nv != 0)) || (out && (ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(out) & 15u))) ||
+  if (K % kb_elems != 0 || N % 32 != 0 || (N > 256 && N % 256 != 0) || (ln && N > 256) ||
+      (planes && (ln || relu || residual || out16)) || (planes && (Nv <= 0 || M % Nv != 0)) ||
+      (out && (ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(out) & 15u))) ||
+      (out16 && (ldc16 % 8 != 0 || (reinterpret_cast<uintptr_t>(out16) & 15u))) ||
       (residual && (ldr % 4 != 0 || (reinterpret_cast<uintptr_t>(residual) & 15u))) || N > 1024) {
     set_error("%s: shape not covered (M=%d N=%d K=%d flags=%d)", fn, M, N, K, flags);
     return UB_EUNSUPPORTED;
@@ -499,28 +598,34 @@ extern "C" int ub_linear_tf32(const float* A, const float* W, const float* bias,
   a.M = M, a.N = N, a.K = K, a.BN = N > 256 ? 256 : N;
   a.n_tiles_m = (M + kBM - 1) / kBM, a.n_tiles_n = N / a.BN;
   a.eps = eps, a.relu = relu, a.ln = ln;
-  a.A = A, a.residual = residual, a.out = out, a.ldr = ldr, a.ldc = ldc;
-  // cluster size: the W tile is split into `cs` slices of whole 8-row swizzle groups
+  a.A = nullptr, a.residual = residual, a.out = out, a.ldr = ldr, a.ldc = ldc;
+  a.out16 = reinterpret_cast<__half*>(out16), a.ldc16 = ldc16;
+  a.f16 = f16, a.kb_elems = kb_elems;
   a.trace = g_gemm_trace;
-  a.cs = g_gemm_cluster;
+  const int k_blocks = K / kb_elems;
+  const size_t fixed = kEpiWarps * kStageBuf + (size_t)3 * N * sizeof(float);
+  const size_t budget = 232448 - 5120 - 1024;   // minus static shared memory and slack
+  // W resident: every k-block of the (single) W tile stays in shared memory, with at least 3 A stages next to it
+  a.w_res = a.n_tiles_n == 1 && k_blocks <= kMaxStages &&
+            fixed + (size_t)k_blocks * a.BN * 128 + 3 * (size_t)kBM * 128 <= budget;
+  // cluster size (streaming W only): the W k-block is split into `cs` slices of whole 8-row swizzle groups
+  a.cs = a.w_res ? 1 : g_gemm_cluster;
   while (a.cs > 1 && ((a.BN / a.cs) % 8 != 0 || a.BN % a.cs != 0 || a.n_tiles_m < a.cs)) a.cs >>= 1;
   CUtensorMap ma, mw;
+  const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   {
-    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)K * 4};
-    const uint32_t box[2] = {kBK, kBM};
-    if (int rc = make_tensor_map(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
-      return rc;
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)K * esize};
+    const uint32_t box[2] = {(uint32_t)kb_elems, kBM};
+    if (int rc = make_tensor_map(&ma, dt, 2, A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)K * 4};
-    const uint32_t box[2] = {kBK, (uint32_t)(a.BN / a.cs)};
-    if (int rc = make_tensor_map(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, W, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
-      return rc;
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)K * esize};
+    const uint32_t box[2] = {(uint32_t)kb_elems, (uint32_t)(a.BN / a.cs)};
+    if (int rc = make_tensor_map(&mw, dt, 2, W, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
-  // ring depths: W shallow, A as deep as the 227 KB of shared memory allow (up to 8)
-  const size_t fixed = kEpiWarps * kStageBuf + (size_t)3 * N * sizeof(float);
-  a.SW = a.BN > 128 ? 3 : 4;
-  const size_t budget = 232448 - 3072 - 1024;   // minus static shared memory and slack
+  a.balanced = a.n_tiles_n == 1 && a.cs == 1 && M >= 4 * kNumSMs;
+  // ring depths: W resident or shallow, A as deep as the 227 KB of shared memory allow (up to 8)
+  a.SW = a.w_res ? k_blocks : (a.BN > 128 ? 3 : 4);
   a.SA = (int)((budget - fixed - (size_t)a.SW * a.BN * 128) / (kBM * 128));
   if (a.SA > kMaxStages) a.SA = kMaxStages;
   if (a.SA < 2) {
@@ -559,11 +664,36 @@ extern "C" int ub_linear_tf32(const float* A, const float* W, const float* bias,
     max_clusters[a.cs] = n, max_clusters_smem[a.cs] = smem;
   }
   int clusters = max_clusters[a.cs];
-  if (clusters > n_groups) clusters = n_groups;
+  if (clusters > n_groups && !a.balanced) clusters = n_groups;
   cfg.gridDim = dim3(clusters * a.cs);
   if (cudaLaunchKernelEx(&cfg, gemm_tf32_kernel, a, ma, mw) != cudaSuccess) {
     set_error("%s: launch failed: %s", fn, cudaGetErrorString(cudaGetLastError()));
     return UB_ECUDA;
   }
   return check_launch(fn);
+}
+
+// out = epilogue(A (M, K) @ W (N, K)^T), fp32 operands (TF32 MMA).  flags: bit 0 relu, bit 1 layernorm (gamma, beta,
+// N <= 256).  planes != NULL: fp16 head-major output (G = M / Nv groups, H = N / 32 heads), `out` ignored.
+extern "C" int ub_linear_tf32(const float* A, const float* W, const float* bias, const float* residual, int ldr,
+                              const float* gamma, const float* beta, float eps, float* out, int ldc, void* planes,
+                              int Nv, int M, int N, int K, int flags, ub_stream_t stream) {
+  return launch_linear("ub_linear_tf32", 0, A, W, bias, residual, ldr, gamma, beta, eps, out, ldc, nullptr, 0, planes, Nv, M,
+                       N, K, flags, stream);
+}
+// ub_linear_tf32 that also writes the fp16 copy `out16` (row stride ldc16) of the result rows
+extern "C" int ub_linear_tf32_dual(const float* A, const float* W, const float* bias, const float* residual, int ldr,
+                                   const float* gamma, const float* beta, float eps, float* out, int ldc, void* out16,
+                                   int ldc16, int M, int N, int K, int flags, ub_stream_t stream) {
+  return launch_linear("ub_linear_tf32_dual", 0, A, W, bias, residual, ldr, gamma, beta, eps, out, ldc, out16, ldc16, nullptr,
+                       0, M, N, K, flags, stream);
+}
+
+// The same with fp16 operands A (M, K) / W (N, K) (same 11-bit significand as TF32, half the bytes: W usually stays
+// resident in shared memory) and an optional fp16 copy `out16` of the result, the A operand of the next projection.
+extern "C" int ub_linear_f16(const void* A16, const void* W16, const float* bias, const float* residual, int ldr,
+                             const float* gamma, const float* beta, float eps, float* out, int ldc, void* out16, int ldc16,
+                             void* planes, int Nv, int M, int N, int K, int flags, ub_stream_t stream) {
+  return launch_linear("ub_linear_f16", 1, A16, W16, bias, residual, ldr, gamma, beta, eps, out, ldc, out16, ldc16, planes,
+                       Nv, M, N, K, flags, stream);
 }

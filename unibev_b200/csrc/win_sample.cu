@@ -46,7 +46,8 @@ constexpr int kImgThreads = kWorkerWarps * 32;
 constexpr int kTQ = 16;                                    // BEV tile: 16 x 16 queries
 constexpr int kUnitItems = kWorkerWarps * kWarpItems;      // items per unit
 
-static int g_bev_halo = 0;  // 0 = default (P + 1)
+static int g_bev_halo = 0;       // 0 = default (P + 1)
+static int g_bev_round_tf32 = 0; // round the BEV kernels' outputs to TF32 (their consumer is a TF32 GEMM)
 
 // ---------------------------------------------------------------------------------------------------------
 // fp32 token-major value rows -> fp16 head-major planes.  Thread = 8 channels of one (row, head).
@@ -214,6 +215,11 @@ __device__ __forceinline__ void fhfma8(float (&acc)[8], const uint4& v, uint32_t
   }
 }
 
+__device__ __forceinline__ float round_tf32(float x) {   // round to nearest (ties away) at 10 mantissa bits
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+  return __uint_as_float(t);
+}
 __device__ __forceinline__ void red_add4(float* p, const float4& v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -293,6 +299,7 @@ struct BevWinArgs {
   int WW, WH, R;
   int off_col, logit_col;
   float sx, sy;
+  int round_tf32;
 };
 
 struct __align__(16) UnitInfo {
@@ -493,10 +500,17 @@ __global__ void __launch_bounds__(kBevThreads, 1)
                             const int qx = w.tx0 + item;
                             if (row_ok && qx < a.bev_w) {
                               float* dst = a.out + ((int64_t)w.b * Nq + qy * a.bev_w + qx) * C + w.h * 32 + cq * 8 + half * 4;
-                              if (any_far)
+                              if (any_far) {
                                 red_add4(dst, o);
-                              else
+                              } else if (!a.round_tf32) {
                                 st_stream4(dst, o);
+                              } else {
+                                // the consumer is the output projection's TF32 tensor-core GEMM, which truncates
+                                // its operands: round to nearest here instead
+                                float4 r;
+                                r.x = round_tf32(o.x), r.y = round_tf32(o.y), r.z = round_tf32(o.z), r.w = round_tf32(o.w);
+                                st_stream4(dst, r);
+                              }
                             }
                           });
     __syncwarp();   // every lane is done with the window and the descriptors
@@ -852,6 +866,11 @@ extern "C" int ub_set_window_halo(int halo) {
   return UB_OK;
 }
 
+extern "C" int ub_set_window_round_tf32(int on) {
+  g_bev_round_tf32 = on ? 1 : 0;
+  return UB_OK;
+}
+
 extern "C" int ub_value_to_half(const float* value, void* value16, int G, int Nv, int H, int Dh, ub_stream_t stream) {
   UB_REQUIRE(value && value16, "ub_value_to_half: null pointer");
   UB_REQUIRE(G > 0 && Nv > 0 && H > 0 && Dh > 0 && Dh % 8 == 0, "ub_value_to_half: need positive dims and Dh %% 8 == 0");
@@ -890,6 +909,7 @@ extern "C" int ub_bev_sample_win_fwd(const void* value16, const float* qproj, fl
   a.WW = (int)ceilf((kTQ - 1) * a.sx) + 2 * a.R + 3;
   a.WH = (int)ceilf((kTQ - 1) * a.sy) + 2 * a.R + 3;
   a.off_col = off_col, a.logit_col = logit_col;
+  a.round_tf32 = g_bev_round_tf32;
   if (a.WW > 256 || a.WH > 256) {
     set_error("%s: window %d x %d exceeds the TMA box limit", fn, a.WW, a.WH);
     return UB_EUNSUPPORTED;

@@ -185,7 +185,7 @@ def img_sample_win(value16, qproj, ref_cam, hits, bev_h, bev_w, fH, fW, H, P, of
     return out
 
 
-def linear_tf32(x, weight, bias=None, residual=None, relu=False, ln=None, out=None, planes_nv=None):
+def linear_tf32(x, weight, bias=None, residual=None, relu=False, ln=None, out=None, planes_nv=None, out16=None):
     """x (M, K) @ weight (N, K)^T on the tcgen05 tensor cores (TF32) with the epilogue fused:
     + bias, + residual (M, N), ReLU, LayerNorm (ln = (gamma, beta, eps)); ``planes_nv`` = rows per value map:
     return fp16 head-major planes (M // planes_nv, N // 32, planes_nv, 32) instead of an fp32 (M, N) matrix."""
@@ -222,13 +222,63 @@ def linear_tf32(x, weight, bias=None, residual=None, relu=False, ln=None, out=No
             raise ValueError('linear_tf32: `out` must be an fp32 CUDA (M, N) matrix with unit column stride')
         res = out
         out_ptr, ldc = _ptr(out), out.stride(0)
+    if out16 is not None:
+        if planes is not None or out16.shape != (M, N) or out16.dtype != torch.float16 or out16.stride(1) != 1:
+            raise ValueError('linear_tf32: `out16` must be an fp16 CUDA (M, N) matrix (not with planes)')
+        _cabi.check(_cabi.lib().ub_linear_tf32_dual(_ptr(x), _ptr(weight), _ptr(bias), _ptr(residual), ldr, _ptr(gamma),
+                                                    _ptr(beta), eps, out_ptr, ldc, _ptr(out16), out16.stride(0), M, N, K,
+                                                    flags, _stream()), 'ub_linear_tf32_dual')
+        return res
     _cabi.check(_cabi.lib().ub_linear_tf32(_ptr(x), _ptr(weight), _ptr(bias), _ptr(residual), ldr, _ptr(gamma), _ptr(beta),
                                            eps, out_ptr, ldc, _ptr(planes), planes_nv or 0, M, N, K, flags, _stream()),
                 'ub_linear_tf32')
     return res
 
 
-def add_layernorm(x, gamma, beta, bias=None, residual=None, eps=1e-5, out=None):
+def linear_f16(x16, w16, bias=None, residual=None, relu=False, ln=None, out=None, out16=None, fp32_out=True,
+               f16_out=False, planes_nv=None):
+    """fp16-operand variant of ``linear_tf32``: x16 (M, K) fp16 @ w16 (N, K)^T fp16, fp32 accumulation and epilogue.
+    Returns ``planes`` (with ``planes_nv``) or the pair (fp32 result or None, fp16 copy or None)."""
+    x16, w16 = _need(x16, 'x16', torch.float16), _need(w16, 'w16', torch.float16)
+    M, K = x16.shape
+    N = w16.shape[0]
+    if w16.shape[1] != K:
+        raise ValueError(f'linear_f16: x{tuple(x16.shape)} vs weight{tuple(w16.shape)}')
+    bias = _need(bias, 'bias') if bias is not None else None
+    flags = (1 if relu else 0) | (2 if ln is not None else 0)
+    gamma = beta = None
+    eps = 0.0
+    if ln is not None:
+        gamma, beta, eps = _need(ln[0], 'gamma'), _need(ln[1], 'beta'), float(ln[2])
+    ldr = 0
+    if residual is not None:
+        if residual.shape != (M, N):
+            raise ValueError('linear_f16: residual shape mismatch')
+        if not (residual.is_cuda and residual.dtype == torch.float32 and residual.stride(1) == 1):
+            residual = _need(residual, 'residual')
+        ldr = residual.stride(0)
+    planes = None
+    if planes_nv is not None:
+        if M % planes_nv or N % 32:
+            raise ValueError('linear_f16: planes need M % Nv == 0 and N % 32 == 0')
+        planes = torch.empty(M // planes_nv, N // 32, planes_nv, 32, device=x16.device, dtype=torch.float16)
+        out = out16 = None
+    else:
+        if out is None and fp32_out:
+            out = torch.empty(M, N, device=x16.device, dtype=torch.float32)
+        if out16 is None and f16_out:
+            out16 = torch.empty(M, N, device=x16.device, dtype=torch.float16)
+        for t, dt in ((out, torch.float32), (out16, torch.float16)):
+            if t is not None and (t.shape != (M, N) or t.stride(1) != 1 or t.dtype != dt or not t.is_cuda):
+                raise ValueError('linear_f16: outputs must be CUDA (M, N) matrices with unit column stride')
+    _cabi.check(_cabi.lib().ub_linear_f16(_ptr(x16), _ptr(w16), _ptr(bias), _ptr(residual), ldr, _ptr(gamma), _ptr(beta),
+                                          eps, _ptr(out), out.stride(0) if out is not None else 0, _ptr(out16),
+                                          out16.stride(0) if out16 is not None else 0, _ptr(planes), planes_nv or 0,
+                                          M, N, K, flags, _stream()), 'ub_linear_f16')
+    return planes if planes is not None else (out, out16)
+
+
+def add_layernorm(x, gamma, beta, bias=None, residual=None, eps=1e-5, out=None, out16=None):
     x = _need(x, 'x')
     C = x.shape[-1]
     rows = x.numel() // C
@@ -239,6 +289,12 @@ def add_layernorm(x, gamma, beta, bias=None, residual=None, eps=1e-5, out=None):
         raise ValueError('add_layernorm: residual shape mismatch')
     if out is None:
         out = torch.empty_like(x)
+    if out16 is not None:
+        if out16.shape != x.shape or out16.dtype != torch.float16 or not out16.is_cuda or not out16.is_contiguous():
+            raise ValueError('add_layernorm: `out16` must be a contiguous fp16 CUDA tensor of the shape of x')
+        _cabi.check(_cabi.lib().ub_add_layernorm16(_ptr(x), _ptr(bias), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(out),
+                                                   _ptr(out16), rows, C, float(eps), _stream()), 'ub_add_layernorm16')
+        return out
     _cabi.check(_cabi.lib().ub_add_layernorm(_ptr(x), _ptr(bias), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(out),
                                              rows, C, float(eps), _stream()), 'ub_add_layernorm')
     return out

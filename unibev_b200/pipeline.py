@@ -15,6 +15,40 @@ import numpy as np
 import torch
 
 
+class GraphedEncoder:
+    """``UniBEVTransformer.encode`` for fixed shapes, captured once into a CUDA graph and replayed: the ~80 kernel
+    launches of a frame cost one ``cudaGraphLaunch``.  Inputs are static device buffers owned by the caller (write
+    the next frame into them, then ``replay()``); the returned tensor is the graph's static output buffer.
+
+    Everything the fused pipeline does is capturable: no host synchronisation, no host-dependent shapes (camera hit
+    lists stay on the device), shared-memory / occupancy attributes and the tensor-map cache are warmed by the two
+    eager runs that precede the capture."""
+
+    def __init__(self, model, img_feat, pts_feat, bev_queries, bev_h, bev_w, bev_pos=None, lidar2img=None,
+                 img_hw=None):
+        self.model = model
+        self.img_feat, self.pts_feat, self.lidar2img = img_feat, pts_feat, lidar2img
+        args = dict(bev_pos=bev_pos, img_metas=None, lidar2img=lidar2img, img_shape=img_hw)
+
+        def run():
+            with torch.no_grad():
+                return model.encode([img_feat] if img_feat is not None else None,
+                                    [pts_feat] if pts_feat is not None else None, bev_queries, bev_h, bev_w, **args)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                run()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = run()
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+
 class _Slot:
     def __init__(self, img_shape, pts_shape, n_cams, out_shape, dev):
         f32 = torch.float32
@@ -37,7 +71,7 @@ class FramePipeline:
     fused_bev_embed is in pinned host memory and returns it (valid until the slot is reused ``depth`` submits later)."""
 
     def __init__(self, model, bev_queries, bev_h, bev_w, bev_pos=None, img_shape=None, pts_shape=None,
-                 img_hw=None, depth=2, device=None):
+                 img_hw=None, depth=2, device=None, graphs=False):
         if img_shape is None and pts_shape is None:
             raise ValueError('at least one of img_shape / pts_shape is required')
         self.model = model
@@ -52,6 +86,10 @@ class FramePipeline:
         self.slots = [_Slot(img_shape, pts_shape, n_cams, out_shape, self.dev) for _ in range(depth)]
         self.s_in, self.s_compute, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
         self.n_submitted = 0
+        # graphs=True: the encoder of every slot is captured into a CUDA graph on first use (needs img_hw up front
+        # when there are cameras, and an eval-mode model whose fused pipeline covers the shapes)
+        self.graphs = graphs and (img_shape is None or img_hw is not None)
+        self._graphed = [None] * depth
         self.h2d_bytes = sum(t.numel() * 4 for t in (self.slots[0].img_host, self.slots[0].pts_host,
                                                       self.slots[0].l2i_host) if t is not None)
         self.d2h_bytes = self.slots[0].out_host.numel() * 4
@@ -79,15 +117,24 @@ class FramePipeline:
             slot.copied_in.record(self.s_in)
         with torch.cuda.stream(self.s_compute), torch.no_grad():
             self.s_compute.wait_event(slot.copied_in)
-            out = self.model.encode([slot.img_dev] if slot.img_dev is not None else None,
-                                    [slot.pts_dev] if slot.pts_dev is not None else None,
-                                    self.bev_queries, self.bev_h, self.bev_w, bev_pos=self.bev_pos,
-                                    img_metas=img_metas, lidar2img=slot.l2i_dev, img_shape=img_hw)
+            if self.graphs:
+                k = ticket % len(self.slots)
+                if self._graphed[k] is None:
+                    self._graphed[k] = GraphedEncoder(self.model, slot.img_dev, slot.pts_dev, self.bev_queries, self.bev_h,
+                                                      self.bev_w, bev_pos=self.bev_pos, lidar2img=slot.l2i_dev,
+                                                      img_hw=img_hw)
+                out = self._graphed[k].replay()
+            else:
+                out = self.model.encode([slot.img_dev] if slot.img_dev is not None else None,
+                                        [slot.pts_dev] if slot.pts_dev is not None else None,
+                                        self.bev_queries, self.bev_h, self.bev_w, bev_pos=self.bev_pos,
+                                        img_metas=img_metas, lidar2img=slot.l2i_dev, img_shape=img_hw)
             slot.computed.record(self.s_compute)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(slot.computed)
             slot.out_host.copy_(out, non_blocking=True)
-            out.record_stream(self.s_out)
+            if not self.graphs:
+                out.record_stream(self.s_out)
             slot.copied_out.record(self.s_out)
         self.n_submitted += 1
         return ticket

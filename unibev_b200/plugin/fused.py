@@ -103,6 +103,14 @@ class _LayerWeights:
         self.w1, self.b1 = f.layers[0][0].weight.detach(), f.layers[0][0].bias.detach()
         self.w2, self.b2 = f.layers[1].weight.detach(), f.layers[1].bias.detach()
         self.ln = [(n.weight.detach(), n.bias.detach(), n.eps) for n in layer.norms]
+        self._half = None
+
+    def half(self):
+        """fp16 copies of the projection weights read with fp16 operands (built once)."""
+        if self._half is None:
+            self._half = {k: getattr(self, k).half().contiguous()
+                          for k in ('sa_wq', 'sa_wv', 'ca_wq', 'ca_wv', 'w1', 'w2')}
+        return self._half
 
 
 class FusedEncoder:
@@ -114,7 +122,9 @@ class FusedEncoder:
         self.tf32 = precision == 'tf32'
         self.fast_sampling = self.tf32      # window-staged fp16 sampling kernels where the shape is covered
         self.tc_gemm = self.tf32            # hand-written tcgen05 GEMM with fused epilogues where the shape is covered
+        self.fuse_ln = False                # LayerNorm inside the GEMM epilogue (else GEMM + one streaming LN pass)
         self._w = {}
+        self._rn = {}
 
     def _weights(self, name):
         if name not in self._w:
@@ -124,54 +134,89 @@ class FusedEncoder:
             self._w[name] = (layers, pos_w)
         return self._w[name]
 
+    def _tf32(self, w):
+        """Weight rounded to nearest TF32 (once): tcgen05 kind::tf32 truncates fp32 operands, which would bias every
+        product low; a pre-rounded weight is read exactly."""
+        key = (w.data_ptr(), tuple(w.shape))
+        if key not in self._rn:
+            bits = w.contiguous().view(torch.int32)
+            self._rn[key] = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+        return self._rn[key]
+
     # dense projections ------------------------------------------------------------------------------
-    def _lin(self, x, w, b, residual=None, relu=False, ln=None, out=None):
-        """epilogue(x @ w^T): the tcgen05 GEMM with the epilogue fused (precision='tf32'), else cuBLAS + one
-        elementwise kernel.  ln = (gamma, beta, eps)."""
+    # An activation travels as a pair (fp32 rows, fp16 copy or None).  With precision='tf32' the LayerNorm epilogues
+    # emit the fp16 copy next to the fp32 rows, and the projections that read it run with fp16 operands (the
+    # significand of TF32 in half the bytes, weight tile resident in shared memory).
+    def _lin(self, x, w, b, residual=None, relu=False, ln=None, out=None, w16=None, want16=False, only16=False):
+        """epilogue(x @ w^T) -> (fp32 rows or None, fp16 copy or None).  x: fp32 rows or a (fp32, fp16) pair."""
+        x32, x16 = x if isinstance(x, tuple) else (x, None)
         if self.tc_gemm:
             try:
-                return ops.linear_tf32(x, w, b, residual=residual, relu=relu, ln=ln, out=out)
+                if ln is not None and not self.fuse_ln:
+                    # projection (bias in the epilogue) + one streaming residual/LayerNorm pass that also emits the
+                    # fp16 copy: measured faster than the LayerNorm epilogue, whose residual reads are latency-bound
+                    o, _ = self._lin(x, w, b, w16=w16)
+                    o16 = torch.empty(o.shape, device=o.device, dtype=torch.float16) if want16 else None
+                    return ops.add_layernorm(o, ln[0], ln[1], residual=residual, eps=ln[2], out=o, out16=o16), o16
+                if x16 is not None and w16 is not None:
+                    return ops.linear_f16(x16, w16, b, residual=residual, relu=relu, ln=ln, out=out,
+                                          fp32_out=not only16, f16_out=want16 or only16)
+                if x32 is not None and not only16:
+                    o16 = torch.empty(x32.shape[0], w.shape[0], device=x32.device, dtype=torch.float16) if want16 else None
+                    return ops.linear_tf32(x32, self._tf32(w), b, residual=residual, relu=relu, ln=ln, out=out,
+                                           out16=o16), o16
             except _cabi.UnsupportedShape:
                 pass
+        if x32 is None:
+            x32 = x16.float()
         if ln is not None:
-            o = torch.mm(x, w.t())
-            return ops.add_layernorm(o, ln[0], ln[1], bias=b, residual=residual, eps=ln[2], out=o)
-        if relu:
-            o = torch._addmm_activation(b, x, w.t(), use_gelu=False)
+            o = torch.mm(x32, w.t())
+            o = ops.add_layernorm(o, ln[0], ln[1], bias=b, residual=residual, eps=ln[2], out=o)
         else:
-            o = torch.addmm(b, x, w.t()) if b is not None else torch.mm(x, w.t())
-        if residual is not None:
-            o += residual
+            if relu:
+                o = torch._addmm_activation(b, x32, w.t(), use_gelu=False)
+            else:
+                o = torch.addmm(b, x32, w.t()) if b is not None else torch.mm(x32, w.t())
+            if residual is not None:
+                o += residual
         if out is not None:
             out.copy_(o)
-            return out
-        return o
+            o = out
+        return o, None
 
-    def _project_value(self, tokens, w, b, G, Nv, H, P):
-        """value_proj of `tokens` (G*Nv, C) -> (fp16 head-major planes for the window kernels or None, fp32 rows or
+    def _project_value(self, x, w, b, G, Nv, H, P, w16=None):
+        """value_proj of the rows x (G*Nv, C) -> (fp16 head-major planes for the window kernels or None, fp32 rows or
         None).  With the tcgen05 GEMM the planes come straight out of the epilogue."""
+        x32, x16 = x if isinstance(x, tuple) else (x, None)
         C = w.shape[0]
         if self.fast_sampling and ops.window_supported(C // H, P):
             if self.tc_gemm:
                 try:
-                    return ops.linear_tf32(tokens, w, b, planes_nv=Nv), None
+                    if x16 is not None and w16 is not None:
+                        return ops.linear_f16(x16, w16, b, planes_nv=Nv), None
+                    return ops.linear_tf32(x32, self._tf32(w), b, planes_nv=Nv), None
                 except _cabi.UnsupportedShape:
                     pass
-            rows = torch.addmm(b, tokens, w.t())
+            rows = torch.addmm(b, x32, w.t())
             return ops.value_to_half(rows, G, Nv, H), rows
-        return None, torch.addmm(b, tokens, w.t())
+        return None, torch.addmm(b, x32, w.t())
 
-    def _bev_sample(self, tokens, w, b, qp, B, bev_h, bev_w, fh, fw, H, P):
-        """value_proj + BEV-grid sampling: tokens (B*fh*fw, C) un-projected -> sampled (B, Nq, C)."""
+    def _bev_sample(self, x, w, b, qp, B, bev_h, bev_w, fh, fw, H, P, w16=None):
+        """value_proj + BEV-grid sampling: rows x (B*fh*fw, C) un-projected -> sampled (B, Nq, C)."""
         C = w.shape[0]
-        planes, rows = self._project_value(tokens, w, b, B, fh * fw, H, P)
+        planes, rows = self._project_value(x, w, b, B, fh * fw, H, P, w16)
         if planes is not None and qp.shape[2] % 4 == 0:
             try:
+                # the sampled rows feed the TF32 output projection: have the kernel round them to nearest
+                _cabi.lib().ub_set_window_round_tf32(1 if self.tc_gemm else 0)
                 return ops.bev_sample_win(planes, qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2)
             except _cabi.UnsupportedShape:
                 pass
+            finally:
+                _cabi.lib().ub_set_window_round_tf32(0)
         if rows is None:
-            rows = torch.addmm(b, tokens, w.t())
+            x32 = x[0] if isinstance(x, tuple) else x
+            rows = torch.addmm(b, x32, w.t())
         return ops.bev_sample(rows.view(B, fh * fw, C), qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2)
 
     # one BEV encoder ------------------------------------------------------------------------------
@@ -180,28 +225,41 @@ class FusedEncoder:
         sample_cross(lw, value_tokens, qp) -> sampled (B, Nq, C)."""
         layers, pos_w = self._weights(name)
         B, Nq, C = x.shape
-        x = x.reshape(B * Nq, C).contiguous()
+        x32 = x.reshape(B * Nq, C).contiguous()
+        f16 = self.tc_gemm and C % 64 == 0
+        x = (x32, x32.half() if f16 else None)
+        if f16:
+            value_tokens = (value_tokens, value_tokens.half())   # fp16 copy once per frame, read by every layer
         pos_q = None
         if pos is not None:
             # positional part of every layer's self-attention offset|logit rows, once per frame
             n_q = [lw.sa_wq.shape[0] for lw in layers]
-            buf = torch.empty(B * Nq, sum(n_q), device=x.device, dtype=torch.float32)
+            buf = torch.empty(B * Nq, sum(n_q), device=x32.device, dtype=torch.float32)
             pos_q = buf.split(n_q, dim=1)
             for lw, dst in zip(layers, pos_q):
                 self._lin(pos, lw.sa_wq, None, out=dst)
         for i, lw in enumerate(layers):
+            h = lw.half() if f16 else None
             # --- BEV self-attention (mmcv MultiScaleDeformableAttention, value = query, 1 level)
-            qp = self._lin(x, lw.sa_wq, lw.sa_bq, residual=pos_q[i] if pos_q is not None else None)
-            s = self._bev_sample(x, lw.sa_wv, lw.sa_bv, qp.view(B, Nq, -1), B, bev_h, bev_w, bev_h, bev_w, lw.H_s, lw.P_s)
-            x = self._lin(s.view(B * Nq, C), lw.sa_wo, lw.sa_bo, residual=x, ln=lw.ln[0])
+            qp, _ = self._lin(x, lw.sa_wq, lw.sa_bq, residual=pos_q[i] if pos_q is not None else None,
+                              w16=h and h['sa_wq'])
+            s = self._bev_sample(x, lw.sa_wv, lw.sa_bv, qp.view(B, Nq, -1), B, bev_h, bev_w, bev_h, bev_w, lw.H_s, lw.P_s,
+                                 w16=h and h['sa_wv'])
+            x = self._lin(s.view(B * Nq, C), lw.sa_wo, lw.sa_bo, residual=x[0], ln=lw.ln[0], want16=f16)
+            if f16 and x[1] is None:
+                x = (x[0], x[0].half())
             # --- spatial cross-attention (query_pos is None for attentions[1])
-            qp = self._lin(x, lw.ca_wq, lw.ca_bq)
+            qp, _ = self._lin(x, lw.ca_wq, lw.ca_bq, w16=h and h['ca_wq'])
             s = sample_cross(lw, value_tokens, qp.view(B, Nq, -1))
-            x = self._lin(s.view(B * Nq, C), lw.ca_wo, lw.ca_bo, residual=x, ln=lw.ln[1])
+            x = self._lin(s.view(B * Nq, C), lw.ca_wo, lw.ca_bo, residual=x[0], ln=lw.ln[1], want16=f16)
+            if f16 and x[1] is None:
+                x = (x[0], x[0].half())
             # --- FFN
-            h = self._lin(x, lw.w1, lw.b1, relu=True)
-            x = self._lin(h, lw.w2, lw.b2, residual=x, ln=lw.ln[2])
-        return x.view(B, Nq, C)
+            hid = self._lin(x, lw.w1, lw.b1, relu=True, w16=h and h['w1'], only16=f16)
+            x = self._lin(hid, lw.w2, lw.b2, residual=x[0], ln=lw.ln[2], w16=h and h['w2'], want16=f16 and i + 1 < len(layers))
+            if f16 and x[1] is None and i + 1 < len(layers):
+                x = (x[0], x[0].half())
+        return x[0].view(B, Nq, C)
 
     def __call__(self, img_feats, pts_feats, bev_queries, bev_h, bev_w, bev_pos, img_metas, lidar2img=None,
                  img_shape=None):
@@ -236,7 +294,8 @@ class FusedEncoder:
                 hits = []
 
                 def cross(lw, tokens, qp):
-                    planes, rows = self._project_value(tokens, lw.ca_wv, lw.ca_bv, B * N, fh * fw, lw.H_c, lw.P_c)
+                    planes, rows = self._project_value(tokens, lw.ca_wv, lw.ca_bv, B * N, fh * fw, lw.H_c, lw.P_c,
+                                                       w16=lw.half()['ca_wv'] if isinstance(tokens, tuple) else None)
                     if planes is not None and (fh + 2) * (fw + 2) * 64 <= 150 * 1024 and qp.shape[2] % 4 == 0:
                         if not hits:
                             hits.append(ops.build_hits(mask))
@@ -246,7 +305,7 @@ class FusedEncoder:
                         except _cabi.UnsupportedShape:
                             pass
                     if rows is None:
-                        rows = torch.addmm(lw.ca_bv, tokens, lw.ca_wv.t())
+                        rows = torch.addmm(lw.ca_bv, tokens[0] if isinstance(tokens, tuple) else tokens, lw.ca_wv.t())
                     return ops.img_sample(rows.view(B, N, fh * fw, C), qp, ref_cam, mask, bev_h, bev_w, fh, fw,
                                           lw.H_c, lw.P_c, 0, lw.H_c * lw.P_c * 2)
                 x0 = q_img.detach().unsqueeze(0).expand(B, Nq, C)
@@ -258,7 +317,8 @@ class FusedEncoder:
                 tokens = ops.flatten_feats(feat, None, m.pts_level_embeds[0])
 
                 def cross(lw, tokens, qp, fh=fh, fw=fw):
-                    return self._bev_sample(tokens, lw.ca_wv, lw.ca_bv, qp, B, bev_h, bev_w, fh, fw, lw.H_c, lw.P_c)
+                    return self._bev_sample(tokens, lw.ca_wv, lw.ca_bv, qp, B, bev_h, bev_w, fh, fw, lw.H_c, lw.P_c,
+                                            w16=lw.half()['ca_wv'] if isinstance(tokens, tuple) else None)
                 x0 = q_pts.detach().unsqueeze(0).expand(B, Nq, C)
                 pts = self._run_encoder('pts_bev_encoder', x0, pos, tokens.view(B * fh * fw, C), cross, bev_h, bev_w)
             return ops.cnw_fuse(img, pts, getattr(m, 'img_channel_weights', None), getattr(m, 'pts_channel_weights', None),
