@@ -23,10 +23,15 @@
  *   [R6] UniBEVTransformer.channel_feature_norm / spatial_feature_norm / multi_modal_fusion,
  *        transformer_fusion.py:316-337, 386-413, 280-314.
  *   [R7] UniBEVTransformer._pre_process_img_feats / _pre_process_pts_feats, transformer_fusion.py:231-278.
+ *   [R8] UniBEV.voxelize -> self.pts_voxel_layer(res) (mmdet3d Voxelization / hard_voxelize_forward, max_num_points=10,
+ *        voxel_size=[0.075, 0.075, 0.2], max_voxels=(90000, 120000)) and the HardSimpleVFE mean,
+ *        projects/UniBEV/unibev_plugin/models/detectors/unibev_detector.py:151-175, :112-124;
+ *        configs/unibev/unibev_nus_LC_cnw_256_modality_dropout.py:186-193.
  */
 #ifndef UNIBEV_B200_H_
 #define UNIBEV_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -174,6 +179,23 @@ int ub_cnw_fuse(const float* img, const float* pts, const float* w_img, const fl
  * embed_a / embed_b may be NULL. */
 int ub_flatten_feats(const float* in, const float* embed_a, int n_a, const float* embed_b, float* out,
                      int G, int C, int HW, ub_stream_t stream);
+
+/* ---- [R8] LiDAR hard voxelisation (integer index path, bit-exact with the sequential CPU algorithm) ----
+ * points (N, C) fp32 with x, y, z in columns 0..2 (C >= 3).  voxel_size (3) and pc_range (6) are HOST arrays
+ * (x, y, z order).  A point belongs to cell floor((p - range_min) / voxel_size) (fp32) and is dropped when the cell
+ * is outside grid = round((range_max - range_min) / voxel_size).  Voxel ids follow the order of first occurrence
+ * in the point list; a voxel keeps its first max_points points in point order; voxels beyond max_voxels are
+ * dropped.  Outputs (sized for max_voxels): voxels (max_voxels, max_points, C), zero where empty;
+ * coors (max_voxels, 3) int32 (z, y, x); num_points_per_voxel (max_voxels) int32; voxel_num (1) int32 on the
+ * DEVICE (no host sync).  workspace: ub_voxelize_workspace_bytes(N) bytes, 256-byte aligned. */
+int ub_voxelize_workspace_bytes(int num_points, size_t* bytes /* host */);
+int ub_hard_voxelize(const float* points, int N, int C, const float* voxel_size /* host */,
+                     const float* pc_range /* host */, int max_points, int max_voxels, float* voxels, int* coors,
+                     int* num_points_per_voxel, int* voxel_num, void* workspace, size_t workspace_bytes,
+                     ub_stream_t stream);
+/* HardSimpleVFE: out (M, num_features) = sum over the points of a voxel / num_points_per_voxel. */
+int ub_voxel_mean(const float* voxels, const int* num_points_per_voxel, int M, int max_points, int C,
+                  int num_features, float* out, ub_stream_t stream);
 
 #ifdef __cplusplus
 }

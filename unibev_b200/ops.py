@@ -327,3 +327,49 @@ def flatten_feats(feat, embed_a=None, embed_b=None):
     _cabi.check(_cabi.lib().ub_flatten_feats(_ptr(feat), _ptr(embed_a), n_a, _ptr(embed_b), _ptr(out), G, C, h * w,
                                              _stream()), 'ub_flatten_feats')
     return out
+
+
+# ---------------------------------------------------------------------------------------------- [R8] voxelize
+_vox_ws = {}
+
+
+def hard_voxelize(points, voxel_size, pc_range, max_points, max_voxels):
+    """points (N, C) fp32 on the device -> (voxels (max_voxels, max_points, C), coors (max_voxels, 3) int32 (z, y, x),
+    num_points_per_voxel (max_voxels) int32, voxel_num (1,) int32 ON THE DEVICE).  Rows >= voxel_num are padding.
+    Asynchronous: the caller decides when (if ever) to read voxel_num back."""
+    points = _need(points, 'points')
+    if points.dim() != 2 or points.size(1) < 3:
+        raise ValueError(f'hard_voxelize: points must be (N, C>=3), got {tuple(points.shape)}')
+    N, C = points.shape
+    dev = points.device
+    voxels = torch.empty(max_voxels, max_points, C, device=dev, dtype=torch.float32)
+    coors = torch.zeros(max_voxels, 3, device=dev, dtype=torch.int32)
+    num = torch.empty(max_voxels, device=dev, dtype=torch.int32)
+    voxel_num = torch.zeros(1, device=dev, dtype=torch.int32)
+    if N == 0:
+        voxels.zero_()
+        num.zero_()
+        return voxels, coors, num, voxel_num
+    nbytes = ctypes.c_size_t(0)
+    _cabi.check(_cabi.lib().ub_voxelize_workspace_bytes(N, ctypes.byref(nbytes)), 'ub_voxelize_workspace_bytes')
+    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    ws = _vox_ws.get(key)
+    if ws is None or ws.numel() < nbytes.value:
+        ws = _vox_ws[key] = torch.empty(nbytes.value, device=dev, dtype=torch.uint8)
+    vs = (ctypes.c_float * 3)(*[float(v) for v in voxel_size])
+    pr = (ctypes.c_float * 6)(*[float(v) for v in pc_range])
+    _cabi.check(_cabi.lib().ub_hard_voxelize(_ptr(points), N, C, vs, pr, int(max_points), int(max_voxels), _ptr(voxels),
+                                             _ptr(coors), _ptr(num), _ptr(voxel_num), _ptr(ws), ws.numel(), _stream()),
+                'ub_hard_voxelize')
+    return voxels, coors, num, voxel_num
+
+
+def voxel_mean(voxels, num_points, num_features):
+    """HardSimpleVFE: (M, max_points, C), (M,) int32 -> (M, num_features)."""
+    voxels = _need(voxels, 'voxels')
+    num_points = _need(num_points, 'num_points', torch.int32)
+    M, T, C = voxels.shape
+    out = torch.empty(M, num_features, device=voxels.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().ub_voxel_mean(_ptr(voxels), _ptr(num_points), M, T, C, int(num_features), _ptr(out),
+                                          _stream()), 'ub_voxel_mean')
+    return out

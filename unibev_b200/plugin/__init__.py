@@ -4,7 +4,8 @@ from .attention import (MSDeformableAttention3DImg, MSDeformableAttention3DPts, 
                         SpatialCrossAttentionImg, SpatialCrossAttentionPts)
 from .encoder import FFN, ImgEncoder, ImgLayer, PtsEncoder, PtsLayer
 from .transformer import UniBEVTransformer
+from .voxelize import HardSimpleVFE, Voxelization, voxelize
 
 __all__ = ['MSDeformableAttention3DImg', 'MSDeformableAttention3DPts', 'MultiScaleDeformableAttention',
            'SpatialCrossAttentionImg', 'SpatialCrossAttentionPts', 'FFN', 'ImgEncoder', 'ImgLayer', 'PtsEncoder',
-           'PtsLayer', 'UniBEVTransformer']
+           'PtsLayer', 'UniBEVTransformer', 'HardSimpleVFE', 'Voxelization', 'voxelize']

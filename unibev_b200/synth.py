@@ -136,3 +136,26 @@ def build_model(workload, seed=0, **cfg_overrides):
     model.init_weights()
     randomize_sampling_weights(model, seed)
     return model, cfg
+
+
+# LiDAR voxel layer of the L / LC configs (unibev_nus_LC_cnw_256_modality_dropout.py:186-190)
+VOXEL_LAYER = dict(max_num_points=10, voxel_size=[0.075, 0.075, 0.2], max_voxels=(90000, 120000),
+                   point_cloud_range=PC_RANGE)
+
+
+def make_cloud(n=262144, seed=0, real_like=True):
+    """Synthetic 10-sweep nuScenes-shaped cloud: (n, 5) fp32 = x, y, z, intensity, dt.
+    ``real_like`` concentrates the points near the ego vehicle (range ~ exponential) so voxels hold several points, as
+    sweeps do; otherwise x, y are uniform over +-54 m.  A few points fall outside the range on purpose."""
+    g = np.random.default_rng(seed)
+    if real_like:
+        r = np.minimum(g.exponential(14.0, n) + 1.0, 60.0)
+        th = g.uniform(0, 2 * math.pi, n)
+        x, y = r * np.cos(th), r * np.sin(th)
+        z = g.normal(-1.5, 0.9, n)
+    else:
+        x, y = g.uniform(-54, 54, n), g.uniform(-54, 54, n)
+        z = g.uniform(-5, 3, n)
+    inten = g.uniform(0, 255, n)
+    dt = g.integers(0, 10, n) * 0.05
+    return np.stack((x, y, z, inten, dt), 1).astype(np.float32)
