@@ -110,8 +110,10 @@ int ub_img_sample_fwd(const float* value, const float* qproj, const float* ref_c
  *
  * ub_value_to_half: value (G*Nv, H*Dh) fp32 token-major  ->  value16 (G, H, Nv, Dh) fp16 (saturating). */
 int ub_value_to_half(const float* value, void* value16, int G, int Nv, int H, int Dh, ub_stream_t stream);
-/* value16 (B, H, fH*fW, 32) fp16; qproj / out as in ub_bev_sample_fwd (ld, off_col, logit_col multiples of 4). */
-int ub_bev_sample_win_fwd(const void* value16, const float* qproj, float* out,
+/* value16 (B, H, fH*fW, 32) fp16; qproj / out as in ub_bev_sample_fwd (ld, off_col, logit_col multiples of 4).
+ * out_f16 != 0: `out` is (B, Nq, H*32) fp16 instead of fp32 -- the A operand of ub_linear_f16 (the output projection);
+ * the rounding is the one a TF32 projection would apply to its operand anyway (11-bit significand). */
+int ub_bev_sample_win_fwd(const void* value16, const float* qproj, void* out, int out_f16,
                           int B, int bev_h, int bev_w, int fH, int fW, int H, int Dh, int P,
                           int ld, int off_col, int logit_col, ub_stream_t stream);
 /* Halo (value-map pixels) the BEV windows extend beyond the tile's reference points; 0 = default (P + 1).
@@ -120,16 +122,20 @@ int ub_set_window_halo(int halo);
 /* on != 0: ub_bev_sample_win_fwd rounds its outputs to the nearest TF32 value (10 mantissa bits).  For callers that
  * feed them to a TF32 tensor-core projection (ub_linear_tf32), whose operand fetch truncates instead. */
 int ub_set_window_round_tf32(int on);
-/* mask (B, Nq, N) from ub_project_points -> hit_idx (N, Nq) int32: the queries batch item 0 sees in camera n,
- * ascending (spatial_cross_attention_img.py:141-152); hit_cnt (N) int32; inv_cnt (B, Nq) = 1 / max(1, #cameras
- * whose mask for (b, q) is non-zero) (:209-212). */
+/* mask (B, Nq, N) from ub_project_points -> the queries batch item 0 sees in camera n
+ * (spatial_cross_attention_img.py:141-152), split by rank: hit_idx (N + 1, Nq) int32, row n = the hits whose lowest
+ * seeing camera is n ("first", ascending, from the front) and the other hits of camera n ("later", from the back:
+ * hit_idx[n][Nq - 1 - k]); row N = the queries no camera sees.  hit_cnt (2 N + 1) int32 = first counts, later
+ * counts, unseen count.  inv_cnt (B, Nq) = 1 / max(1, #cameras whose mask for (b, q) is non-zero) (:209-212). */
 int ub_build_hits(const uint8_t* mask, int* hit_idx, int* hit_cnt, float* inv_cnt, int B, int N, int Nq,
                   ub_stream_t stream);
-/* value16 (B, N, H, fH*fW, 32) fp16; out (B, Nq, H*32) is zero-filled by the call, then accumulated with
- * red.global.add (sums over more than two cameras are order-dependent in the last bit). */
+/* value16 (B, N, H, fH*fW, 32) fp16; hit_idx / hit_cnt / inv_cnt from ub_build_hits.  Every row of out
+ * (B, Nq, H*32) is written: first hits with plain stores (zero rows for unseen queries), later hits accumulated with
+ * red.global.add on top (sums over more than three cameras are order-dependent in the last bit).  out_f16 as in
+ * ub_bev_sample_win_fwd (later hits are then accumulated in fp16). */
 int ub_img_sample_win_fwd(const void* value16, const float* qproj, const float* ref_cam, const int* hit_idx,
-                          const int* hit_cnt, const float* inv_cnt, float* out, int B, int N, int bev_h, int bev_w,
-                          int fH, int fW, int H, int Dh, int P, int D, int ld, int off_col, int logit_col,
+                          const int* hit_cnt, const float* inv_cnt, void* out, int out_f16, int B, int N, int bev_h,
+                          int bev_w, int fH, int fW, int H, int Dh, int P, int D, int ld, int off_col, int logit_col,
                           ub_stream_t stream);
 
 /* ---- [R5] dense projection on the tcgen05 tensor cores with fused epilogue -------------------------

@@ -48,6 +48,7 @@ def _bev_case(ops, B, bev_h, bev_w, fH, fW, H, P, off_scale, seed, halo=0):
         v16 = ops.value_to_half(vg.view(B * fH * fW, C), B, fH * fW, H)
         got = ops.bev_sample_win(v16, qg, bev_h, bev_w, fH, fW, H, P, 0, H * P * 2).cpu()
         got2 = ops.bev_sample_win(v16, qg, bev_h, bev_w, fH, fW, H, P, 0, H * P * 2).cpu()   # counters re-armed
+        got16 = ops.bev_sample_win(v16, qg, bev_h, bev_w, fH, fW, H, P, 0, H * P * 2, out_dtype=torch.float16).cpu()
     finally:
         _cabi.lib().ub_set_window_halo(0)
     fp32 = ops.bev_sample(vg, qg, bev_h, bev_w, fH, fW, H, P, 0, H * P * 2).cpu()
@@ -58,6 +59,9 @@ def _bev_case(ops, B, bev_h, bev_w, fH, fW, H, P, off_scale, seed, halo=0):
     assert float(err.mean()) <= 1.5e-4, float(err.mean())
     assert float(err_q.max()) <= 1e-3 * vmax and float(err_q.mean()) <= 2e-5, (float(err_q.max()), float(err_q.mean()))
     torch.testing.assert_close(got2, got, rtol=0, atol=1e-6)
+    # fp16 output rows: the fp32 result rounded once (rows merged from the slow path by fp16 red.add: a few more ulps)
+    assert got16.dtype == torch.float16
+    torch.testing.assert_close(got16.float(), got, rtol=2e-3 if off_scale > 4 or halo else 1e-3, atol=2e-3 * vmax / 4)
 
 
 @pytest.mark.parametrize('B,bev,f,H,P,off_scale', [
@@ -124,13 +128,23 @@ def test_build_hits_exact(ops):
     _, mask = ops.project_points(l2i.cuda(), zs, [-54, -54, -5, 54, 54, 3], 928, 1600, 40, 36)
     hit_idx, hit_cnt, inv_cnt = (t.cpu() for t in ops.build_hits(mask))
     m = mask.cpu()
+    Nq = m.shape[1]
+    seen_before = torch.zeros(Nq, dtype=torch.bool)
     for n in range(6):
-        want = (m[0, :, n] != 0).nonzero().squeeze(1).int()
-        assert int(hit_cnt[n]) == want.numel()
-        assert torch.equal(hit_idx[n, :want.numel()], want)
+        hit = m[0, :, n] != 0
+        n_first, n_later = int(hit_cnt[n]), int(hit_cnt[6 + n])
+        # first hits (no lower camera sees the query) ascending from the front, later hits from the back
+        assert torch.equal(hit_idx[n, :n_first], (hit & ~seen_before).nonzero().squeeze(1).int())
+        assert torch.equal(hit_idx[n, Nq - n_later:].flip(0), (hit & seen_before).nonzero().squeeze(1).int())
+        # together: exactly the reference's per-camera list (spatial_cross_attention_img.py:141-152)
+        both = torch.cat((hit_idx[n, :n_first], hit_idx[n, Nq - n_later:])).sort().values
+        assert torch.equal(both, hit.nonzero().squeeze(1).int())
+        seen_before |= hit
+    assert torch.equal(hit_idx[6, :int(hit_cnt[12])], (~seen_before).nonzero().squeeze(1).int())
+    assert int(hit_cnt[6:12].sum()) > 0 and int(hit_cnt[12]) > 0      # the case has multi-camera and unseen queries
     want_inv = 1.0 / (m != 0).sum(-1).clamp(min=1).float()
     assert torch.equal(inv_cnt, want_inv)
-    assert int(hit_cnt.sum()) > 0
+    assert int(hit_cnt[:6].sum()) > 0
 
 
 @pytest.mark.parametrize('B,bev,fhw,P', [(1, (40, 36), (29, 50), 8), (2, (50, 50), (29, 50), 8), (2, (24, 24), (8, 22), 4)])
@@ -145,6 +159,16 @@ def test_img_sample_win_vs_fp32_kernel(ops, B, bev, fhw, P):
     hits = ops.build_hits(mask)
     v16 = ops.value_to_half(vg.view(-1, H * 32), B * 6, fh * fw, H).view(B, 6, H, fh * fw, 32)
     got = ops.img_sample_win(v16, qg, ref_cam, hits, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2).cpu()
+    got16 = ops.img_sample_win(v16, qg, ref_cam, hits, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2,
+                               out_dtype=torch.float16).cpu()
+    assert got16.dtype == torch.float16
+    torch.testing.assert_close(got16.float(), got, rtol=2e-3, atol=5e-4 * float(value.abs().max()))
+    # every row is written by the call itself (no zero-fill pass): poison the output buffer first
+    poisoned = torch.full_like(got, float('nan')).cuda()
+    ops.img_sample_win(v16, qg, ref_cam, hits, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2, out=poisoned)
+    torch.testing.assert_close(poisoned.cpu(), got, rtol=0, atol=1e-6)
+    if bev == (40, 36):
+        assert int((got.abs().sum(-1) == 0).sum()) > 0              # this case has rows no camera sees
     assert float(fp32.abs().max()) > 0.1                           # the rig does see the grid
     err = (got - fp32).abs()
     assert float(err.max()) <= 1e-3 * float(value.abs().max()), float(err.max())

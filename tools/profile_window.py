@@ -16,7 +16,7 @@ from unibev_b200.plugin.encoder import anchor_heights
 def main():
     dev = torch.device('cuda')
     torch.manual_seed(0)
-    B, Nq, C, H = 1, 40000, 256, 8
+    B, Nq, C, H = (int(sys.argv[1]) if len(sys.argv) > 1 else 1), 40000, 256, 8
     model, _ = synth.build_model('unibev_nus_LC_cnw_256', num_layers=1)
     model = model.to(dev)
     x = torch.randn(B, Nq, C, device=dev)

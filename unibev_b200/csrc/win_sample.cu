@@ -32,7 +32,9 @@
 //
 // Camera mode: unit = 256 hits of one camera x one head; the whole (camera, head) plane plus a one-pixel zero
 // halo is the window (reloaded when the CTA's contiguous unit range crosses into a new plane); contributions are
-// pre-scaled by 1/count and accumulated with red.global.add.v4.f32 into a zero-filled output.
+// pre-scaled by 1/count.  The hit lists are split by rank: every query's first camera is written with plain
+// stores (pass 0, which also zero-fills the rows no camera sees), only the further cameras of a query (pass 1)
+// use red.global.add.v4.f32 -- no zero-fill pass and no read-modify-write for the bulk of the pairs.
 #include <cuda_fp16.h>
 
 #include "ub_tma.cuh"
@@ -224,6 +226,15 @@ __device__ __forceinline__ void red_add4(float* p, const float4& v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// fp16 output rows: this lane's four channels as 8 bytes
+__device__ __forceinline__ void st_half4(__half* p, const float4& v) {
+  asm volatile("st.global.cs.v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(pack_h2(v.x, v.y)), "r"(pack_h2(v.z, v.w)) : "memory");
+}
+__device__ __forceinline__ void red_add_half4(__half* p, const float4& v) {
+  asm volatile("red.global.add.noftz.v2.f16x2 [%0], {%1,%2};" ::"l"(p), "r"(pack_h2(v.x, v.y)), "r"(pack_h2(v.z, v.w))
+               : "memory");
+}
+
 // The gather of one warp's 16 items: lane group `grp` (8 lanes) reduces items grp, grp + 4, grp + 8, grp + 12, two
 // at a time.  sm_w / sm_idx: the warp's descriptor arrays (shared-space byte addresses); win: window base
 // + sub * 16; ROWB > 0: bytes per window row known at compile time (immediate offset of the bottom-row load).
@@ -292,7 +303,8 @@ __device__ __forceinline__ void gather_warp(uint32_t sm_w, uint32_t sm_idx, uint
 // ---------------------------------------------------------------------------------------------------------
 struct BevWinArgs {
   const __half* value16;  // (B*H, fH, fW, 32): far path
-  float* out;             // (B, Nq, H*32)
+  float* out;             // (B, Nq, H*32) fp32 rows, or null when out16 is set
+  __half* out16;          // (B, Nq, H*32) fp16 rows (the A operand of the fp16 output projection), or null
   int* counters;          // [0] next unit, [1] CTAs done
   int B, bev_h, bev_w, fH, fW, H;
   int tiles_x, tiles_y, n_units;
@@ -452,9 +464,13 @@ __global__ void __launch_bounds__(kBevThreads, 1)
 #pragma unroll
         for (int e = lane; e < kWarpItems * 8; e += 32) {
           const int item = e >> 3, c4 = e & 7;
-          if (w.tx0 + item < a.bev_w)
-            *reinterpret_cast<float4*>(a.out + ((int64_t)w.b * Nq + qy * a.bev_w + w.tx0 + item) * C + w.h * 32 + c4 * 4) =
-                make_float4(0.f, 0.f, 0.f, 0.f);
+          if (w.tx0 + item < a.bev_w) {
+            const int64_t o = ((int64_t)w.b * Nq + qy * a.bev_w + w.tx0 + item) * C + w.h * 32 + c4 * 4;
+            if (a.out16)
+              *reinterpret_cast<uint2*>(a.out16 + o) = make_uint2(0u, 0u);
+            else
+              *reinterpret_cast<float4*>(a.out + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
       }
       __syncwarp();
@@ -486,8 +502,13 @@ __global__ void __launch_bounds__(kBevThreads, 1)
             v.x += __shfl_xor_sync(0xffffffffu, v.x, o), v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
             v.z += __shfl_xor_sync(0xffffffffu, v.z, o), v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
           }
-          if (lane < 8)
-            red_add4(a.out + ((int64_t)w.b * Nq + qy * a.bev_w + w.tx0 + item) * C + w.h * 32 + c4 * 4, v);
+          if (lane < 8) {
+            const int64_t o = ((int64_t)w.b * Nq + qy * a.bev_w + w.tx0 + item) * C + w.h * 32 + c4 * 4;
+            if (a.out16)
+              red_add_half4(a.out16 + o, v);
+            else
+              red_add4(a.out + o, v);
+          }
         }
       }
       __syncwarp();
@@ -499,7 +520,15 @@ __global__ void __launch_bounds__(kBevThreads, 1)
                           half, [&](int item, const float4& o) {
                             const int qx = w.tx0 + item;
                             if (row_ok && qx < a.bev_w) {
-                              float* dst = a.out + ((int64_t)w.b * Nq + qy * a.bev_w + qx) * C + w.h * 32 + cq * 8 + half * 4;
+                              const int64_t oo = ((int64_t)w.b * Nq + qy * a.bev_w + qx) * C + w.h * 32 + cq * 8 + half * 4;
+                              if (a.out16) {
+                                if (any_far)
+                                  red_add_half4(a.out16 + oo, o);
+                                else
+                                  st_half4(a.out16 + oo, o);
+                                return;
+                              }
+                              float* dst = a.out + oo;
                               if (any_far) {
                                 red_add4(dst, o);
                               } else if (!a.round_tf32) {
@@ -520,44 +549,61 @@ __global__ void __launch_bounds__(kBevThreads, 1)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Per-camera hit lists (ascending query index) from batch item 0's visibility bits (reference quirk,
-// spatial_cross_attention_img.py:142) and 1 / max(1, #cameras that see (b, q)) (:209-212).
+// Per-camera hit lists from batch item 0's visibility bits (reference quirk, spatial_cross_attention_img.py:142),
+// split by RANK: a hit (n, q) is "first" when no camera n' < n sees q, "later" otherwise.  Row n of hit_idx holds
+// the first hits ascending from the front and the later hits from the back (hit_idx[n][Nq - 1 - k]); row N lists the
+// queries no camera sees.  hit_cnt = {first counts (N), later counts (N), unseen count}.  The sampling kernel
+// writes first hits with plain stores (and zero rows for the unseen queries), then accumulates the later ones:
+// no zero-fill pass, no read-modify-write for the ~88 % of pairs that are a query's only camera.
+// inv_cnt = 1 / max(1, #cameras that see (b, q)) (:209-212).
 __global__ void __launch_bounds__(1024) build_hits_kernel(const uint8_t* __restrict__ mask, int* __restrict__ hit_idx,
                                                           int* __restrict__ hit_cnt, float* __restrict__ inv_cnt, int B,
                                                           int N, int Nq) {
-  __shared__ int s_warp[32];
-  __shared__ int s_base;
+  __shared__ int s_warp[2][32];
+  __shared__ int s_base[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if ((int)blockIdx.x < N) {
-    const int n = blockIdx.x;
-    if (tid == 0) s_base = 0;
+  if ((int)blockIdx.x <= N) {
+    const int n = blockIdx.x;          // n == N: the unseen list
+    if (tid < 2) s_base[tid] = 0;
     __syncthreads();
     for (int q0 = 0; q0 < Nq; q0 += 1024) {
       const int q = q0 + tid;
-      const bool hit = q < Nq && mask[(int64_t)q * N + n] != 0;
-      const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      if (lane == 0) s_warp[warp] = __popc(bal);
+      bool below = false, own = false;
+      if (q < Nq) {
+        for (int m = 0; m < n; ++m) below |= mask[(int64_t)q * N + m] != 0;
+        own = n < N ? mask[(int64_t)q * N + n] != 0 : !below;
+      }
+      const bool k0 = own && !below;                 // first hit of q (or: unseen, when n == N)
+      const bool k1 = own && below && n < N;         // later hit
+      const unsigned b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
+      if (lane == 0) s_warp[0][warp] = __popc(b0), s_warp[1][warp] = __popc(b1);
       __syncthreads();
-      if (warp == 0) {
-        int v = s_warp[lane];
+      if (warp < 2) {
+        int v = s_warp[warp][lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const int t = __shfl_up_sync(0xffffffffu, v, o);
           if (lane >= o) v += t;
         }
-        s_warp[lane] = v;  // inclusive
+        s_warp[warp][lane] = v;  // inclusive
       }
       __syncthreads();
-      const int base = s_base + (warp ? s_warp[warp - 1] : 0);
-      if (hit) hit_idx[(int64_t)n * Nq + base + __popc(bal & ((1u << lane) - 1u))] = q;
+      const unsigned below_me = (1u << lane) - 1u;
+      if (k0) hit_idx[(int64_t)n * Nq + s_base[0] + (warp ? s_warp[0][warp - 1] : 0) + __popc(b0 & below_me)] = q;
+      if (k1) hit_idx[(int64_t)n * Nq + Nq - 1 - (s_base[1] + (warp ? s_warp[1][warp - 1] : 0) + __popc(b1 & below_me))] = q;
       __syncthreads();
-      if (tid == 0) s_base += s_warp[31];
+      if (tid < 2) s_base[tid] += s_warp[tid][31];
       __syncthreads();
     }
-    if (tid == 0) hit_cnt[n] = s_base;
+    if (tid == 0) {
+      if (n < N)
+        hit_cnt[n] = s_base[0], hit_cnt[N + n] = s_base[1];
+      else
+        hit_cnt[2 * N] = s_base[0];
+    }
   } else {
-    const int64_t nb = gridDim.x - N;
-    for (int64_t i = (int64_t)(blockIdx.x - N) * blockDim.x + tid; i < (int64_t)B * Nq; i += nb * blockDim.x) {
+    const int64_t nb = gridDim.x - (N + 1);
+    for (int64_t i = (int64_t)(blockIdx.x - (N + 1)) * blockDim.x + tid; i < (int64_t)B * Nq; i += nb * blockDim.x) {
       int c = 0;
       for (int n = 0; n < N; ++n) c += mask[i * N + n] != 0 ? 1 : 0;
       inv_cnt[i] = 1.f / (float)max(c, 1);
@@ -570,11 +616,13 @@ struct ImgWinArgs {
   const float* qproj;
   const float* ref_cam;   // (B, Nq, N, D, 2)
   const float* inv_cnt;   // (B, Nq)
-  const int* hit_idx;     // (N, Nq)
-  const int* hit_cnt;     // (N)
-  float* out;             // (B, Nq, H*32), zero-filled
+  const int* hit_idx;     // (N + 1, Nq): first hits from the front, later hits from the back; row N = unseen queries
+  const int* hit_cnt;     // (2 N + 1): first counts, later counts, unseen count
+  float* out;             // (B, Nq, H*32) fp32 rows, or null when out16 is set
+  __half* out16;          // (B, Nq, H*32) fp16 rows, or null
   int B, N, Nq, fH, fW, H, P, D, ld, off_col, logit_col;
   int WW, WH;
+  int part;               // 0: first hits (plain stores) + zero rows of the unseen queries; 1: later hits (red.add)
 };
 
 template <int PP>
@@ -587,6 +635,8 @@ struct ImgSmem {
 // chunk * 256 + 16 w .. + 15.  Per unit and warp: descriptors from registers prefetched during the previous gather
 // (hit index -> offsets / logits / projected anchor / 1/count straight from global memory), then the gather.
 // The only CTA-wide barrier is at a plane change (the window is reloaded once every warp has left the old plane).
+// Launched twice per call: part 0 stores the contribution of every query's FIRST camera (and zero rows for the
+// queries no camera sees), part 1 accumulates the remaining (camera, query) pairs on top.
 template <int PP, int ROWB>
 __global__ void __launch_bounds__(kImgThreads, 1)
     img_sample_win_kernel(const ImgWinArgs a, const __grid_constant__ CUtensorMap map_val) {
@@ -601,9 +651,25 @@ __global__ void __launch_bounds__(kImgThreads, 1)
   const uint32_t sm_q = sm_idx + D::idx_bytes;   // query index per item
   const int C = a.H * 32;
 
+  const int* cnt_p = a.hit_cnt + a.part * a.N;
+  if (a.part == 0) {   // rows of the queries no camera sees
+    const int n_zero = __ldg(a.hit_cnt + 2 * a.N);
+    const int per_row = C / 4;
+    for (int64_t e = (int64_t)blockIdx.x * kImgThreads + tid; e < (int64_t)a.B * n_zero * per_row;
+         e += (int64_t)gridDim.x * kImgThreads) {
+      const int c4 = (int)(e % per_row);
+      const int64_t r = e / per_row;
+      const int q = __ldg(a.hit_idx + (int64_t)a.N * a.Nq + (int)(r % n_zero));
+      const int64_t o = ((r / n_zero) * a.Nq + q) * C + c4 * 4;
+      if (a.out16)
+        *reinterpret_cast<uint2*>(a.out16 + o) = make_uint2(0u, 0u);
+      else
+        st_stream4(a.out + o, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+  }
   // units: (b, camera, head, chunk of 256 hits), contiguous range per CTA
   int chunks_tot = 0;
-  for (int n = 0; n < a.N; ++n) chunks_tot += (__ldg(a.hit_cnt + n) + kUnitItems - 1) / kUnitItems;
+  for (int n = 0; n < a.N; ++n) chunks_tot += (__ldg(cnt_p + n) + kUnitItems - 1) / kUnitItems;
   const int per_b = chunks_tot * a.H, total = per_b * a.B;
   const int per = total / gridDim.x, rem = total % gridDim.x;
   const int u_beg = blockIdx.x * per + min((int)blockIdx.x, rem);
@@ -618,7 +684,7 @@ __global__ void __launch_bounds__(kImgThreads, 1)
     int r = uu % per_b;
     w.n = 0, w.cnt = 0, w.h = 0, w.chunk = 0;
     for (int n = 0; n < a.N; ++n) {
-      const int cnt = __ldg(a.hit_cnt + n), ch = (cnt + kUnitItems - 1) / kUnitItems;
+      const int cnt = __ldg(cnt_p + n), ch = (cnt + kUnitItems - 1) / kUnitItems;
       if (r < ch * a.H) {
         w.n = n, w.cnt = cnt, w.h = r / ch, w.chunk = r % ch;
         break;
@@ -647,7 +713,7 @@ __global__ void __launch_bounds__(kImgThreads, 1)
   int qq;
   auto prefetch = [&](const Unit& wu) {
     const int ord = wu.chunk * kUnitItems + warp * kWarpItems + item_l;
-    qq = ord < wu.cnt ? __ldg(a.hit_idx + (int64_t)wu.n * a.Nq + ord) : -1;
+    qq = ord < wu.cnt ? __ldg(a.hit_idx + (int64_t)wu.n * a.Nq + (a.part ? a.Nq - 1 - ord : ord)) : -1;
     ic = 0.f;
 #pragma unroll
     for (int i = 0; i < PPL; ++i) off[2 * i] = 0.f, off[2 * i + 1] = 0.f, lg[i] = 0.f, ref[2 * i] = 0.f, ref[2 * i + 1] = 0.f;
@@ -714,8 +780,19 @@ __global__ void __launch_bounds__(kImgThreads, 1)
                           [&](int item, const float4& o) {
                             int q;
                             asm volatile("ld.shared.b32 %0, [%1];" : "=r"(q) : "r"(sm_q + (uint32_t)item * 4u));
-                            if (q >= 0)
-                              red_add4(a.out + ((int64_t)w_cur.b * a.Nq + q) * C + w_cur.h * 32 + cq * 8 + half * 4, o);
+                            if (q >= 0) {
+                              const int64_t oo = ((int64_t)w_cur.b * a.Nq + q) * C + w_cur.h * 32 + cq * 8 + half * 4;
+                              if (a.out16) {
+                                if (a.part)
+                                  red_add_half4(a.out16 + oo, o);
+                                else
+                                  st_half4(a.out16 + oo, o);
+                              } else if (a.part) {
+                                red_add4(a.out + oo, o);
+                              } else {
+                                st_stream4(a.out + oo, o);
+                              }
+                            }
                           });
     __syncwarp();
     if (u + 1 < u_end && w.plane != loaded) {   // uniform per CTA: every warp leaves the old plane, then reload
@@ -828,6 +905,10 @@ static int launch_img_win_v(ImgWinArgs& a, const CUtensorMap& mv, size_t smem, c
     if (int rc = set_smem(img_sample_win_kernel<PP, ROWB>, smem, fn)) return rc;
     configured = smem;
   }
+  a.part = 0;
+  img_sample_win_kernel<PP, ROWB><<<kNumSMs, kImgThreads, smem, s>>>(a, mv);
+  if (int rc = check_launch(fn)) return rc;
+  a.part = 1;   // (camera, query) pairs beyond a query's first camera: ~12 % of the pairs on the nuScenes rig
   img_sample_win_kernel<PP, ROWB><<<kNumSMs, kImgThreads, smem, s>>>(a, mv);
   return check_launch(fn);
 }
@@ -848,10 +929,6 @@ static int launch_img_win(ImgWinArgs& a, const void* value16, cudaStream_t s) {
   if (int rc = make_tensor_map(&mv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, value16, dims, str, box,
                                CU_TENSOR_MAP_SWIZZLE_NONE))
     return rc;
-  if (cudaMemsetAsync(a.out, 0, (size_t)a.B * a.Nq * a.H * 32 * sizeof(float), s) != cudaSuccess) {
-    set_error("%s: cudaMemsetAsync failed", fn);
-    return UB_ECUDA;
-  }
   if (a.WW == 52) return launch_img_win_v<PP, 52 * 64>(a, mv, smem, s);  // nuScenes 1600 x 928 / 32 -> 50 + 2
   return launch_img_win_v<PP, 0>(a, mv, smem, s);
 }
@@ -883,8 +960,8 @@ extern "C" int ub_value_to_half(const float* value, void* value16, int G, int Nv
   return check_launch("ub_value_to_half");
 }
 
-extern "C" int ub_bev_sample_win_fwd(const void* value16, const float* qproj, float* out, int B, int bev_h, int bev_w,
-                                     int fH, int fW, int H, int Dh, int P, int ld, int off_col, int logit_col,
+extern "C" int ub_bev_sample_win_fwd(const void* value16, const float* qproj, void* out, int out_f16, int B, int bev_h,
+                                     int bev_w, int fH, int fW, int H, int Dh, int P, int ld, int off_col, int logit_col,
                                      ub_stream_t stream) {
   const char* fn = "ub_bev_sample_win_fwd";
   UB_REQUIRE(value16 && qproj && out, "%s: null pointer", fn);
@@ -900,7 +977,8 @@ extern "C" int ub_bev_sample_win_fwd(const void* value16, const float* qproj, fl
     return UB_EUNSUPPORTED;
   }
   BevWinArgs a;
-  a.value16 = reinterpret_cast<const __half*>(value16), a.out = out, a.counters = nullptr;
+  a.value16 = reinterpret_cast<const __half*>(value16), a.counters = nullptr;
+  a.out = out_f16 ? nullptr : reinterpret_cast<float*>(out), a.out16 = out_f16 ? reinterpret_cast<__half*>(out) : nullptr;
   a.B = B, a.bev_h = bev_h, a.bev_w = bev_w, a.fH = fH, a.fW = fW, a.H = H;
   a.tiles_x = (bev_w + kTQ - 1) / kTQ, a.tiles_y = (bev_h + kTQ - 1) / kTQ;
   a.n_units = B * H * a.tiles_x * a.tiles_y;
@@ -924,13 +1002,13 @@ extern "C" int ub_build_hits(const uint8_t* mask, int* hit_idx, int* hit_cnt, fl
   UB_REQUIRE(B > 0 && N > 0 && N <= 32 && Nq > 0, "ub_build_hits: bad dimension (B=%d N=%d Nq=%d)", B, N, Nq);
   int extra = (int)(((int64_t)B * Nq + 1023) / 1024);
   if (extra > kNumSMs) extra = kNumSMs;
-  build_hits_kernel<<<N + extra, 1024, 0, (cudaStream_t)stream>>>(mask, hit_idx, hit_cnt, inv_cnt, B, N, Nq);
+  build_hits_kernel<<<N + 1 + extra, 1024, 0, (cudaStream_t)stream>>>(mask, hit_idx, hit_cnt, inv_cnt, B, N, Nq);
   return check_launch("ub_build_hits");
 }
 
 extern "C" int ub_img_sample_win_fwd(const void* value16, const float* qproj, const float* ref_cam, const int* hit_idx,
-                                     const int* hit_cnt, const float* inv_cnt, float* out, int B, int N, int bev_h,
-                                     int bev_w, int fH, int fW, int H, int Dh, int P, int D, int ld, int off_col,
+                                     const int* hit_cnt, const float* inv_cnt, void* out, int out_f16, int B, int N,
+                                     int bev_h, int bev_w, int fH, int fW, int H, int Dh, int P, int D, int ld, int off_col,
                                      int logit_col, ub_stream_t stream) {
   const char* fn = "ub_img_sample_win_fwd";
   UB_REQUIRE(value16 && qproj && ref_cam && hit_idx && hit_cnt && inv_cnt && out, "%s: null pointer", fn);
@@ -950,7 +1028,8 @@ extern "C" int ub_img_sample_win_fwd(const void* value16, const float* qproj, co
     return UB_EUNSUPPORTED;
   }
   ImgWinArgs a;
-  a.qproj = qproj, a.ref_cam = ref_cam, a.inv_cnt = inv_cnt, a.hit_idx = hit_idx, a.hit_cnt = hit_cnt, a.out = out;
+  a.qproj = qproj, a.ref_cam = ref_cam, a.inv_cnt = inv_cnt, a.hit_idx = hit_idx, a.hit_cnt = hit_cnt;
+  a.out = out_f16 ? nullptr : reinterpret_cast<float*>(out), a.out16 = out_f16 ? reinterpret_cast<__half*>(out) : nullptr;
   a.B = B, a.N = N, a.Nq = bev_h * bev_w, a.fH = fH, a.fW = fW, a.H = H, a.P = P, a.D = D;
   a.ld = ld, a.off_col = off_col, a.logit_col = logit_col;
   a.WW = fW + 2, a.WH = fH + 2;

@@ -140,33 +140,36 @@ def window_supported(Dh, P):
     return Dh == 32 and P in (4, 8)
 
 
-def bev_sample_win(value16, qproj, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out=None):
+def bev_sample_win(value16, qproj, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out=None, out_dtype=torch.float32):
     """value16 (B, H, fH*fW, 32) fp16 from value_to_half; qproj (B, Nq, ld) -> (B, Nq, H*32) fp32."""
     value16, qproj = _need(value16, 'value16', torch.float16), _need(qproj, 'qproj')
     B, Hh, Nv, Dh = value16.shape
     if Hh != H or Nv != fH * fW or qproj.shape[0] != B or qproj.shape[1] != bev_h * bev_w:
         raise ValueError(f'bev_sample_win: inconsistent shapes value16{tuple(value16.shape)} qproj{tuple(qproj.shape)}')
     if out is None:
-        out = torch.empty(B, bev_h * bev_w, H * Dh, device=qproj.device, dtype=torch.float32)
-    _cabi.check(_cabi.lib().ub_bev_sample_win_fwd(_ptr(value16), _ptr(qproj), _ptr(out), B, bev_h, bev_w, fH, fW, H, Dh,
+        out = torch.empty(B, bev_h * bev_w, H * Dh, device=qproj.device, dtype=out_dtype)
+    _cabi.check(_cabi.lib().ub_bev_sample_win_fwd(_ptr(value16), _ptr(qproj), _ptr(out), int(out.dtype == torch.float16),
+                                                  B, bev_h, bev_w, fH, fW, H, Dh,
                                                   P, qproj.shape[2], off_col, logit_col, _stream()),
                 'ub_bev_sample_win_fwd')
     return out
 
 
 def build_hits(mask):
-    """mask (B, Nq, N) uint8 -> hit_idx (N, Nq) int32, hit_cnt (N) int32, inv_cnt (B, Nq) fp32 (all on the device)."""
+    """mask (B, Nq, N) uint8 -> hit_idx (N + 1, Nq) int32 (rank-split lists, row N = unseen queries), hit_cnt (2N + 1)
+    int32 (first counts, later counts, unseen count), inv_cnt (B, Nq) fp32 (all on the device; see ub_build_hits)."""
     mask = _need(mask, 'mask', torch.uint8)
     B, Nq, N = mask.shape
-    hit_idx = torch.empty(N, Nq, device=mask.device, dtype=torch.int32)
-    hit_cnt = torch.empty(N, device=mask.device, dtype=torch.int32)
+    hit_idx = torch.empty(N + 1, Nq, device=mask.device, dtype=torch.int32)
+    hit_cnt = torch.empty(2 * N + 1, device=mask.device, dtype=torch.int32)
     inv_cnt = torch.empty(B, Nq, device=mask.device, dtype=torch.float32)
     _cabi.check(_cabi.lib().ub_build_hits(_ptr(mask), _ptr(hit_idx), _ptr(hit_cnt), _ptr(inv_cnt), B, N, Nq, _stream()),
                 'ub_build_hits')
     return hit_idx, hit_cnt, inv_cnt
 
 
-def img_sample_win(value16, qproj, ref_cam, hits, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out=None):
+def img_sample_win(value16, qproj, ref_cam, hits, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out=None,
+                   out_dtype=torch.float32):
     """value16 (B, N, H, fH*fW, 32) fp16; hits = build_hits(mask); -> (B, Nq, H*32) fp32."""
     value16, qproj, ref_cam = _need(value16, 'value16', torch.float16), _need(qproj, 'qproj'), _need(ref_cam, 'ref_cam')
     hit_idx, hit_cnt, inv_cnt = hits
@@ -174,12 +177,13 @@ def img_sample_win(value16, qproj, ref_cam, hits, bev_h, bev_w, fH, fW, H, P, of
     D = ref_cam.shape[3]
     Nq = bev_h * bev_w
     if (Hh != H or Nv != fH * fW or qproj.shape[:2] != (B, Nq) or ref_cam.shape != (B, Nq, N, D, 2)
-            or hit_idx.shape != (N, Nq) or inv_cnt.shape != (B, Nq)):
+            or hit_idx.shape != (N + 1, Nq) or hit_cnt.shape != (2 * N + 1,) or inv_cnt.shape != (B, Nq)):
         raise ValueError('img_sample_win: inconsistent shapes')
     if out is None:
-        out = torch.empty(B, Nq, H * Dh, device=qproj.device, dtype=torch.float32)
+        out = torch.empty(B, Nq, H * Dh, device=qproj.device, dtype=out_dtype)
     _cabi.check(_cabi.lib().ub_img_sample_win_fwd(_ptr(value16), _ptr(qproj), _ptr(ref_cam), _ptr(hit_idx), _ptr(hit_cnt),
-                                                  _ptr(inv_cnt), _ptr(out), B, N, bev_h, bev_w, fH, fW, H, Dh, P, D,
+                                                  _ptr(inv_cnt), _ptr(out), int(out.dtype == torch.float16), B, N, bev_h,
+                                                  bev_w, fH, fW, H, Dh, P, D,
                                                   qproj.shape[2], off_col, logit_col, _stream()),
                 'ub_img_sample_win_fwd')
     return out

@@ -27,6 +27,7 @@ encoder_unibev_detr_img.py:189-289,413-479; encoder_unibev_detr_pts.py:129-209;
 spatial_cross_attention_img.py:141-215,381-419; spatial_cross_attention_pts.py:159-206.
 """
 import contextlib
+import os
 
 import numpy as np
 import torch
@@ -109,7 +110,7 @@ class _LayerWeights:
         """fp16 copies of the projection weights read with fp16 operands (built once)."""
         if self._half is None:
             self._half = {k: getattr(self, k).half().contiguous()
-                          for k in ('sa_wq', 'sa_wv', 'ca_wq', 'ca_wv', 'w1', 'w2')}
+                          for k in ('sa_wq', 'sa_wv', 'sa_wo', 'ca_wq', 'ca_wv', 'ca_wo', 'w1', 'w2')}
         return self._half
 
 
@@ -122,7 +123,10 @@ class FusedEncoder:
         self.tf32 = precision == 'tf32'
         self.fast_sampling = self.tf32      # window-staged fp16 sampling kernels where the shape is covered
         self.tc_gemm = self.tf32            # hand-written tcgen05 GEMM with fused epilogues where the shape is covered
-        self.fuse_ln = False                # LayerNorm inside the GEMM epilogue (else GEMM + one streaming LN pass)
+        # LayerNorm inside the GEMM epilogue (else GEMM + one streaming LN pass)
+        self.fuse_ln = os.environ.get('UB_FUSE_LN', '0') == '1'
+        # sampled rows leave the window kernels as fp16 (the A operand of the fp16 output projection)
+        self.half_samples = os.environ.get('UB_HALF_SAMPLES', '1') == '1' 
         self._w = {}
         self._rn = {}
 
@@ -184,6 +188,12 @@ class FusedEncoder:
             o = out
         return o, None
 
+    @staticmethod
+    def _rows(s, rows, C):
+        """sampled (B, Nq, C) -> the (fp32 rows, fp16 rows) pair `_lin` takes"""
+        s = s.view(rows, C)
+        return (None, s) if s.dtype == torch.float16 else s
+
     def _project_value(self, x, w, b, G, Nv, H, P, w16=None):
         """value_proj of the rows x (G*Nv, C) -> (fp16 head-major planes for the window kernels or None, fp32 rows or
         None).  With the tcgen05 GEMM the planes come straight out of the epilogue."""
@@ -207,6 +217,8 @@ class FusedEncoder:
         planes, rows = self._project_value(x, w, b, B, fh * fw, H, P, w16)
         if planes is not None and qp.shape[2] % 4 == 0:
             try:
+                if self.tc_gemm and self.half_samples and w16 is not None:
+                    return ops.bev_sample_win(planes, qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2, out_dtype=torch.float16)
                 # the sampled rows feed the TF32 output projection: have the kernel round them to nearest
                 _cabi.lib().ub_set_window_round_tf32(1 if self.tc_gemm else 0)
                 return ops.bev_sample_win(planes, qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2)
@@ -245,13 +257,15 @@ class FusedEncoder:
                               w16=h and h['sa_wq'])
             s = self._bev_sample(x, lw.sa_wv, lw.sa_bv, qp.view(B, Nq, -1), B, bev_h, bev_w, bev_h, bev_w, lw.H_s, lw.P_s,
                                  w16=h and h['sa_wv'])
-            x = self._lin(s.view(B * Nq, C), lw.sa_wo, lw.sa_bo, residual=x[0], ln=lw.ln[0], want16=f16)
+            x = self._lin(self._rows(s, B * Nq, C), lw.sa_wo, lw.sa_bo, residual=x[0], ln=lw.ln[0], want16=f16,
+                          w16=h and h['sa_wo'])
             if f16 and x[1] is None:
                 x = (x[0], x[0].half())
             # --- spatial cross-attention (query_pos is None for attentions[1])
             qp, _ = self._lin(x, lw.ca_wq, lw.ca_bq, w16=h and h['ca_wq'])
             s = sample_cross(lw, value_tokens, qp.view(B, Nq, -1))
-            x = self._lin(s.view(B * Nq, C), lw.ca_wo, lw.ca_bo, residual=x[0], ln=lw.ln[1], want16=f16)
+            x = self._lin(self._rows(s, B * Nq, C), lw.ca_wo, lw.ca_bo, residual=x[0], ln=lw.ln[1], want16=f16,
+                          w16=h and h['ca_wo'])
             if f16 and x[1] is None:
                 x = (x[0], x[0].half())
             # --- FFN
@@ -300,8 +314,10 @@ class FusedEncoder:
                         if not hits:
                             hits.append(ops.build_hits(mask))
                         try:
+                            half = self.tc_gemm and self.half_samples and isinstance(tokens, tuple)
                             return ops.img_sample_win(planes.view(B, N, lw.H_c, fh * fw, -1), qp, ref_cam, hits[0], bev_h,
-                                                      bev_w, fh, fw, lw.H_c, lw.P_c, 0, lw.H_c * lw.P_c * 2)
+                                                      bev_w, fh, fw, lw.H_c, lw.P_c, 0, lw.H_c * lw.P_c * 2,
+                                                      out_dtype=torch.float16 if half else torch.float32)
                         except _cabi.UnsupportedShape:
                             pass
                     if rows is None:
