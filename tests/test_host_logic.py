@@ -201,3 +201,54 @@ def test_two_rank_sharding_over_gloo(tmp_path):
                          capture_output=True, text=True, timeout=240, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     assert 'SHARD_OK' in out.stdout
+
+
+_GRAD_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from unibev_b200.train import GradBuckets
+dist.init_process_group('gloo')
+r, w = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(0)                                   # same weights on every rank (the reference seeds ranks alike)
+net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 4), torch.nn.Linear(4, 3))
+unused = torch.nn.Linear(3, 3)                         # never part of rank 1's graph: contributes zeros there
+params = list(net.parameters()) + list(unused.parameters())
+buckets = GradBuckets(params, bucket_bytes=64)         # tiny buckets: several collectives, launched during backward
+assert len(buckets.buckets) > 2
+xs = [torch.randn(7, 6, generator=torch.Generator().manual_seed(10 + k)) for k in range(w)]
+def loss_of(k, with_unused):
+    y = net(xs[k])
+    if with_unused:
+        y = unused(y)
+    return y.square().mean()
+for step in range(2):                                  # hooks re-arm after finish()
+    for p in params:
+        p.grad = None
+    loss_of(r, with_unused=(r == 0)).backward()
+    buckets.finish()
+    got = [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    want_loss = sum(loss_of(k, with_unused=(k == 0)) for k in range(w)) / w
+    want_loss.backward()
+    for p, g in zip(params, got):
+        torch.testing.assert_close(g, p.grad, rtol=1e-6, atol=1e-7)
+dist.barrier()
+if r == 0:
+    print('GRAD_OK', len(buckets.buckets), buckets.nbytes())
+dist.destroy_process_group()
+'''
+
+
+def test_gradient_buckets_average_over_two_gloo_ranks(tmp_path):
+    """N > 1 training path (BASELINE configs[4]): bucketed gradient all-reduce == the gradient of the mean loss over
+    the ranks' shards, including a parameter group one rank never touched (modality dropout)."""
+    script = tmp_path / 'grad_worker.py'
+    script.write_text(_GRAD_WORKER)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1')
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29533', str(script), ROOT],
+                         capture_output=True, text=True, timeout=240, env=env)
+    assert out.returncode == 0, (out.stdout[-1000:], out.stderr[-3000:])
+    assert 'GRAD_OK' in out.stdout

@@ -13,11 +13,14 @@
 //   warp 1   one lane issues tcgen05.mma (kind::tf32, M = 128, N = BN, K = 8 per instruction) into one of two
 //            TMEM accumulators, tcgen05.commit releases ring slots / publishes the accumulator
 //   warp 2   allocates / frees tensor memory
-//   warps 4-7 epilogue: thread = one row of the tile (its TMEM lane).  Rows are exchanged with global memory in
-//            32-column chunks through per-warp 128-byte-swizzled shared-memory buffers moved by TMA (residual in,
-//            result out), so global traffic is coalesced and the warps never synchronise with each other.  The
-//            LayerNorm statistics are thread-private (one thread owns the whole row); the pre-norm row is parked
-//            back in TMEM between the two passes.
+//   warps 4-19 epilogue: thread = one row of the tile (its TMEM lane); the four warps of a lane quarter share the
+//            16-column chunks of their rows.  Result rows reach global memory through per-warp swizzled
+//            shared-memory buffers (coalesced 16-byte stores).
+//   residual  never touches the epilogue: the producer streams the residual tile through the A ring (fp32 boxes of
+//            32 columns x 128 rows, the same 128-byte-swizzled layout as a TF32 A k-block) and the MMA lane copies
+//            each box straight into the accumulator with tcgen05.cp (smem -> TMEM) BEFORE the tile's MMAs, which
+//            then accumulate on top of it.  The residual so rides the deep asynchronous TMA pipeline instead of
+//            exposing its DRAM latency to the epilogue threads, and LayerNorm needs no second TMEM write pass.
 // The GEMMs here are bound by their activation traffic, not by math: the point of the kernel is to touch each
 // activation row once (no separate bias / residual / LayerNorm / fp16-conversion passes).
 #include <cuda_fp16.h>
@@ -52,6 +55,7 @@ struct GemmArgs {
   __half* out16;        // optional fp16 copy of the result rows (row stride ldc16), the next GEMM's A operand
   int ldc16;
   int cs;               // CTAs per cluster: they work on `cs` consecutive row tiles and share W by TMA multicast
+  int res_chunks;       // residual boxes (32 fp32 columns x 128 rows) per tile preloaded into the accumulator, 0 = none
   unsigned long long* trace;   // optional per-CTA event timestamps (tools/trace_gemm.py), else null
 };
 
@@ -101,6 +105,11 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
+}
+// 128 rows x 32 bytes (eight fp32 columns) of a K-major 128-byte-swizzled shared-memory tile -> TMEM lanes 0..127,
+// columns taddr .. taddr + 7.  Ordered with the tcgen05.mma instructions of the issuing thread.
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -198,7 +207,8 @@ __device__ __forceinline__ uint32_t swz(uint32_t base, int row, int j) {
 // k-blocks are re-read from L2 by every tile and need only a shallow ring.  Each ring has its own producer lane.
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
-    gemm_tf32_kernel(const GemmArgs a, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w) {
+    gemm_tf32_kernel(const GemmArgs a, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                     const __grid_constant__ CUtensorMap map_r) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t s_fa[kMaxStages], s_ea[kMaxStages], s_fw[kMaxStages], s_ew[kMaxStages], s_tfull[2],
       s_tempty[2];
@@ -263,22 +273,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ A producer (+ L2 prefetch two tiles ahead)
+    // ------------------------------------------------------------------ A producer: per tile the residual boxes
+    // (copied into the accumulator by the MMA lane), then the A k-blocks, all through the same ring
     if (lane == 0) {
       tma_prefetch_desc(&map_a);
-      auto prefetch_tile = [&](int i) {   // the residual rows of tile i -> L2, ahead of the epilogue that reads them
-        if (i >= n_iter) return;
-        const int m0 = tile_m0(i), n0 = tile_n0(i);
-        if (m0 >= r_end) return;
-        const int rows = min(kBM, r_end - m0);
-        if (a.residual && a.ldr == a.BN) bulk_prefetch_l2(a.residual + (size_t)m0 * a.ldr + n0, (uint32_t)(rows * a.ldr * 4));
-      };
-      prefetch_tile(0);
+      if (a.res_chunks) tma_prefetch_desc(&map_r);
       int stage = 0, ev = 0;
       uint32_t phase = 0;
       for (int i = 0; i < n_iter; ++i) {
-        const int m0 = tile_m0(i);
-        prefetch_tile(i + 1);
+        const int m0 = tile_m0(i), n0 = tile_n0(i);
+        for (int rc = 0; rc < a.res_chunks; ++rc) {
+          mbar_wait(smem_u32(&s_ea[stage]), phase ^ 1u);
+          const uint32_t bar = smem_u32(&s_fa[stage]);
+          mbar_arrive_expect_tx(bar, a_bytes);
+          tma_load_2d(sm_a + (uint32_t)stage * a_bytes, &map_r, bar, n0 + rc * 32, m0);
+          if (++stage == SA) stage = 0, phase ^= 1u;
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(smem_u32(&s_ea[stage]), phase ^ 1u);
           const uint32_t bar = smem_u32(&s_fa[stage]);
@@ -332,6 +342,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         mbar_wait(smem_u32(&s_tempty[acc]), (uint32_t)(((it >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
+        // accumulator <- residual tile, 32 columns per ring slot (four copies of eight columns each)
+        for (int rc = 0; rc < a.res_chunks; ++rc) {
+          mbar_wait(smem_u32(&s_fa[sa]), pa);
+          tc_fence_after();
+          const uint64_t rdesc = smem_desc_k128(sm_a + (uint32_t)sa * a_bytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tmem_cp_128x256b(tmem_d + (uint32_t)(rc * 32 + k * 8), rdesc + (uint64_t)(k * 2));
+          mma_commit(smem_u32(&s_ea[sa]));
+          if (++sa == SA) sa = 0, pa ^= 1u;
+        }
+        const uint32_t acc0 = a.res_chunks ? 1u : 0u;       // accumulate on top of the preloaded residual
         for (int kb = 0; kb < k_blocks; ++kb) {
           if (a.w_res) sw = kb, pw = 0;                     // resident: slot kb, its only phase
           mbar_wait(smem_u32(&s_fw[sw]), pw);
@@ -344,11 +365,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           if (a.f16) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              mma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+              mma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : acc0);
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              mma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+              mma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : acc0);
           }
           mma_commit(smem_u32(&s_ea[sa]));
           if (++sa == SA) sa = 0, pa ^= 1u;
@@ -379,30 +400,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       const uint32_t tbase = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
       const bool rows_live = row0 < r_end;                      // warp-uniform (and equal for the warps of the quarter)
 
-      float4 rr[4];                                           // residual chunk in flight (coalesced layout)
-      auto load_res = [&](int c) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = row0 + crow + 8 * i;
-          rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row < r_end) rr[i] = ld_stream4(a.residual + (size_t)row * a.ldr + n0 + c * kChunk + ccol * 4);
-        }
-      };
-      auto add_res = [&](float (&f)[16]) {                    // registers -> swizzled buffer -> this thread's row
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(swz(buf, crow + 8 * i, ccol)), "f"(rr[i].x), "f"(rr[i].y),
-                       "f"(rr[i].z), "f"(rr[i].w)
-                       : "memory");
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float4 r;
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(swz(buf, lane, j)));
-          f[4 * j] += r.x, f[4 * j + 1] += r.y, f[4 * j + 2] += r.z, f[4 * j + 3] += r.w;
-        }
-        __syncwarp();
-      };
       auto store_rows = [&](int c, const float (&f)[16]) {    // this thread's row chunk -> global
         if (a.out) {                                          // fp32 rows, coalesced through the buffer
 #pragma unroll
@@ -442,13 +439,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         return *reinterpret_cast<const float4*>(p + 4 * j);
       };
 
-      if (a.residual && rows_live && part < n_chunks) load_res(part);   // in flight while the accumulator is computed
       mbar_wait(smem_u32(&s_tfull[acc]), (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       if (ew == 0 && lane == 0) trace_event(a, 2, 2 * it);
 
       float sum = 0.f, sumsq = 0.f;
-      // ---- pass A: acc + bias (+ residual); LayerNorm: statistics, row parked back in TMEM
+      // ---- pass A: acc (+ residual, already in the accumulator) + bias; LayerNorm: row statistics only
       //              otherwise: activation and store
       for (int c = part; c < n_chunks; c += 4) {
         uint32_t v[16];
@@ -462,18 +458,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           f[4 * j] = __uint_as_float(v[4 * j]) + b4.x, f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
           f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z, f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
         }
-        if (a.residual) {
-          add_res(f);                                         // consumes rr
-          if (c + 4 < n_chunks) load_res(c + 4);              // the next chunk's loads fly during this chunk's tail
-        }
         if (a.ln) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             sum += f[j];
             sumsq = fmaf(f[j], f[j], sumsq);
-            v[j] = __float_as_uint(f[j]);
           }
-          tmem_st16(tbase + (uint32_t)(c * kChunk), v);
         } else if (a.planes) {
           // fp16 head-major planes: chunk c of the row is half (c & 1) of head (n0 / 32 + c / 2) of token (row % Nv)
           // in group row / Nv
@@ -524,15 +514,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             uint32_t v[16];
             tmem_ld16(tbase + (uint32_t)(c * kChunk), v);
             float f[16];
+            const float* bias = s_par + n0 + c * kChunk;
             const float* gam = s_par + a.N + n0 + c * kChunk;
             const float* bet = s_par + 2 * a.N + n0 + c * kChunk;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 g4 = params4(gam, j), b4 = params4(bet, j);
-              f[4 * j] = (__uint_as_float(v[4 * j]) - mean) * rstd * g4.x + b4.x;
-              f[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * g4.y + b4.y;
-              f[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) - mean) * rstd * g4.z + b4.z;
-              f[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) - mean) * rstd * g4.w + b4.w;
+              const float4 g4 = params4(gam, j), b4 = params4(bet, j), c4 = params4(bias, j);
+              f[4 * j] = (__uint_as_float(v[4 * j]) + c4.x - mean) * rstd * g4.x + b4.x;
+              f[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) + c4.y - mean) * rstd * g4.y + b4.y;
+              f[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) + c4.z - mean) * rstd * g4.z + b4.z;
+              f[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + c4.w - mean) * rstd * g4.w + b4.w;
             }
             store_rows(c, f);
           }
@@ -611,7 +602,7 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   // cluster size (streaming W only): the W k-block is split into `cs` slices of whole 8-row swizzle groups
   a.cs = a.w_res ? 1 : g_gemm_cluster;
   while (a.cs > 1 && ((a.BN / a.cs) % 8 != 0 || a.BN % a.cs != 0 || a.n_tiles_m < a.cs)) a.cs >>= 1;
-  CUtensorMap ma, mw;
+  CUtensorMap ma, mw, mr;
   const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)K * esize};
@@ -622,6 +613,15 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)K * esize};
     const uint32_t box[2] = {(uint32_t)kb_elems, (uint32_t)(a.BN / a.cs)};
     if (int rc = make_tensor_map(&mw, dt, 2, W, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  }
+  a.res_chunks = 0;
+  mr = ma;
+  if (residual) {   // fp32 boxes of 32 columns x 128 rows, laid out in shared memory like a TF32 A k-block
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, str[1] = {(uint64_t)ldr * 4};
+    const uint32_t box[2] = {32, kBM};
+    if (int rc = make_tensor_map(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, residual, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+    a.res_chunks = a.BN / 32;
   }
   a.balanced = a.n_tiles_n == 1 && a.cs == 1 && M >= 4 * kNumSMs;
   // ring depths: W resident or shallow, A as deep as the 227 KB of shared memory allow (up to 8)
@@ -666,7 +666,7 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   int clusters = max_clusters[a.cs];
   if (clusters > n_groups && !a.balanced) clusters = n_groups;
   cfg.gridDim = dim3(clusters * a.cs);
-  if (cudaLaunchKernelEx(&cfg, gemm_tf32_kernel, a, ma, mw) != cudaSuccess) {
+  if (cudaLaunchKernelEx(&cfg, gemm_tf32_kernel, a, ma, mw, mr) != cudaSuccess) {
     set_error("%s: launch failed: %s", fn, cudaGetErrorString(cudaGetLastError()));
     return UB_ECUDA;
   }

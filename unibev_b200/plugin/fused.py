@@ -123,8 +123,8 @@ class FusedEncoder:
         self.tf32 = precision == 'tf32'
         self.fast_sampling = self.tf32      # window-staged fp16 sampling kernels where the shape is covered
         self.tc_gemm = self.tf32            # hand-written tcgen05 GEMM with fused epilogues where the shape is covered
-        # LayerNorm inside the GEMM epilogue (else GEMM + one streaming LN pass)
-        self.fuse_ln = os.environ.get('UB_FUSE_LN', '0') == '1'
+        # residual + LayerNorm inside the GEMM (residual preloaded into the accumulator; else GEMM + one streaming LN pass)
+        self.fuse_ln = os.environ.get('UB_FUSE_LN', '1') == '1'
         # sampled rows leave the window kernels as fp16 (the A operand of the fp16 output projection)
         self.half_samples = os.environ.get('UB_HALF_SAMPLES', '1') == '1' 
         self._w = {}
@@ -163,6 +163,15 @@ class FusedEncoder:
                     o16 = torch.empty(o.shape, device=o.device, dtype=torch.float16) if want16 else None
                     return ops.add_layernorm(o, ln[0], ln[1], residual=residual, eps=ln[2], out=o, out16=o16), o16
                 if x16 is not None and w16 is not None:
+                    N = w16.shape[0]
+                    if only16 and N == 512 and residual is None and ln is None and out is None:
+                        # two column halves, each with its weight tile resident in shared memory (a 512-row W does
+                        # not fit and would be re-streamed from L2 for every row tile)
+                        o16 = torch.empty(x16.shape[0], N, device=x16.device, dtype=torch.float16)
+                        for h0 in (0, 256):
+                            ops.linear_f16(x16, w16[h0:h0 + 256], b[h0:h0 + 256], relu=relu, fp32_out=False,
+                                           out16=o16[:, h0:h0 + 256])
+                        return None, o16
                     return ops.linear_f16(x16, w16, b, residual=residual, relu=relu, ln=ln, out=out,
                                           fp32_out=not only16, f16_out=want16 or only16)
                 if x32 is not None and not only16:
