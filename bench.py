@@ -252,11 +252,11 @@ def main():
 
     # ---- end to end through the public streaming API with pinned HOST buffers -------------------------------
     # every step: H2D of that step's feature tensors + calibration, encode, D2H of fused_bev_embed into pinned
-    # host memory; FramePipeline overlaps the copies of neighbouring steps with the kernels (3 streams, 2 slots)
+    # host memory; FramePipeline overlaps the copies of neighbouring steps with the kernels (3 streams, 3 slots)
     h0 = host_sets[0]
     pipe = FramePipeline(model, bev_q, h0['bev_h'], h0['bev_w'], bev_pos=dev_sets[0]['bev_pos'],
                          img_shape=tuple(h0['img_feats'][0].shape), pts_shape=tuple(h0['pts_feats'][0].shape),
-                         img_hw=img_hw, depth=2, device=dev, graphs=use_graphs)
+                         img_hw=img_hw, depth=3, device=dev, graphs=use_graphs)
 
     def e2e_run(steps):
         barrier()
@@ -268,9 +268,10 @@ def main():
         for i in range(steps):
             h = host_sets[i % N_INPUT_SETS]
             t = pipe.submit(h['img_feats'][0], h['pts_feats'][0], h['img_metas'])
-            if t >= 1:
-                checksum += float(pipe.result(t - 1)[0, 0, 0])       # the host reads every step's result
-        checksum += float(pipe.result(pipe.n_submitted - 1)[0, 0, 0])
+            if t >= 2:                                               # the host reads every step's result, two steps
+                checksum += float(pipe.result(t - 2)[0, 0, 0])       # behind the submit front (three slots in flight)
+        for t in range(max(0, pipe.n_submitted - 2), pipe.n_submitted):
+            checksum += float(pipe.result(t)[0, 0, 0])
         for sl in pipe.slots:
             cur.wait_event(sl.copied_out)
         e1.record(cur)

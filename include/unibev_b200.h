@@ -185,6 +185,13 @@ int ub_cnw_fuse(const float* img, const float* pts, const float* w_img, const fl
  * embed_a / embed_b may be NULL. */
 int ub_flatten_feats(const float* in, const float* embed_a, int n_a, const float* embed_b, float* out,
                      int G, int C, int HW, ub_stream_t stream);
+/* The same with an fp16 copy out16 (G, HW, C) next to / instead of the fp32 `out` (either may be NULL): the A operand
+ * of the fp16 value projection (ub_linear_f16). */
+int ub_flatten_feats16(const float* in, const float* embed_a, int n_a, const float* embed_b, float* out, void* out16,
+                       int G, int C, int HW, ub_stream_t stream);
+/* BEV query table (rows, C) repeated for the B samples of a batch (transformer_fusion.py:493-498): out32 (B, rows, C)
+ * fp32 and / or out16 (B, rows, C) fp16 (either may be NULL).  C % 8 == 0. */
+int ub_broadcast_rows(const float* src, int64_t rows, int C, int B, float* out32, void* out16, ub_stream_t stream);
 
 /* ---- [R8] LiDAR hard voxelisation (integer index path, bit-exact with the sequential CPU algorithm) ----
  * points (N, C) fp32 with x, y, z in columns 0..2 (C >= 3).  voxel_size (3) and pc_range (6) are HOST arrays

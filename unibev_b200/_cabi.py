@@ -38,6 +38,8 @@ PROTOTYPES = {
     'ub_add_layernorm16': ([_p] * 7 + [_i64, _i, _f, _p], _i),
     'ub_cnw_fuse': ([_p] * 8 + [_i64, _i, _i, _i, _i, _i, _p], _i),
     'ub_flatten_feats': ([_p, _p, _i, _p, _p, _i, _i, _i, _p], _i),
+    'ub_flatten_feats16': ([_p, _p, _i, _p, _p, _p, _i, _i, _i, _p], _i),
+    'ub_broadcast_rows': ([_p, _i64, _i, _i, _p, _p, _p], _i),
     'ub_voxelize_workspace_bytes': ([_i, ctypes.POINTER(ctypes.c_size_t)], _i),
     'ub_hard_voxelize': ([_p, _i, _i, ctypes.POINTER(_f), ctypes.POINTER(_f), _i, _i, _p, _p, _p, _p, _p,
                           ctypes.c_size_t, _p], _i),

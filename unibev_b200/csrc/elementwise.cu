@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) cnw_fuse_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) flatten_feats_kernel(const float* __restrict__ in,
                                                             const float* __restrict__ embed_a, int n_a,
                                                             const float* __restrict__ embed_b, float* __restrict__ out,
-                                                            int C, int HW) {
+                                                            __half* __restrict__ out16, int C, int HW) {
   __shared__ float tile[32][33];
   const int g = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) flatten_feats_kernel(const float* __restr
     tile[ty + j][tx] = (c < C && p < HW) ? __ldg(src + (int64_t)c * HW + p) : 0.f;
   }
   __syncthreads();
-  float* dst = out + (int64_t)g * HW * C;
+  const int64_t dst0 = (int64_t)g * HW * C;
   const int c = c0 + tx;
   float e1 = 0.f, e2 = 0.f;
   if (c < C) {
@@ -179,7 +179,32 @@ __global__ void __launch_bounds__(256) flatten_feats_kernel(const float* __restr
       float v = tile[tx][ty + j];
       if (embed_a) v = __fadd_rn(v, e1);
       if (embed_b) v = __fadd_rn(v, e2);
-      dst[(int64_t)p * C + c] = v;
+      if (out) out[dst0 + (int64_t)p * C + c] = v;
+      if (out16) out16[dst0 + (int64_t)p * C + c] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    }
+  }
+}
+
+// src (rows, C) -> out32 / out16 (B, rows, C): the BEV query table repeated for every sample of the batch
+// (transformer_fusion.py:493-498 `bev_queries.unsqueeze(1).repeat(1, bs, 1)`), with the fp16 copy the first
+// projections read.  Thread = 8 channels of one source row.
+__global__ void __launch_bounds__(256) broadcast_rows_kernel(const float* __restrict__ src, int64_t n8, int B,
+                                                             float* __restrict__ out32, __half* __restrict__ out16) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    uint4 h;
+    const float lim = 65504.f;
+    auto pk = [lim](float x, float y) {
+      const __half2 t = __floats2half2_rn(fminf(fmaxf(x, -lim), lim), fminf(fmaxf(y, -lim), lim));
+      return *reinterpret_cast<const uint32_t*>(&t);
+    };
+    h.x = pk(a.x, a.y), h.y = pk(a.z, a.w), h.z = pk(b.x, b.y), h.w = pk(b.z, b.w);
+    for (int r = 0; r < B; ++r) {
+      if (out32) {
+        st_stream4(out32 + (r * n8 + i) * 8, a);
+        st_stream4(out32 + (r * n8 + i) * 8 + 4, b);
+      }
+      if (out16) reinterpret_cast<uint4*>(out16)[r * n8 + i] = h;
     }
   }
 }
@@ -242,12 +267,33 @@ extern "C" int ub_cnw_fuse(const float* img, const float* pts, const float* w_im
   return check_launch("ub_cnw_fuse");
 }
 
-extern "C" int ub_flatten_feats(const float* in, const float* embed_a, int n_a, const float* embed_b, float* out, int G,
-                                int C, int HW, ub_stream_t stream) {
-  UB_REQUIRE(in && out, "ub_flatten_feats: null pointer");
+extern "C" int ub_flatten_feats16(const float* in, const float* embed_a, int n_a, const float* embed_b, float* out,
+                                  void* out16, int G, int C, int HW, ub_stream_t stream) {
+  UB_REQUIRE(in && (out || out16), "ub_flatten_feats: null pointer");
   UB_REQUIRE(G > 0 && G <= 65535 && C > 0 && HW > 0, "ub_flatten_feats: bad shape (G=%d C=%d HW=%d)", G, C, HW);
   UB_REQUIRE(embed_a == nullptr || n_a > 0, "ub_flatten_feats: embed_a given with n_a=%d", n_a);
   dim3 grid((HW + 31) / 32, (C + 31) / 32, G);
-  flatten_feats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, embed_a, n_a > 0 ? n_a : 1, embed_b, out, C, HW);
+  flatten_feats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, embed_a, n_a > 0 ? n_a : 1, embed_b, out,
+                                                               reinterpret_cast<__half*>(out16), C, HW);
   return check_launch("ub_flatten_feats");
+}
+
+extern "C" int ub_flatten_feats(const float* in, const float* embed_a, int n_a, const float* embed_b, float* out, int G,
+                                int C, int HW, ub_stream_t stream) {
+  UB_REQUIRE(out, "ub_flatten_feats: null pointer");
+  return ub_flatten_feats16(in, embed_a, n_a, embed_b, out, nullptr, G, C, HW, stream);
+}
+
+extern "C" int ub_broadcast_rows(const float* src, int64_t rows, int C, int B, float* out32, void* out16,
+                                 ub_stream_t stream) {
+  UB_REQUIRE(src && (out32 || out16), "ub_broadcast_rows: null pointer");
+  UB_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && B > 0, "ub_broadcast_rows: need rows > 0, C %% 8 == 0, B > 0");
+  UB_REQUIRE_ALIGNED16(src);
+  if (out32) UB_REQUIRE_ALIGNED16(out32);
+  if (out16) UB_REQUIRE_ALIGNED16(out16);
+  const int64_t n8 = rows * C / 8;
+  int blocks = (int)((n8 + 255) / 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  broadcast_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, n8, B, out32, reinterpret_cast<__half*>(out16));
+  return check_launch("ub_broadcast_rows");
 }

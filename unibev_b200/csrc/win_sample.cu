@@ -631,8 +631,8 @@ struct ImgSmem {
   static size_t total(int win_bytes) { return (size_t)win_bytes + (size_t)kWorkerWarps * warp_bytes; }
 };
 
-// Camera mode.  Units (b, camera, head, chunk of 256 hits) in a contiguous range per CTA; warp w owns hits
-// chunk * 256 + 16 w .. + 15.  Per unit and warp: descriptors from registers prefetched during the previous gather
+// Camera mode.  Units (b, camera, chunk of 256 hits) x head, a contiguous range of chunks per group of H CTAs (one
+// head each, see below); warp w owns hits chunk * 256 + 16 w .. + 15.  Per unit and warp: descriptors from registers prefetched during the previous gather
 // (hit index -> offsets / logits / projected anchor / 1/count straight from global memory), then the gather.
 // The only CTA-wide barrier is at a plane change (the window is reloaded once every warp has left the old plane).
 // Launched twice per call: part 0 stores the contribution of every query's FIRST camera (and zero rows for the
@@ -667,29 +667,34 @@ __global__ void __launch_bounds__(kImgThreads, 1)
         st_stream4(a.out + o, make_float4(0.f, 0.f, 0.f, 0.f));
     }
   }
-  // units: (b, camera, head, chunk of 256 hits), contiguous range per CTA
+  // Units = (b, camera, chunk of 256 hits) x this CTA's head.  CTAs are grouped by H: the H CTAs of a group walk the
+  // same contiguous range of chunks, one head each, at about the same time -- so a query's offset|logit row, its
+  // projected anchors and its hit-list entry come from DRAM once and from L2 for the other heads -- and a CTA
+  // changes its window only when the range crosses into another camera.
   int chunks_tot = 0;
   for (int n = 0; n < a.N; ++n) chunks_tot += (__ldg(cnt_p + n) + kUnitItems - 1) / kUnitItems;
-  const int per_b = chunks_tot * a.H, total = per_b * a.B;
-  const int per = total / gridDim.x, rem = total % gridDim.x;
-  const int u_beg = blockIdx.x * per + min((int)blockIdx.x, rem);
-  const int u_end = u_beg + per + ((int)blockIdx.x < rem ? 1 : 0);
+  const int n_grp = (int)gridDim.x / a.H, cgrp = (int)blockIdx.x / a.H, my_h = (int)blockIdx.x % a.H;
+  if (cgrp >= n_grp) return;
+  const int total = chunks_tot * a.B;
+  const int per = total / n_grp, rem = total % n_grp;
+  const int u_beg = cgrp * per + min(cgrp, rem);
+  const int u_end = u_beg + per + (cgrp < rem ? 1 : 0);
 
   struct Unit {
     int b, n, h, chunk, cnt, plane;
   };
   auto decode = [&](int uu) {
     Unit w;
-    w.b = uu / per_b;
-    int r = uu % per_b;
-    w.n = 0, w.cnt = 0, w.h = 0, w.chunk = 0;
+    w.b = uu / chunks_tot;
+    int r = uu % chunks_tot;
+    w.n = 0, w.cnt = 0, w.h = my_h, w.chunk = 0;
     for (int n = 0; n < a.N; ++n) {
       const int cnt = __ldg(cnt_p + n), ch = (cnt + kUnitItems - 1) / kUnitItems;
-      if (r < ch * a.H) {
-        w.n = n, w.cnt = cnt, w.h = r / ch, w.chunk = r % ch;
+      if (r < ch) {
+        w.n = n, w.cnt = cnt, w.chunk = r;
         break;
       }
-      r -= ch * a.H;
+      r -= ch;
     }
     w.plane = (w.b * a.N + w.n) * a.H + w.h;
     return w;
@@ -1023,7 +1028,7 @@ extern "C" int ub_img_sample_win_fwd(const void* value16, const float* qproj, co
              "%s: ref_cam / qproj not 8-byte aligned", fn);
   if (Dh != 32 || (P != 4 && P != 8) || ld % 4 != 0 || off_col % 4 != 0 || logit_col % 4 != 0 ||
       (reinterpret_cast<uintptr_t>(qproj) & 15u) != 0 || fW + 2 > 256 || fH + 2 > 256 ||
-      (int64_t)(fH + 2) * (fW + 2) > 65535 || (int64_t)B * N * H > (1 << 20)) {
+      (int64_t)(fH + 2) * (fW + 2) > 65535 || (int64_t)B * N * H > (1 << 20) || H > kNumSMs) {
     set_error("%s: shape not covered by the window kernels (Dh=%d P=%d fH=%d fW=%d)", fn, Dh, P, fH, fW);
     return UB_EUNSUPPORTED;
   }

@@ -319,18 +319,31 @@ def cnw_fuse(img, pts, w_img, w_pts, mode, c_flag, l_flag, s_img=None, s_pts=Non
     return out
 
 
-def flatten_feats(feat, embed_a=None, embed_b=None):
-    """feat (..., C, h, w) with G = prod(leading dims) -> (G, h*w, C) + embed_a[g % len(embed_a)] + embed_b."""
+def flatten_feats(feat, embed_a=None, embed_b=None, fp32=True, fp16=False):
+    """feat (..., C, h, w) with G = prod(leading dims) -> (G, h*w, C) + embed_a[g % len(embed_a)] + embed_b.
+    Returns the fp32 tensor, or with ``fp16=True`` the pair (fp32 or None, fp16 copy)."""
     feat = _need(feat, 'feat')
     C, h, w = feat.shape[-3:]
     G = feat.numel() // (C * h * w)
     embed_a = _need(embed_a, 'embed_a') if embed_a is not None else None
     embed_b = _need(embed_b, 'embed_b') if embed_b is not None else None
     n_a = embed_a.shape[0] if embed_a is not None else 0
-    out = torch.empty(G, h * w, C, device=feat.device, dtype=torch.float32)
-    _cabi.check(_cabi.lib().ub_flatten_feats(_ptr(feat), _ptr(embed_a), n_a, _ptr(embed_b), _ptr(out), G, C, h * w,
-                                             _stream()), 'ub_flatten_feats')
-    return out
+    out = torch.empty(G, h * w, C, device=feat.device, dtype=torch.float32) if fp32 or not fp16 else None
+    out16 = torch.empty(G, h * w, C, device=feat.device, dtype=torch.float16) if fp16 else None
+    _cabi.check(_cabi.lib().ub_flatten_feats16(_ptr(feat), _ptr(embed_a), n_a, _ptr(embed_b), _ptr(out), _ptr(out16), G, C,
+                                               h * w, _stream()), 'ub_flatten_feats16')
+    return (out, out16) if fp16 else out
+
+
+def broadcast_rows(src, B, fp32=True, fp16=True):
+    """src (rows, C) -> (fp32 (B, rows, C) or None, fp16 (B, rows, C) or None): the query table repeated per sample."""
+    src = _need(src, 'src')
+    rows, C = src.shape
+    out32 = torch.empty(B, rows, C, device=src.device, dtype=torch.float32) if fp32 else None
+    out16 = torch.empty(B, rows, C, device=src.device, dtype=torch.float16) if fp16 else None
+    _cabi.check(_cabi.lib().ub_broadcast_rows(_ptr(src), rows, C, B, _ptr(out32), _ptr(out16), _stream()),
+                'ub_broadcast_rows')
+    return out32, out16
 
 
 # ---------------------------------------------------------------------------------------------- [R8] voxelize

@@ -129,6 +129,7 @@ class FusedEncoder:
         self.half_samples = os.environ.get('UB_HALF_SAMPLES', '1') == '1' 
         self._w = {}
         self._rn = {}
+        self._pos_w = {}
 
     def _weights(self, name):
         if name not in self._w:
@@ -213,12 +214,13 @@ class FusedEncoder:
                 try:
                     if x16 is not None and w16 is not None:
                         return ops.linear_f16(x16, w16, b, planes_nv=Nv), None
-                    return ops.linear_tf32(x32, self._tf32(w), b, planes_nv=Nv), None
+                    if x32 is not None:
+                        return ops.linear_tf32(x32, self._tf32(w), b, planes_nv=Nv), None
                 except _cabi.UnsupportedShape:
                     pass
-            rows = torch.addmm(b, x32, w.t())
+            rows = torch.addmm(b, self._rows32(x), w.t())
             return ops.value_to_half(rows, G, Nv, H), rows
-        return None, torch.addmm(b, x32, w.t())
+        return None, torch.addmm(b, self._rows32(x), w.t())
 
     def _bev_sample(self, x, w, b, qp, B, bev_h, bev_w, fh, fw, H, P, w16=None):
         """value_proj + BEV-grid sampling: rows x (B*fh*fw, C) un-projected -> sampled (B, Nq, C)."""
@@ -236,29 +238,62 @@ class FusedEncoder:
             finally:
                 _cabi.lib().ub_set_window_round_tf32(0)
         if rows is None:
-            x32 = x[0] if isinstance(x, tuple) else x
-            rows = torch.addmm(b, x32, w.t())
+            rows = torch.addmm(b, self._rows32(x), w.t())
         return ops.bev_sample(rows.view(B, fh * fw, C), qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2)
 
     # one BEV encoder ------------------------------------------------------------------------------
-    def _run_encoder(self, name, x, pos, value_tokens, sample_cross, bev_h, bev_w):
-        """x (B, Nq, C) initial queries; pos (B*Nq, C) or None; value_tokens (rows, C) un-projected features;
-        sample_cross(lw, value_tokens, qp) -> sampled (B, Nq, C)."""
-        layers, pos_w = self._weights(name)
-        B, Nq, C = x.shape
-        x32 = x.reshape(B * Nq, C).contiguous()
-        f16 = self.tc_gemm and C % 64 == 0
-        x = (x32, x32.half() if f16 else None)
-        if f16:
-            value_tokens = (value_tokens, value_tokens.half())   # fp16 copy once per frame, read by every layer
-        pos_q = None
-        if pos is not None:
-            # positional part of every layer's self-attention offset|logit rows, once per frame
-            n_q = [lw.sa_wq.shape[0] for lw in layers]
-            buf = torch.empty(B * Nq, sum(n_q), device=x32.device, dtype=torch.float32)
-            pos_q = buf.split(n_q, dim=1)
-            for lw, dst in zip(layers, pos_q):
+    def _use_f16(self, C):
+        return self.tc_gemm and C % 64 == 0
+
+    def _pos_rows(self, names, pos, rows):
+        """Positional part of every layer's self-attention offset|logit rows, once per frame and for all encoders
+        together: -> {encoder name: [per-layer (rows, n_q) views]}.  pos: fp32 rows or a (fp32, fp16) pair."""
+        if pos is None:
+            return {n: None for n in names}
+        blocks = [(n, lw) for n in names for lw in self._weights(n)[0]]
+        widths = [lw.sa_wq.shape[0] for _, lw in blocks]
+        dev = (pos[1] if isinstance(pos, tuple) and pos[0] is None else (pos[0] if isinstance(pos, tuple) else pos)).device
+        buf = torch.empty(rows, sum(widths), device=dev, dtype=torch.float32)
+        views = buf.split(widths, dim=1)
+        done = False
+        if isinstance(pos, tuple) and pos[1] is not None and all(w == widths[0] and w % 32 == 0 for w in widths):
+            # fp16 operands, as many layers per GEMM as fit one 256-column tile with its weights resident
+            key = tuple(names)
+            if key not in self._pos_w:
+                self._pos_w[key] = torch.cat([lw.sa_wq for _, lw in blocks], 0).half().contiguous()
+            w_all, per = self._pos_w[key], max(1, 256 // widths[0])
+            try:
+                for b0 in range(0, len(blocks), per):
+                    c0, c1 = b0 * widths[0], min(len(blocks), b0 + per) * widths[0]
+                    ops.linear_f16(pos[1], w_all[c0:c1], None, out=buf[:, c0:c1])
+                done = True
+            except _cabi.UnsupportedShape:
+                pass
+        if not done:
+            for (_, lw), dst in zip(blocks, views):
                 self._lin(pos, lw.sa_wq, None, out=dst)
+        out, k = {}, 0
+        for n in names:
+            nl = len(self._weights(n)[0])
+            out[n] = views[k:k + nl]
+            k += nl
+        return out
+
+    def _run_encoder(self, name, queries, B, pos_q, value_tokens, sample_cross, bev_h, bev_w):
+        """queries (Nq, C) the BEV query table (every sample starts from it, transformer_fusion.py:493-498); pos_q: per-layer
+        positional offset|logit rows or None; value_tokens: un-projected feature rows, fp32 or a (fp32 | None, fp16)
+        pair; sample_cross(lw, value_tokens, qp) -> sampled (B, Nq, C)."""
+        layers, pos_w = self._weights(name)
+        Nq, C = queries.shape
+        f16 = self._use_f16(C)
+        if C % 8 == 0:
+            x32, x16 = ops.broadcast_rows(queries.detach(), B, fp32=True, fp16=f16)
+        else:
+            x32 = queries.detach().unsqueeze(0).expand(B, Nq, C).contiguous()
+            x16 = x32.half() if f16 else None
+        x = (x32.view(B * Nq, C), x16.view(B * Nq, C) if f16 else None)
+        if f16 and not isinstance(value_tokens, tuple):
+            value_tokens = (value_tokens, value_tokens.half())   # fp16 copy once per frame, read by every layer
         for i, lw in enumerate(layers):
             h = lw.half() if f16 else None
             # --- BEV self-attention (mmcv MultiScaleDeformableAttention, value = query, 1 level)
@@ -297,14 +332,21 @@ class FusedEncoder:
             q_img, q_pts = bev_queries
         else:
             q_img = q_pts = bev_queries
-        pos = ops.flatten_feats(bev_pos).view(B * Nq, C) if bev_pos is not None else None
+        f16 = self._use_f16(C)
+        pos = None
+        if bev_pos is not None:
+            pos = ops.flatten_feats(bev_pos, fp32=not f16, fp16=f16)
+            pos = tuple(t.view(B * Nq, C) if t is not None else None for t in pos) if f16 else pos.view(B * Nq, C)
         img = pts = None
+        names = (['img_bev_encoder'] if img_feats is not None else []) + (['pts_bev_encoder'] if pts_feats is not None else [])
         with torch.no_grad(), _matmul_precision(self.tf32):
+            pos_q = self._pos_rows(names, pos, B * Nq)
             if img_feats is not None:
                 feat = img_feats[0]
                 _, N, _, fh, fw = feat.shape
                 enc = m.img_bev_encoder
-                tokens = ops.flatten_feats(feat, m.cams_embeds if m.use_cams_embeds else None, m.img_level_embeds[0])
+                tokens = self._tokens(feat, m.cams_embeds if m.use_cams_embeds else None, m.img_level_embeds[0], f16,
+                                      B * N * fh * fw, C)
                 if lidar2img is not None:
                     l2i = lidar2img
                     ih, iw = img_shape
@@ -330,22 +372,34 @@ class FusedEncoder:
                         except _cabi.UnsupportedShape:
                             pass
                     if rows is None:
-                        rows = torch.addmm(lw.ca_bv, tokens[0] if isinstance(tokens, tuple) else tokens, lw.ca_wv.t())
+                        rows = torch.addmm(lw.ca_bv, self._rows32(tokens), lw.ca_wv.t())
                     return ops.img_sample(rows.view(B, N, fh * fw, C), qp, ref_cam, mask, bev_h, bev_w, fh, fw,
                                           lw.H_c, lw.P_c, 0, lw.H_c * lw.P_c * 2)
-                x0 = q_img.detach().unsqueeze(0).expand(B, Nq, C)
-                img = self._run_encoder('img_bev_encoder', x0, pos, tokens.view(B * N * fh * fw, C), cross, bev_h, bev_w)
+                img = self._run_encoder('img_bev_encoder', q_img, B, pos_q['img_bev_encoder'], tokens, cross, bev_h, bev_w)
             if pts_feats is not None:
                 feat = pts_feats[0]
                 _, _, fh, fw = feat.shape
                 enc = m.pts_bev_encoder
-                tokens = ops.flatten_feats(feat, None, m.pts_level_embeds[0])
+                tokens = self._tokens(feat, None, m.pts_level_embeds[0], f16, B * fh * fw, C)
 
                 def cross(lw, tokens, qp, fh=fh, fw=fw):
                     return self._bev_sample(tokens, lw.ca_wv, lw.ca_bv, qp, B, bev_h, bev_w, fh, fw, lw.H_c, lw.P_c,
                                             w16=lw.half()['ca_wv'] if isinstance(tokens, tuple) else None)
-                x0 = q_pts.detach().unsqueeze(0).expand(B, Nq, C)
-                pts = self._run_encoder('pts_bev_encoder', x0, pos, tokens.view(B * fh * fw, C), cross, bev_h, bev_w)
+                pts = self._run_encoder('pts_bev_encoder', q_pts, B, pos_q['pts_bev_encoder'], tokens, cross, bev_h, bev_w)
             return ops.cnw_fuse(img, pts, getattr(m, 'img_channel_weights', None), getattr(m, 'pts_channel_weights', None),
                                 m.fusion_method, m.c_flag, m.l_flag, getattr(m, 'img_spatial_weights', None),
                                 getattr(m, 'pts_spatial_weights', None), m._modal_embed())
+
+    @staticmethod
+    def _tokens(feat, embed_a, embed_b, f16, rows, C):
+        """backbone map -> token rows: fp32, or (None, fp16) when every reader takes fp16 operands"""
+        if f16:
+            _, t16 = ops.flatten_feats(feat, embed_a, embed_b, fp32=False, fp16=True)
+            return (None, t16.view(rows, C))
+        return ops.flatten_feats(feat, embed_a, embed_b).view(rows, C)
+
+    @staticmethod
+    def _rows32(x):
+        if isinstance(x, tuple):
+            return x[0] if x[0] is not None else x[1].float()
+        return x
