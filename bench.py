@@ -348,7 +348,9 @@ def main():
     if dominant:
         k = kernels[dominant]
         try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(dominant) if B == 1 else None
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
+            # the same kernel at the same batch (profiles/ncu_traffic.json, keyed by frames per step)
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(str(B), {}).get(dominant)
         except OSError:
             traffic = None
         roofline = {'bound': 'hbm', 'kernel': {'bev_self': 'bev_sample_win_kernel (BEV self-attn, P=4)',

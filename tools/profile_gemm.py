@@ -41,6 +41,9 @@ def main():
         ('ffn2 plain fp32 out       (K512 N256)', lambda: ops.linear_f16(a512, w[256, 512], bias[256], out=out), 2 * M * 512 + 4 * M * 256),
         ('ffn2 + LN, both outs      (K512 N256)', lambda: ops.linear_f16(a512, w[256, 512], bias[256], residual=r, ln=(g, bt, 1e-5), out=out, out16=o16_256), 2 * M * 512 + 4 * M * 256 * 2 + 2 * M * 256),
     ]
+    if os.environ.get('UB_STREAM_W') == '1':
+        from unibev_b200 import _cabi
+        _cabi.lib().ub_set_gemm_stream_w_with_residual(1)
     for name, fn, nbytes in cases:
         for _ in range(1 if once else 3):
             fn()

@@ -51,6 +51,7 @@ struct GemmArgs {
   int f16;              // operands are fp16 (kind::f16, 64-element k-blocks) instead of fp32 / TF32 (32-element k-blocks)
   int kb_elems;         // elements per k-block: one 128-byte swizzled row
   int balanced;         // contiguous, equally sized row range per CTA (see the kernel)
+  int n_split;          // balanced mode: CTAs per row range, one column tile each (1 or n_tiles_n)
   int w_res;            // the whole W tile stays resident in the W ring (loaded once per CTA)
   __half* out16;        // optional fp16 copy of the result rows (row stride ldc16), the next GEMM's A operand
   int ldc16;
@@ -232,11 +233,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   // in 128-row tiles; the last tile of a range is partial (its extra rows belong to the next CTA and are computed
   // but not stored), so all CTAs carry the same load instead of 2 or 3 whole tiles.
   int r_beg = 0, r_end = a.M, n_iter;
+  // With several column tiles (n_split > 1) the CTAs blockIdx = g * n_split + j share row range g and take column
+  // tile j each: neighbours in time and space, so the second read of an A tile is an L2 hit, and every CTA keeps
+  // its own W tile resident.
+  const int my_n0 = a.balanced ? ((int)blockIdx.x % a.n_split) * a.BN : 0;
   if (a.balanced) {
-    const int base = a.M / (int)gridDim.x, rem = a.M % (int)gridDim.x;
-    r_beg = (int)blockIdx.x * base + min((int)blockIdx.x, rem);
-    r_end = r_beg + base + ((int)blockIdx.x < rem ? 1 : 0);
-    n_iter = (r_end - r_beg + kBM - 1) / kBM;
+    const int n_ranges = (int)gridDim.x / a.n_split, rg = (int)blockIdx.x / a.n_split;
+    const int base = a.M / n_ranges, rem = a.M % n_ranges;
+    r_beg = rg * base + min(rg, rem);
+    r_end = r_beg + base + (rg < rem ? 1 : 0);
+    n_iter = rg < n_ranges ? (r_end - r_beg + kBM - 1) / kBM : 0;
   } else {
     n_iter = cluster_id < n_groups ? (n_groups - cluster_id + n_clusters - 1) / n_clusters : 0;
   }
@@ -245,7 +251,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const int g = cluster_id + i * n_clusters;
     return ((g % groups_m) * cs + rank) * kBM;
   };
-  auto tile_n0 = [&](int i) { return a.balanced ? 0 : ((cluster_id + i * n_clusters) / groups_m) * a.BN; };
+  auto tile_n0 = [&](int i) { return a.balanced ? my_n0 : ((cluster_id + i * n_clusters) / groups_m) * a.BN; };
 
   for (int i = tid; i < a.N; i += kGemmThreads) {
     s_par[i] = a.bias ? a.bias[i] : 0.f;
@@ -309,7 +315,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           for (int kb = 0; kb < k_blocks; ++kb) {
             const uint32_t bar = smem_u32(&s_fw[kb]);
             mbar_arrive_expect_tx(bar, w_bytes);
-            tma_load_2d(sm_w + (uint32_t)kb * w_bytes, &map_w, bar, kb * a.kb_elems, 0);
+            tma_load_2d(sm_w + (uint32_t)kb * w_bytes, &map_w, bar, kb * a.kb_elems, my_n0);
           }
       } else {
         int stage = 0;
@@ -551,6 +557,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 using namespace ub;
 
 static int g_gemm_cluster = 4;
+static int g_gemm_stream_w_res = 1;   // stream W (deeper A / residual ring) when a residual rides the ring: 103 vs 107 us
+extern "C" int ub_set_gemm_stream_w_with_residual(int on) {
+  g_gemm_stream_w_res = on ? 1 : 0;
+  return UB_OK;
+}
 static unsigned long long* g_gemm_trace = nullptr;
 // debugging aid (tools/trace_gemm.py): device buffer of 148 x 128 u64 that the next launches fill with timestamps
 extern "C" int ub_set_gemm_trace(void* buf) {
@@ -597,7 +608,9 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   const size_t fixed = kEpiWarps * kStageBuf + (size_t)3 * N * sizeof(float);
   const size_t budget = 232448 - 5120 - 1024;   // minus static shared memory and slack
   // W resident: every k-block of the (single) W tile stays in shared memory, with at least 3 A stages next to it
-  a.w_res = a.n_tiles_n == 1 && k_blocks <= kMaxStages &&
+  // (with several column tiles: one CTA per column tile and row range, see n_split in the kernel)
+  const bool split_ok = a.n_tiles_n > 1 && kNumSMs % a.n_tiles_n == 0 && M >= 4 * kNumSMs;
+  a.w_res = (a.n_tiles_n == 1 || split_ok) && k_blocks <= kMaxStages && !(residual && ln && g_gemm_stream_w_res) &&
             fixed + (size_t)k_blocks * a.BN * 128 + 3 * (size_t)kBM * 128 <= budget;
   // cluster size (streaming W only): the W k-block is split into `cs` slices of whole 8-row swizzle groups
   a.cs = a.w_res ? 1 : g_gemm_cluster;
@@ -623,7 +636,8 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
       return rc;
     a.res_chunks = a.BN / 32;
   }
-  a.balanced = a.n_tiles_n == 1 && a.cs == 1 && M >= 4 * kNumSMs;
+  a.balanced = (a.n_tiles_n == 1 || (split_ok && a.w_res)) && a.cs == 1 && M >= 4 * kNumSMs;
+  a.n_split = a.balanced ? a.n_tiles_n : 1;
   // ring depths: W resident or shallow, A as deep as the 227 KB of shared memory allow (up to 8)
   a.SW = a.w_res ? k_blocks : (a.BN > 128 ? 3 : 4);
   a.SA = (int)((budget - fixed - (size_t)a.SW * a.BN * 128) / (kBM * 128));

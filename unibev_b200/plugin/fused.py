@@ -126,7 +126,10 @@ class FusedEncoder:
         # residual + LayerNorm inside the GEMM (residual preloaded into the accumulator; else GEMM + one streaming LN pass)
         self.fuse_ln = os.environ.get('UB_FUSE_LN', '1') == '1'
         # sampled rows leave the window kernels as fp16 (the A operand of the fp16 output projection)
-        self.half_samples = os.environ.get('UB_HALF_SAMPLES', '1') == '1' 
+        self.half_samples = os.environ.get('UB_HALF_SAMPLES', '1') == '1'
+        # FFN1 as two launches over column halves, each with its weights resident (measured 82 us vs 91 us for one launch
+        # whose CTA pairs share a row range, M = 160 000)
+        self.ffn1_halves = os.environ.get('UB_FFN1_HALVES', '1') == '1'
         self._w = {}
         self._rn = {}
         self._pos_w = {}
@@ -165,7 +168,7 @@ class FusedEncoder:
                     return ops.add_layernorm(o, ln[0], ln[1], residual=residual, eps=ln[2], out=o, out16=o16), o16
                 if x16 is not None and w16 is not None:
                     N = w16.shape[0]
-                    if only16 and N == 512 and residual is None and ln is None and out is None:
+                    if self.ffn1_halves and only16 and N == 512 and residual is None and ln is None and out is None:
                         # two column halves, each with its weight tile resident in shared memory (a 512-row W does
                         # not fit and would be re-streamed from L2 for every row tile)
                         o16 = torch.empty(x16.shape[0], N, device=x16.device, dtype=torch.float16)
