@@ -31,7 +31,7 @@ def main():
     l2i = torch.from_numpy(np.asarray([m['lidar2img'] for m in metas], dtype=np.float32)).to(dev)
     ref_cam, mask = ops.project_points(l2i, anchor_heights(8, 4).tolist(), synth.PC_RANGE, 928, 1600, 200, 200)
     hits = ops.build_hits(mask)
-    out = torch.empty(B, Nq, C, device=dev)
+    out = torch.empty(B, Nq, C, device=dev, dtype=torch.float16)   # fp16 rows, as the fused pipeline asks for
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for i in range(3):
         h_self = ops.value_to_half(torch.randn(B * Nq, C, device=dev), B, Nq, H)
