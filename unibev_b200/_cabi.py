@@ -50,6 +50,7 @@ _PRIVATE = {
     'ub_set_tuning': ([_i] * 3, _i),
     'ub_set_gemm_cluster': ([_i], _i),
     'ub_set_gemm_trace': ([_p], _i),
+    'ub_set_img_two_windows': ([_i], _i),
     'ub_set_gemm_stream_w_with_residual': ([_i], _i),
 }
 

@@ -49,6 +49,7 @@ constexpr int kTQ = 16;                                    // BEV tile: 16 x 16 
 constexpr int kUnitItems = kWorkerWarps * kWarpItems;      // items per unit
 
 static int g_bev_halo = 0;       // 0 = default (P + 1)
+static int g_img_two_win = 0;    // camera mode: double-buffer the plane windows when two fit
 static int g_bev_round_tf32 = 0; // round the BEV kernels' outputs to TF32 (their consumer is a TF32 GEMM)
 
 // ---------------------------------------------------------------------------------------------------------
@@ -623,12 +624,13 @@ struct ImgWinArgs {
   int B, N, Nq, fH, fW, H, P, D, ld, off_col, logit_col;
   int WW, WH;
   int part;               // 0: first hits (plain stores) + zero rows of the unseen queries; 1: later hits (red.add)
+  int two_win;            // two window buffers fit: the next camera plane streams in behind the current one
 };
 
 template <int PP>
 struct ImgSmem {
   static constexpr int warp_bytes = (Desc<PP>::bytes + kWarpItems * 4 + 127) & ~127;
-  static size_t total(int win_bytes) { return (size_t)win_bytes + (size_t)kWorkerWarps * warp_bytes; }
+  static size_t total(int win_bytes, int n_win) { return (size_t)n_win * win_bytes + (size_t)kWorkerWarps * warp_bytes; }
 };
 
 // Camera mode.  Units (b, camera, chunk of 256 hits) x head, a contiguous range of chunks per group of H CTAs (one
@@ -642,12 +644,13 @@ __global__ void __launch_bounds__(kImgThreads, 1)
     img_sample_win_kernel(const ImgWinArgs a, const __grid_constant__ CUtensorMap map_val) {
   using D = Desc<PP>;
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ __align__(8) uint64_t s_bar[2];
 
   const int win_bytes = (a.WW * a.WH * 64 + 127) & ~127;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t sm_win = smem_u32(smem), bar = smem_u32(&s_bar);
-  const uint32_t sm_w = sm_win + (uint32_t)win_bytes + (uint32_t)warp * ImgSmem<PP>::warp_bytes, sm_idx = sm_w + D::w_bytes;
+  const uint32_t sm_win = smem_u32(smem), bar = smem_u32(&s_bar[0]);
+  const uint32_t sm_w = sm_win + (uint32_t)(a.two_win ? 2 : 1) * (uint32_t)win_bytes + (uint32_t)warp * ImgSmem<PP>::warp_bytes;
+  const uint32_t sm_idx = sm_w + D::w_bytes;
   const uint32_t sm_q = sm_idx + D::idx_bytes;   // query index per item
   const int C = a.H * 32;
 
@@ -702,12 +705,28 @@ __global__ void __launch_bounds__(kImgThreads, 1)
 
   if (u_beg >= u_end) return;   // uniform per CTA
   Unit w = decode(u_beg);
+  // first plane other than `plane` among the units v >= u_from of this CTA's range (-1: none)
+  auto next_plane = [&](int u_from, int plane) {
+    for (int v = u_from; v < u_end; ++v) {
+      const int p = decode(v).plane;
+      if (p != plane) return p;
+    }
+    return -1;
+  };
+  auto load_plane = [&](int buf, int plane) {   // one thread
+    mbar_arrive_expect_tx(bar + 8u * buf, (uint32_t)(a.WW * a.WH * 64));
+    tma_load_4d(sm_win + (uint32_t)buf * win_bytes, &map_val, bar + 8u * buf, 0, -1, -1, plane);
+  };
   if (tid == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar + 8u, 1);
     mbar_init_fence();
     tma_prefetch_desc(&map_val);
-    mbar_arrive_expect_tx(bar, (uint32_t)(a.WW * a.WH * 64));
-    tma_load_4d(sm_win, &map_val, bar, 0, -1, -1, w.plane);
+    load_plane(0, w.plane);
+    if (a.two_win) {
+      const int np = next_plane(u_beg + 1, w.plane);
+      if (np >= 0) load_plane(1, np);
+    }
   }
   __syncthreads();
 
@@ -740,17 +759,27 @@ __global__ void __launch_bounds__(kImgThreads, 1)
         lg[0] = t.x, lg[1] = t.y;
       }
       const float2* rp = reinterpret_cast<const float2*>(a.ref_cam) + (bq * a.N + wu.n) * a.D;
+      if (a.D % PPL == 0) {   // the lane's PPL anchors are consecutive: 16-byte loads
+        const float4* r4 = reinterpret_cast<const float4*>(rp + p0 % a.D);
 #pragma unroll
-      for (int i = 0; i < PPL; ++i) {
-        const float2 t = __ldg(rp + (p0 + i) % a.D);
-        ref[2 * i] = t.x, ref[2 * i + 1] = t.y;
+        for (int i = 0; i < PPL / 2; ++i) {
+          const float4 t = __ldg(r4 + i);
+          ref[4 * i] = t.x, ref[4 * i + 1] = t.y, ref[4 * i + 2] = t.z, ref[4 * i + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+          const float2 t = __ldg(rp + (p0 + i) % a.D);
+          ref[2 * i] = t.x, ref[2 * i + 1] = t.y;
+        }
       }
       ic = __ldg(a.inv_cnt + bq);
     }
   };
   prefetch(w);
 
-  int loaded = w.plane, n_waited = 0;
+  int loaded = w.plane, cur = 0;
+  uint32_t phbits = 0u;   // bit k: phase of window barrier k
   bool fresh = true;
   for (int u = u_beg; u < u_end; ++u) {
     // ---- P1 from the prefetched registers
@@ -777,11 +806,11 @@ __global__ void __launch_bounds__(kImgThreads, 1)
     }
     // ---- P2
     if (fresh) {
-      mbar_wait(bar, (uint32_t)(n_waited & 1));
-      ++n_waited;
+      mbar_wait(bar + 8u * cur, (phbits >> cur) & 1u);
+      phbits ^= 1u << cur;
       fresh = false;
     }
-    gather_warp<PP, ROWB>(sm_w, sm_idx, sm_win + sub * 16u, (uint32_t)a.WW * 64u, grp, half,
+    gather_warp<PP, ROWB>(sm_w, sm_idx, sm_win + (uint32_t)cur * win_bytes + sub * 16u, (uint32_t)a.WW * 64u, grp, half,
                           [&](int item, const float4& o) {
                             int q;
                             asm volatile("ld.shared.b32 %0, [%1];" : "=r"(q) : "r"(sm_q + (uint32_t)item * 4u));
@@ -800,11 +829,17 @@ __global__ void __launch_bounds__(kImgThreads, 1)
                             }
                           });
     __syncwarp();
-    if (u + 1 < u_end && w.plane != loaded) {   // uniform per CTA: every warp leaves the old plane, then reload
+    if (u + 1 < u_end && w.plane != loaded) {   // uniform per CTA: every warp leaves the old plane first
       __syncthreads();
-      if (tid == 0) {
-        mbar_arrive_expect_tx(bar, (uint32_t)(a.WW * a.WH * 64));
-        tma_load_4d(sm_win, &map_val, bar, 0, -1, -1, w.plane);
+      if (a.two_win) {
+        // the next plane is already (being) loaded into the other buffer; the one just left takes the plane after it
+        if (tid == 0) {
+          const int np = next_plane(u + 2, w.plane);
+          if (np >= 0) load_plane(cur, np);
+        }
+        cur ^= 1;
+      } else if (tid == 0) {
+        load_plane(0, w.plane);
       }
       loaded = w.plane;
       fresh = true;
@@ -922,7 +957,9 @@ template <int PP>
 static int launch_img_win(ImgWinArgs& a, const void* value16, cudaStream_t s) {
   const char* fn = "ub_img_sample_win_fwd";
   const int win_bytes = (a.WW * a.WH * 64 + 127) & ~127;
-  const size_t smem = ImgSmem<PP>::total(win_bytes);
+  // off by default: the second 100 KB window leaves the scattered P1 loads almost no L1 (measured 279 vs 196 us)
+  a.two_win = g_img_two_win && ImgSmem<PP>::total(win_bytes, 2) <= kSmemBudget ? 1 : 0;
+  const size_t smem = ImgSmem<PP>::total(win_bytes, a.two_win ? 2 : 1);
   if (smem > kSmemBudget) {
     set_error("%s: plane %d x %d needs %zu bytes of shared memory", fn, a.fH, a.fW, smem);
     return UB_EUNSUPPORTED;
@@ -945,6 +982,11 @@ using namespace ub;
 extern "C" int ub_set_window_halo(int halo) {
   UB_REQUIRE(halo >= 0 && halo <= 64, "ub_set_window_halo: halo must be in 0..64 (0 = default, points + 1)");
   g_bev_halo = halo;
+  return UB_OK;
+}
+
+extern "C" int ub_set_img_two_windows(int on) {
+  g_img_two_win = on ? 1 : 0;
   return UB_OK;
 }
 
