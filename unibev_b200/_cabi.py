@@ -51,6 +51,8 @@ _PRIVATE = {
     'ub_set_gemm_cluster': ([_i], _i),
     'ub_set_gemm_trace': ([_p], _i),
     'ub_set_img_two_windows': ([_i], _i),
+    'ub_set_img_stage': ([_i], _i),
+    'ub_set_img_vec_ref': ([_i], _i),
     'ub_set_gemm_stream_w_with_residual': ([_i], _i),
 }
 
@@ -75,6 +77,11 @@ def lib():
                 fn.argtypes = argtypes
                 fn.restype = restype
         _lib = handle
+        # tuning knobs for A/B runs (defaults are the measured-best settings)
+        for env, fn in (('UB_IMG_STAGE', 'ub_set_img_stage'), ('UB_IMG_TWO_WINDOWS', 'ub_set_img_two_windows'),
+                        ('UB_IMG_VECREF', 'ub_set_img_vec_ref')):
+            if env in os.environ:
+                getattr(handle, fn)(int(os.environ[env]))
     return _lib
 
 

@@ -50,6 +50,9 @@ constexpr int kUnitItems = kWorkerWarps * kWarpItems;      // items per unit
 
 static int g_bev_halo = 0;       // 0 = default (P + 1)
 static int g_img_two_win = 0;    // camera mode: double-buffer the plane windows when two fit
+static int g_img_vec_ref = 1;
+static int g_img_stage = 0;      // camera mode: P1 inputs through bulk async copies instead of register prefetch; off:
+                                 // 768 small copies per unit cost the TMA engine more than the LSU loads (247 vs 218 us)
 static int g_bev_round_tf32 = 0; // round the BEV kernels' outputs to TF32 (their consumer is a TF32 GEMM)
 
 // ---------------------------------------------------------------------------------------------------------
@@ -625,13 +628,27 @@ struct ImgWinArgs {
   int WW, WH;
   int part;               // 0: first hits (plain stores) + zero rows of the unseen queries; 1: later hits (red.add)
   int two_win;            // two window buffers fit: the next camera plane streams in behind the current one
+  int vec_ref;            // anchors of a lane are consecutive and may be read with 16-byte loads
 };
 
 template <int PP>
 struct ImgSmem {
-  static constexpr int warp_bytes = (Desc<PP>::bytes + kWarpItems * 4 + 127) & ~127;
-  static size_t total(int win_bytes, int n_win) { return (size_t)n_win * win_bytes + (size_t)kWorkerWarps * warp_bytes; }
+  static constexpr int desc_bytes = (Desc<PP>::bytes + kWarpItems * 4 + 127) & ~127;
+  // staged P1 inputs of the warp's 16 items: offsets (PP x 8 B), logits (PP x 4 B), projected anchors (up to 8 x 8 B)
+  static constexpr int slice_off = kWarpItems * PP * 8, slice_lg = kWarpItems * PP * 4, slice_ref = kWarpItems * 64;
+  static constexpr int slice_bytes = slice_off + slice_lg + slice_ref;
+  __host__ __device__ static constexpr int warp_bytes(bool stage) { return desc_bytes + (stage ? slice_bytes : 0); }
+  static size_t total(int win_bytes, int n_win, bool stage) {
+    return (size_t)n_win * win_bytes + (size_t)kWorkerWarps * warp_bytes(stage);
+  }
 };
+
+// global -> shared bulk copy (TMA engine, no tensor map); completes `bar` with `bytes`.  16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
 
 // Camera mode.  Units (b, camera, chunk of 256 hits) x head, a contiguous range of chunks per group of H CTAs (one
 // head each, see below); warp w owns hits chunk * 256 + 16 w .. + 15.  Per unit and warp: descriptors from registers prefetched during the previous gather
@@ -639,18 +656,25 @@ struct ImgSmem {
 // The only CTA-wide barrier is at a plane change (the window is reloaded once every warp has left the old plane).
 // Launched twice per call: part 0 stores the contribution of every query's FIRST camera (and zero rows for the
 // queries no camera sees), part 1 accumulates the remaining (camera, query) pairs on top.
-template <int PP, int ROWB>
+// STAGE: the hit-ordered P1 inputs (offset / logit pieces of the query's GEMM row, projected anchors) are brought into
+// a per-warp shared-memory slice by bulk async copies one unit ahead (TMA engine: they cost no LSU / L1 wavefronts and
+// no registers); otherwise they are prefetched into registers with ordinary loads.
+template <int PP, int ROWB, bool STAGE>
 __global__ void __launch_bounds__(kImgThreads, 1)
     img_sample_win_kernel(const ImgWinArgs a, const __grid_constant__ CUtensorMap map_val) {
   using D = Desc<PP>;
+  using SM = ImgSmem<PP>;
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ __align__(8) uint64_t s_bar[2], s_qp[kWorkerWarps];
 
   const int win_bytes = (a.WW * a.WH * 64 + 127) & ~127;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sm_win = smem_u32(smem), bar = smem_u32(&s_bar[0]);
-  const uint32_t sm_w = sm_win + (uint32_t)(a.two_win ? 2 : 1) * (uint32_t)win_bytes + (uint32_t)warp * ImgSmem<PP>::warp_bytes;
+  const uint32_t sm_w = sm_win + (uint32_t)(a.two_win ? 2 : 1) * (uint32_t)win_bytes + (uint32_t)warp * SM::warp_bytes(STAGE);
   const uint32_t sm_idx = sm_w + D::w_bytes;
+  const uint32_t sl_off = sm_w + SM::desc_bytes, sl_lg = sl_off + SM::slice_off, sl_ref = sl_lg + SM::slice_lg;
+  const uint32_t bar_qp = smem_u32(&s_qp[warp]);
+  const uint32_t ref_bytes = (uint32_t)a.D * 8u;      // per item (a multiple of 16 in STAGE mode)
   const uint32_t sm_q = sm_idx + D::idx_bytes;   // query index per item
   const int C = a.H * 32;
 
@@ -720,6 +744,7 @@ __global__ void __launch_bounds__(kImgThreads, 1)
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_init(bar + 8u, 1);
+    for (int i = 0; i < kWorkerWarps; ++i) mbar_init(smem_u32(&s_qp[i]), 1);
     mbar_init_fence();
     tma_prefetch_desc(&map_val);
     load_plane(0, w.plane);
@@ -735,9 +760,12 @@ __global__ void __launch_bounds__(kImgThreads, 1)
   const int grp = lane >> 3, sub = lane & 7, half = sub >> 2, cq = sub & 3;
   float off[PPL * 2], lg[PPL], ref[PPL * 2], ic;
   int qq;
-  auto prefetch = [&](const Unit& wu) {
+  auto lookup = [&](const Unit& wu) {   // the query of this lane pair's item in unit wu, or -1
     const int ord = wu.chunk * kUnitItems + warp * kWarpItems + item_l;
-    qq = ord < wu.cnt ? __ldg(a.hit_idx + (int64_t)wu.n * a.Nq + (a.part ? a.Nq - 1 - ord : ord)) : -1;
+    return ord < wu.cnt ? __ldg(a.hit_idx + (int64_t)wu.n * a.Nq + (a.part ? a.Nq - 1 - ord : ord)) : -1;
+  };
+  auto prefetch = [&](const Unit& wu) {  // !STAGE: everything P1 needs into registers
+    qq = lookup(wu);
     ic = 0.f;
 #pragma unroll
     for (int i = 0; i < PPL; ++i) off[2 * i] = 0.f, off[2 * i + 1] = 0.f, lg[i] = 0.f, ref[2 * i] = 0.f, ref[2 * i + 1] = 0.f;
@@ -759,7 +787,7 @@ __global__ void __launch_bounds__(kImgThreads, 1)
         lg[0] = t.x, lg[1] = t.y;
       }
       const float2* rp = reinterpret_cast<const float2*>(a.ref_cam) + (bq * a.N + wu.n) * a.D;
-      if (a.D % PPL == 0) {   // the lane's PPL anchors are consecutive: 16-byte loads
+      if (a.vec_ref) {   // the lane's PPL anchors are consecutive: 16-byte loads
         const float4* r4 = reinterpret_cast<const float4*>(rp + p0 % a.D);
 #pragma unroll
         for (int i = 0; i < PPL / 2; ++i) {
@@ -776,15 +804,66 @@ __global__ void __launch_bounds__(kImgThreads, 1)
       ic = __ldg(a.inv_cnt + bq);
     }
   };
-  prefetch(w);
+  // STAGE: bulk copies of unit wu's P1 inputs into the warp's slice (even lane of a pair: offsets, odd lane: logits and
+  // anchors); lane 0 posts the byte count of the warp's valid items
+  auto issue = [&](const Unit& wu, int q) {
+    const int valid = min(kWarpItems, max(0, wu.cnt - (wu.chunk * kUnitItems + warp * kWarpItems)));
+    if (lane == 0) mbar_arrive_expect_tx(bar_qp, (uint32_t)valid * ((uint32_t)PP * 12u + ref_bytes));
+    if (q >= 0) {
+      const int64_t bq = (int64_t)wu.b * a.Nq + q;
+      const float* rowp = a.qproj + bq * a.ld;
+      if ((lane & 1) == 0) {
+        bulk_g2s(sl_off + (uint32_t)item_l * (PP * 8), rowp + a.off_col + wu.h * PP * 2, PP * 8, bar_qp);
+      } else {
+        bulk_g2s(sl_lg + (uint32_t)item_l * (PP * 4), rowp + a.logit_col + wu.h * PP, PP * 4, bar_qp);
+        bulk_g2s(sl_ref + (uint32_t)item_l * 64u, a.ref_cam + ((bq * a.N + wu.n) * a.D) * 2, ref_bytes, bar_qp);
+      }
+    }
+  };
+  int qn = -1;        // STAGE: query of the item in the NEXT unit
+  float icn = 0.f;    //        and its 1 / count
+  if (STAGE) {
+    qq = lookup(w);
+    issue(w, qq);
+    ic = qq >= 0 ? __ldg(a.inv_cnt + (int64_t)w.b * a.Nq + qq) : 0.f;
+    if (u_beg + 1 < u_end) qn = lookup(decode(u_beg + 1));
+  } else {
+    prefetch(w);
+  }
 
   int loaded = w.plane, cur = 0;
   uint32_t phbits = 0u;   // bit k: phase of window barrier k
   bool fresh = true;
   for (int u = u_beg; u < u_end; ++u) {
-    // ---- P1 from the prefetched registers
+    // ---- P1 from the staged slice / the prefetched registers
     {
       const bool ok = qq >= 0;
+      if (STAGE) {
+        mbar_wait(bar_qp, (uint32_t)((u - u_beg) & 1));
+        const uint32_t oa = sl_off + (uint32_t)(item_l * PP + p0) * 8u, la = sl_lg + (uint32_t)(item_l * PP + p0) * 4u;
+#pragma unroll
+        for (int i = 0; i < PPL / 2; ++i)
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(off[4 * i]), "=f"(off[4 * i + 1]), "=f"(off[4 * i + 2]), "=f"(off[4 * i + 3])
+                       : "r"(oa + i * 16));
+        if (PPL == 4)
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(lg[0]), "=f"(lg[1]), "=f"(lg[2]), "=f"(lg[PPL - 1]) : "r"(la));
+        else
+          asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(lg[0]), "=f"(lg[1]) : "r"(la));
+        const uint32_t ra = sl_ref + (uint32_t)item_l * 64u;
+        if (a.vec_ref) {
+#pragma unroll
+          for (int i = 0; i < PPL / 2; ++i)
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(ref[4 * i]), "=f"(ref[4 * i + 1]), "=f"(ref[4 * i + 2]), "=f"(ref[4 * i + 3])
+                         : "r"(ra + (uint32_t)(p0 % a.D) * 8u + i * 16));
+        } else {
+#pragma unroll
+          for (int i = 0; i < PPL; ++i)
+            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(ref[2 * i]), "=f"(ref[2 * i + 1])
+                         : "r"(ra + (uint32_t)((p0 + i) % a.D) * 8u));
+        }
+      }
       float aw[PPL];
       softmax_pair<PPL>(lg, ok, ic, aw);
       uint32_t wl[PPL], wr[PPL], idx[PPL];
@@ -802,7 +881,15 @@ __global__ void __launch_bounds__(kImgThreads, 1)
     const Unit w_cur = w;
     if (u + 1 < u_end) {
       w = decode(u + 1);
-      prefetch(w);
+      if (STAGE) {
+        // the slice has been consumed: stream in the next unit's inputs, then look one unit further ahead
+        issue(w, qn);
+        icn = qn >= 0 ? __ldg(a.inv_cnt + (int64_t)w.b * a.Nq + qn) : 0.f;
+        const int q2 = u + 2 < u_end ? lookup(decode(u + 2)) : -1;
+        qq = qn, ic = icn, qn = q2;
+      } else {
+        prefetch(w);
+      }
     }
     // ---- P2
     if (fresh) {
@@ -937,19 +1024,19 @@ static int launch_bev_win(BevWinArgs& a, const void* value16, const float* qproj
   return launch_bev_win_v<PP, 0>(a, mv, mo, ml, smem, s);
 }
 
-template <int PP, int ROWB>
+template <int PP, int ROWB, bool STAGE>
 static int launch_img_win_v(ImgWinArgs& a, const CUtensorMap& mv, size_t smem, cudaStream_t s) {
   const char* fn = "ub_img_sample_win_fwd";
   static size_t configured = 0;
   if (smem > configured) {
-    if (int rc = set_smem(img_sample_win_kernel<PP, ROWB>, smem, fn)) return rc;
+    if (int rc = set_smem(img_sample_win_kernel<PP, ROWB, STAGE>, smem, fn)) return rc;
     configured = smem;
   }
   a.part = 0;
-  img_sample_win_kernel<PP, ROWB><<<kNumSMs, kImgThreads, smem, s>>>(a, mv);
+  img_sample_win_kernel<PP, ROWB, STAGE><<<kNumSMs, kImgThreads, smem, s>>>(a, mv);
   if (int rc = check_launch(fn)) return rc;
   a.part = 1;   // (camera, query) pairs beyond a query's first camera: ~12 % of the pairs on the nuScenes rig
-  img_sample_win_kernel<PP, ROWB><<<kNumSMs, kImgThreads, smem, s>>>(a, mv);
+  img_sample_win_kernel<PP, ROWB, STAGE><<<kNumSMs, kImgThreads, smem, s>>>(a, mv);
   return check_launch(fn);
 }
 
@@ -958,8 +1045,11 @@ static int launch_img_win(ImgWinArgs& a, const void* value16, cudaStream_t s) {
   const char* fn = "ub_img_sample_win_fwd";
   const int win_bytes = (a.WW * a.WH * 64 + 127) & ~127;
   // off by default: the second 100 KB window leaves the scattered P1 loads almost no L1 (measured 279 vs 196 us)
-  a.two_win = g_img_two_win && ImgSmem<PP>::total(win_bytes, 2) <= kSmemBudget ? 1 : 0;
-  const size_t smem = ImgSmem<PP>::total(win_bytes, a.two_win ? 2 : 1);
+  // bulk-staged P1 inputs need 16-byte pieces: an even number of Z-anchors and a 16-byte aligned anchor tensor
+  const bool stage = g_img_stage && a.D % 2 == 0 && (reinterpret_cast<uintptr_t>(a.ref_cam) & 15u) == 0 &&
+                     ImgSmem<PP>::total(win_bytes, 1, true) <= kSmemBudget;
+  a.two_win = g_img_two_win && ImgSmem<PP>::total(win_bytes, 2, stage) <= kSmemBudget ? 1 : 0;
+  const size_t smem = ImgSmem<PP>::total(win_bytes, a.two_win ? 2 : 1, stage);
   if (smem > kSmemBudget) {
     set_error("%s: plane %d x %d needs %zu bytes of shared memory", fn, a.fH, a.fW, smem);
     return UB_EUNSUPPORTED;
@@ -971,8 +1061,9 @@ static int launch_img_win(ImgWinArgs& a, const void* value16, cudaStream_t s) {
   if (int rc = make_tensor_map(&mv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, value16, dims, str, box,
                                CU_TENSOR_MAP_SWIZZLE_NONE))
     return rc;
-  if (a.WW == 52) return launch_img_win_v<PP, 52 * 64>(a, mv, smem, s);  // nuScenes 1600 x 928 / 32 -> 50 + 2
-  return launch_img_win_v<PP, 0>(a, mv, smem, s);
+  if (a.WW == 52)   // nuScenes 1600 x 928 / 32 -> 50 + 2
+    return stage ? launch_img_win_v<PP, 52 * 64, true>(a, mv, smem, s) : launch_img_win_v<PP, 52 * 64, false>(a, mv, smem, s);
+  return stage ? launch_img_win_v<PP, 0, true>(a, mv, smem, s) : launch_img_win_v<PP, 0, false>(a, mv, smem, s);
 }
 
 }  // namespace ub
@@ -987,6 +1078,14 @@ extern "C" int ub_set_window_halo(int halo) {
 
 extern "C" int ub_set_img_two_windows(int on) {
   g_img_two_win = on ? 1 : 0;
+  return UB_OK;
+}
+extern "C" int ub_set_img_vec_ref(int on) {
+  g_img_vec_ref = on ? 1 : 0;
+  return UB_OK;
+}
+extern "C" int ub_set_img_stage(int on) {
+  g_img_stage = on ? 1 : 0;
   return UB_OK;
 }
 
@@ -1080,5 +1179,6 @@ extern "C" int ub_img_sample_win_fwd(const void* value16, const float* qproj, co
   a.B = B, a.N = N, a.Nq = bev_h * bev_w, a.fH = fH, a.fW = fW, a.H = H, a.P = P, a.D = D;
   a.ld = ld, a.off_col = off_col, a.logit_col = logit_col;
   a.WW = fW + 2, a.WH = fH + 2;
+  a.vec_ref = g_img_vec_ref && D % (P / 2) == 0 && (reinterpret_cast<uintptr_t>(ref_cam) & 15u) == 0;
   return P == 8 ? launch_img_win<8>(a, value16, (cudaStream_t)stream) : launch_img_win<4>(a, value16, (cudaStream_t)stream);
 }
