@@ -299,6 +299,90 @@ class BaseTransformerLayer(BaseModule):
             self.norms.append(build_norm_layer(norm_cfg, self.embed_dims)[1])
 
 
+def _base_layer_forward(self, query, key=None, value=None, query_pos=None, key_pos=None, attn_masks=None,
+                        query_key_padding_mask=None, key_padding_mask=None, **kwargs):
+    """mmcv 1.3.17 BaseTransformerLayer.forward (operation dispatch)."""
+    norm_index = attn_index = ffn_index = 0
+    identity = query
+    if attn_masks is None:
+        attn_masks = [None for _ in range(self.num_attn)]
+    for layer in self.operation_order:
+        if layer == 'self_attn':
+            temp_key = temp_value = query
+            query = self.attentions[attn_index](query, temp_key, temp_value, identity if self.pre_norm else None,
+                                                query_pos=query_pos, key_pos=query_pos, attn_mask=attn_masks[attn_index],
+                                                key_padding_mask=query_key_padding_mask, **kwargs)
+            attn_index += 1
+            identity = query
+        elif layer == 'norm':
+            query = self.norms[norm_index](query)
+            norm_index += 1
+        elif layer == 'cross_attn':
+            query = self.attentions[attn_index](query, key, value, identity if self.pre_norm else None,
+                                                query_pos=query_pos, key_pos=key_pos, attn_mask=attn_masks[attn_index],
+                                                key_padding_mask=key_padding_mask, **kwargs)
+            attn_index += 1
+            identity = query
+        elif layer == 'ffn':
+            query = self.ffns[ffn_index](query, identity if self.pre_norm else None)
+            ffn_index += 1
+    return query
+
+
+BaseTransformerLayer.forward = _base_layer_forward
+
+
+@ATTENTION.register_module()
+class MultiheadAttention(BaseModule):
+    """mmcv 1.3.17 MultiheadAttention wrapper (published behaviour)."""
+
+    def __init__(self, embed_dims, num_heads, attn_drop=0., proj_drop=0., dropout_layer=dict(type='Dropout', drop_prob=0.),
+                 init_cfg=None, batch_first=False, **kwargs):
+        super().__init__(init_cfg)
+        dropout_layer = dict(dropout_layer)
+        if 'dropout' in kwargs:
+            attn_drop = kwargs['dropout']
+            dropout_layer['drop_prob'] = kwargs.pop('dropout')
+        self.embed_dims, self.num_heads, self.batch_first = embed_dims, num_heads, batch_first
+        self.attn = nn.MultiheadAttention(embed_dims, num_heads, attn_drop, **kwargs)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.dropout_layer = nn.Dropout(dropout_layer['drop_prob']) if dropout_layer else nn.Identity()
+
+    def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_pos=None, attn_mask=None,
+                key_padding_mask=None, **kwargs):
+        if key is None:
+            key = query
+        if value is None:
+            value = key
+        if identity is None:
+            identity = query
+        if key_pos is None:
+            if query_pos is not None:
+                if query_pos.shape == key.shape:
+                    key_pos = query_pos
+        if query_pos is not None:
+            query = query + query_pos
+        if key_pos is not None:
+            key = key + key_pos
+        if self.batch_first:
+            query, key, value = query.transpose(0, 1), key.transpose(0, 1), value.transpose(0, 1)
+        out = self.attn(query=query, key=key, value=value, attn_mask=attn_mask, key_padding_mask=key_padding_mask)[0]
+        if self.batch_first:
+            out = out.transpose(0, 1)
+        return identity + self.dropout_layer(self.proj_drop(out))
+
+
+@TRANSFORMER_LAYER.register_module()
+class DetrTransformerDecoderLayer(BaseTransformerLayer):
+    def __init__(self, attn_cfgs, feedforward_channels, ffn_dropout=0.0, operation_order=None,
+                 act_cfg=dict(type='ReLU', inplace=True), norm_cfg=dict(type='LN'), ffn_num_fcs=2, **kwargs):
+        super().__init__(attn_cfgs=attn_cfgs, feedforward_channels=feedforward_channels, ffn_dropout=ffn_dropout,
+                         operation_order=operation_order, act_cfg=act_cfg, norm_cfg=norm_cfg, ffn_num_fcs=ffn_num_fcs,
+                         **kwargs)
+        assert len(operation_order) == 6
+        assert set(operation_order) == set(['self_attn', 'norm', 'cross_attn', 'ffn'])
+
+
 class TransformerLayerSequence(BaseModule):
     def __init__(self, transformerlayers=None, num_layers=None, init_cfg=None):
         super().__init__(init_cfg)
@@ -347,6 +431,7 @@ def install_stubs():
     mod('fontTools', ttLib=sys.modules['fontTools.ttLib'])
     mod('matplotlib.pyplot')
     mod('matplotlib', pyplot=sys.modules['matplotlib.pyplot'])
+    mod('cv2')
 
 
 def import_reference():
@@ -615,6 +700,47 @@ def golden_encoder_half(fusion_mod, tag, seed, bs=2, bev_hw=(10, 12), img_fhw=(6
     save('encoder_half_' + tag, **arrays)
 
 
+def golden_decoder(seed=700, C=32, heads=4, layers=3, nq=37, bs=2, bev_hw=(10, 12)):
+    """The reference's own DetectionTransformerDecoder + CustomMSDeformableAttention (decoder.py, unmodified) over the mmcv
+    layer / MultiheadAttention stubs: 3 layers, iterative reference-point refinement through seeded reg branches."""
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        dec_mod = importlib.import_module('refmods.decoder')
+    cfg = dict(type='DetectionTransformerDecoder', num_layers=layers, return_intermediate=True,
+               transformerlayers=dict(
+                   type='DetrTransformerDecoderLayer',
+                   attn_cfgs=[dict(type='MultiheadAttention', embed_dims=C, num_heads=heads, dropout=0.0),
+                              dict(type='CustomMSDeformableAttention', embed_dims=C, num_heads=heads, num_levels=1,
+                                   dropout=0.0)],
+                   ffn_cfgs=dict(type='FFN', embed_dims=C), feedforward_channels=2 * C, ffn_dropout=0.0,
+                   operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm')))
+    dec = TRANSFORMER_LAYER_SEQUENCE.build(copy.deepcopy(cfg))
+    assert type(dec) is dec_mod.DetectionTransformerDecoder
+    assert type(dec.layers[0].attentions[1]) is dec_mod.CustomMSDeformableAttention
+    randomize_(dec, seed)
+    reg = nn.ModuleList([nn.Sequential(nn.Linear(C, C), nn.ReLU(), nn.Linear(C, 10)) for _ in range(layers)])
+    randomize_(reg, seed + 1)
+    dec.eval()
+    g = torch.Generator().manual_seed(seed + 2)
+    Hb, Wb = bev_hw
+    query, query_pos = torch.randn(nq, bs, C, generator=g), torch.randn(nq, bs, C, generator=g)
+    value = torch.randn(Hb * Wb, bs, C, generator=g)
+    ref = torch.rand(bs, nq, 3, generator=g)
+    ref[0, 0, :2] = torch.tensor([0.0, 1.0])          # border reference points
+    ref[0, 1, :2] = torch.tensor([0.999, 0.001])
+    args = dict(key=None, value=value, query_pos=query_pos, spatial_shapes=torch.tensor([[Hb, Wb]]),
+                level_start_index=torch.tensor([0]))
+    with torch.no_grad():
+        inter, inter_ref = dec(query, reference_points=ref, reg_branches=reg, cls_branches=None, **args)
+        inter_noreg, ref_noreg = dec(query, reference_points=ref, reg_branches=None, **args)
+    arrays = dict(query=query, query_pos=query_pos, value=value, reference_points=ref, bev_hw=np.array(bev_hw),
+                  inter_states=inter, inter_references=inter_ref, inter_states_noreg=inter_noreg,
+                  inter_references_noreg=ref_noreg, cfg_json=np.array(__import__('json').dumps(cfg)))
+    arrays.update({'p.' + k: t for k, t in dec.state_dict().items()})
+    arrays.update({'p.reg.' + k: t for k, t in reg.state_dict().items()})
+    save('decoder', **arrays)
+
+
 def main():
     torch.set_num_threads(1)
     fusion_mod, enc_img, sca_img, sca_pts = import_reference()
@@ -630,6 +756,7 @@ def main():
     golden_encoder_half(fusion_mod, 'lc_cnw_dropflags', 600, train_flags=True, drop_modality=1.0)
     golden_encoder_half(fusion_mod, 'lc_cnw_dropdict', 601, train_flags=True,
                         drop_modality=dict(dropout_prob=1.0, lidar_prob=0.0))
+    golden_decoder()
 
 
 if __name__ == '__main__':

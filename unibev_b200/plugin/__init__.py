@@ -2,10 +2,13 @@
 (ATTENTION / TRANSFORMER_LAYER / TRANSFORMER_LAYER_SEQUENCE / TRANSFORMER registries)."""
 from .attention import (MSDeformableAttention3DImg, MSDeformableAttention3DPts, MultiScaleDeformableAttention,
                         SpatialCrossAttentionImg, SpatialCrossAttentionPts)
+from .decoder import (CustomMSDeformableAttention, DetectionTransformerDecoder, DetrTransformerDecoderLayer,
+                      MultiheadAttention)
 from .encoder import FFN, ImgEncoder, ImgLayer, PtsEncoder, PtsLayer
 from .transformer import UniBEVTransformer
 from .voxelize import HardSimpleVFE, Voxelization, voxelize
 
 __all__ = ['MSDeformableAttention3DImg', 'MSDeformableAttention3DPts', 'MultiScaleDeformableAttention',
            'SpatialCrossAttentionImg', 'SpatialCrossAttentionPts', 'FFN', 'ImgEncoder', 'ImgLayer', 'PtsEncoder',
-           'PtsLayer', 'UniBEVTransformer', 'HardSimpleVFE', 'Voxelization', 'voxelize']
+           'PtsLayer', 'UniBEVTransformer', 'HardSimpleVFE', 'Voxelization', 'voxelize', 'CustomMSDeformableAttention',
+           'DetectionTransformerDecoder', 'DetrTransformerDecoderLayer', 'MultiheadAttention']
