@@ -286,11 +286,25 @@ def main():
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
 
-    # ---- per-kernel CUDA-event timing (instrumented eager pass over the same rotating inputs) ---------------
-    records = {}
+    # ---- per-kernel timing ---------------------------------------------------------------------------------
+    # (1) one instrumented eager step: the sampling launches are RECORDED (arguments cloned, so every recorded call owns
+    #     distinct buffers), every other libunibev_b200 op is timed in place with CUDA events (informational: eager
+    #     launches include host gaps);
+    # (2) per sampling kernel, the recorded calls (6 / 3 / 3 per step: one per layer and encoder, ~150-250 MB of distinct
+    #     inputs and outputs each, i.e. more than L2 between two uses of the same buffer) are replayed back to back from a
+    #     CUDA graph and timed with CUDA events on the launching stream: no host gaps, no L2 reuse.
+    records, calls = {}, {}
     op_names = ('bev_sample', 'img_sample', 'bev_sample_win', 'img_sample_win', 'linear_tf32', 'linear_f16',
-                'add_layernorm', 'value_to_half', 'flatten_feats', 'cnw_fuse', 'build_hits', 'project_points')
+                'add_layernorm', 'value_to_half', 'flatten_feats', 'cnw_fuse', 'build_hits', 'project_points',
+                'broadcast_rows')
     real = {n: getattr(ops, n) for n in op_names}
+
+    def clone_arg(v):
+        if isinstance(v, torch.Tensor):
+            return v.clone()
+        if isinstance(v, tuple) and v and all(isinstance(t, torch.Tensor) for t in v):
+            return tuple(t.clone() for t in v)
+        return v
 
     def wrap(name):
         def inner(*a, **k):
@@ -301,7 +315,10 @@ def main():
             else:
                 key = name
             if key in ('bev_self', 'pts_cross', 'img_cross'):
-                real[name](*a, **k)      # queued first, so the timed launch below never waits for the host
+                r = real[name](*a, **k)
+                kk = {x: y for x, y in k.items() if x != 'out'}
+                calls.setdefault(key, []).append((name, tuple(clone_arg(v) for v in a), kk, torch.empty_like(r)))
+                return r
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             r = real[name](*a, **k)
@@ -312,12 +329,39 @@ def main():
     for n in real:
         setattr(ops, n, wrap(n))
     try:
-        for i in range(min(args.steps, 8)):
-            eager_step(dev_sets[i % N_INPUT_SETS])
+        eager_step(dev_sets[0])
         torch.cuda.synchronize()
     finally:
         for n, f in real.items():
             setattr(ops, n, f)
+    sample_us = {}
+    side = torch.cuda.Stream()
+    for key, lst in calls.items():
+        def run_all():
+            for name, a, kk, out in lst:
+                real[name](*a, out=out, **kk)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run_all()
+            run_all()
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(2):
+                    run_all()
+        torch.cuda.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        sample_us[key] = (e0.elapsed_time(e1) * 1e3 / (reps * 2 * len(lst)), len(lst))
+        del g
+    calls.clear()
     clk.__exit__(None, None, None)
     peaks = {}
     try:
@@ -334,16 +378,14 @@ def main():
            'pts_cross': algorithmic_bytes('pts', B, C, H, Nq, 180 * 180, 8),
            'img_cross': algorithmic_bytes('img', B, C, H, Nq, 6 * 1450, 8) + B * (pairs * 4 * 2 * 4 + 2 * Nq * 6)}
     kernels, other = {}, {}
-    frames_timed = min(args.steps, 8)
+    for key, (mean_us, per_step) in sample_us.items():
+        kernels[key] = {'launches_per_step': per_step, 'avg_us': mean_us, 'alg_bytes': alg[key],
+                        'achieved_gbs': alg[key] / mean_us / 1e3, 'frac': alg[key] / mean_us / 1e3 / peak,
+                        'timing': 'CUDA graph of the step\'s recorded launches replayed back to back, CUDA events'}
     for key, evs in records.items():
         us = [a.elapsed_time(b) * 1e3 for a, b in evs]
-        mean_us = sum(us) / len(us)
-        if key in alg:
-            kernels[key] = {'launches': len(us), 'avg_us': mean_us, 'alg_bytes': alg[key],
-                            'achieved_gbs': alg[key] / mean_us / 1e3, 'frac': alg[key] / mean_us / 1e3 / peak}
-        else:
-            other[key] = {'launches_per_step': len(us) / frames_timed, 'avg_us': mean_us}
-    dominant = max(kernels, key=lambda k: kernels[k]['avg_us'] * kernels[k]['launches']) if kernels else None
+        other[key] = {'launches_per_step': len(us), 'avg_us_eager': sum(us) / len(us)}
+    dominant = max(kernels, key=lambda k: kernels[k]['avg_us'] * kernels[k]['launches_per_step']) if kernels else None
     roofline = None
     if dominant:
         k = kernels[dominant]

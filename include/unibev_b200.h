@@ -126,15 +126,18 @@ int ub_set_window_round_tf32(int on);
  * (spatial_cross_attention_img.py:141-152), split by rank: hit_idx (N + 1, Nq) int32, row n = the hits whose lowest
  * seeing camera is n ("first", ascending, from the front) and the other hits of camera n ("later", from the back:
  * hit_idx[n][Nq - 1 - k]); row N = the queries no camera sees.  hit_cnt (2 N + 1) int32 = first counts, later
- * counts, unseen count.  inv_cnt (B, Nq) = 1 / max(1, #cameras whose mask for (b, q) is non-zero) (:209-212). */
-int ub_build_hits(const uint8_t* mask, int* hit_idx, int* hit_cnt, float* inv_cnt, int B, int N, int Nq,
+ * counts, unseen count.  inv_cnt (B, Nq) = 1 / max(1, #cameras whose mask for (b, q) is non-zero) (:209-212).
+ * hit_ic (B, N, Nq) or NULL: inv_cnt in hit-list order (hit_ic[b][n][pos] = inv_cnt[b][hit_idx[n][pos]]), which the
+ * sampling kernel reads coalesced. */
+int ub_build_hits(const uint8_t* mask, int* hit_idx, int* hit_cnt, float* inv_cnt, float* hit_ic, int B, int N, int Nq,
                   ub_stream_t stream);
 /* value16 (B, N, H, fH*fW, 32) fp16; hit_idx / hit_cnt / inv_cnt from ub_build_hits.  Every row of out
  * (B, Nq, H*32) is written: first hits with plain stores (zero rows for unseen queries), later hits accumulated with
  * red.global.add on top (sums over more than three cameras are order-dependent in the last bit).  out_f16 as in
  * ub_bev_sample_win_fwd (later hits are then accumulated in fp16). */
 int ub_img_sample_win_fwd(const void* value16, const float* qproj, const float* ref_cam, const int* hit_idx,
-                          const int* hit_cnt, const float* inv_cnt, void* out, int out_f16, int B, int N, int bev_h,
+                          const int* hit_cnt, const float* inv_cnt, const float* hit_ic /* or NULL */, void* out,
+                          int out_f16, int B, int N, int bev_h,
                           int bev_w, int fH, int fW, int H, int Dh, int P, int D, int ld, int off_col, int logit_col,
                           ub_stream_t stream);
 

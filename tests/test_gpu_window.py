@@ -123,10 +123,14 @@ def _camera_inputs(B, bev_h, bev_w, fh, fw, H, P, seed, perturb=True):
     return l2i, value, qproj, zs
 
 
+def want_inv_of(m):
+    return 1.0 / (m != 0).sum(-1).clamp(min=1).float()
+
+
 def test_build_hits_exact(ops):
     l2i, _, _, zs = _camera_inputs(2, 40, 36, 29, 50, 8, 8, 3)
     _, mask = ops.project_points(l2i.cuda(), zs, [-54, -54, -5, 54, 54, 3], 928, 1600, 40, 36)
-    hit_idx, hit_cnt, inv_cnt = (t.cpu() for t in ops.build_hits(mask))
+    hit_idx, hit_cnt, inv_cnt, hit_ic = (t.cpu() for t in ops.build_hits(mask))
     m = mask.cpu()
     Nq = m.shape[1]
     seen_before = torch.zeros(Nq, dtype=torch.bool)
@@ -139,6 +143,10 @@ def test_build_hits_exact(ops):
         # together: exactly the reference's per-camera list (spatial_cross_attention_img.py:141-152)
         both = torch.cat((hit_idx[n, :n_first], hit_idx[n, Nq - n_later:])).sort().values
         assert torch.equal(both, hit.nonzero().squeeze(1).int())
+        # 1 / count in list order, for both batch items
+        for b in range(m.shape[0]):
+            assert torch.equal(hit_ic[b, n, :n_first], want_inv_of(m)[b, hit_idx[n, :n_first].long()])
+            assert torch.equal(hit_ic[b, n, Nq - n_later:], want_inv_of(m)[b, hit_idx[n, Nq - n_later:].long()])
         seen_before |= hit
     assert torch.equal(hit_idx[6, :int(hit_cnt[12])], (~seen_before).nonzero().squeeze(1).int())
     assert int(hit_cnt[6:12].sum()) > 0 and int(hit_cnt[12]) > 0      # the case has multi-camera and unseen queries

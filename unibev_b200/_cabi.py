@@ -29,8 +29,8 @@ PROTOTYPES = {
     'ub_bev_sample_win_fwd': ([_p] * 3 + [_i] * 12 + [_p], _i),
     'ub_set_window_halo': ([_i], _i),
     'ub_set_window_round_tf32': ([_i], _i),
-    'ub_build_hits': ([_p] * 4 + [_i] * 3 + [_p], _i),
-    'ub_img_sample_win_fwd': ([_p] * 7 + [_i] * 14 + [_p], _i),
+    'ub_build_hits': ([_p] * 5 + [_i] * 3 + [_p], _i),
+    'ub_img_sample_win_fwd': ([_p] * 8 + [_i] * 14 + [_p], _i),
     'ub_linear_tf32': ([_p] * 4 + [_i, _p, _p, _f, _p, _i, _p] + [_i] * 5 + [_p], _i),
     'ub_linear_tf32_dual': ([_p] * 4 + [_i, _p, _p, _f, _p, _i, _p] + [_i] * 5 + [_p], _i),
     'ub_linear_f16': ([_p] * 4 + [_i, _p, _p, _f, _p, _i, _p, _i, _p] + [_i] * 5 + [_p], _i),

@@ -49,6 +49,12 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
                : "l"(p));
   return r;
 }
+// 32 contiguous bytes in one request (LDG.256, sm_100+): p must be 32-byte aligned
+__device__ __forceinline__ void ld_stream8(const float* p, float (&r)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p));
+}
 __device__ __forceinline__ float2 ld_stream2(const float* p) {
   float2 r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));

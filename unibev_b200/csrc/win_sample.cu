@@ -615,11 +615,25 @@ __global__ void __launch_bounds__(1024) build_hits_kernel(const uint8_t* __restr
   }
 }
 
+// 1 / count in hit-list order: hit_ic[b][n][pos] = inv_cnt[b][hit_idx[n][pos]] for the valid positions of row n, so the
+// sampling kernel reads it with the same coalesced access as the hit list (instead of one scattered load per hit).
+__global__ void __launch_bounds__(256) hit_ic_kernel(const int* __restrict__ hit_idx, const int* __restrict__ hit_cnt,
+                                                     const float* __restrict__ inv_cnt, float* __restrict__ hit_ic, int B,
+                                                     int N, int Nq) {
+  const int64_t total = (int64_t)B * N * Nq;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int pos = (int)(i % Nq), n = (int)((i / Nq) % N), b = (int)(i / ((int64_t)Nq * N));
+    if (pos < hit_cnt[n] || pos >= Nq - hit_cnt[N + n])
+      hit_ic[i] = inv_cnt[(int64_t)b * Nq + hit_idx[(int64_t)n * Nq + pos]];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 struct ImgWinArgs {
   const float* qproj;
   const float* ref_cam;   // (B, Nq, N, D, 2)
   const float* inv_cnt;   // (B, Nq)
+  const float* hit_ic;    // (B, N, Nq) 1 / count in hit-list order, or null
   const int* hit_idx;     // (N + 1, Nq): first hits from the front, later hits from the back; row N = unseen queries
   const int* hit_cnt;     // (2 N + 1): first counts, later counts, unseen count
   float* out;             // (B, Nq, H*32) fp32 rows, or null when out16 is set
@@ -629,6 +643,7 @@ struct ImgWinArgs {
   int part;               // 0: first hits (plain stores) + zero rows of the unseen queries; 1: later hits (red.add)
   int two_win;            // two window buffers fit: the next camera plane streams in behind the current one
   int vec_ref;            // anchors of a lane are consecutive and may be read with 16-byte loads
+  int vec8;               // P = 8, D = 4 and 32-byte aligned rows: a lane's offsets / anchors are one 256-bit load each
 };
 
 template <int PP>
@@ -764,19 +779,33 @@ __global__ void __launch_bounds__(kImgThreads, 1)
     const int ord = wu.chunk * kUnitItems + warp * kWarpItems + item_l;
     return ord < wu.cnt ? __ldg(a.hit_idx + (int64_t)wu.n * a.Nq + (a.part ? a.Nq - 1 - ord : ord)) : -1;
   };
+  auto inv_count = [&](const Unit& wu, int q) {   // 1 / #cameras of the item: list-ordered copy when the caller has one
+    if (a.hit_ic) {
+      const int ord = wu.chunk * kUnitItems + warp * kWarpItems + item_l;
+      return ord < wu.cnt ? __ldg(a.hit_ic + ((int64_t)wu.b * a.N + wu.n) * a.Nq + (a.part ? a.Nq - 1 - ord : ord)) : 0.f;
+    }
+    return q >= 0 ? __ldg(a.inv_cnt + (int64_t)wu.b * a.Nq + q) : 0.f;
+  };
   auto prefetch = [&](const Unit& wu) {  // !STAGE: everything P1 needs into registers
     qq = lookup(wu);
-    ic = 0.f;
+    ic = inv_count(wu, qq);
 #pragma unroll
     for (int i = 0; i < PPL; ++i) off[2 * i] = 0.f, off[2 * i + 1] = 0.f, lg[i] = 0.f, ref[2 * i] = 0.f, ref[2 * i + 1] = 0.f;
     if (qq >= 0) {
       const int64_t bq = (int64_t)wu.b * a.Nq + qq;
       const float* rowp = a.qproj + bq * a.ld;
       const float4* op = reinterpret_cast<const float4*>(rowp + a.off_col + (wu.h * PP + p0) * 2);
+      if (PPL == 4 && a.vec8) {
+        float t[8];
+        ld_stream8(reinterpret_cast<const float*>(op), t);
 #pragma unroll
-      for (int i = 0; i < PPL / 2; ++i) {
-        const float4 t = ld_stream4(reinterpret_cast<const float*>(op + i));
-        off[4 * i] = t.x, off[4 * i + 1] = t.y, off[4 * i + 2] = t.z, off[4 * i + 3] = t.w;
+        for (int i = 0; i < 8; ++i) off[i % (PPL * 2)] = t[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < PPL / 2; ++i) {
+          const float4 t = ld_stream4(reinterpret_cast<const float*>(op + i));
+          off[4 * i] = t.x, off[4 * i + 1] = t.y, off[4 * i + 2] = t.z, off[4 * i + 3] = t.w;
+        }
       }
       const float* lp = rowp + a.logit_col + wu.h * PP + p0;
       if (PPL == 4) {
@@ -787,7 +816,12 @@ __global__ void __launch_bounds__(kImgThreads, 1)
         lg[0] = t.x, lg[1] = t.y;
       }
       const float2* rp = reinterpret_cast<const float2*>(a.ref_cam) + (bq * a.N + wu.n) * a.D;
-      if (a.vec_ref) {   // the lane's PPL anchors are consecutive: 16-byte loads
+      if (PPL == 4 && a.vec8) {
+        float t[8];
+        ld_stream8(reinterpret_cast<const float*>(rp), t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ref[i % (PPL * 2)] = t[i];
+      } else if (a.vec_ref) {   // the lane's PPL anchors are consecutive: 16-byte loads
         const float4* r4 = reinterpret_cast<const float4*>(rp + p0 % a.D);
 #pragma unroll
         for (int i = 0; i < PPL / 2; ++i) {
@@ -801,7 +835,6 @@ __global__ void __launch_bounds__(kImgThreads, 1)
           ref[2 * i] = t.x, ref[2 * i + 1] = t.y;
         }
       }
-      ic = __ldg(a.inv_cnt + bq);
     }
   };
   // STAGE: bulk copies of unit wu's P1 inputs into the warp's slice (even lane of a pair: offsets, odd lane: logits and
@@ -825,7 +858,7 @@ __global__ void __launch_bounds__(kImgThreads, 1)
   if (STAGE) {
     qq = lookup(w);
     issue(w, qq);
-    ic = qq >= 0 ? __ldg(a.inv_cnt + (int64_t)w.b * a.Nq + qq) : 0.f;
+    ic = inv_count(w, qq);
     if (u_beg + 1 < u_end) qn = lookup(decode(u_beg + 1));
   } else {
     prefetch(w);
@@ -884,7 +917,7 @@ __global__ void __launch_bounds__(kImgThreads, 1)
       if (STAGE) {
         // the slice has been consumed: stream in the next unit's inputs, then look one unit further ahead
         issue(w, qn);
-        icn = qn >= 0 ? __ldg(a.inv_cnt + (int64_t)w.b * a.Nq + qn) : 0.f;
+        icn = inv_count(w, qn);
         const int q2 = u + 2 < u_end ? lookup(decode(u + 2)) : -1;
         qq = qn, ic = icn, qn = q2;
       } else {
@@ -1142,18 +1175,26 @@ extern "C" int ub_bev_sample_win_fwd(const void* value16, const float* qproj, vo
                 : launch_bev_win<4>(a, value16, qproj, ld, (cudaStream_t)stream);
 }
 
-extern "C" int ub_build_hits(const uint8_t* mask, int* hit_idx, int* hit_cnt, float* inv_cnt, int B, int N, int Nq,
-                             ub_stream_t stream) {
+extern "C" int ub_build_hits(const uint8_t* mask, int* hit_idx, int* hit_cnt, float* inv_cnt, float* hit_ic, int B, int N,
+                             int Nq, ub_stream_t stream) {
   UB_REQUIRE(mask && hit_idx && hit_cnt && inv_cnt, "ub_build_hits: null pointer");
   UB_REQUIRE(B > 0 && N > 0 && N <= 32 && Nq > 0, "ub_build_hits: bad dimension (B=%d N=%d Nq=%d)", B, N, Nq);
   int extra = (int)(((int64_t)B * Nq + 1023) / 1024);
   if (extra > kNumSMs) extra = kNumSMs;
   build_hits_kernel<<<N + 1 + extra, 1024, 0, (cudaStream_t)stream>>>(mask, hit_idx, hit_cnt, inv_cnt, B, N, Nq);
-  return check_launch("ub_build_hits");
+  if (int rc = check_launch("ub_build_hits")) return rc;
+  if (hit_ic) {
+    int blocks = (int)(((int64_t)B * N * Nq + 255) / 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    hit_ic_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(hit_idx, hit_cnt, inv_cnt, hit_ic, B, N, Nq);
+    return check_launch("ub_build_hits");
+  }
+  return UB_OK;
 }
 
 extern "C" int ub_img_sample_win_fwd(const void* value16, const float* qproj, const float* ref_cam, const int* hit_idx,
-                                     const int* hit_cnt, const float* inv_cnt, void* out, int out_f16, int B, int N,
+                                     const int* hit_cnt, const float* inv_cnt, const float* hit_ic, void* out, int out_f16,
+                                     int B, int N,
                                      int bev_h, int bev_w, int fH, int fW, int H, int Dh, int P, int D, int ld, int off_col,
                                      int logit_col, ub_stream_t stream) {
   const char* fn = "ub_img_sample_win_fwd";
@@ -1174,11 +1215,13 @@ extern "C" int ub_img_sample_win_fwd(const void* value16, const float* qproj, co
     return UB_EUNSUPPORTED;
   }
   ImgWinArgs a;
-  a.qproj = qproj, a.ref_cam = ref_cam, a.inv_cnt = inv_cnt, a.hit_idx = hit_idx, a.hit_cnt = hit_cnt;
+  a.qproj = qproj, a.ref_cam = ref_cam, a.inv_cnt = inv_cnt, a.hit_ic = hit_ic, a.hit_idx = hit_idx, a.hit_cnt = hit_cnt;
   a.out = out_f16 ? nullptr : reinterpret_cast<float*>(out), a.out16 = out_f16 ? reinterpret_cast<__half*>(out) : nullptr;
   a.B = B, a.N = N, a.Nq = bev_h * bev_w, a.fH = fH, a.fW = fW, a.H = H, a.P = P, a.D = D;
   a.ld = ld, a.off_col = off_col, a.logit_col = logit_col;
   a.WW = fW + 2, a.WH = fH + 2;
   a.vec_ref = g_img_vec_ref && D % (P / 2) == 0 && (reinterpret_cast<uintptr_t>(ref_cam) & 15u) == 0;
+  a.vec8 = g_img_vec_ref && P == 8 && D == 4 && (reinterpret_cast<uintptr_t>(ref_cam) & 31u) == 0 &&
+           ((reinterpret_cast<uintptr_t>(qproj) + (size_t)off_col * 4) & 31u) == 0 && (ld * 4) % 32 == 0;
   return P == 8 ? launch_img_win<8>(a, value16, (cudaStream_t)stream) : launch_img_win<4>(a, value16, (cudaStream_t)stream);
 }

@@ -157,22 +157,25 @@ def bev_sample_win(value16, qproj, bev_h, bev_w, fH, fW, H, P, off_col, logit_co
 
 def build_hits(mask):
     """mask (B, Nq, N) uint8 -> hit_idx (N + 1, Nq) int32 (rank-split lists, row N = unseen queries), hit_cnt (2N + 1)
-    int32 (first counts, later counts, unseen count), inv_cnt (B, Nq) fp32 (all on the device; see ub_build_hits)."""
+    int32 (first counts, later counts, unseen count), inv_cnt (B, Nq) fp32, hit_ic (B, N, Nq) fp32 = inv_cnt in hit-list
+    order (all on the device; see ub_build_hits)."""
     mask = _need(mask, 'mask', torch.uint8)
     B, Nq, N = mask.shape
     hit_idx = torch.empty(N + 1, Nq, device=mask.device, dtype=torch.int32)
     hit_cnt = torch.empty(2 * N + 1, device=mask.device, dtype=torch.int32)
     inv_cnt = torch.empty(B, Nq, device=mask.device, dtype=torch.float32)
-    _cabi.check(_cabi.lib().ub_build_hits(_ptr(mask), _ptr(hit_idx), _ptr(hit_cnt), _ptr(inv_cnt), B, N, Nq, _stream()),
-                'ub_build_hits')
-    return hit_idx, hit_cnt, inv_cnt
+    hit_ic = torch.empty(B, N, Nq, device=mask.device, dtype=torch.float32)      # inv_cnt in hit-list order
+    _cabi.check(_cabi.lib().ub_build_hits(_ptr(mask), _ptr(hit_idx), _ptr(hit_cnt), _ptr(inv_cnt), _ptr(hit_ic), B, N, Nq,
+                                          _stream()), 'ub_build_hits')
+    return hit_idx, hit_cnt, inv_cnt, hit_ic
 
 
 def img_sample_win(value16, qproj, ref_cam, hits, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out=None,
                    out_dtype=torch.float32):
     """value16 (B, N, H, fH*fW, 32) fp16; hits = build_hits(mask); -> (B, Nq, H*32) fp32."""
     value16, qproj, ref_cam = _need(value16, 'value16', torch.float16), _need(qproj, 'qproj'), _need(ref_cam, 'ref_cam')
-    hit_idx, hit_cnt, inv_cnt = hits
+    hit_idx, hit_cnt, inv_cnt = hits[:3]
+    hit_ic = hits[3] if len(hits) > 3 else None
     B, N, Hh, Nv, Dh = value16.shape
     D = ref_cam.shape[3]
     Nq = bev_h * bev_w
@@ -182,7 +185,8 @@ def img_sample_win(value16, qproj, ref_cam, hits, bev_h, bev_w, fH, fW, H, P, of
     if out is None:
         out = torch.empty(B, Nq, H * Dh, device=qproj.device, dtype=out_dtype)
     _cabi.check(_cabi.lib().ub_img_sample_win_fwd(_ptr(value16), _ptr(qproj), _ptr(ref_cam), _ptr(hit_idx), _ptr(hit_cnt),
-                                                  _ptr(inv_cnt), _ptr(out), int(out.dtype == torch.float16), B, N, bev_h,
+                                                  _ptr(inv_cnt), _ptr(hit_ic), _ptr(out), int(out.dtype == torch.float16), B, N,
+                                                  bev_h,
                                                   bev_w, fH, fW, H, Dh, P, D,
                                                   qproj.shape[2], off_col, logit_col, _stream()),
                 'ub_img_sample_win_fwd')
