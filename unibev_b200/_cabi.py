@@ -50,6 +50,7 @@ _PRIVATE = {
     'ub_set_tuning': ([_i] * 3, _i),
     'ub_set_gemm_cluster': ([_i], _i),
     'ub_set_gemm_trace': ([_p], _i),
+    'ub_set_pdl': ([_i], _i),
     'ub_set_img_two_windows': ([_i], _i),
     'ub_set_img_stage': ([_i], _i),
     'ub_set_img_vec_ref': ([_i], _i),
@@ -79,7 +80,7 @@ def lib():
         _lib = handle
         # tuning knobs for A/B runs (defaults are the measured-best settings)
         for env, fn in (('UB_IMG_STAGE', 'ub_set_img_stage'), ('UB_IMG_TWO_WINDOWS', 'ub_set_img_two_windows'),
-                        ('UB_IMG_VECREF', 'ub_set_img_vec_ref')):
+                        ('UB_IMG_VECREF', 'ub_set_img_vec_ref'), ('UB_PDL', 'ub_set_pdl')):
             if env in os.environ:
                 getattr(handle, fn)(int(os.environ[env]))
     return _lib

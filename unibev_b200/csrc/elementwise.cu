@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(256) flatten_feats_kernel(const float* __restr
                                                             const float* __restrict__ embed_b, float* __restrict__ out,
                                                             __half* __restrict__ out16, int C, int HW) {
   __shared__ float tile[32][33];
+  pdl_trigger();
   const int g = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(256) flatten_feats_kernel(const float* __restr
 // projections read.  Thread = 8 channels of one source row.
 __global__ void __launch_bounds__(256) broadcast_rows_kernel(const float* __restrict__ src, int64_t n8, int B,
                                                              float* __restrict__ out32, __half* __restrict__ out16) {
+  pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
     uint4 h;

@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   if (cs > 1) cluster_sync_all();   // every CTA's barriers exist before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
+  pdl_trigger();   // the next kernel in the stream may be scheduled onto SMs as they drain
   if (a.trace && tid == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -284,6 +285,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     if (lane == 0) {
       tma_prefetch_desc(&map_a);
       if (a.res_chunks) tma_prefetch_desc(&map_r);
+      // A and the residual come from the predecessor kernel (and this kernel's outputs may alias buffers it still
+      // reads): everything up to here -- barriers, TMEM, parameters, the resident weight tile -- overlapped its tail
+      pdl_wait();
       int stage = 0, ev = 0;
       uint32_t phase = 0;
       for (int i = 0; i < n_iter; ++i) {
@@ -661,10 +665,12 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = a.cs, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr, cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 2 : 1;
   // persistent grid: as many clusters as can be resident at once (one CTA per SM; clusters do not span GPCs)
   static int max_clusters[5] = {0, 0, 0, 0, 0};
   static size_t max_clusters_smem[5] = {0, 0, 0, 0, 0};

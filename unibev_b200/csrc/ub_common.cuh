@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 #include "unibev_b200.h"
 
 namespace ub {
@@ -28,6 +30,21 @@ void count_launch();
       return UB_EALIGN;                                                 \
     }                                                                   \
   } while (0)
+
+// Programmatic dependent launch (see pdl_trigger / pdl_wait below): on unless ub_set_pdl(0).
+bool pdl_enabled();
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-serialization attribute when enabled
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -70,6 +87,14 @@ __device__ __forceinline__ void st_stream4(float* p, float4 v) {
                "f"(v.w)
                : "memory");
 }
+
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start while
+// its predecessor in the stream is still draining.  pdl_trigger() lets the successor's CTAs be scheduled as soon as SMs
+// free up; pdl_wait() blocks until the predecessor grid has completed and its memory is visible -- call it before the
+// first access to anything a predecessor may have written (or may still be reading, for buffers this kernel overwrites).
+// Both are no-ops for kernels launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
   acc.x = fmaf(w, v.x, acc.x);

@@ -359,6 +359,8 @@ __global__ void __launch_bounds__(kBevThreads, 1)
     mbar_init_fence();
   }
   __syncthreads();
+  pdl_trigger();
+  pdl_wait();   // value planes / offset|logit rows come from the predecessor kernels
 
   if (warp == kWorkerWarps) {
     // ---------------- scheduler warp (one lane)
@@ -565,6 +567,7 @@ __global__ void __launch_bounds__(1024) build_hits_kernel(const uint8_t* __restr
                                                           int N, int Nq) {
   __shared__ int s_warp[2][32];
   __shared__ int s_base[2];
+  pdl_trigger();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if ((int)blockIdx.x <= N) {
     const int n = blockIdx.x;          // n == N: the unseen list
@@ -620,6 +623,7 @@ __global__ void __launch_bounds__(1024) build_hits_kernel(const uint8_t* __restr
 __global__ void __launch_bounds__(256) hit_ic_kernel(const int* __restrict__ hit_idx, const int* __restrict__ hit_cnt,
                                                      const float* __restrict__ inv_cnt, float* __restrict__ hit_ic, int B,
                                                      int N, int Nq) {
+  pdl_trigger();
   const int64_t total = (int64_t)B * N * Nq;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int pos = (int)(i % Nq), n = (int)((i / Nq) % N), b = (int)(i / ((int64_t)Nq * N));
@@ -693,6 +697,8 @@ __global__ void __launch_bounds__(kImgThreads, 1)
   const uint32_t sm_q = sm_idx + D::idx_bytes;   // query index per item
   const int C = a.H * 32;
 
+  pdl_trigger();
+  pdl_wait();   // hit lists, planes, offset|logit rows come from the predecessor kernels; `out` may alias their inputs
   const int* cnt_p = a.hit_cnt + a.part * a.N;
   if (a.part == 0) {   // rows of the queries no camera sees
     const int n_zero = __ldg(a.hit_cnt + 2 * a.N);
@@ -1002,7 +1008,7 @@ static int launch_bev_win_v(BevWinArgs& a, const CUtensorMap& mv, const CUtensor
     configured = smem;
   }
   const int grid = a.n_units < kNumSMs ? a.n_units : kNumSMs;
-  bev_sample_win_kernel<PP, ROWB><<<grid, kBevThreads, smem, s>>>(a, mv, mo, ml);
+  launch_pdl(bev_sample_win_kernel<PP, ROWB>, dim3(grid), dim3(kBevThreads), smem, s, a, mv, mo, ml);
   return check_launch(fn);
 }
 
@@ -1066,10 +1072,10 @@ static int launch_img_win_v(ImgWinArgs& a, const CUtensorMap& mv, size_t smem, c
     configured = smem;
   }
   a.part = 0;
-  img_sample_win_kernel<PP, ROWB, STAGE><<<kNumSMs, kImgThreads, smem, s>>>(a, mv);
+  launch_pdl(img_sample_win_kernel<PP, ROWB, STAGE>, dim3(kNumSMs), dim3(kImgThreads), smem, s, a, mv);
   if (int rc = check_launch(fn)) return rc;
   a.part = 1;   // (camera, query) pairs beyond a query's first camera: ~12 % of the pairs on the nuScenes rig
-  img_sample_win_kernel<PP, ROWB, STAGE><<<kNumSMs, kImgThreads, smem, s>>>(a, mv);
+  launch_pdl(img_sample_win_kernel<PP, ROWB, STAGE>, dim3(kNumSMs), dim3(kImgThreads), smem, s, a, mv);
   return check_launch(fn);
 }
 
