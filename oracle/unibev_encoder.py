@@ -16,6 +16,7 @@ reference config, unchanged.
 """
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 from .mmcv_semantics import (ffn_forward, layer_norm, linear, mmcv_msda_forward,
                              msda_core)
@@ -257,9 +258,29 @@ def channel_norm_weights(p, cfg, img, pts, c_flag, l_flag):
         else:
             wi, wp = w[0:1].softmax(0)[0], w[1:2].softmax(0)[0]
         img, pts = img * wi, pts * wp
+    elif cfg.get('feature_norm') in _MLP_ACTS:          # fusion:345-366
+        w = F.linear(torch.cat([img, pts], dim=1).permute(0, 2, 1), p['channel_weights_proj.0.weight'],
+                     p['channel_weights_proj.0.bias'])
+        w = _MLP_ACTS[cfg['feature_norm']](w)            # (bs, C, 2)
+        if c_flag == 1 and l_flag == 1:
+            n = F.softmax(w, dim=-1)
+            wi, wp = n[:, :, 0], n[:, :, 1]
+        else:
+            wi, wp = F.softmax(w[:, :, :1], dim=-1).squeeze(-1), F.softmax(w[:, :, 1:], dim=-1).squeeze(-1)
+        img, pts = img * wi[:, None, :], pts * wp[:, None, :]
+    elif cfg.get('feature_norm') == 'ModalityProjection':   # fusion:26-47, 375-381
+        def proj(prefix, x):
+            h = F.relu(F.linear(x, p[prefix + '.net.0.weight'], p[prefix + '.net.0.bias']))
+            w = p[prefix + '.net.2.weight']
+            return x + F.layer_norm(h, (w.numel(),), w, p[prefix + '.net.2.bias'], 1e-5)
+        img, pts = torch.cat([img, proj('l_modal_proj', img)], -1), torch.cat([proj('c_modal_proj', pts), pts], -1)
     elif cfg.get('feature_norm') is not None:
         raise NotImplementedError(cfg['feature_norm'])
     return img, pts
+
+
+_MLP_ACTS = {'MLP_ChannelNormWeights': F.relu, 'Leaky_ReLU_MLP_ChannelNormWeights': F.leaky_relu,
+             'ELU_MLP_ChannelNormWeights': F.elu, 'Sigmoid_MLP_ChannelNormWeights': torch.sigmoid}
 
 
 def spatial_norm_weights(p, cfg, img, pts, c_flag, l_flag):
@@ -276,17 +297,27 @@ def spatial_norm_weights(p, cfg, img, pts, c_flag, l_flag):
 
 
 def fuse(p, cfg, img, pts, c_flag, l_flag):
-    """fusion:280-314 (the 'ModalityProjection' cat variant is not covered)."""
+    """fusion:280-314."""
     m = cfg.get('fusion_method', 'linear')
     if m == 'linear':
         out = c_flag * img + l_flag * pts
     elif m == 'avg':
         out = img * c_flag / (c_flag + l_flag) + pts * l_flag / (c_flag + l_flag)
+    elif m == 'cat' and cfg.get('feature_norm') == 'ModalityProjection':    # fusion:287-300
+        C = img.shape[-1] // 2
+        img_flags = torch.cat((torch.full((C,), float(c_flag)), torch.full((C,), float(1 - l_flag))))
+        pts_flags = torch.cat((torch.full((C,), float(1 - c_flag)), torch.full((C,), float(l_flag))))
+        out = img * img_flags + pts * pts_flags
     elif m == 'cat':
         out = torch.cat((img * c_flag, pts * l_flag), -1)
     else:
         raise NotImplementedError(m)
-    if cfg.get('use_modal_embeds') == 'Fixed':
+    if cfg.get('use_modal_embeds') == 'MLP':            # fusion:304-307
+        s = torch.tensor([float(c_flag), float(l_flag)])
+        e = F.relu(F.linear(F.relu(F.linear(s, p['modal_embbeding_mlp.0.weight'], p['modal_embbeding_mlp.0.bias'])),
+                            p['modal_embbeding_mlp.2.weight'], p['modal_embbeding_mlp.2.bias']))
+        out = out + e
+    elif cfg.get('use_modal_embeds') == 'Fixed':
         out = out + c_flag * p['modal_embbeding_C'] + l_flag * p['modal_embbeding_L']
     elif cfg.get('use_modal_embeds') is not None:
         raise NotImplementedError(cfg['use_modal_embeds'])

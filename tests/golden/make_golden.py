@@ -488,7 +488,8 @@ def camera_rig(num_cams, img_hw, seed=0, jitter=0.0):
 
 def transformer_cfg(C=32, heads=4, layers=2, cams=3, fusion='linear', feature_norm='ChannelNormWeights',
                     with_img=True, with_pts=True, d_img=4, d_pts=4, points=8, drop_modality=None,
-                    pc_range=(-54, -54, -5, 54, 54, 3), spatial_norm=None, dual_queries=False, bev_h=200, bev_w=200):
+                    pc_range=(-54, -54, -5, 54, 54, 3), spatial_norm=None, dual_queries=False, bev_h=200, bev_w=200,
+                    use_modal_embeds=None):
     def layer(kind):
         return dict(
             type=f'{kind}Layer',
@@ -503,7 +504,8 @@ def transformer_cfg(C=32, heads=4, layers=2, cams=3, fusion='linear', feature_no
             operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm'))
     cfg = dict(type='UniBEVTransformer', embed_dims=C, num_cams=cams, fusion_method=fusion,
                drop_modality=drop_modality, feature_norm=feature_norm, spatial_norm=spatial_norm,
-               dual_queries=dual_queries, bev_h=bev_h, bev_w=bev_w, decoder=dict(type='NullDecoder'))
+               dual_queries=dual_queries, bev_h=bev_h, bev_w=bev_w, decoder=dict(type='NullDecoder'),
+               use_modal_embeds=use_modal_embeds)
     if with_img:
         cfg['img_encoder'] = dict(type='ImgEncoder', num_layers=layers, pc_range=list(pc_range),
                                   num_points_in_pillar=d_img, return_intermediate=False,
@@ -681,8 +683,16 @@ def golden_encoder_half(fusion_mod, tag, seed, bs=2, bev_hw=(10, 12), img_fhw=(6
     if train_flags:
         model.train()                       # every dropout p is 0.0 in this cfg; only the flags are random
         np.random.seed(seed)
-    with torch.no_grad():
-        fused = model(img_feats, pts_feats, bev_q, obj_q, Hb, Wb, bev_pos=bev_pos, img_metas=metas)[0]
+    # the ModalityProjection / MLP-modal-embedding branches move their flag tensors with `.cuda()`
+    # (transformer_fusion.py:297-298,305); there is no GPU in the build container, so that call is made a no-op while
+    # the reference runs (everything else stays on the CPU anyway)
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        with torch.no_grad():
+            fused = model(img_feats, pts_feats, bev_q, obj_q, Hb, Wb, bev_pos=bev_pos, img_metas=metas)[0]
+    finally:
+        torch.Tensor.cuda = real_cuda
     fused = fused.permute(1, 0, 2)          # fusion.py:549 hands (Nq, B, C) to the decoder; store batch-first
     arrays = dict(fused=fused, bev_pos=bev_pos, bev_hw=np.array(bev_hw), img_hw=np.array(img_hw),
                   lidar2img=np.asarray([m['lidar2img'] for m in metas]), flags=np.array([model.c_flag, model.l_flag]),
@@ -756,6 +766,13 @@ def main():
     golden_encoder_half(fusion_mod, 'lc_cnw_dropflags', 600, train_flags=True, drop_modality=1.0)
     golden_encoder_half(fusion_mod, 'lc_cnw_dropdict', 601, train_flags=True,
                         drop_modality=dict(dropout_prob=1.0, lidar_prob=0.0))
+    golden_encoder_half(fusion_mod, 'lc_mlp_cnw', 610, feature_norm='MLP_ChannelNormWeights')
+    golden_encoder_half(fusion_mod, 'lc_sigmoid_mlp_cnw_dropflags', 611, feature_norm='Sigmoid_MLP_ChannelNormWeights',
+                        train_flags=True, drop_modality=1.0)
+    golden_encoder_half(fusion_mod, 'lc_modproj_cat', 612, feature_norm='ModalityProjection', fusion='cat')
+    golden_encoder_half(fusion_mod, 'lc_modproj_cat_dropflags', 613, feature_norm='ModalityProjection', fusion='cat',
+                        train_flags=True, drop_modality=dict(dropout_prob=1.0, lidar_prob=1.0))
+    golden_encoder_half(fusion_mod, 'lc_cnw_modal_mlp', 614, use_modal_embeds='MLP')
     golden_decoder()
 
 

@@ -8,7 +8,8 @@ import torch
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 ENCODER_HALF_TAGS = ['lc_cnw_linear', 'lc_cat', 'lc_avg_spatial', 'c_only', 'l_only_cnw',
-                     'lc_cnw_dropflags', 'lc_cnw_dropdict']
+                     'lc_cnw_dropflags', 'lc_cnw_dropdict', 'lc_mlp_cnw', 'lc_sigmoid_mlp_cnw_dropflags', 'lc_modproj_cat',
+                     'lc_modproj_cat_dropflags', 'lc_cnw_modal_mlp']
 
 
 def load_golden(name):

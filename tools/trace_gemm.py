@@ -11,7 +11,7 @@ from unibev_b200 import _cabi, ops
 
 
 def main():
-    M, N, K = 40000, int(sys.argv[1]) if len(sys.argv) > 1 else 256, 256
+    M, N, K = int(os.environ.get('UB_TRACE_M', 40000)), int(sys.argv[1]) if len(sys.argv) > 1 else 256, 256
     cs = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     mode = sys.argv[3] if len(sys.argv) > 3 else 'plain'
     dev = 'cuda'

@@ -389,9 +389,7 @@ class FusedEncoder:
                     return self._bev_sample(tokens, lw.ca_wv, lw.ca_bv, qp, B, bev_h, bev_w, fh, fw, lw.H_c, lw.P_c,
                                             w16=lw.half()['ca_wv'] if isinstance(tokens, tuple) else None)
                 pts = self._run_encoder('pts_bev_encoder', q_pts, B, pos_q['pts_bev_encoder'], tokens, cross, bev_h, bev_w)
-            return ops.cnw_fuse(img, pts, getattr(m, 'img_channel_weights', None), getattr(m, 'pts_channel_weights', None),
-                                m.fusion_method, m.c_flag, m.l_flag, getattr(m, 'img_spatial_weights', None),
-                                getattr(m, 'pts_spatial_weights', None), m._modal_embed())
+            return m.fuse(img, pts)
 
     @staticmethod
     def _tokens(feat, embed_a, embed_b, f16, rows, C):

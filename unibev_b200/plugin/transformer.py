@@ -18,9 +18,27 @@ from ..registry import TRANSFORMER, build_transformer_layer_sequence
 from .attention import MSDeformableAttention3DImg, MSDeformableAttention3DPts, MultiScaleDeformableAttention
 from .fused import FusedEncoder, fused_supported
 
-_FEATURE_NORMS = (None, 'ChannelNormWeights')
-_UNSUPPORTED_NORMS = ('MLP_ChannelNormWeights', 'Leaky_ReLU_MLP_ChannelNormWeights', 'ELU_MLP_ChannelNormWeights',
-                      'Sigmoid_MLP_ChannelNormWeights', 'ModalityProjection')
+_MLP_NORMS = {'MLP_ChannelNormWeights': lambda: nn.ReLU(inplace=True),
+              'Leaky_ReLU_MLP_ChannelNormWeights': lambda: nn.LeakyReLU(inplace=True),
+              'ELU_MLP_ChannelNormWeights': lambda: nn.ELU(inplace=True),
+              'Sigmoid_MLP_ChannelNormWeights': nn.Sigmoid}
+_FEATURE_NORMS = (None, 'ChannelNormWeights', 'ModalityProjection') + tuple(_MLP_NORMS)
+
+
+class ModalityProjectionModule(nn.Module):
+    """transformer_fusion.py:26-47: Linear - ReLU - LayerNorm with an identity shortcut."""
+
+    def __init__(self, embed_dims, with_norm=True, with_residual=True):
+        super().__init__()
+        layers = [nn.Linear(embed_dims, embed_dims), nn.ReLU(inplace=True)]
+        if with_norm:
+            layers.append(nn.LayerNorm(embed_dims))
+        self.net = nn.Sequential(*layers)
+        self.with_residual = with_residual
+
+    def forward(self, x):
+        out = self.net(x)
+        return x + out if self.with_residual else out
 
 
 @TRANSFORMER.register_module()
@@ -36,14 +54,14 @@ class UniBEVTransformer(nn.Module):
             self.scale_factor = 2
         else:
             raise ValueError('Unrecognizable fusion method:{}'.format(fusion_method))
-        if feature_norm in _UNSUPPORTED_NORMS:
-            raise NotImplementedError(f'feature_norm={feature_norm!r} is not part of the B200 hot path yet')
         if feature_norm not in _FEATURE_NORMS:
             raise ValueError(f'unknown feature_norm {feature_norm!r}')
+        if feature_norm == 'ModalityProjection' and fusion_method != 'cat':
+            raise ValueError("feature_norm='ModalityProjection' needs fusion_method='cat' (transformer_fusion.py:151)")
         if spatial_norm not in (None, 'SpatialNormWeights'):
             raise ValueError(f'unknown spatial_norm {spatial_norm!r}')
-        if use_modal_embeds not in (None, 'Fixed'):
-            raise NotImplementedError(f'use_modal_embeds={use_modal_embeds!r} is not part of the B200 hot path yet')
+        if use_modal_embeds not in (None, 'Fixed', 'MLP'):
+            raise ValueError(f'unknown use_modal_embeds {use_modal_embeds!r}')
         if vis_output is not None:
             raise NotImplementedError('vis_output dumping is not supported')
         if img_encoder is not None:
@@ -84,6 +102,12 @@ class UniBEVTransformer(nn.Module):
         if self.feature_norm == 'ChannelNormWeights':
             self.pts_channel_weights = nn.Parameter(torch.zeros(C))
             self.img_channel_weights = nn.Parameter(torch.zeros(C))
+        elif self.feature_norm in _MLP_NORMS:     # transformer_fusion.py:136-150
+            self.channel_weights_proj = nn.Sequential(nn.Linear(self.bev_h * self.bev_w * 2, 2),
+                                                      _MLP_NORMS[self.feature_norm]())
+        elif self.feature_norm == 'ModalityProjection':
+            self.c_modal_proj = ModalityProjectionModule(C)
+            self.l_modal_proj = ModalityProjectionModule(C)
         if self.spatial_norm == 'SpatialNormWeights':
             self.pts_spatial_weights = nn.Parameter(torch.zeros(self.bev_h * self.bev_w))
             self.img_spatial_weights = nn.Parameter(torch.zeros(self.bev_h * self.bev_w))
@@ -92,7 +116,10 @@ class UniBEVTransformer(nn.Module):
             self.cams_embeds = nn.Parameter(torch.zeros(self.num_cams, C))
         if self.with_pts_bev_encoder:
             self.pts_level_embeds = nn.Parameter(torch.zeros(self.num_feature_levels, C))
-        if self.use_modal_embeds == 'Fixed':
+        if self.use_modal_embeds == 'MLP':        # transformer_fusion.py:171-176
+            self.modal_embbeding_mlp = nn.Sequential(nn.Linear(2, C // 2), nn.ReLU(inplace=True), nn.Linear(C // 2, C),
+                                                     nn.ReLU(inplace=True))
+        elif self.use_modal_embeds == 'Fixed':
             self.modal_embbeding_C = nn.Parameter(torch.zeros(C))
             self.modal_embbeding_L = nn.Parameter(torch.zeros(C))
         self.reference_points = nn.Linear(C * self.scale_factor, 3)
@@ -214,6 +241,16 @@ class UniBEVTransformer(nn.Module):
             w = torch.stack((self.img_channel_weights, self.pts_channel_weights), 0)
             wi, wp = (w.softmax(0)) if (c == 1 and l == 1) else (w[0:1].softmax(0)[0], w[1:2].softmax(0)[0])
             img, pts = img * wi, pts * wp
+        elif self.feature_norm in _MLP_NORMS:       # transformer_fusion.py:345-366: weights from the BEV maps themselves
+            w = self.channel_weights_proj(torch.cat([img, pts], dim=1).permute(0, 2, 1))       # (bs, C, 2)
+            if c == 1 and l == 1:
+                n = torch.softmax(w, dim=-1)
+                wi, wp = n[:, :, 0], n[:, :, 1]
+            else:
+                wi, wp = torch.softmax(w[:, :, :1], dim=-1).squeeze(-1), torch.softmax(w[:, :, 1:], dim=-1).squeeze(-1)
+            img, pts = img * wi[:, None, :], pts * wp[:, None, :]
+        elif self.feature_norm == 'ModalityProjection':   # :375-381: each modality also predicts the other one
+            img, pts = torch.cat([img, self.l_modal_proj(img)], dim=-1), torch.cat([self.c_modal_proj(pts), pts], dim=-1)
         if self.spatial_norm == 'SpatialNormWeights':
             w = torch.stack((self.img_spatial_weights, self.pts_spatial_weights), 0)
             wi, wp = (w.softmax(0)) if (c == 1 and l == 1) else (w[:1].softmax(0)[0], w[1:].softmax(0)[0])
@@ -222,11 +259,33 @@ class UniBEVTransformer(nn.Module):
             fused = c * img + l * pts
         elif self.fusion_method == 'avg':
             fused = img * c / (c + l) + pts * l / (c + l)
+        elif self.feature_norm == 'ModalityProjection':   # :287-300: true halves by flag, pseudo halves by 1 - flag
+            C = self.embed_dims
+            img_flags = torch.cat((img.new_full((C,), float(c)), img.new_full((C,), float(1 - l))))
+            pts_flags = torch.cat((img.new_full((C,), float(1 - c)), img.new_full((C,), float(l))))
+            fused = img * img_flags + pts * pts_flags
         else:
             fused = torch.cat((img * c, pts * l), -1)
-        if self.use_modal_embeds == 'Fixed':
+        if self.use_modal_embeds == 'MLP':
+            fused = fused + self.modal_embbeding_mlp(fused.new_tensor([float(c), float(l)]))
+        elif self.use_modal_embeds == 'Fixed':
             fused = fused + c * self.modal_embbeding_C + l * self.modal_embbeding_L
         return fused
+
+    def _kernel_fusable(self):
+        """ub_cnw_fuse covers feature_norm None / ChannelNormWeights, SpatialNormWeights, linear / avg / cat and the fixed
+        modal embeddings; the ablation variants (MLP norms, ModalityProjection, MLP modal embeds) are torch glue."""
+        return self.feature_norm in (None, 'ChannelNormWeights') and self.use_modal_embeds in (None, 'Fixed')
+
+    def fuse(self, img, pts):
+        """CNW / spatial norm / fusion of the two BEV maps (either may be None) in inference."""
+        if not self._kernel_fusable():
+            with torch.no_grad():
+                return self._fuse_modules(img, pts)
+        return ops.cnw_fuse(img, pts, getattr(self, 'img_channel_weights', None),
+                            getattr(self, 'pts_channel_weights', None), self.fusion_method, self.c_flag, self.l_flag,
+                            getattr(self, 'img_spatial_weights', None), getattr(self, 'pts_spatial_weights', None),
+                            self._modal_embed())
 
     # ------------------------------------------------------------------ public
     def encode(self, img_mlvl_feats, pts_mlvl_feats, bev_queries, bev_h, bev_w, bev_pos=None, flags=None, **kwargs):
@@ -251,10 +310,7 @@ class UniBEVTransformer(nn.Module):
         img, pts = self._encode_modules(img_mlvl_feats, pts_mlvl_feats, bev_queries, bev_h, bev_w, bev_pos, **kwargs)
         if grad:
             return self._fuse_modules(img, pts)
-        return ops.cnw_fuse(img, pts, getattr(self, 'img_channel_weights', None),
-                            getattr(self, 'pts_channel_weights', None), self.fusion_method, self.c_flag, self.l_flag,
-                            getattr(self, 'img_spatial_weights', None), getattr(self, 'pts_spatial_weights', None),
-                            self._modal_embed())
+        return self.fuse(img, pts)
 
     def _modal_embed(self):
         if self.use_modal_embeds != 'Fixed':
