@@ -33,12 +33,15 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=2, help='samples per GPU (configs[4]: 16 over 8 GPUs)')
     ap.add_argument('--bucket-mb', type=float, default=8.0)
+    ap.add_argument('--fp32-matmul', action='store_true', help='strict fp32 (SIMT) GEMMs instead of TF32 tensor cores')
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('WORLD_SIZE', 1), ('LOCAL_RANK', 0)))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+    # TF32 tensor-core matmuls: what torch 1.10, the reference's stack, does by default on Ampere and later
+    torch.backends.cuda.matmul.allow_tf32 = not args.fp32_matmul
     np.random.seed(0)                                    # same flags on every rank
     model, cfg = synth.build_model(WORKLOAD, drop_modality=0.5)
     model = model.to(dev).train()
@@ -80,7 +83,8 @@ def main():
         print(json.dumps({
             'metric': 'nuScenes frames/sec train step (L+C cat-128, modality dropout)', 'unit': 'frames/s',
             'value': world * args.batch * args.steps / (float(ms.item()) / 1e3), 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': float(ms.item()) / args.steps, 'scaling': 'weak', 'dtype': 'f32',
+            'warmup': args.warmup, 'ms_per_step': float(ms.item()) / args.steps, 'scaling': 'weak',
+            'dtype': 'f32' if args.fp32_matmul else 'tf32',
             'data': 'synthetic', 'loss': float(loss), 'params_in_sync': in_sync,
             'allreduce_bytes_per_step': buckets.nbytes() if world > 1 else 0, 'buckets': len(buckets.buckets),
             'gpu_launches': _cabi.launch_count(),
