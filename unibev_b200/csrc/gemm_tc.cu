@@ -197,6 +197,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// sixteen fp32 values -> sixteen fp16 (saturating) -> one 32-byte store (STG.256); p must be 32-byte aligned
+__device__ __forceinline__ void st_half16(__half* p, const float (&f)[16]) {
+  const float lim = 65504.f;
+  uint32_t w[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const __half2 h = __floats2half2_rn(fminf(fmaxf(f[2 * e], -lim), lim), fminf(fmaxf(f[2 * e + 1], -lim), lim));
+    w[e] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
 // 16-byte chunk j (0..3) of row `row` (0..31) in a warp's staging buffer: rows of 64 bytes, chunks XOR-swizzled so
 // that both the thread-per-row side and the coalesced side (8 rows x 64 B per instruction) are bank-conflict free
 __device__ __forceinline__ uint32_t swz(uint32_t base, int row, int j) {
@@ -428,22 +442,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           }
           __syncwarp();
         }
-        if (a.out16 && row0 + lane < r_end) {                   // fp16 copy: 32 bytes of this thread's row
-          uint4* dst = reinterpret_cast<uint4*>(a.out16 + (size_t)(row0 + lane) * a.ldc16 + n0 + c * kChunk);
-          const float lim = 65504.f;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            uint4 o;
-            uint32_t* ow = &o.x;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const __half2 h = __floats2half2_rn(fminf(fmaxf(f[8 * j + 2 * e], -lim), lim),
-                                                  fminf(fmaxf(f[8 * j + 2 * e + 1], -lim), lim));
-              ow[e] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            dst[j] = o;
-          }
-        }
+        if (a.out16 && row0 + lane < r_end)                     // fp16 copy: 32 bytes of this thread's row, one store
+          st_half16(a.out16 + (size_t)(row0 + lane) * a.ldc16 + n0 + c * kChunk, f);
       };
       auto params4 = [&](const float* p, int j) {             // 16-byte broadcast read of bias / gamma / beta
         return *reinterpret_cast<const float4*>(p + 4 * j);
@@ -480,21 +480,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           const int row = row0 + lane;
           if (row < r_end) {
             const int gi = row / a.Nv, tok = row - gi * a.Nv;
-            uint4* dst = reinterpret_cast<uint4*>(a.planes + (((int64_t)gi * a.H + (n0 / 32 + (c >> 1))) * a.Nv + tok) * 32 +
-                                                  (c & 1) * 16);
-            const float lim = 65504.f;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              uint4 o;
-              uint32_t* ow = &o.x;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __half2 h = __floats2half2_rn(fminf(fmaxf(f[8 * j + 2 * e], -lim), lim),
-                                                    fminf(fmaxf(f[8 * j + 2 * e + 1], -lim), lim));
-                ow[e] = *reinterpret_cast<const uint32_t*>(&h);
-              }
-              dst[j] = o;
-            }
+            st_half16(a.planes + (((int64_t)gi * a.H + (n0 / 32 + (c >> 1))) * a.Nv + tok) * 32 + (c & 1) * 16, f);
           }
         } else {
           if (a.relu) {
@@ -593,7 +579,8 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   if (K % kb_elems != 0 || N % 32 != 0 || (N > 256 && N % 256 != 0) || (ln && N > 256) ||
       (planes && (ln || relu || residual || out16)) || (planes && (Nv <= 0 || M % Nv != 0)) ||
       (out && (ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(out) & 15u))) ||
-      (out16 && (ldc16 % 8 != 0 || (reinterpret_cast<uintptr_t>(out16) & 15u))) ||
+      (out16 && (ldc16 % 16 != 0 || (reinterpret_cast<uintptr_t>(out16) & 31u))) ||
+      (planes && (reinterpret_cast<uintptr_t>(planes) & 31u)) ||
       (residual && (ldr % 4 != 0 || (reinterpret_cast<uintptr_t>(residual) & 15u))) || N > 1024) {
     set_error("%s: shape not covered (M=%d N=%d K=%d flags=%d)", fn, M, N, K, flags);
     return UB_EUNSUPPORTED;
