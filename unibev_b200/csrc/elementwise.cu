@@ -80,31 +80,30 @@ struct FuseParams {
 };
 
 // thread = one float4 of channels of one row.  Per-channel CNW weights are recomputed per thread (2 exps).
-__global__ void __launch_bounds__(256) cnw_fuse_kernel(const float* __restrict__ img, const float* __restrict__ pts,
+__global__ void __launch_bounds__(1024) cnw_fuse_kernel(const float* __restrict__ img, const float* __restrict__ pts,
                                                        const float* __restrict__ w_img, const float* __restrict__ w_pts,
                                                        const float* __restrict__ s_img, const float* __restrict__ s_pts,
                                                        const float* __restrict__ modal, float* __restrict__ out,
                                                        int64_t rows, FuseParams fp) {
   const int C4 = fp.C / 4;
-  const int64_t total = rows * C4;
   const float cf = (float)fp.c_flag, lf = (float)fp.l_flag;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C4) * 4;
-    const int64_t r = idx / C4;
-    float wi[4] = {1.f, 1.f, 1.f, 1.f}, wp[4] = {1.f, 1.f, 1.f, 1.f};
-    if (w_img) {  // feature_norm == 'ChannelNormWeights'
-      if (fp.c_flag == 1 && fp.l_flag == 1) {
-        const float4 a = ldg4(w_img + c), b = ldg4(w_pts + c);
-        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+  // blockDim is a multiple of C4 (host): a thread keeps its channel quad for the whole launch, so the per-channel CNW
+  // softmax is evaluated once per thread instead of once per element, and no 64-bit div / mod runs in the loop
+  const int c = ((int)threadIdx.x % C4) * 4;
+  const int rows_per_block = (int)blockDim.x / C4;
+  float wi[4] = {1.f, 1.f, 1.f, 1.f}, wp[4] = {1.f, 1.f, 1.f, 1.f};
+  if (w_img && fp.c_flag == 1 && fp.l_flag == 1) {  // feature_norm == 'ChannelNormWeights'; a single row softmaxes to 1
+    const float4 a = ldg4(w_img + c), b = ldg4(w_pts + c);
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float m = fmaxf(av[k], bv[k]);
-          const float ea = expf(av[k] - m), eb = expf(bv[k] - m), s = ea + eb;
-          wi[k] = ea / s, wp[k] = eb / s;
-        }
-      }  // else: softmax over a single row == 1
+    for (int k = 0; k < 4; ++k) {
+      const float m = fmaxf(av[k], bv[k]);
+      const float ea = expf(av[k] - m), eb = expf(bv[k] - m), s = ea + eb;
+      wi[k] = ea / s, wp[k] = eb / s;
     }
+  }
+  for (int64_t r = (int64_t)blockIdx.x * rows_per_block + (int)threadIdx.x / C4; r < rows;
+       r += (int64_t)gridDim.x * rows_per_block) {
     float si = 1.f, sp = 1.f;
     if (s_img) {  // spatial_norm == 'SpatialNormWeights'
       const int q = (int)(r % fp.rows_per_item);
@@ -262,9 +261,14 @@ extern "C" int ub_cnw_fuse(const float* img, const float* pts, const float* w_im
   if (w_img) { UB_REQUIRE_ALIGNED16(w_img); UB_REQUIRE_ALIGNED16(w_pts); }
   if (modal_embed) UB_REQUIRE_ALIGNED16(modal_embed);
   FuseParams fp{mode, c_flag, l_flag, rows_per_item, C};
-  int64_t blocks = (rows * (C / 4) + 255) / 256;
+  // threads per block: the largest multiple of C / 4 that fits 256 (a thread keeps one channel quad), C / 4 <= 1024
+  const int C4 = C / 4;
+  UB_REQUIRE(C4 <= 1024, "ub_cnw_fuse: C = %d too large (max 4096)", C);
+  const int threads = C4 >= 256 ? C4 : (256 / C4) * C4;
+  const int rows_per_block = threads / C4;
+  int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
   if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
-  cnw_fuse_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(img, pts, w_img, w_pts, s_img, s_pts, modal_embed, out,
+  cnw_fuse_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(img, pts, w_img, w_pts, s_img, s_pts, modal_embed, out,
                                                                  rows, fp);
   return check_launch("ub_cnw_fuse");
 }
