@@ -406,7 +406,8 @@ def main():
                 'vs_baseline': None, 'dtype': 'tf32' if args.precision == 'tf32' else 'f32', 'data': 'synthetic',
                 'config': {'workload': f'{WORKLOAD} inference, {B} frames per GPU per step, {world} GPU(s), batch-sharded, '
                                        'no collective (BASELINE configs[3]: 32 frames over 8 GPUs = 4 per GPU; --batch 1 = configs[2])',
-                           'frames_per_step': world * B, 'bev': '200x200', 'embed_dims': 256, 'layers': 3,
+                           'frames_per_step': world * B, 'shapes': 'BEV 200x200 queries, 256 channels, 3 encoder layers per modality, '
+                                                                    '6 cameras x 29x50 tokens, LiDAR map 180x180',
                            'l2_policy': f'rotating over {N_INPUT_SETS} input sets (> L2) + >1 GB of intermediates per frame',
                            'gemm_math': 'tcgen05 TF32 / fp16 operands, fp32 accumulate' if args.precision == 'tf32' else 'fp32',
                            'sampling_math': 'fp16-staged value maps and weights, fp32 accumulate' if args.precision == 'tf32' else 'fp32',

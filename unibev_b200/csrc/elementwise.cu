@@ -201,10 +201,10 @@ __global__ void __launch_bounds__(256) broadcast_rows_kernel(const float* __rest
     };
     h.x = pk(a.x, a.y), h.y = pk(a.z, a.w), h.z = pk(b.x, b.y), h.w = pk(b.z, b.w);
     for (int r = 0; r < B; ++r) {
-      if (out32) {
-        st_stream4(out32 + (r * n8 + i) * 8, a);
-        st_stream4(out32 + (r * n8 + i) * 8 + 4, b);
-      }
+      if (out32)   // 32 bytes in one store (STG.256)
+        asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(out32 + (r * n8 + i) * 8),
+                     "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+                     : "memory");
       if (out16) reinterpret_cast<uint4*>(out16)[r * n8 + i] = h;
     }
   }
@@ -295,7 +295,7 @@ extern "C" int ub_broadcast_rows(const float* src, int64_t rows, int C, int B, f
   UB_REQUIRE(src && (out32 || out16), "ub_broadcast_rows: null pointer");
   UB_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && B > 0, "ub_broadcast_rows: need rows > 0, C %% 8 == 0, B > 0");
   UB_REQUIRE_ALIGNED16(src);
-  if (out32) UB_REQUIRE_ALIGNED16(out32);
+  UB_REQUIRE(!out32 || (reinterpret_cast<uintptr_t>(out32) & 31u) == 0, "ub_broadcast_rows: out32 must be 32-byte aligned");
   if (out16) UB_REQUIRE_ALIGNED16(out16);
   const int64_t n8 = rows * C / 8;
   int blocks = (int)((n8 + 255) / 256);
