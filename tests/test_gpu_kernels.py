@@ -192,3 +192,27 @@ def test_flatten_feats(ops, G, C, h, w):
     got = ops.flatten_feats(feat.cuda(), ea.cuda(), eb.cuda()).cpu()
     assert torch.equal(got, want)
     assert torch.equal(ops.flatten_feats(feat.cuda()).cpu(), feat.flatten(2).permute(0, 2, 1))
+
+
+@pytest.mark.parametrize('G,C,h,w', [(6, 256, 29, 50), (2, 32, 9, 9), (3, 33, 5, 7), (1, 130, 4, 40)])
+def test_flatten_feats_fp16_outputs(ops, G, C, h, w):
+    """fp16 rows next to / instead of the fp32 rows: the fp32 result rounded once (bit-exact), on both kernels (the
+    64-channel fp16-only kernel needs an even C; odd C takes the generic one)."""
+    g = torch.Generator().manual_seed(G + C)
+    feat = torch.randn(G, C, h, w, generator=g)
+    ea, eb = torch.randn(3, C, generator=g), torch.randn(C, generator=g)
+    want = ((feat.flatten(2).permute(0, 2, 1) + ea[torch.arange(G) % 3][:, None]) + eb).half()
+    both32, both16 = ops.flatten_feats(feat.cuda(), ea.cuda(), eb.cuda(), fp32=True, fp16=True)
+    none32, only16 = ops.flatten_feats(feat.cuda(), ea.cuda(), eb.cuda(), fp32=False, fp16=True)
+    assert none32 is None and both32.dtype == torch.float32 and only16.dtype == torch.float16
+    assert torch.equal(both16.cpu(), want) and torch.equal(only16.cpu(), want)
+    assert torch.equal(ops.flatten_feats(feat.cuda(), fp32=False, fp16=True)[1].cpu(), feat.flatten(2).permute(0, 2, 1).half())
+
+
+def test_broadcast_rows(ops):
+    g = torch.Generator().manual_seed(0)
+    src = torch.randn(1000, 256, generator=g)
+    o32, o16 = ops.broadcast_rows(src.cuda(), 3)
+    assert torch.equal(o32.cpu(), src.unsqueeze(0).expand(3, -1, -1)) and torch.equal(o16.cpu(), src.half().unsqueeze(0).expand(3, -1, -1))
+    o32, o16 = ops.broadcast_rows(src.cuda(), 2, fp32=False)
+    assert o32 is None and torch.equal(o16.cpu()[1], src.half())

@@ -185,6 +185,44 @@ __global__ void __launch_bounds__(256) flatten_feats_kernel(const float* __restr
   }
 }
 
+// fp16-only output (the fused fp16 pipeline): 64 channels x 32 pixels per block, a lane converts two neighbouring
+// channels, so every store instruction writes full 128-byte row segments.
+__global__ void __launch_bounds__(256) flatten_feats_h_kernel(const float* __restrict__ in,
+                                                              const float* __restrict__ embed_a, int n_a,
+                                                              const float* __restrict__ embed_b,
+                                                              __half* __restrict__ out16, int C, int HW) {
+  __shared__ float tile[64][33];
+  pdl_trigger();
+  const int g = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* src = in + (int64_t)g * C * HW;
+#pragma unroll
+  for (int j = 0; j < 64; j += 8) {
+    const int c = c0 + ty + j, p = p0 + tx;
+    tile[ty + j][tx] = (c < C && p < HW) ? __ldg(src + (int64_t)c * HW + p) : 0.f;
+  }
+  __syncthreads();
+  const int c = c0 + 2 * tx;     // this lane's channel pair (C is even)
+  if (c >= C) return;
+  float ea[2] = {0.f, 0.f}, eb[2] = {0.f, 0.f};
+  if (embed_a) ea[0] = __ldg(embed_a + (int64_t)(g % n_a) * C + c), ea[1] = __ldg(embed_a + (int64_t)(g % n_a) * C + c + 1);
+  if (embed_b) eb[0] = __ldg(embed_b + c), eb[1] = __ldg(embed_b + c + 1);
+  __half* dst = out16 + (int64_t)g * HW * C + c;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int p = p0 + ty + j;
+    if (p < HW) {
+      float v0 = tile[2 * tx][ty + j], v1 = tile[2 * tx + 1][ty + j];
+      if (embed_a) v0 = __fadd_rn(v0, ea[0]), v1 = __fadd_rn(v1, ea[1]);
+      if (embed_b) v0 = __fadd_rn(v0, eb[0]), v1 = __fadd_rn(v1, eb[1]);
+      const float lim = 65504.f;
+      *reinterpret_cast<__half2*>(dst + (int64_t)p * C) =
+          __floats2half2_rn(fminf(fmaxf(v0, -lim), lim), fminf(fmaxf(v1, -lim), lim));
+    }
+  }
+}
+
 // src (rows, C) -> out32 / out16 (B, rows, C): the BEV query table repeated for every sample of the batch
 // (transformer_fusion.py:493-498 `bev_queries.unsqueeze(1).repeat(1, bs, 1)`), with the fp16 copy the first
 // projections read.  Thread = 8 channels of one source row.
@@ -278,6 +316,12 @@ extern "C" int ub_flatten_feats16(const float* in, const float* embed_a, int n_a
   UB_REQUIRE(in && (out || out16), "ub_flatten_feats: null pointer");
   UB_REQUIRE(G > 0 && G <= 65535 && C > 0 && HW > 0, "ub_flatten_feats: bad shape (G=%d C=%d HW=%d)", G, C, HW);
   UB_REQUIRE(embed_a == nullptr || n_a > 0, "ub_flatten_feats: embed_a given with n_a=%d", n_a);
+  if (!out && C % 2 == 0 && (reinterpret_cast<uintptr_t>(out16) & 3u) == 0) {
+    dim3 grid((HW + 31) / 32, (C + 63) / 64, G);
+    flatten_feats_h_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, embed_a, n_a > 0 ? n_a : 1, embed_b,
+                                                                   reinterpret_cast<__half*>(out16), C, HW);
+    return check_launch("ub_flatten_feats");
+  }
   dim3 grid((HW + 31) / 32, (C + 31) / 32, G);
   flatten_feats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, embed_a, n_a > 0 ? n_a : 1, embed_b, out,
                                                                reinterpret_cast<__half*>(out16), C, HW);
