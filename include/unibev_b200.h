@@ -4,9 +4,14 @@
  * Drop-in boundary for the UniBEV uniform-BEV-encoder hot path.  Plain pointers
  * and sizes only: no torch types cross this boundary.  All pointers are DEVICE
  * pointers unless the parameter comment says "host".  Every call is asynchronous
- * on `stream` (a cudaStream_t), allocates nothing, and returns 0 on success or a
- * negative UB_E* code (message: ub_last_error(), thread-local).  Tensors are
- * contiguous row-major fp32 unless stated.
+ * on `stream` (a cudaStream_t) and returns 0 on success or a negative UB_E* code
+ * (message: ub_last_error(), thread-local).  The caller owns every tensor and
+ * workspace; the library itself keeps only (a) a 512-byte device array of work
+ * counters allocated on the first window-kernel call, (b) a mutex-guarded host
+ * cache of encoded TMA tensor maps and (c) the process-wide tuning knobs set by
+ * the ub_set_* calls (performance only; results do not depend on them, except
+ * ub_set_window_round_tf32).  Calls may be captured into CUDA graphs.  Tensors
+ * are contiguous row-major fp32 unless stated.
  *
  * Reference interfaces replaced (paths under /root/reference):
  *   [R1] mmcv MultiScaleDeformableAttnFunction.apply / ext_module.ms_deform_attn_forward|backward,
