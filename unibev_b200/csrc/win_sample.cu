@@ -792,8 +792,10 @@ __global__ void __launch_bounds__(kImgThreads, 1)
     }
     return q >= 0 ? __ldg(a.inv_cnt + (int64_t)wu.b * a.Nq + q) : 0.f;
   };
-  auto prefetch = [&](const Unit& wu) {  // !STAGE: everything P1 needs into registers
-    qq = lookup(wu);
+  // !STAGE: everything P1 needs into registers.  `q` (the item's query in unit wu) was itself loaded one unit earlier,
+  // so the row loads below go out at once instead of waiting for the hit-list entry
+  auto prefetch = [&](const Unit& wu, int q) {
+    qq = q;
     ic = inv_count(wu, qq);
 #pragma unroll
     for (int i = 0; i < PPL; ++i) off[2 * i] = 0.f, off[2 * i + 1] = 0.f, lg[i] = 0.f, ref[2 * i] = 0.f, ref[2 * i + 1] = 0.f;
@@ -867,7 +869,8 @@ __global__ void __launch_bounds__(kImgThreads, 1)
     ic = inv_count(w, qq);
     if (u_beg + 1 < u_end) qn = lookup(decode(u_beg + 1));
   } else {
-    prefetch(w);
+    prefetch(w, lookup(w));
+    if (u_beg + 1 < u_end) qn = lookup(decode(u_beg + 1));
   }
 
   int loaded = w.plane, cur = 0;
@@ -927,7 +930,8 @@ __global__ void __launch_bounds__(kImgThreads, 1)
         const int q2 = u + 2 < u_end ? lookup(decode(u + 2)) : -1;
         qq = qn, ic = icn, qn = q2;
       } else {
-        prefetch(w);
+        prefetch(w, qn);
+        qn = u + 2 < u_end ? lookup(decode(u + 2)) : -1;
       }
     }
     // ---- P2
