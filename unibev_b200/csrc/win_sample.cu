@@ -406,6 +406,7 @@ __global__ void __launch_bounds__(kBevThreads, 1)
   const uint32_t sm_slice = sm_win + 2u * win_bytes + (uint32_t)warp * S::warp_bytes;  // {offsets, logits}
   const uint32_t sm_w = sm_slice + S::slice_bytes, sm_idx = sm_w + D::w_bytes;
   const uint32_t bar_qp = smem_u32(&s_qp[warp]);
+  const uint32_t bar_unit = smem_u32(&s_unit[0]), bar_full = smem_u32(&s_full[0]), bar_empty = smem_u32(&s_empty[0]);
   constexpr int PPL = PP / 2;                // sampling points per lane in P1 (two lanes per item)
   const int item_l = lane >> 1, p0 = (lane & 1) * PPL;
   const int grp = lane >> 3, sub = lane & 7, half = sub >> 2, cq = sub & 3;
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(kBevThreads, 1)
     tma_load_4d(sm_slice + S::slice_off_bytes, &map_lg, bar_qp, a.logit_col + w.h * PP, w.tx0, w.ty0 + warp, w.b);
   };
 
-  mbar_wait(smem_u32(&s_unit[0]), 0u);
+  mbar_wait(bar_unit, 0u);
   UnitInfo w = s_ring[0];
   if (w.u >= 0 && lane == 0) issue_slice(w);
 
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(kBevThreads, 1)
     const bool any_far = __any_sync(0xffffffffu, far_bits != 0u);
     __syncwarp();   // descriptor stores visible to the whole warp
     // ---- the slice buffer is free: stream in the next unit's row
-    mbar_wait(smem_u32(&s_unit[(k + 1) & 3]), (uint32_t)(((k + 1) >> 2) & 1));
+    mbar_wait(bar_unit + 8u * (uint32_t)((k + 1) & 3), (uint32_t)(((k + 1) >> 2) & 1));
     const UnitInfo wn = s_ring[(k + 1) & 3];
     if (wn.u >= 0 && lane == 0) issue_slice(wn);
 
@@ -521,12 +522,14 @@ __global__ void __launch_bounds__(kBevThreads, 1)
     }
 
     // ---- P2
-    mbar_wait(smem_u32(&s_full[k & 1]), (uint32_t)((k >> 1) & 1));
+    // element offset of this lane's four channels in the first query of the warp's row
+    const int64_t out0 = ((int64_t)w.b * Nq + qy * a.bev_w + w.tx0) * C + w.h * 32 + cq * 8 + half * 4;
+    mbar_wait(bar_full + 8u * (uint32_t)(k & 1), (uint32_t)((k >> 1) & 1));
     gather_warp<PP, ROWB>(sm_w, sm_idx, sm_win + (uint32_t)(k & 1) * win_bytes + sub * 16u, (uint32_t)a.WW * 64u, grp,
                           half, [&](int item, const float4& o) {
                             const int qx = w.tx0 + item;
                             if (row_ok && qx < a.bev_w) {
-                              const int64_t oo = ((int64_t)w.b * Nq + qy * a.bev_w + qx) * C + w.h * 32 + cq * 8 + half * 4;
+                              const int64_t oo = out0 + item * C;
                               if (a.out16) {
                                 if (any_far)
                                   red_add_half4(a.out16 + oo, o);
@@ -549,7 +552,7 @@ __global__ void __launch_bounds__(kBevThreads, 1)
                             }
                           });
     __syncwarp();   // every lane is done with the window and the descriptors
-    if (lane == 0) mbar_arrive(smem_u32(&s_empty[k & 1]));
+    if (lane == 0) mbar_arrive(bar_empty + 8u * (uint32_t)(k & 1));
     w = wn;
   }
 }
