@@ -252,3 +252,21 @@ def test_gradient_buckets_average_over_two_gloo_ranks(tmp_path):
                          capture_output=True, text=True, timeout=240, env=env)
     assert out.returncode == 0, (out.stdout[-1000:], out.stderr[-3000:])
     assert 'GRAD_OK' in out.stdout
+
+
+def test_learned_positional_encoding_matches_oracle():
+    """bev_pos producer (unibev_head.py:179-182): plugin class vs the oracle restatement of mmdet's module."""
+    import torch
+    from oracle.mmcv_semantics import learned_pos_encoding
+    from unibev_b200.plugin import LearnedPositionalEncoding
+    torch.manual_seed(0)
+    enc = LearnedPositionalEncoding(num_feats=8, row_num_embed=6, col_num_embed=7)
+    assert set(enc.state_dict()) == {'row_embed.weight', 'col_embed.weight'}
+    pos = enc(torch.zeros(3, 5, 7))
+    assert pos.shape == (3, 16, 5, 7)
+    p = {'pe.' + k: v.detach() for k, v in enc.state_dict().items()}
+    torch.testing.assert_close(pos, learned_pos_encoding(p, 'pe', 3, 5, 7), rtol=0, atol=0)
+    assert torch.equal(pos[0], pos[2])                                   # batch-invariant
+    assert torch.equal(pos[0, :8, 0], pos[0, :8, 4]) and torch.equal(pos[0, 8:, :, 0], pos[0, 8:, :, 6])
+    with pytest.raises(ValueError):
+        enc(torch.zeros(1, 7, 7))

@@ -5,10 +5,11 @@ from .attention import (MSDeformableAttention3DImg, MSDeformableAttention3DPts, 
 from .decoder import (CustomMSDeformableAttention, DetectionTransformerDecoder, DetrTransformerDecoderLayer,
                       MultiheadAttention)
 from .encoder import FFN, ImgEncoder, ImgLayer, PtsEncoder, PtsLayer
+from .positional import LearnedPositionalEncoding
 from .transformer import UniBEVTransformer
 from .voxelize import HardSimpleVFE, Voxelization, voxelize
 
 __all__ = ['MSDeformableAttention3DImg', 'MSDeformableAttention3DPts', 'MultiScaleDeformableAttention',
            'SpatialCrossAttentionImg', 'SpatialCrossAttentionPts', 'FFN', 'ImgEncoder', 'ImgLayer', 'PtsEncoder',
            'PtsLayer', 'UniBEVTransformer', 'HardSimpleVFE', 'Voxelization', 'voxelize', 'CustomMSDeformableAttention',
-           'DetectionTransformerDecoder', 'DetrTransformerDecoderLayer', 'MultiheadAttention']
+           'DetectionTransformerDecoder', 'DetrTransformerDecoderLayer', 'MultiheadAttention', 'LearnedPositionalEncoding']
