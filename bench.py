@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = 'unibev_nus_LC_cnw_256'
-METRIC = 'nuScenes frames/sec fwd (L+C CNW-256)'
+METRIC = 'nuScenes frames/sec fwd (L+C CNW-256) at 1/2/4/8 B200 vs ref CPU'      # BASELINE.json's metric, verbatim
 UNIT = 'frames/s'
 N_INPUT_SETS = 4          # 4 x 42 MB of features > 126 MB L2: consecutive steps never reuse L2-resident inputs
 
