@@ -152,3 +152,20 @@ def test_linear_f16_planes_and_strided_outputs(ops):
         ops.linear_f16(x.half().cuda(), w2[h * 256:(h + 1) * 256].half().cuda(), b2[h * 256:(h + 1) * 256].cuda(),
                        relu=True, fp32_out=False, out16=buf[:, h * 256:(h + 1) * 256])
     torch.testing.assert_close(buf.cpu().float(), F.linear(x, w2, b2).relu().half().float(), rtol=1e-3, atol=1e-3)
+
+
+def test_linear_f16_strided_residual_and_output_views(ops):
+    """The self-attention offset|logit rows: residual = one column block of the per-frame positional buffer (row stride
+    wider than N), output written into a column block of another buffer -- both ride TMA maps with the caller's stride."""
+    g = torch.Generator().manual_seed(11)
+    M, N, K = 3000, 96, 256
+    x, w, b = _exact((M, K), g), _exact((N, K), g, 64), _exact((N,), g)
+    pos_all = _exact((M, 6 * N), g).cuda()                   # six layers' blocks side by side
+    out_all = torch.zeros(M, 2 * N, device='cuda')
+    for blk in (0, 4):
+        res = pos_all[:, blk * N:(blk + 1) * N]
+        assert not res.is_contiguous()
+        got, _ = ops.linear_f16(x.half().cuda(), w.half().cuda(), b.cuda(), residual=res, out=out_all[:, N:])
+        want = (F.linear(x.double(), w.double(), b.double()) + res.cpu().double()).float()
+        torch.testing.assert_close(got.cpu(), want, rtol=0, atol=1e-4)
+        assert float(out_all[:, :N].abs().max()) == 0.0       # the neighbouring block is untouched
