@@ -45,6 +45,9 @@ def parse():
     ap.add_argument('--no-graphs', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
     ap.add_argument('--precision', default='tf32', choices=['tf32', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--e2e-result-dtype', default='fp32', choices=['fp32', 'fp16'],
+                    help='dtype of the result copied back to the host in the e2e leg (fp32 = what the API returns; fp16 is the '
+                         'opt-in FramePipeline(result_dtype=torch.float16) for hosts with a slow inbound DMA path)')
     ap.add_argument('--cpu-budget-s', type=float, default=20.0)
     return ap.parse_args()
 
@@ -256,7 +259,8 @@ def main():
     h0 = host_sets[0]
     pipe = FramePipeline(model, bev_q, h0['bev_h'], h0['bev_w'], bev_pos=dev_sets[0]['bev_pos'],
                          img_shape=tuple(h0['img_feats'][0].shape), pts_shape=tuple(h0['pts_feats'][0].shape),
-                         img_hw=img_hw, depth=3, device=dev, graphs=use_graphs)
+                         img_hw=img_hw, depth=3, device=dev, graphs=use_graphs,
+                         result_dtype=torch.float16 if args.e2e_result_dtype == 'fp16' else torch.float32)
 
     def e2e_run(steps):
         barrier()
@@ -413,6 +417,7 @@ def main():
                            'sampling_math': 'fp16-staged value maps and weights, fp32 accumulate' if args.precision == 'tf32' else 'fp32',
                            'cuda_graphs': use_graphs},
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        'result_dtype': args.e2e_result_dtype,
                         'ms_per_step': e2e_ms / args.steps},
                 'gpu_launches': launches, 'clocks': clk.summary(), 'roofline': roofline, 'kernels': kernels,
                 'other_kernels': other, 'cpu_baseline': cpu}

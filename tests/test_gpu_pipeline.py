@@ -69,3 +69,20 @@ def test_graphed_encoder_follows_rewritten_input_buffers():
     pts.copy_(f1['pts_feats'][0])
     l2i.copy_(torch.from_numpy(np.asarray([m['lidar2img'] for m in f1['img_metas']], dtype=np.float32)))
     torch.testing.assert_close(g.replay().cpu(), _eager(model, f1, bev_q, bev_pos[:1]).cpu(), rtol=0, atol=1e-5)
+
+
+def test_frame_pipeline_half_result_option():
+    """Opt-in fp16 result (half the device->host bytes): the fp32 result rounded once."""
+    from unibev_b200.pipeline import FramePipeline
+    model, frames, bev_q, bev_pos = _setup(batch=1, n_frames=2)
+    f0 = frames[0]
+    pipe = FramePipeline(model, bev_q, BEV, BEV, bev_pos=bev_pos[:1], img_shape=tuple(f0['img_feats'][0].shape),
+                         pts_shape=tuple(f0['pts_feats'][0].shape), img_hw=tuple(f0['img_metas'][0]['img_shape'][0][:2]),
+                         depth=2, graphs=True, result_dtype=torch.float16)
+    for f in frames:
+        t = pipe.submit(f['img_feats'][0], f['pts_feats'][0], f['img_metas'])
+    out = pipe.result(t).clone()
+    pipe.drain()
+    assert out.dtype == torch.float16 and pipe.d2h_bytes == BEV * BEV * 256 * 2
+    want = _eager(model, frames[1], bev_q, bev_pos[:1]).cpu()
+    torch.testing.assert_close(out.float(), want.half().float(), rtol=0, atol=1e-3)
