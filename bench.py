@@ -35,6 +35,11 @@ UNIT = 'frames/s'
 N_INPUT_SETS = 4          # 4 x 42 MB of features > 126 MB L2: consecutive steps never reuse L2-resident inputs
 
 
+def workload_string(B, world):
+    return (f'{WORKLOAD} inference, {B} frames per GPU per step, {world} GPU(s), batch-sharded, no collective '
+            '(BASELINE configs[3]: 32 frames over 8 GPUs = 4 per GPU; --batch 1 = configs[2])')
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -171,7 +176,9 @@ def main():
         line = {'metric': METRIC, 'value': ref['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': ref['steps'],
                 'warmup': args.warmup, 'ms_per_step': ref['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
-                'config': {'workload': WORKLOAD + ' inference, batch 1 (CPU oracle port of the reference path)'},
+                'config': {'workload': workload_string(args.batch, args.gpus),
+                           'reference_sample': 'CPU oracle port of the reference path, one frame per step (frames/s does not '
+                                               'depend on the batch on the CPU), all host threads, rank 0 only'},
                 'cpu_baseline': {k: ref[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
                 'e2e': {'value': ref['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
                 'gpu_launches': 0}
@@ -408,8 +415,7 @@ def main():
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'tf32' if args.precision == 'tf32' else 'f32', 'data': 'synthetic',
-                'config': {'workload': f'{WORKLOAD} inference, {B} frames per GPU per step, {world} GPU(s), batch-sharded, '
-                                       'no collective (BASELINE configs[3]: 32 frames over 8 GPUs = 4 per GPU; --batch 1 = configs[2])',
+                'config': {'workload': workload_string(B, world),
                            'frames_per_step': world * B, 'shapes': 'BEV 200x200 queries, 256 channels, 3 encoder layers per modality, '
                                                                     '6 cameras x 29x50 tokens, LiDAR map 180x180',
                            'l2_policy': f'rotating over {N_INPUT_SETS} input sets (> L2) + >1 GB of intermediates per frame',
