@@ -140,8 +140,12 @@ def test_full_size_vs_oracle_fp32(workload, batch):
     torch.testing.assert_close(out, want, **TOL_FP32)
 
 
-def test_full_size_vs_oracle_tf32():
-    out, want = _full_size('unibev_nus_LC_cnw_256', 1, 'tf32')
+@pytest.mark.parametrize('workload,batch', [('unibev_nus_LC_cnw_256', 1), ('unibev_nus_LC_cnw_256', 3), ('unibev_nus_C', 1),
+                                            ('unibev_nus_L', 2), ('unibev_nus_LC_cat_128', 1)])
+def test_full_size_vs_oracle_tf32(workload, batch):
+    """The bench configuration (fp16 / TF32 tensor-core operands, window-staged sampling, fused epilogues) at full size,
+    single-modality and 128-channel variants included: rtol 1e-3 / atol 4e-3."""
+    out, want = _full_size(workload, batch, 'tf32')
     torch.testing.assert_close(out, want, **TOL_TF32)
 
 
