@@ -425,7 +425,11 @@ def main():
                            'l2_policy': f'rotating over {N_INPUT_SETS} input sets (> L2) + >1 GB of intermediates per frame',
                            'gemm_math': 'tcgen05 kind::f16 (fp16 operands), fp32 accumulate in TMEM' if args.precision == 'tf32' else 'fp32',
                            'sampling_math': 'fp16-staged value maps and weights, fp32 accumulate' if args.precision == 'tf32' else 'fp32',
-                           'cuda_graphs': use_graphs},
+                           'cuda_graphs': use_graphs,
+                           'parity': ('fused_bev_embed vs the CPU oracle at this size: rtol 1e-3 / atol 4e-3, measured max |err| '
+                                      '3.0e-3, mean |err| 3.6e-4 on O(1) outputs (tests/test_gpu_encoder.py::'
+                                      'test_full_size_vs_oracle_tf32)') if args.precision == 'tf32' else
+                                     'rtol 1e-3 / atol 1e-4 (tests/test_gpu_encoder.py::test_full_size_vs_oracle_fp32)'},
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'result_dtype': args.e2e_result_dtype,
                         'ms_per_step': e2e_ms / args.steps},
