@@ -400,9 +400,10 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(str(B), {}).get(dominant)
         except OSError:
             traffic = None
-        roofline = {'bound': 'hbm', 'kernel': {'bev_self': 'bev_sample_win_kernel (BEV self-attn, P=4)',
-                                               'pts_cross': 'bev_sample_win_kernel (LiDAR cross-attn, P=8)',
-                                               'img_cross': 'img_sample_win_kernel (camera cross-attn, P=8)'}[dominant],
+        win = '_win' if args.precision == 'tf32' else ''      # fp32 class: the fp32 tile kernels of tile_sample.cu
+        roofline = {'bound': 'hbm', 'kernel': {'bev_self': f'bev_sample{win}_kernel (BEV self-attn, P=4)',
+                                               'pts_cross': f'bev_sample{win}_kernel (LiDAR cross-attn, P=8)',
+                                               'img_cross': f'img_sample{win}_kernel (camera cross-attn, P=8)'}[dominant],
                     'achieved': k['achieved_gbs'], 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
                     'frac': k['frac'], 'traffic': traffic, 'avg_us': k['avg_us'], 'alg_bytes_per_launch': k['alg_bytes']}
 
