@@ -21,6 +21,10 @@
 //            each box straight into the accumulator with tcgen05.cp (smem -> TMEM) BEFORE the tile's MMAs, which
 //            then accumulate on top of it.  The residual so rides the deep asynchronous TMA pipeline instead of
 //            exposing its DRAM latency to the epilogue threads, and LayerNorm needs no second TMEM write pass.
+//   fp16 copies of the result rows / value planes leave each epilogue thread as one 32-byte store (STG.256): the
+//            thread-per-row epilogue is bound by LSU line lookups, not by bytes.
+//   launch   programmatic dependent launch: set-up (barriers, TMEM, parameters, resident W) overlaps the predecessor's
+//            tail; the A producer waits for the predecessor (griddepcontrol.wait) before its first load.
 // The GEMMs here are bound by their activation traffic, not by math: the point of the kernel is to touch each
 // activation row once (no separate bias / residual / LayerNorm / fp16-conversion passes).
 #include <cuda_fp16.h>
