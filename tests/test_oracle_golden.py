@@ -114,3 +114,17 @@ def test_c_oracle_matches_kat_and_torch_oracle():
     want = ms.msda_core(value, shapes, loc, w)
     got = c_msda.msda_forward(value.numpy(), shapes, loc.numpy(), w.numpy())
     np.testing.assert_allclose(got, want.numpy(), rtol=1e-5, atol=2e-6)
+
+
+def test_config1_camera_only_cpu_plumbing():
+    """BASELINE configs[0]: unibev_nus_C (camera only, 6 x (3 x 256 x 704) -> 8 x 22 stride-32 maps, 1 sample) end to end on
+    the CPU through the oracle, with the parameters of the plugin model built from the same config subtree."""
+    from unibev_b200 import synth
+    model, cfg = synth.build_model('unibev_nus_C')
+    inp = synth.make_inputs('unibev_nus_C', batch=1)
+    params = {k: v.detach() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        out = oe.encoder_half(params, cfg, inp['img_feats'], None, inp['bev_queries'], inp['bev_h'], inp['bev_w'],
+                              bev_pos=inp['bev_pos'], img_metas=inp['img_metas'])
+    assert out.shape == (1, 200 * 200, 256) and bool(torch.isfinite(out).all())
+    assert float(out.std()) > 0.1                       # LayerNorm'd BEV features, not a degenerate map
