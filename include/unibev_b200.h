@@ -6,12 +6,13 @@
  * pointers unless the parameter comment says "host".  Every call is asynchronous
  * on `stream` (a cudaStream_t) and returns 0 on success or a negative UB_E* code
  * (message: ub_last_error(), thread-local).  The caller owns every tensor and
- * workspace; the library itself keeps only (a) a 512-byte device array of work
- * counters allocated on the first window-kernel call, (b) a mutex-guarded host
- * cache of encoded TMA tensor maps and (c) the process-wide tuning knobs set by
- * the ub_set_* calls (performance only; results do not depend on them, except
- * ub_set_window_round_tf32).  Calls may be captured into CUDA graphs.  Tensors
- * are contiguous row-major fp32 unless stated.
+ * workspace, and makes the tensors' device current before calling.  No entry point
+ * allocates device memory or keeps per-call device state.  Host-side state is
+ * limited to: the thread-local error text, two diagnostic counters
+ * (ub_launch_count / ub_unsupported_count), a mutex-guarded cache of encoded TMA
+ * tensor maps, and per-(kernel, device) records of the shared-memory opt-in.
+ * Calls are re-entrant and may be captured into CUDA graphs.  Tensors are
+ * contiguous row-major fp32 unless stated.
  *
  * Reference interfaces replaced (paths under /root/reference):
  *   [R1] mmcv MultiScaleDeformableAttnFunction.apply / ext_module.ms_deform_attn_forward|backward,
@@ -62,6 +63,8 @@ const char* ub_last_error(void);
 /* Number of kernels this library has launched since load / since the last reset (bench bookkeeping). */
 int64_t ub_launch_count(void);
 void ub_launch_count_reset(void);
+/* Calls that returned UB_EUNSUPPORTED since the last ub_launch_count_reset (each made the caller take a generic entry point). */
+int64_t ub_unsupported_count(void);
 
 /* ---- [R1] generic multi-scale deformable attention -------------------------------------------------
  * value (B, Nv, H, D); spatial_shapes (L, 2) int64 (h, w); level_start_index (L) int64;
@@ -118,15 +121,14 @@ int ub_value_to_half(const float* value, void* value16, int G, int Nv, int H, in
 /* value16 (B, H, fH*fW, 32) fp16; qproj / out as in ub_bev_sample_fwd (ld, off_col, logit_col multiples of 4).
  * out_f16 != 0: `out` is (B, Nq, H*32) fp16 instead of fp32 -- the A operand of ub_linear_f16 (the output projection);
  * the rounding is the one a TF32 projection would apply to its operand anyway (11-bit significand). */
+/* workspace: 2 ints owned by the caller, zero before the first use and left zero by every call (the persistent CTAs
+ * draw their work units from it); calls that may run concurrently need distinct workspaces.
+ * flags bit 0 (UB_WIN_ROUND_TF32): round the fp32 outputs to the nearest TF32 value -- for callers that feed them to
+ * ub_linear_tf32, whose operand fetch truncates instead. */
+enum { UB_WIN_ROUND_TF32 = 1 };
 int ub_bev_sample_win_fwd(const void* value16, const float* qproj, void* out, int out_f16,
                           int B, int bev_h, int bev_w, int fH, int fW, int H, int Dh, int P,
-                          int ld, int off_col, int logit_col, ub_stream_t stream);
-/* Halo (value-map pixels) the BEV windows extend beyond the tile's reference points; 0 = default (P + 1).
- * Samples outside the window are still exact (slow path), so this is a performance knob only. */
-int ub_set_window_halo(int halo);
-/* on != 0: ub_bev_sample_win_fwd rounds its outputs to the nearest TF32 value (10 mantissa bits).  For callers that
- * feed them to a TF32 tensor-core projection (ub_linear_tf32), whose operand fetch truncates instead. */
-int ub_set_window_round_tf32(int on);
+                          int ld, int off_col, int logit_col, int* workspace, int flags, ub_stream_t stream);
 /* mask (B, Nq, N) from ub_project_points -> the queries batch item 0 sees in camera n
  * (spatial_cross_attention_img.py:141-152), split by rank: hit_idx (N + 1, Nq) int32, row n = the hits whose lowest
  * seeing camera is n ("first", ascending, from the front) and the other hits of camera n ("later", from the back:
@@ -171,6 +173,23 @@ int ub_linear_tf32_dual(const float* A, const float* W, const float* bias, const
 int ub_linear_f16(const void* A16, const void* W16, const float* bias, const float* residual, int ldr,
                   const float* gamma, const float* beta, float eps, float* out, int ldc, void* out16, int ldc16,
                   void* planes, int Nv, int M, int N, int K, int flags, ub_stream_t stream);
+
+/* fp32-grade projection on the tensor cores ("3xTF32"): every product a*w is evaluated as a_hi*w_hi + a_lo*w_hi +
+ * a_hi*w_lo with three tcgen05 kind::tf32 MMAs into the same fp32 accumulator (x_hi = upper 19 bits of x, x_lo = x - x_hi),
+ * error ~2^-21 relative per product -- the arithmetic class of the reference's fp32 nn.Linear
+ * (spatial_cross_attention_img.py:381-389, encoder_unibev_detr_img.py:434-436,476-479).  A (M, K) fp32 is split on chip;
+ * W_hi / W_lo (N, K) come from ub_split_tf32 (once per weight).  Epilogues, flags and shape limits as ub_linear_tf32.
+ *   planes32 != NULL: instead of `out`, write fp32 (acc + bias) as half-head planes (M / Nv, N / 16, Nv, 16), the value-map
+ *   layout of the fp32 window-staged sampling kernels (no ReLU / residual / LayerNorm). */
+int ub_linear_tf32x3(const float* A, const float* W_hi, const float* W_lo, const float* bias, const float* residual, int ldr,
+                     const float* gamma, const float* beta, float eps, float* out, int ldc, float* planes32, int Nv,
+                     int M, int N, int K, int flags, ub_stream_t stream);
+/* Generic fp32 (FFMA) projection for shapes the tensor-core entry points reject (UB_EUNSUPPORTED): any M, N, K.
+ * out (M, N; row stride ldc) = [relu](A (M, K) @ W (N, K)^T + bias + residual (row stride ldr)); bias / residual may be NULL. */
+int ub_linear_simt(const float* A, const float* W, const float* bias, const float* residual, int ldr, float* out, int ldc,
+                   int M, int N, int K, int relu, ub_stream_t stream);
+/* w (n) -> hi (n) = w with the 13 low mantissa bits cleared, lo (n) = round_to_tf32(w - hi). */
+int ub_split_tf32(const float* w, float* hi, float* lo, int64_t n, ub_stream_t stream);
 
 /* ---- [R5] y = LayerNorm(x + bias + residual) * gamma + beta over the last dim C ---------------------
  * bias (C) and residual (rows, C) may be NULL.  C % 4 == 0, C <= 1024.  out may alias x. */

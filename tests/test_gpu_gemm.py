@@ -169,3 +169,101 @@ def test_linear_f16_strided_residual_and_output_views(ops):
         want = (F.linear(x.double(), w.double(), b.double()) + res.cpu().double()).float()
         torch.testing.assert_close(got.cpu(), want, rtol=0, atol=1e-4)
         assert float(out_all[:, :N].abs().max()) == 0.0       # the neighbouring block is untouched
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ub_linear_tf32x3: fp32-grade products from three TF32 MMAs.  Gaussian (NOT TF32-representable) operands, float64
+# reference, fp32-class tolerance: |err| <= a few 2^-21 * sqrt(K) * |a||w| -- two orders below a single TF32 pass.
+def _x3(ops, x, w, b=None, **kw):
+    return ops.linear_tf32x3(x.cuda(), ops.split_tf32(w.cuda()), b.cuda() if b is not None else None, **kw).cpu()
+
+
+def test_split_tf32_is_exact_hi_plus_lo(ops):
+    g = torch.Generator().manual_seed(11)
+    w = torch.randn(300, 256, generator=g) * torch.logspace(-6, 3, 256)
+    hi, lo = (t.cpu() for t in ops.split_tf32(w.cuda()))
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0          # hi is what kind::tf32 reads of w
+    assert int((lo.view(torch.int32) & 0x1FFF).abs().max()) == 0          # lo is a TF32 value too
+    rel = ((hi.double() + lo.double() - w.double()).abs() / w.double().abs()).max()
+    assert float(rel) < 2.0 ** -21
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 256, 256), (1000, 256, 256), (40000, 256, 256), (333, 96, 256),
+                                   (700, 192, 256), (513, 512, 256), (260, 256, 512), (129, 128, 128), (64, 32, 32)])
+@pytest.mark.parametrize('relu', [False, True])
+def test_linear_x3_gaussian(ops, M, N, K, relu):
+    g = torch.Generator().manual_seed(M + N + K)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    want = F.linear(x.double(), w.double(), b.double())
+    want = (want.relu() if relu else want).float()
+    got = _x3(ops, x, w, b, relu=relu)
+    err = (got - want).abs()
+    assert float(err.max()) < 2e-5 and float(err.mean()) < 1.5e-6, (float(err.max()), float(err.mean()))
+    # an fp32 FFMA GEMM (torch on the CPU) is no closer to the float64 result
+    ref32 = F.linear(x, w, b)
+    ref32 = ref32.relu() if relu else ref32
+    assert float(err.max()) <= 4 * float((ref32 - want).abs().max()) + 1e-6
+
+
+def test_linear_x3_large_dynamic_range(ops):
+    """8-bit exponent: no saturation / flush where fp16 operands would fail (|x| up to 1e6, weights down to 1e-6)."""
+    g = torch.Generator().manual_seed(4)
+    M, N, K = 777, 256, 256
+    x = torch.randn(M, K, generator=g) * torch.logspace(-3, 6, K)
+    w = torch.randn(N, K, generator=g) * torch.logspace(-6, 0, N)[:, None]
+    want = F.linear(x.double(), w.double()).float()
+    got = _x3(ops, x, w)
+    scale = F.linear(x.double().abs(), w.double().abs()).float()            # sum |a||w| per output
+    assert float(((got - want).abs() / scale).max()) < 2e-6
+
+
+def test_linear_x3_residual_strided_and_layernorm(ops):
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 1777, 256, 512
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    r = torch.randn(M, N, generator=g)
+    gam, bet = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    pre = F.linear(x.double(), w.double(), b.double()) + r.double()
+    got = _x3(ops, x, w, b, residual=r.cuda())
+    torch.testing.assert_close(got, pre.float(), rtol=1e-5, atol=2e-5)
+    want = F.layer_norm(pre, (N,), gam.double(), bet.double(), 1e-5).float()
+    got = _x3(ops, x, w, b, residual=r.cuda(), ln=(gam.cuda(), bet.cuda(), 1e-5))
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=2e-5)
+    # strided output / residual views (column blocks of wider matrices)
+    wide_o, wide_r = torch.zeros(M, 3 * N).cuda(), torch.randn(M, 2 * N, generator=g).cuda()
+    ops.linear_tf32x3(x.cuda(), ops.split_tf32(w.cuda()), b.cuda(), residual=wide_r[:, N:], out=wide_o[:, N:2 * N])
+    want = (F.linear(x.double(), w.double(), b.double()) + wide_r[:, N:].cpu().double()).float()
+    torch.testing.assert_close(wide_o[:, N:2 * N].cpu(), want, rtol=1e-5, atol=2e-5)
+    assert float(wide_o[:, :N].abs().max()) == 0 and float(wide_o[:, 2 * N:].abs().max()) == 0
+
+
+@pytest.mark.parametrize('G,Nv', [(1, 1000), (6, 1450), (2, 333)])
+def test_linear_x3_fp32_half_head_planes(ops, G, Nv):
+    g = torch.Generator().manual_seed(Nv)
+    N, K = 256, 256
+    x, w, b = torch.randn(G * Nv, K, generator=g), torch.randn(N, K, generator=g) / 16, torch.randn(N, generator=g)
+    want = F.linear(x.double(), w.double(), b.double()).float().view(G, Nv, N // 16, 16).permute(0, 2, 1, 3)
+    got = _x3(ops, x, w, b, planes_nv=Nv)
+    assert got.shape == (G, N // 16, Nv, 16)
+    torch.testing.assert_close(got, want.contiguous(), rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('M,N,K', [(100, 24, 32), (333, 48, 40), (1000, 96, 256), (65, 7, 3)])
+def test_linear_simt_any_shape(ops, M, N, K):
+    g = torch.Generator().manual_seed(M)
+    x, w, b, r = (torch.randn(s, generator=g) for s in ((M, K), (N, K), (N,), (M, N)))
+    want = (F.linear(x.double(), w.double(), b.double()) + r.double()).relu().float()
+    got = ops.linear_simt(x.cuda(), w.cuda(), b.cuda(), residual=r.cuda(), relu=True).cpu()
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(ops.linear_simt(x.cuda(), w.cuda()).cpu(), F.linear(x, w), rtol=1e-5, atol=1e-5)
+
+
+def test_unsupported_shapes_are_counted(ops):
+    from unibev_b200 import _cabi
+    _cabi.reset_launch_count()
+    x, w = torch.randn(64, 40).cuda(), torch.randn(24, 40).cuda()
+    with pytest.raises(_cabi.UnsupportedShape):
+        ops.linear_tf32x3(x, ops.split_tf32(w))
+    assert _cabi.unsupported_count() == 1
+    _cabi.reset_launch_count()
+    assert _cabi.unsupported_count() == 0

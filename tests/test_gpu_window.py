@@ -46,8 +46,10 @@ def _bev_case(ops, B, bev_h, bev_w, fH, fW, H, P, off_scale, seed, halo=0):
     _cabi.check(_cabi.lib().ub_set_window_halo(halo), 'ub_set_window_halo')
     try:
         v16 = ops.value_to_half(vg.view(B * fH * fW, C), B, fH * fW, H)
-        got = ops.bev_sample_win(v16, qg, bev_h, bev_w, fH, fW, H, P, 0, H * P * 2).cpu()
-        got2 = ops.bev_sample_win(v16, qg, bev_h, bev_w, fH, fW, H, P, 0, H * P * 2).cpu()   # counters re-armed
+        ws = torch.zeros(2, dtype=torch.int32).cuda()      # caller-owned work counters, left zero by every call
+        got = ops.bev_sample_win(v16, qg, bev_h, bev_w, fH, fW, H, P, 0, H * P * 2, workspace=ws).cpu()
+        got2 = ops.bev_sample_win(v16, qg, bev_h, bev_w, fH, fW, H, P, 0, H * P * 2, workspace=ws).cpu()
+        assert ws.cpu().tolist() == [0, 0]
         got16 = ops.bev_sample_win(v16, qg, bev_h, bev_w, fH, fW, H, P, 0, H * P * 2, out_dtype=torch.float16).cpu()
     finally:
         _cabi.lib().ub_set_window_halo(0)
@@ -183,3 +185,36 @@ def test_img_sample_win_vs_fp32_kernel(ops, B, bev, fhw, P):
     assert float(err.mean()) <= 1.5e-4, float(err.mean())
     # quantisation-aware check through the oracle's semantics for camera 0 .. N-1 of item 0 is covered by the
     # encoder-level tests (test_gpu_encoder.py::test_full_size_vs_oracle_tf32)
+
+
+def test_bev_sample_win_concurrent_graph_replays(ops):
+    """no shared work counters -- two CUDA graphs of the same call, each with its own workspace,
+    replayed at the same time on two streams give the same result as the serial call."""
+    g = torch.Generator().manual_seed(9)
+    B, bev, f, H, P = 2, 200, 180, 8, 8
+    v16 = ops.value_to_half(torch.randn(B * f * f, H * 32, generator=g).cuda(), B, f * f, H)
+    qp = torch.cat((torch.randn(B, bev * bev, H * P * 2, generator=g) * 3, torch.randn(B, bev * bev, H * P, generator=g)),
+                   -1).cuda()
+    want = ops.bev_sample_win(v16, qp, bev, bev, f, f, H, P, 0, H * P * 2)
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    graphs, outs = [], []
+    for s in streams:
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            ops.bev_sample_win(v16, qp, bev, bev, f, f, H, P, 0, H * P * 2)
+            s.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=s):
+                outs.append(ops.bev_sample_win(v16, qp, bev, bev, f, f, H, P, 0, H * P * 2))
+        graphs.append(gr)
+    torch.cuda.synchronize()
+    for _ in range(5):
+        for o in outs:
+            o.zero_()
+        torch.cuda.synchronize()
+        for s, gr in zip(streams, graphs):
+            with torch.cuda.stream(s):
+                gr.replay()
+        torch.cuda.synchronize()
+        for o in outs:
+            torch.testing.assert_close(o, want, rtol=0, atol=1e-6)

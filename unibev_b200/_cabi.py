@@ -20,19 +20,21 @@ PROTOTYPES = {
     'ub_last_error': ([], ctypes.c_char_p),
     'ub_launch_count': ([], _i64),
     'ub_launch_count_reset': ([], None),
+    'ub_unsupported_count': ([], _i64),
     'ub_msda_fwd': ([_p] * 6 + [_i] * 7 + [_p], _i),
     'ub_msda_bwd': ([_p] * 9 + [_i] * 7 + [_p], _i),
     'ub_project_points': ([_p, _p, _p, _f, _f, _p, _p] + [_i] * 5 + [_p], _i),
     'ub_bev_sample_fwd': ([_p] * 3 + [_i] * 11 + [_p], _i),
     'ub_img_sample_fwd': ([_p] * 5 + [_i] * 13 + [_p], _i),
     'ub_value_to_half': ([_p, _p] + [_i] * 4 + [_p], _i),
-    'ub_bev_sample_win_fwd': ([_p] * 3 + [_i] * 12 + [_p], _i),
-    'ub_set_window_halo': ([_i], _i),
-    'ub_set_window_round_tf32': ([_i], _i),
+    'ub_bev_sample_win_fwd': ([_p] * 3 + [_i] * 12 + [_p, _i, _p], _i),
     'ub_build_hits': ([_p] * 5 + [_i] * 3 + [_p], _i),
     'ub_img_sample_win_fwd': ([_p] * 8 + [_i] * 14 + [_p], _i),
     'ub_linear_tf32': ([_p] * 4 + [_i, _p, _p, _f, _p, _i, _p] + [_i] * 5 + [_p], _i),
     'ub_linear_tf32_dual': ([_p] * 4 + [_i, _p, _p, _f, _p, _i, _p] + [_i] * 5 + [_p], _i),
+    'ub_linear_tf32x3': ([_p] * 5 + [_i, _p, _p, _f, _p, _i, _p] + [_i] * 5 + [_p], _i),
+    'ub_linear_simt': ([_p] * 4 + [_i, _p] + [_i] * 5 + [_p], _i),
+    'ub_split_tf32': ([_p, _p, _p, _i64, _p], _i),
     'ub_linear_f16': ([_p] * 4 + [_i, _p, _p, _f, _p, _i, _p, _i, _p] + [_i] * 5 + [_p], _i),
     'ub_add_layernorm': ([_p] * 6 + [_i64, _i, _f, _p], _i),
     'ub_add_layernorm16': ([_p] * 7 + [_i64, _i, _f, _p], _i),
@@ -45,9 +47,10 @@ PROTOTYPES = {
                           ctypes.c_size_t, _p], _i),
     'ub_voxel_mean': ([_p, _p, _i, _i, _i, _i, _p, _p], _i),
 }
-# not part of the public header: tuning hook used by bench/sweeps
+# not part of the public header: process-wide performance knobs for A/B runs (tools/, sweeps); results never depend on them
 _PRIVATE = {
     'ub_set_tuning': ([_i] * 3, _i),
+    'ub_set_window_halo': ([_i], _i),
     'ub_set_gemm_cluster': ([_i], _i),
     'ub_set_gemm_trace': ([_p], _i),
     'ub_set_pdl': ([_i], _i),
@@ -109,6 +112,11 @@ def launch_count():
 
 def reset_launch_count():
     lib().ub_launch_count_reset()
+
+
+def unsupported_count():
+    """Calls that returned UB_EUNSUPPORTED (and so sent their caller to a generic entry point) since the last reset."""
+    return int(lib().ub_unsupported_count())
 
 
 def set_tuning(which, tile_w=8, ctas_per_sm=0):

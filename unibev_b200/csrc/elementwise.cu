@@ -270,7 +270,7 @@ extern "C" int ub_add_layernorm16(const float* x, const float* bias, const float
   if (bias) UB_REQUIRE_ALIGNED16(bias);
   if (residual) UB_REQUIRE_ALIGNED16(residual);
   int64_t blocks = (rows + 7) / 8;
-  if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
+  if (blocks > sm_count() * 32) blocks = sm_count() * 32;
   cudaStream_t s = (cudaStream_t)stream;
   const int nv = (C + 127) / 128;
 #define UB_LN(NV) add_layernorm_kernel<NV><<<(int)blocks, 256, 0, s>>>(x, bias, residual, gamma, beta, out, reinterpret_cast<uint2*>(out16), rows, C, eps)
@@ -305,7 +305,7 @@ extern "C" int ub_cnw_fuse(const float* img, const float* pts, const float* w_im
   const int threads = C4 >= 256 ? C4 : (256 / C4) * C4;
   const int rows_per_block = threads / C4;
   int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
-  if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
+  if (blocks > sm_count() * 32) blocks = sm_count() * 32;
   cnw_fuse_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(img, pts, w_img, w_pts, s_img, s_pts, modal_embed, out,
                                                                  rows, fp);
   return check_launch("ub_cnw_fuse");
@@ -343,7 +343,7 @@ extern "C" int ub_broadcast_rows(const float* src, int64_t rows, int C, int B, f
   if (out16) UB_REQUIRE_ALIGNED16(out16);
   const int64_t n8 = rows * C / 8;
   int blocks = (int)((n8 + 255) / 256);
-  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   broadcast_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, n8, B, out32, reinterpret_cast<__half*>(out16));
   return check_launch("ub_broadcast_rows");
 }

@@ -29,11 +29,16 @@
 // activation row once (no separate bias / residual / LayerNorm / fp16-conversion passes).
 #include <cuda_fp16.h>
 
+#include <atomic>
+
 #include "ub_tma.cuh"
 
 namespace ub {
 
 constexpr int kGemmThreads = 640;                 // 4 control warps + 16 epilogue warps
+constexpr int kConvExtraWarps = 2;                // 3xTF32 mode: warp 2 + two extra warps split the A k-blocks into hi / lo
+constexpr int kConvWarps = 1 + kConvExtraWarps;
+constexpr int kGemmThreadsSplit = kGemmThreads + 32 * kConvExtraWarps;
 constexpr int kBM = 128, kMaxStages = 8;
 constexpr int kEpiWarps = 16, kChunk = 16;         // epilogue warps (four per TMEM lane quarter), column chunk
 constexpr int kStageBuf = kChunk * 32 * 4;         // one warp's 32 rows x 16 columns staging buffer (2 KB)
@@ -62,6 +67,8 @@ struct GemmArgs {
   int cs;               // CTAs per cluster: they work on `cs` consecutive row tiles and share W by TMA multicast
   int res_chunks;       // residual boxes (32 fp32 columns x 128 rows) per tile preloaded into the accumulator, 0 = none
   unsigned long long* trace;   // optional per-CTA event timestamps (tools/trace_gemm.py), else null
+  int SL;               // 3xTF32 mode: depth of the A_lo ring
+  float* planes32;      // fp32 half-head planes (G, N / 16, Nv, 16): the value-map layout of the fp32 window kernels, or null
 };
 
 // trace slots per CTA: [0] start, [1 + 32 r + i]: role r (0 producer, 1 mma, 2 epilogue warp 0), event i
@@ -225,21 +232,32 @@ __device__ __forceinline__ uint32_t swz(uint32_t base, int row, int j) {
 // Shared-memory rings: the A k-blocks come from DRAM (about 1.5 us away under load), so their ring is deep; the W
 // k-blocks are re-read from L2 by every tile and need only a shallow ring.  Each ring has its own producer lane.
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+//
+// SPLIT (3xTF32, ub_linear_tf32x3): fp32-grade products from three TF32 MMAs per k-step.  kind::tf32 reads the upper 19
+// bits of each fp32 operand, so  a * w  ~=  a_hi * w_hi + a_lo * w_hi + a_hi * w_lo  with x_hi = x & ~0x1fff and
+// x_lo = x - x_hi (exact; rounded to TF32): the dropped term a_lo * w_lo is 2^-22 relative.  W arrives pre-split from the
+// host (two tensors, W ring slots alternate hi / lo k-blocks); the A k-blocks are split on chip by three converter warps
+// (warp 2 and two extra warps): they mask the TMA-written A slot in place (a_hi, so the result does not depend on how
+// the tensor core rounds its operands) and write a_lo into a second, identically laid out (swizzle and all: the
+// transform is element-wise) ring, which the MMA lane consumes through the same kind of descriptors.  All three products
+// accumulate into the same TMEM columns, so residual-via-tcgen05.cp and the epilogues are unchanged.
+template <bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
     gemm_tf32_kernel(const GemmArgs a, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                     const __grid_constant__ CUtensorMap map_r) {
+                     const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_wl) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t s_fa[kMaxStages], s_ea[kMaxStages], s_fw[kMaxStages], s_ew[kMaxStages], s_tfull[2],
-      s_tempty[2];
+      s_tempty[2], s_fl[4], s_el[4];
   __shared__ uint32_t s_tmem;
   __shared__ float2 s_stat[4][kBM];   // LayerNorm partial (sum, sum of squares) per epilogue warp of a lane quarter
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int SA = a.SA, SW = a.SW;
   const uint32_t a_bytes = kBM * 128, w_bytes = (uint32_t)a.BN * 128;
-  const uint32_t sm_a = smem_u32(smem), sm_w = sm_a + (uint32_t)SA * a_bytes;
+  const int SL = SPLIT ? a.SL : 0;
+  const uint32_t sm_a = smem_u32(smem), sm_l = sm_a + (uint32_t)SA * a_bytes, sm_w = sm_l + (uint32_t)SL * a_bytes;
   const uint32_t sm_stage_buf = sm_w + (uint32_t)SW * w_bytes;                  // [16 warps] x 2 KB
-  float* s_par = reinterpret_cast<float*>(smem + (size_t)SA * a_bytes + (size_t)SW * w_bytes + kEpiWarps * kStageBuf);
+  float* s_par = reinterpret_cast<float*>(smem + (size_t)(SA + SL) * a_bytes + (size_t)SW * w_bytes + kEpiWarps * kStageBuf);
   const int k_blocks = a.K / a.kb_elems;
   // Work = groups of `cs` consecutive row tiles of one column tile; cluster c takes groups c, c + n_clusters, ...
   // and CTA rank r of the cluster the r-th row tile of the group (possibly past M: loads zero-fill, nothing is stored).
@@ -271,7 +289,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   };
   auto tile_n0 = [&](int i) { return a.balanced ? my_n0 : ((cluster_id + i * n_clusters) / groups_m) * a.BN; };
 
-  for (int i = tid; i < a.N; i += kGemmThreads) {
+  for (int i = tid; i < a.N; i += (int)blockDim.x) {
     s_par[i] = a.bias ? a.bias[i] : 0.f;
     if (a.ln) s_par[a.N + i] = a.gamma[i], s_par[2 * a.N + i] = a.beta[i];
   }
@@ -279,6 +297,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     for (int i = 0; i < SA; ++i) mbar_init(smem_u32(&s_fa[i]), 1), mbar_init(smem_u32(&s_ea[i]), 1);
     for (int i = 0; i < SW; ++i) mbar_init(smem_u32(&s_fw[i]), 1), mbar_init(smem_u32(&s_ew[i]), cs);
     for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&s_tfull[i]), 1), mbar_init(smem_u32(&s_tempty[i]), kEpiWarps);
+    for (int i = 0; i < SL; ++i) mbar_init(smem_u32(&s_fl[i]), kConvWarps), mbar_init(smem_u32(&s_el[i]), 1);
     mbar_init_fence();
   }
   if (warp == 2) {
@@ -342,19 +361,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       } else {
         int stage = 0;
         uint32_t phase = 0;
+        if (SPLIT) tma_prefetch_desc(&map_wl);
         for (int i = 0; i < n_iter; ++i) {
           const int n0 = tile_n0(i);
           for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait(smem_u32(&s_ew[stage]), phase ^ 1u);   // every CTA of the cluster has consumed the slot
-            const uint32_t bar = smem_u32(&s_fw[stage]);
-            const uint32_t dst = sm_w + (uint32_t)stage * w_bytes;
-            mbar_arrive_expect_tx(bar, w_bytes);             // all `cs` slices of the W k-block
-            if (cs == 1)
-              tma_load_2d(dst, &map_w, bar, kb * a.kb_elems, n0);
-            else
-              tma_load_2d_multicast(dst + (uint32_t)rank * w_slice_bytes, &map_w, bar, kb * a.kb_elems,
-                                    n0 + rank * (int)w_slice_rows, cta_mask);
-            if (++stage == SW) stage = 0, phase ^= 1u;
+#pragma unroll
+            for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {   // SPLIT: the hi k-block, then the lo k-block
+              const CUtensorMap* mw = part ? &map_wl : &map_w;
+              mbar_wait(smem_u32(&s_ew[stage]), phase ^ 1u);   // every CTA of the cluster has consumed the slot
+              const uint32_t bar = smem_u32(&s_fw[stage]);
+              const uint32_t dst = sm_w + (uint32_t)stage * w_bytes;
+              mbar_arrive_expect_tx(bar, w_bytes);             // all `cs` slices of the W k-block
+              if (cs == 1)
+                tma_load_2d(dst, mw, bar, kb * a.kb_elems, n0);
+              else
+                tma_load_2d_multicast(dst + (uint32_t)rank * w_slice_bytes, mw, bar, kb * a.kb_elems,
+                                      n0 + rank * (int)w_slice_rows, cta_mask);
+              if (++stage == SW) stage = 0, phase ^= 1u;
+            }
           }
         }
       }
@@ -363,8 +387,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = a.f16 ? idesc_f16(a.BN) : idesc_tf32(a.BN);
-      int sa = 0, sw = 0, ev = 0;
-      uint32_t pa = 0, pw = 0;
+      int sa = 0, sw = 0, sl = 0, ev = 0;
+      uint32_t pa = 0, pw = 0, pl = 0;
       for (int it = 0; it < n_iter; ++it) {
         const int acc = it & 1;
         mbar_wait(smem_u32(&s_tempty[acc]), (uint32_t)(((it >> 1) & 1) ^ 1));
@@ -381,6 +405,42 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           if (++sa == SA) sa = 0, pa ^= 1u;
         }
         const uint32_t acc0 = a.res_chunks ? 1u : 0u;       // accumulate on top of the preloaded residual
+        if (SPLIT) {
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(smem_u32(&s_fa[sa]), pa);
+            mbar_wait(smem_u32(&s_fl[sl]), pl);             // the converters have masked the A slot and filled the lo slot
+            mbar_wait(smem_u32(&s_fw[sw]), pw);             // W_hi k-block
+            trace_event(a, 1, ev++);
+            tc_fence_after();
+            const uint64_t adesc = smem_desc_k128(sm_a + (uint32_t)sa * a_bytes);
+            const uint64_t ldesc = smem_desc_k128(sm_l + (uint32_t)sl * a_bytes);
+            uint64_t bdesc = smem_desc_k128(sm_w + (uint32_t)sw * w_bytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : acc0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_tf32(tmem_d, ldesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+            if (cs == 1)
+              mma_commit(smem_u32(&s_ew[sw]));
+            else
+              mma_commit_multicast(smem_u32(&s_ew[sw]), cta_mask);
+            if (++sw == SW) sw = 0, pw ^= 1u;
+            mbar_wait(smem_u32(&s_fw[sw]), pw);             // W_lo k-block
+            tc_fence_after();
+            bdesc = smem_desc_k128(sm_w + (uint32_t)sw * w_bytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+            if (cs == 1)
+              mma_commit(smem_u32(&s_ew[sw]));
+            else
+              mma_commit_multicast(smem_u32(&s_ew[sw]), cta_mask);
+            if (++sw == SW) sw = 0, pw ^= 1u;
+            mma_commit(smem_u32(&s_ea[sa]));
+            mma_commit(smem_u32(&s_el[sl]));
+            if (++sa == SA) sa = 0, pa ^= 1u;
+            if (++sl == SL) sl = 0, pl ^= 1u;
+          }
+        } else
         for (int kb = 0; kb < k_blocks; ++kb) {
           if (a.w_res) sw = kb, pw = 0;                     // resident: slot kb, its only phase
           mbar_wait(smem_u32(&s_fw[sw]), pw);
@@ -412,7 +472,39 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         mma_commit(smem_u32(&s_tfull[acc]));
       }
     }
-  } else if (warp >= 4) {
+  } else if (SPLIT && (warp == 2 || warp >= 4 + kEpiWarps)) {
+    // ------------------------------------------------------------------ 3xTF32: A k-block -> (a_hi in place, a_lo slot)
+    const int ct = (warp == 2 ? 0 : warp - (4 + kEpiWarps) + 1) * 32 + lane;   // 0 .. 32 kConvWarps - 1
+    int sa = 0, sl = 0;
+    uint32_t pa = 0, pl = 0;
+    for (int it = 0; it < n_iter; ++it) {
+      for (int rc = 0; rc < a.res_chunks; ++rc)            // residual boxes pass through the ring untouched
+        if (++sa == SA) sa = 0, pa ^= 1u;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(smem_u32(&s_fa[sa]), pa);
+        mbar_wait(smem_u32(&s_el[sl]), pl ^ 1u);
+        const uint32_t src = sm_a + (uint32_t)sa * a_bytes, dst = sm_l + (uint32_t)sl * a_bytes;
+#pragma unroll 4
+        for (uint32_t j = (uint32_t)ct * 16u; j < a_bytes; j += 32u * kConvWarps * 16u) {
+          uint32_t x[4], h[4], l[4];
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(src + j));
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            h[e] = x[e] & 0xffffe000u;
+            const float lo = __uint_as_float(x[e]) - __uint_as_float(h[e]);    // exact
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l[e]) : "f"(lo));
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(src + j), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + j), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+        }
+        fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_fl[sl]));
+        if (++sa == SA) sa = 0, pa ^= 1u;
+        if (++sl == SL) sl = 0, pl ^= 1u;
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
     // ------------------------------------------------------------------ epilogue
     // Thread = one row of the tile (its TMEM lane); the four warps of a lane quarter take the 16-column chunks
     // round-robin.  Rows meet global memory through one swizzled 2 KB buffer per warp: coalesced 16-byte accesses
@@ -485,6 +577,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           if (row < r_end) {
             const int gi = row / a.Nv, tok = row - gi * a.Nv;
             st_half16(a.planes + (((int64_t)gi * a.H + (n0 / 32 + (c >> 1))) * a.Nv + tok) * 32 + (c & 1) * 16, f);
+          }
+        } else if (a.planes32) {
+          // fp32 half-head planes: chunk c of the row is half-plane (n0 / 16 + c) of token (row % Nv) in group row / Nv
+          const int row = row0 + lane;
+          if (row < r_end) {
+            const int gi = row / a.Nv, tok = row - gi * a.Nv;
+            float* p = a.planes32 + (((int64_t)gi * (a.N / 16) + (n0 / 16 + c)) * a.Nv + tok) * 16;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p + 8 * j), "f"(f[8 * j]),
+                           "f"(f[8 * j + 1]), "f"(f[8 * j + 2]), "f"(f[8 * j + 3]), "f"(f[8 * j + 4]), "f"(f[8 * j + 5]),
+                           "f"(f[8 * j + 6]), "f"(f[8 * j + 7])
+                           : "memory");
           }
         } else {
           if (a.relu) {
@@ -569,28 +674,34 @@ extern "C" int ub_set_gemm_cluster(int cs) {
   return UB_OK;
 }
 
-// Shared launcher.  f16 = 0: A / W fp32 (TF32 MMA);  f16 = 1: A / W fp16.
-static int launch_linear(const char* fn, int f16, const void* A, const void* W, const float* bias, const float* residual,
-                         int ldr, const float* gamma, const float* beta, float eps, float* out, int ldc, void* out16,
-                         int ldc16, void* planes, int Nv, int M, int N, int K, int flags, ub_stream_t stream) {
+// Shared launcher.  f16 = 0: A / W fp32 (TF32 MMA);  f16 = 1: A / W fp16.  W_lo != null: 3xTF32 (W = W_hi, see the kernel).
+static int launch_linear(const char* fn, int f16, const void* A, const void* W, const float* W_lo, const float* bias,
+                         const float* residual, int ldr, const float* gamma, const float* beta, float eps, float* out,
+                         int ldc, void* out16, int ldc16, void* planes, float* planes32, int Nv, int M, int N, int K,
+                         int flags, ub_stream_t stream) {
   const int relu = flags & 1, ln = (flags >> 1) & 1;
   const int kb_elems = f16 ? 64 : 32, esize = f16 ? 2 : 4;
-  UB_REQUIRE(A && W && (out || out16 || planes), "%s: null pointer", fn);
+  const bool split = W_lo != nullptr;
+  UB_REQUIRE(A && W && (out || out16 || planes || planes32), "%s: null pointer", fn);
+  UB_REQUIRE(!(split && f16), "%s: the 3xTF32 mode takes fp32 operands", fn);
   UB_REQUIRE(M > 0 && N > 0 && K > 0, "%s: non-positive dimension", fn);
   UB_REQUIRE(!ln || (gamma && beta), "%s: layernorm needs gamma and beta", fn);
   UB_REQUIRE_ALIGNED16(A);
   UB_REQUIRE_ALIGNED16(W);
   if (K % kb_elems != 0 || N % 32 != 0 || (N > 256 && N % 256 != 0) || (ln && N > 256) ||
-      (planes && (ln || relu || residual || out16)) || (planes && (Nv <= 0 || M % Nv != 0)) ||
+      (planes && (ln || relu || residual || out16 || planes32)) || ((planes || planes32) && (Nv <= 0 || M % Nv != 0)) ||
+      (planes32 && (ln || relu || residual || out16 || out || (reinterpret_cast<uintptr_t>(planes32) & 31u))) ||
+      (split && (reinterpret_cast<uintptr_t>(W_lo) & 15u)) ||
       (out && (ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(out) & 15u))) ||
       (out16 && (ldc16 % 16 != 0 || (reinterpret_cast<uintptr_t>(out16) & 31u))) ||
       (planes && (reinterpret_cast<uintptr_t>(planes) & 31u)) ||
       (residual && (ldr % 4 != 0 || (reinterpret_cast<uintptr_t>(residual) & 15u))) || N > 1024) {
     set_error("%s: shape not covered (M=%d N=%d K=%d flags=%d)", fn, M, N, K, flags);
-    return UB_EUNSUPPORTED;
+    return ub::unsupported();
   }
   GemmArgs a;
   a.bias = bias, a.gamma = gamma, a.beta = beta, a.planes = reinterpret_cast<__half*>(planes);
+  a.planes32 = planes32, a.SL = split ? 2 : 0;
   a.Nv = Nv, a.H = N / 32;
   a.M = M, a.N = N, a.K = K, a.BN = N > 256 ? 256 : N;
   a.n_tiles_m = (M + kBM - 1) / kBM, a.n_tiles_n = N / a.BN;
@@ -604,13 +715,14 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   const size_t budget = 232448 - 5120 - 1024;   // minus static shared memory and slack
   // W resident: every k-block of the (single) W tile stays in shared memory, with at least 3 A stages next to it
   // (with several column tiles: one CTA per column tile and row range, see n_split in the kernel)
-  const bool split_ok = a.n_tiles_n > 1 && kNumSMs % a.n_tiles_n == 0 && M >= 4 * kNumSMs;
-  a.w_res = (a.n_tiles_n == 1 || split_ok) && k_blocks <= kMaxStages && !(residual && ln && g_gemm_stream_w_res) &&
+  const int n_sms = sm_count();
+  const bool split_ok = a.n_tiles_n > 1 && n_sms % a.n_tiles_n == 0 && M >= 4 * n_sms;
+  a.w_res = !split && (a.n_tiles_n == 1 || split_ok) && k_blocks <= kMaxStages && !(residual && ln && g_gemm_stream_w_res) &&
             fixed + (size_t)k_blocks * a.BN * 128 + 3 * (size_t)kBM * 128 <= budget;
   // cluster size (streaming W only): the W k-block is split into `cs` slices of whole 8-row swizzle groups
   a.cs = a.w_res ? 1 : g_gemm_cluster;
   while (a.cs > 1 && ((a.BN / a.cs) % 8 != 0 || a.BN % a.cs != 0 || a.n_tiles_m < a.cs)) a.cs >>= 1;
-  CUtensorMap ma, mw, mr;
+  CUtensorMap ma, mw, mr, mwl;
   const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[1] = {(uint64_t)K * esize};
@@ -621,6 +733,9 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)K * esize};
     const uint32_t box[2] = {(uint32_t)kb_elems, (uint32_t)(a.BN / a.cs)};
     if (int rc = make_tensor_map(&mw, dt, 2, W, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    mwl = mw;
+    if (split)
+      if (int rc = make_tensor_map(&mwl, dt, 2, W_lo, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
   a.res_chunks = 0;
   mr = ma;
@@ -631,29 +746,34 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
       return rc;
     a.res_chunks = a.BN / 32;
   }
-  a.balanced = (a.n_tiles_n == 1 || (split_ok && a.w_res)) && a.cs == 1 && M >= 4 * kNumSMs;
+  a.balanced = (a.n_tiles_n == 1 || (split_ok && a.w_res)) && a.cs == 1 && M >= 4 * n_sms;
   a.n_split = a.balanced ? a.n_tiles_n : 1;
   // ring depths: W resident or shallow, A as deep as the 227 KB of shared memory allow (up to 8)
   a.SW = a.w_res ? k_blocks : (a.BN > 128 ? 3 : 4);
-  a.SA = (int)((budget - fixed - (size_t)a.SW * a.BN * 128) / (kBM * 128));
+  if (split) {
+    // W slots alternate hi / lo k-blocks: as many as fit next to three A stages and the A_lo ring (at least three:
+    // one k-block in use, half of the next in flight)
+    const size_t rest = budget - fixed - (size_t)(3 + a.SL) * kBM * 128;
+    a.SW = (int)(rest / ((size_t)a.BN * 128));
+    if (a.SW > 6) a.SW = 6;
+    if (a.SW < 3) {
+      set_error("%s: no room for the operand rings (N=%d)", fn, N);
+      return ub::unsupported();
+    }
+  }
+  a.SA = (int)((budget - fixed - (size_t)a.SW * a.BN * 128) / (kBM * 128)) - a.SL;
   if (a.SA > kMaxStages) a.SA = kMaxStages;
+  if (split && a.SA > 4) a.SA = 4;   // a k-block lasts three MMA groups: a shallow ring already covers the DRAM latency
   if (a.SA < 2) {
     set_error("%s: no room for the operand rings (N=%d)", fn, N);
-    return UB_EUNSUPPORTED;
+    return ub::unsupported();
   }
-  const size_t smem = (size_t)a.SA * kBM * 128 + (size_t)a.SW * a.BN * 128 + fixed;
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      set_error("%s: cannot reserve %zu bytes of shared memory", fn, smem);
-      cudaGetLastError();
-      return UB_ECUDA;
-    }
-    configured = smem;
-  }
+  const size_t smem = (size_t)(a.SA + a.SL) * kBM * 128 + (size_t)a.SW * a.BN * 128 + fixed;
+  auto kernel = split ? gemm_tf32_kernel<true> : gemm_tf32_kernel<false>;
+  if (int rc = ensure_smem(kernel, smem, fn)) return rc;
   const int n_groups = ((a.n_tiles_m + a.cs - 1) / a.cs) * a.n_tiles_n;
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(split ? kGemmThreadsSplit : kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[2];
@@ -663,21 +783,22 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 2 : 1;
   // persistent grid: as many clusters as can be resident at once (one CTA per SM; clusters do not span GPCs)
-  static int max_clusters[5] = {0, 0, 0, 0, 0};
-  static size_t max_clusters_smem[5] = {0, 0, 0, 0, 0};
-  if (max_clusters[a.cs] == 0 || max_clusters_smem[a.cs] != smem) {
-    cfg.gridDim = dim3(kNumSMs / a.cs * a.cs);
+  // (a property of the kernel variant, cluster size and shared-memory size; every B200 answers the same)
+  static std::atomic<int> max_clusters[2][5] = {};
+  static std::atomic<size_t> max_clusters_smem[2][5] = {};
+  if (max_clusters[split][a.cs].load() == 0 || max_clusters_smem[split][a.cs].load() != smem) {
+    cfg.gridDim = dim3(n_sms / a.cs * a.cs);
     int n = 0;
-    if (a.cs == 1 || cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel, &cfg) != cudaSuccess || n <= 0) {
+    if (a.cs == 1 || cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
       cudaGetLastError();
-      n = a.cs == 1 ? kNumSMs : (kNumSMs / a.cs) * 3 / 4;
+      n = a.cs == 1 ? n_sms : (n_sms / a.cs) * 3 / 4;
     }
-    max_clusters[a.cs] = n, max_clusters_smem[a.cs] = smem;
+    max_clusters[split][a.cs].store(n), max_clusters_smem[split][a.cs].store(smem);
   }
-  int clusters = max_clusters[a.cs];
+  int clusters = max_clusters[split][a.cs].load();
   if (clusters > n_groups && !a.balanced) clusters = n_groups;
   cfg.gridDim = dim3(clusters * a.cs);
-  if (cudaLaunchKernelEx(&cfg, gemm_tf32_kernel, a, ma, mw, mr) != cudaSuccess) {
+  if (cudaLaunchKernelEx(&cfg, kernel, a, ma, mw, mr, mwl) != cudaSuccess) {
     set_error("%s: launch failed: %s", fn, cudaGetErrorString(cudaGetLastError()));
     return UB_ECUDA;
   }
@@ -689,15 +810,15 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
 extern "C" int ub_linear_tf32(const float* A, const float* W, const float* bias, const float* residual, int ldr,
                               const float* gamma, const float* beta, float eps, float* out, int ldc, void* planes,
                               int Nv, int M, int N, int K, int flags, ub_stream_t stream) {
-  return launch_linear("ub_linear_tf32", 0, A, W, bias, residual, ldr, gamma, beta, eps, out, ldc, nullptr, 0, planes, Nv, M,
-                       N, K, flags, stream);
+  return launch_linear("ub_linear_tf32", 0, A, W, nullptr, bias, residual, ldr, gamma, beta, eps, out, ldc, nullptr, 0, planes,
+                       nullptr, Nv, M, N, K, flags, stream);
 }
 // ub_linear_tf32 that also writes the fp16 copy `out16` (row stride ldc16) of the result rows
 extern "C" int ub_linear_tf32_dual(const float* A, const float* W, const float* bias, const float* residual, int ldr,
                                    const float* gamma, const float* beta, float eps, float* out, int ldc, void* out16,
                                    int ldc16, int M, int N, int K, int flags, ub_stream_t stream) {
-  return launch_linear("ub_linear_tf32_dual", 0, A, W, bias, residual, ldr, gamma, beta, eps, out, ldc, out16, ldc16, nullptr,
-                       0, M, N, K, flags, stream);
+  return launch_linear("ub_linear_tf32_dual", 0, A, W, nullptr, bias, residual, ldr, gamma, beta, eps, out, ldc, out16, ldc16,
+                       nullptr, nullptr, 0, M, N, K, flags, stream);
 }
 
 // The same with fp16 operands A (M, K) / W (N, K) (same 11-bit significand as TF32, half the bytes: W usually stays
@@ -705,6 +826,39 @@ extern "C" int ub_linear_tf32_dual(const float* A, const float* W, const float* 
 extern "C" int ub_linear_f16(const void* A16, const void* W16, const float* bias, const float* residual, int ldr,
                              const float* gamma, const float* beta, float eps, float* out, int ldc, void* out16, int ldc16,
                              void* planes, int Nv, int M, int N, int K, int flags, ub_stream_t stream) {
-  return launch_linear("ub_linear_f16", 1, A16, W16, bias, residual, ldr, gamma, beta, eps, out, ldc, out16, ldc16, planes,
-                       Nv, M, N, K, flags, stream);
+  return launch_linear("ub_linear_f16", 1, A16, W16, nullptr, bias, residual, ldr, gamma, beta, eps, out, ldc, out16, ldc16,
+                       planes, nullptr, Nv, M, N, K, flags, stream);
+}
+
+// fp32-grade projection on the tensor cores (3xTF32, see the kernel): out = epilogue(A (M, K) @ (W_hi + W_lo) (N, K)^T) with
+// A, W_hi, W_lo fp32; W_hi / W_lo from ub_split_tf32.  Same epilogues as ub_linear_tf32; planes32 != NULL: fp32 half-head
+// planes (G = M / Nv, N / 16, Nv, 16) for the fp32 window-staged sampling kernels, `out` ignored.
+extern "C" int ub_linear_tf32x3(const float* A, const float* W_hi, const float* W_lo, const float* bias, const float* residual,
+                                int ldr, const float* gamma, const float* beta, float eps, float* out, int ldc,
+                                float* planes32, int Nv, int M, int N, int K, int flags, ub_stream_t stream) {
+  UB_REQUIRE(W_lo, "ub_linear_tf32x3: null pointer");
+  return launch_linear("ub_linear_tf32x3", 0, A, W_hi, W_lo, bias, residual, ldr, gamma, beta, eps, planes32 ? nullptr : out, ldc,
+                       nullptr, 0, nullptr, planes32, Nv, M, N, K, flags, stream);
+}
+
+namespace ub {
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi,
+                                                         float* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = w[i];
+    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    uint32_t l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - h));
+    hi[i] = h, lo[i] = __uint_as_float(l);
+  }
+}
+}  // namespace ub
+
+// w (n) -> hi = w with the 13 low mantissa bits cleared (exactly what a TF32 MMA reads of w), lo = tf32(w - hi)
+extern "C" int ub_split_tf32(const float* w, float* hi, float* lo, int64_t n, ub_stream_t stream) {
+  UB_REQUIRE(w && hi && lo && n > 0, "ub_split_tf32: bad argument");
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  split_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, hi, lo, n);
+  return check_launch("ub_split_tf32");
 }

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) msda_bwd_scalar_kernel(const float* __res
 
 static int grid_for(int64_t n_groups, int groups_per_block) {
   int64_t blocks = (n_groups + groups_per_block - 1) / groups_per_block;
-  const int64_t cap = (int64_t)kNumSMs * 32;  // grid-stride beyond 32 resident waves' worth of CTAs
+  const int64_t cap = (int64_t)sm_count() * 32;  // grid-stride beyond 32 resident waves' worth of CTAs
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;

@@ -68,7 +68,7 @@ extern "C" int ub_project_points(const float* lidar2img, const float* zs_host, c
   pp.img_h = img_h, pp.img_w = img_w;
   const int64_t total = (int64_t)B * bev_h * bev_w * N;
   int blocks = (int)((total + 255) / 256);
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
   project_points_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(lidar2img, pp, ref_cam, mask, B, N, bev_h, bev_w, D);
   return check_launch("ub_project_points");
 }

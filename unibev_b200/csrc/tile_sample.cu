@@ -495,26 +495,18 @@ static int pad_pow2(int v) {
 }
 
 template <typename K>
-static int configure_smem(K kernel, size_t smem, bool& configured, const char* fn) {
+static int configure_smem(K kernel, size_t smem, const char* fn) {
   if (smem > 200 * 1024) {
     set_error("%s: this head dim / point count needs %zu bytes of shared memory", fn, smem);
     return UB_EINVAL;
   }
-  if (!configured) {
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      set_error("%s: cannot reserve %zu bytes of shared memory", fn, smem);
-      return UB_ECUDA;
-    }
-    configured = true;
-  }
-  return UB_OK;
+  return ensure_smem(kernel, smem, fn);
 }
 
 static int persistent_grid(int per_sm, int n_units, size_t smem) {
   const int by_smem = (int)((220 * 1024) / (smem + 2048));
   if (per_sm > by_smem) per_sm = by_smem > 0 ? by_smem : 1;
-  const int grid = kNumSMs * per_sm;
+  const int grid = sm_count() * per_sm;
   return grid < n_units ? grid : n_units;
 }
 
@@ -523,8 +515,7 @@ constexpr int kDefaultCtasPerSmBev = 4, kDefaultCtasPerSmImg = 3;  // measured b
 template <int LPG, int PP, int HF, int MINB>
 static int launch_bev_v(SampleArgs& a, cudaStream_t s) {
   using G = Geo<LPG, PP>;
-  static bool configured = false;
-  if (int rc = configure_smem(bev_sample_kernel<LPG, PP, HF, MINB>, G::smem, configured, "ub_bev_sample_fwd")) return rc;
+  if (int rc = configure_smem(bev_sample_kernel<LPG, PP, HF, MINB>, G::smem, "ub_bev_sample_fwd")) return rc;
   a.n_chunks = (a.H + G::HC - 1) / G::HC;
   a.n_units = a.B * a.n_chunks * a.n_tiles;
   bev_sample_kernel<LPG, PP, HF, MINB><<<persistent_grid(MINB, a.n_units, G::smem), kThreads, G::smem, s>>>(a);
@@ -533,8 +524,7 @@ static int launch_bev_v(SampleArgs& a, cudaStream_t s) {
 template <int LPG, int PP, int HF, int MINB>
 static int launch_img_v(SampleArgs& a, cudaStream_t s) {
   using G = Geo<LPG, PP>;
-  static bool configured = false;
-  if (int rc = configure_smem(img_sample_kernel<LPG, PP, HF, MINB>, G::smem, configured, "ub_img_sample_fwd")) return rc;
+  if (int rc = configure_smem(img_sample_kernel<LPG, PP, HF, MINB>, G::smem, "ub_img_sample_fwd")) return rc;
   a.n_chunks = (a.H + G::HC - 1) / G::HC;
   a.n_units = a.B * a.n_chunks * a.n_tiles;
   img_sample_kernel<LPG, PP, HF, MINB><<<persistent_grid(MINB, a.n_units, G::smem), kThreads, G::smem, s>>>(a);

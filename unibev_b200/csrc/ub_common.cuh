@@ -10,10 +10,18 @@
 
 namespace ub {
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs (documentation; launch code asks the device: sm_count())
+
+// Per-device facts and kernel attributes (a process may drive several GPUs): SM count of the CURRENT device, and the
+// dynamic-shared-memory opt-in of `kernel` on the current device raised to at least `smem` bytes (cudaFuncSetAttribute is
+// per device; remembered per (kernel, device)).  Callers make the tensors' device current before calling into the library.
+int sm_count();
+bool smem_config_needed(const void* kernel, size_t smem);   // true: not yet configured for `smem` on the current device
+void smem_config_done(const void* kernel, size_t smem);
 
 void set_error(const char* fmt, ...);
 void count_launch();
+int unsupported();   // counts the event (ub_unsupported_count) and returns UB_EUNSUPPORTED
 
 #define UB_REQUIRE(cond, ...)                 \
   do {                                        \
@@ -44,6 +52,19 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+template <typename K>
+inline int ensure_smem(K kernel, size_t smem, const char* fn) {
+  const void* key = reinterpret_cast<const void*>(kernel);
+  if (smem <= 48 * 1024 || !smem_config_needed(key, smem)) return UB_OK;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    set_error("%s: cannot reserve %zu bytes of shared memory", fn, smem);
+    cudaGetLastError();
+    return UB_ECUDA;
+  }
+  smem_config_done(key, smem);
+  return UB_OK;
 }
 
 inline int check_launch(const char* what) {

@@ -53,7 +53,6 @@ static int g_img_two_win = 0;    // camera mode: double-buffer the plane windows
 static int g_img_vec_ref = 1;
 static int g_img_stage = 0;      // camera mode: P1 inputs through bulk async copies instead of register prefetch; off:
                                  // 768 small copies per unit cost the TMA engine more than the LSU loads (247 vs 218 us)
-static int g_bev_round_tf32 = 0; // round the BEV kernels' outputs to TF32 (their consumer is a TF32 GEMM)
 
 // ---------------------------------------------------------------------------------------------------------
 // fp32 token-major value rows -> fp16 head-major planes.  Thread = 8 channels of one (row, head).
@@ -983,38 +982,14 @@ __global__ void __launch_bounds__(kImgThreads, 1)
 // ---------------------------------------------------------------------------------------------------------
 // host side
 
-static int* g_counters = nullptr;  // 64 slots x {next unit, CTAs done}
-static unsigned g_slot = 0;
-static int* counter_slot() {
-  if (!g_counters) {
-    if (cudaMalloc(&g_counters, 64 * 2 * sizeof(int)) != cudaSuccess) return nullptr;
-    cudaMemset(g_counters, 0, 64 * 2 * sizeof(int));
-  }
-  return g_counters + 2 * (g_slot++ % 64);
-}
-
-template <typename K>
-static int set_smem(K kernel, size_t smem, const char* fn) {
-  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-    set_error("%s: cannot reserve %zu bytes of shared memory", fn, smem);
-    cudaGetLastError();
-    return UB_ECUDA;
-  }
-  return UB_OK;
-}
-
 constexpr size_t kSmemBudget = 232448 - 1024 - 64;  // 227 KB per CTA minus the static part
 
 template <int PP, int ROWB>
 static int launch_bev_win_v(BevWinArgs& a, const CUtensorMap& mv, const CUtensorMap& mo, const CUtensorMap& ml,
                             size_t smem, cudaStream_t s) {
   const char* fn = "ub_bev_sample_win_fwd";
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (int rc = set_smem(bev_sample_win_kernel<PP, ROWB>, smem, fn)) return rc;
-    configured = smem;
-  }
-  const int grid = a.n_units < kNumSMs ? a.n_units : kNumSMs;
+  if (int rc = ensure_smem(bev_sample_win_kernel<PP, ROWB>, smem, fn)) return rc;
+  const int grid = a.n_units < sm_count() ? a.n_units : sm_count();
   launch_pdl(bev_sample_win_kernel<PP, ROWB>, dim3(grid), dim3(kBevThreads), smem, s, a, mv, mo, ml);
   return check_launch(fn);
 }
@@ -1039,7 +1014,7 @@ static int launch_bev_win(BevWinArgs& a, const void* value16, const float* qproj
   const size_t smem = smem_for();
   if (smem > kSmemBudget) {
     set_error("%s: window %d x %d needs %zu bytes of shared memory", fn, a.WW, a.WH, smem);
-    return UB_EUNSUPPORTED;
+    return ub::unsupported();
   }
   CUtensorMap mv, mo, ml;
   {
@@ -1061,11 +1036,6 @@ static int launch_bev_win(BevWinArgs& a, const void* value16, const float* qproj
                                  CU_TENSOR_MAP_SWIZZLE_NONE))
       return rc;
   }
-  a.counters = counter_slot();
-  if (!a.counters) {
-    set_error("%s: cannot allocate the unit counters", fn);
-    return UB_ECUDA;
-  }
   if (fixed) return launch_bev_win_v<PP, kPrefWW * 64>(a, mv, mo, ml, smem, s);
   return launch_bev_win_v<PP, 0>(a, mv, mo, ml, smem, s);
 }
@@ -1073,16 +1043,12 @@ static int launch_bev_win(BevWinArgs& a, const void* value16, const float* qproj
 template <int PP, int ROWB, bool STAGE>
 static int launch_img_win_v(ImgWinArgs& a, const CUtensorMap& mv, size_t smem, cudaStream_t s) {
   const char* fn = "ub_img_sample_win_fwd";
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (int rc = set_smem(img_sample_win_kernel<PP, ROWB, STAGE>, smem, fn)) return rc;
-    configured = smem;
-  }
+  if (int rc = ensure_smem(img_sample_win_kernel<PP, ROWB, STAGE>, smem, fn)) return rc;
   a.part = 0;
-  launch_pdl(img_sample_win_kernel<PP, ROWB, STAGE>, dim3(kNumSMs), dim3(kImgThreads), smem, s, a, mv);
+  launch_pdl(img_sample_win_kernel<PP, ROWB, STAGE>, dim3(sm_count()), dim3(kImgThreads), smem, s, a, mv);
   if (int rc = check_launch(fn)) return rc;
   a.part = 1;   // (camera, query) pairs beyond a query's first camera: ~12 % of the pairs on the nuScenes rig
-  launch_pdl(img_sample_win_kernel<PP, ROWB, STAGE>, dim3(kNumSMs), dim3(kImgThreads), smem, s, a, mv);
+  launch_pdl(img_sample_win_kernel<PP, ROWB, STAGE>, dim3(sm_count()), dim3(kImgThreads), smem, s, a, mv);
   return check_launch(fn);
 }
 
@@ -1098,7 +1064,7 @@ static int launch_img_win(ImgWinArgs& a, const void* value16, cudaStream_t s) {
   const size_t smem = ImgSmem<PP>::total(win_bytes, a.two_win ? 2 : 1, stage);
   if (smem > kSmemBudget) {
     set_error("%s: plane %d x %d needs %zu bytes of shared memory", fn, a.fH, a.fW, smem);
-    return UB_EUNSUPPORTED;
+    return ub::unsupported();
   }
   CUtensorMap mv;
   const uint64_t dims[4] = {32, (uint64_t)a.fW, (uint64_t)a.fH, (uint64_t)a.B * a.N * a.H};
@@ -1135,11 +1101,6 @@ extern "C" int ub_set_img_stage(int on) {
   return UB_OK;
 }
 
-extern "C" int ub_set_window_round_tf32(int on) {
-  g_bev_round_tf32 = on ? 1 : 0;
-  return UB_OK;
-}
-
 extern "C" int ub_value_to_half(const float* value, void* value16, int G, int Nv, int H, int Dh, ub_stream_t stream) {
   UB_REQUIRE(value && value16, "ub_value_to_half: null pointer");
   UB_REQUIRE(G > 0 && Nv > 0 && H > 0 && Dh > 0 && Dh % 8 == 0, "ub_value_to_half: need positive dims and Dh %% 8 == 0");
@@ -1147,16 +1108,16 @@ extern "C" int ub_value_to_half(const float* value, void* value16, int G, int Nv
   UB_REQUIRE_ALIGNED16(value16);
   const int64_t total = (int64_t)G * H * Nv * (Dh / 8);
   int blocks = (int)((total + 255) / 256);
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
   value_to_half_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(value, reinterpret_cast<uint4*>(value16), G, Nv, H, Dh);
   return check_launch("ub_value_to_half");
 }
 
 extern "C" int ub_bev_sample_win_fwd(const void* value16, const float* qproj, void* out, int out_f16, int B, int bev_h,
                                      int bev_w, int fH, int fW, int H, int Dh, int P, int ld, int off_col, int logit_col,
-                                     ub_stream_t stream) {
+                                     int* workspace, int flags, ub_stream_t stream) {
   const char* fn = "ub_bev_sample_win_fwd";
-  UB_REQUIRE(value16 && qproj && out, "%s: null pointer", fn);
+  UB_REQUIRE(value16 && qproj && out && workspace, "%s: null pointer", fn);
   UB_REQUIRE(B > 0 && bev_h > 0 && bev_w > 0 && fH >= 2 && fW >= 2 && H > 0, "%s: non-positive dimension", fn);
   UB_REQUIRE(off_col >= 0 && logit_col >= 0 && ld >= off_col + H * P * 2 && ld >= logit_col + H * P,
              "%s: qproj row stride %d too small", fn, ld);
@@ -1166,10 +1127,10 @@ extern "C" int ub_bev_sample_win_fwd(const void* value16, const float* qproj, vo
   if (Dh != 32 || (P != 4 && P != 8) || ld % 4 != 0 || off_col % 4 != 0 || logit_col % 4 != 0 ||
       (int64_t)B * H > (1 << 20)) {
     set_error("%s: shape not covered by the window kernels (Dh=%d P=%d ld=%d)", fn, Dh, P, ld);
-    return UB_EUNSUPPORTED;
+    return ub::unsupported();
   }
   BevWinArgs a;
-  a.value16 = reinterpret_cast<const __half*>(value16), a.counters = nullptr;
+  a.value16 = reinterpret_cast<const __half*>(value16), a.counters = workspace;
   a.out = out_f16 ? nullptr : reinterpret_cast<float*>(out), a.out16 = out_f16 ? reinterpret_cast<__half*>(out) : nullptr;
   a.B = B, a.bev_h = bev_h, a.bev_w = bev_w, a.fH = fH, a.fW = fW, a.H = H;
   a.tiles_x = (bev_w + kTQ - 1) / kTQ, a.tiles_y = (bev_h + kTQ - 1) / kTQ;
@@ -1179,10 +1140,10 @@ extern "C" int ub_bev_sample_win_fwd(const void* value16, const float* qproj, vo
   a.WW = (int)ceilf((kTQ - 1) * a.sx) + 2 * a.R + 3;
   a.WH = (int)ceilf((kTQ - 1) * a.sy) + 2 * a.R + 3;
   a.off_col = off_col, a.logit_col = logit_col;
-  a.round_tf32 = g_bev_round_tf32;
+  a.round_tf32 = flags & 1;
   if (a.WW > 256 || a.WH > 256) {
     set_error("%s: window %d x %d exceeds the TMA box limit", fn, a.WW, a.WH);
-    return UB_EUNSUPPORTED;
+    return ub::unsupported();
   }
   return P == 8 ? launch_bev_win<8>(a, value16, qproj, ld, (cudaStream_t)stream)
                 : launch_bev_win<4>(a, value16, qproj, ld, (cudaStream_t)stream);
@@ -1193,12 +1154,12 @@ extern "C" int ub_build_hits(const uint8_t* mask, int* hit_idx, int* hit_cnt, fl
   UB_REQUIRE(mask && hit_idx && hit_cnt && inv_cnt, "ub_build_hits: null pointer");
   UB_REQUIRE(B > 0 && N > 0 && N <= 32 && Nq > 0, "ub_build_hits: bad dimension (B=%d N=%d Nq=%d)", B, N, Nq);
   int extra = (int)(((int64_t)B * Nq + 1023) / 1024);
-  if (extra > kNumSMs) extra = kNumSMs;
+  if (extra > sm_count()) extra = sm_count();
   build_hits_kernel<<<N + 1 + extra, 1024, 0, (cudaStream_t)stream>>>(mask, hit_idx, hit_cnt, inv_cnt, B, N, Nq);
   if (int rc = check_launch("ub_build_hits")) return rc;
   if (hit_ic) {
     int blocks = (int)(((int64_t)B * N * Nq + 255) / 256);
-    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     hit_ic_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(hit_idx, hit_cnt, inv_cnt, hit_ic, B, N, Nq);
     return check_launch("ub_build_hits");
   }
@@ -1223,9 +1184,9 @@ extern "C" int ub_img_sample_win_fwd(const void* value16, const float* qproj, co
              "%s: ref_cam / qproj not 8-byte aligned", fn);
   if (Dh != 32 || (P != 4 && P != 8) || ld % 4 != 0 || off_col % 4 != 0 || logit_col % 4 != 0 ||
       (reinterpret_cast<uintptr_t>(qproj) & 15u) != 0 || fW + 2 > 256 || fH + 2 > 256 ||
-      (int64_t)(fH + 2) * (fW + 2) > 65535 || (int64_t)B * N * H > (1 << 20) || H > kNumSMs) {
+      (int64_t)(fH + 2) * (fW + 2) > 65535 || (int64_t)B * N * H > (1 << 20) || H > sm_count()) {
     set_error("%s: shape not covered by the window kernels (Dh=%d P=%d fH=%d fW=%d)", fn, Dh, P, fH, fW);
-    return UB_EUNSUPPORTED;
+    return ub::unsupported();
   }
   ImgWinArgs a;
   a.qproj = qproj, a.ref_cam = ref_cam, a.inv_cnt = inv_cnt, a.hit_ic = hit_ic, a.hit_idx = hit_idx, a.hit_cnt = hit_cnt;

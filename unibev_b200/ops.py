@@ -14,7 +14,18 @@ FUSE_MODES = {'linear': 0, 'avg': 1, 'cat': 2}
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)   # of the current device: see _call
+
+
+def _call(fn, t, *args):
+    """One C-ABI call on the device of tensor ``t`` (made current for the call: kernel attributes, the current stream and
+    cudaMalloc'ed scratch are per device -- mmcv's op wraps its launches in a CUDAGuard the same way) and on that device's
+    current stream."""
+    if t.device.index == torch.cuda.current_device():
+        _cabi.check(getattr(_cabi.lib(), fn)(*args, _stream()), fn)
+    else:
+        with torch.cuda.device(t.device):
+            _cabi.check(getattr(_cabi.lib(), fn)(*args, _stream()), fn)
 
 
 def _ptr(t):
@@ -41,8 +52,8 @@ def msda_forward(value, spatial_shapes, level_start_index, sampling_locations, a
         raise ValueError('msda: inconsistent shapes '
                          f'value{tuple(value.shape)} loc{tuple(loc.shape)} w{tuple(w.shape)} shapes{tuple(shapes.shape)}')
     out = torch.empty(B, Nq, H * D, device=value.device, dtype=torch.float32)
-    _cabi.check(_cabi.lib().ub_msda_fwd(_ptr(value), _ptr(shapes), _ptr(lsi), _ptr(loc), _ptr(w), _ptr(out),
-                                        B, Nv, H, D, Nq, L, P, _stream()), 'ub_msda_fwd')
+    _call('ub_msda_fwd', value, _ptr(value), _ptr(shapes), _ptr(lsi), _ptr(loc), _ptr(w), _ptr(out),
+                                        B, Nv, H, D, Nq, L, P)
     return out
 
 
@@ -72,9 +83,8 @@ class MultiScaleDeformableAttnFunction(torch.autograd.Function):
         g_value = torch.zeros_like(value)
         g_loc = torch.empty_like(loc)
         g_w = torch.empty_like(w)
-        _cabi.check(_cabi.lib().ub_msda_bwd(_ptr(value), _ptr(shapes), _ptr(lsi), _ptr(loc), _ptr(w), _ptr(go),
-                                            _ptr(g_value), _ptr(g_loc), _ptr(g_w), B, Nv, H, D, Nq, L, P, _stream()),
-                    'ub_msda_bwd')
+        _call('ub_msda_bwd', value, _ptr(value), _ptr(shapes), _ptr(lsi), _ptr(loc), _ptr(w), _ptr(go),
+                                            _ptr(g_value), _ptr(g_loc), _ptr(g_w), B, Nv, H, D, Nq, L, P)
         return g_value, None, None, g_loc, g_w, None
 
 
@@ -88,8 +98,8 @@ def project_points(lidar2img, zs, pc_range, img_h, img_w, bev_h, bev_w):
     Nq = bev_h * bev_w
     ref = torch.empty(B, Nq, N, D, 2, device=l2i.device, dtype=torch.float32)
     mask = torch.empty(B, Nq, N, device=l2i.device, dtype=torch.uint8)
-    _cabi.check(_cabi.lib().ub_project_points(_ptr(l2i), zs_c, pc_c, float(img_h), float(img_w), _ptr(ref), _ptr(mask),
-                                              B, N, bev_h, bev_w, D, _stream()), 'ub_project_points')
+    _call('ub_project_points', l2i, _ptr(l2i), zs_c, pc_c, float(img_h), float(img_w), _ptr(ref), _ptr(mask),
+                                              B, N, bev_h, bev_w, D)
     return ref, mask
 
 
@@ -101,8 +111,8 @@ def bev_sample(value, qproj, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out
         raise ValueError(f'bev_sample: inconsistent shapes value{tuple(value.shape)} qproj{tuple(qproj.shape)}')
     if out is None:
         out = torch.empty(B, bev_h * bev_w, C, device=value.device, dtype=torch.float32)
-    _cabi.check(_cabi.lib().ub_bev_sample_fwd(_ptr(value), _ptr(qproj), _ptr(out), B, bev_h, bev_w, fH, fW, H, C // H, P,
-                                              qproj.shape[2], off_col, logit_col, _stream()), 'ub_bev_sample_fwd')
+    _call('ub_bev_sample_fwd', value, _ptr(value), _ptr(qproj), _ptr(out), B, bev_h, bev_w, fH, fW, H, C // H, P,
+                                              qproj.shape[2], off_col, logit_col)
     return out
 
 
@@ -117,9 +127,8 @@ def img_sample(value, qproj, ref_cam, mask, bev_h, bev_w, fH, fW, H, P, off_col,
         raise ValueError('img_sample: inconsistent shapes')
     if out is None:
         out = torch.empty(B, Nq, C, device=value.device, dtype=torch.float32)
-    _cabi.check(_cabi.lib().ub_img_sample_fwd(_ptr(value), _ptr(qproj), _ptr(ref_cam), _ptr(mask), _ptr(out), B, N,
-                                              bev_h, bev_w, fH, fW, H, C // H, P, D, qproj.shape[2], off_col, logit_col,
-                                              _stream()), 'ub_img_sample_fwd')
+    _call('ub_img_sample_fwd', value, _ptr(value), _ptr(qproj), _ptr(ref_cam), _ptr(mask), _ptr(out), B, N,
+                                              bev_h, bev_w, fH, fW, H, C // H, P, D, qproj.shape[2], off_col, logit_col)
     return out
 
 
@@ -131,7 +140,7 @@ def value_to_half(value, G, Nv, H, out=None):
         raise ValueError(f'value_to_half: inconsistent shapes value{tuple(value.shape)} G={G} Nv={Nv} H={H}')
     if out is None:
         out = torch.empty(G, H, Nv, C // H, device=value.device, dtype=torch.float16)
-    _cabi.check(_cabi.lib().ub_value_to_half(_ptr(value), _ptr(out), G, Nv, H, C // H, _stream()), 'ub_value_to_half')
+    _call('ub_value_to_half', value, _ptr(value), _ptr(out), G, Nv, H, C // H)
     return out
 
 
@@ -140,18 +149,23 @@ def window_supported(Dh, P):
     return Dh == 32 and P in (4, 8)
 
 
-def bev_sample_win(value16, qproj, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out=None, out_dtype=torch.float32):
-    """value16 (B, H, fH*fW, 32) fp16 from value_to_half; qproj (B, Nq, ld) -> (B, Nq, H*32) fp32."""
+def bev_sample_win(value16, qproj, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out=None, out_dtype=torch.float32,
+                   workspace=None, round_tf32=False):
+    """value16 (B, H, fH*fW, 32) fp16 from value_to_half; qproj (B, Nq, ld) -> (B, Nq, H*32) fp32 (or fp16).
+    ``workspace``: 2 zeroed int32 owned by the caller (left zero by the call); calls that may overlap in time need
+    distinct ones.  Default: a fresh one per call."""
     value16, qproj = _need(value16, 'value16', torch.float16), _need(qproj, 'qproj')
     B, Hh, Nv, Dh = value16.shape
     if Hh != H or Nv != fH * fW or qproj.shape[0] != B or qproj.shape[1] != bev_h * bev_w:
         raise ValueError(f'bev_sample_win: inconsistent shapes value16{tuple(value16.shape)} qproj{tuple(qproj.shape)}')
     if out is None:
         out = torch.empty(B, bev_h * bev_w, H * Dh, device=qproj.device, dtype=out_dtype)
-    _cabi.check(_cabi.lib().ub_bev_sample_win_fwd(_ptr(value16), _ptr(qproj), _ptr(out), int(out.dtype == torch.float16),
-                                                  B, bev_h, bev_w, fH, fW, H, Dh,
-                                                  P, qproj.shape[2], off_col, logit_col, _stream()),
-                'ub_bev_sample_win_fwd')
+    if workspace is None:
+        workspace = torch.zeros(2, device=qproj.device, dtype=torch.int32)
+    elif workspace.dtype != torch.int32 or workspace.numel() < 2 or workspace.device != qproj.device:
+        raise ValueError('bev_sample_win: `workspace` must be 2 int32 on the device of the inputs')
+    _call('ub_bev_sample_win_fwd', value16, _ptr(value16), _ptr(qproj), _ptr(out), int(out.dtype == torch.float16),
+          B, bev_h, bev_w, fH, fW, H, Dh, P, qproj.shape[2], off_col, logit_col, _ptr(workspace), int(round_tf32))
     return out
 
 
@@ -165,8 +179,7 @@ def build_hits(mask):
     hit_cnt = torch.empty(2 * N + 1, device=mask.device, dtype=torch.int32)
     inv_cnt = torch.empty(B, Nq, device=mask.device, dtype=torch.float32)
     hit_ic = torch.empty(B, N, Nq, device=mask.device, dtype=torch.float32)      # inv_cnt in hit-list order
-    _cabi.check(_cabi.lib().ub_build_hits(_ptr(mask), _ptr(hit_idx), _ptr(hit_cnt), _ptr(inv_cnt), _ptr(hit_ic), B, N, Nq,
-                                          _stream()), 'ub_build_hits')
+    _call('ub_build_hits', mask, _ptr(mask), _ptr(hit_idx), _ptr(hit_cnt), _ptr(inv_cnt), _ptr(hit_ic), B, N, Nq)
     return hit_idx, hit_cnt, inv_cnt, hit_ic
 
 
@@ -184,12 +197,11 @@ def img_sample_win(value16, qproj, ref_cam, hits, bev_h, bev_w, fH, fW, H, P, of
         raise ValueError('img_sample_win: inconsistent shapes')
     if out is None:
         out = torch.empty(B, Nq, H * Dh, device=qproj.device, dtype=out_dtype)
-    _cabi.check(_cabi.lib().ub_img_sample_win_fwd(_ptr(value16), _ptr(qproj), _ptr(ref_cam), _ptr(hit_idx), _ptr(hit_cnt),
+    _call('ub_img_sample_win_fwd', value16, _ptr(value16), _ptr(qproj), _ptr(ref_cam), _ptr(hit_idx), _ptr(hit_cnt),
                                                   _ptr(inv_cnt), _ptr(hit_ic), _ptr(out), int(out.dtype == torch.float16), B, N,
                                                   bev_h,
                                                   bev_w, fH, fW, H, Dh, P, D,
-                                                  qproj.shape[2], off_col, logit_col, _stream()),
-                'ub_img_sample_win_fwd')
+                                                  qproj.shape[2], off_col, logit_col)
     return out
 
 
@@ -233,13 +245,85 @@ def linear_tf32(x, weight, bias=None, residual=None, relu=False, ln=None, out=No
     if out16 is not None:
         if planes is not None or out16.shape != (M, N) or out16.dtype != torch.float16 or out16.stride(1) != 1:
             raise ValueError('linear_tf32: `out16` must be an fp16 CUDA (M, N) matrix (not with planes)')
-        _cabi.check(_cabi.lib().ub_linear_tf32_dual(_ptr(x), _ptr(weight), _ptr(bias), _ptr(residual), ldr, _ptr(gamma),
+        _call('ub_linear_tf32_dual', x, _ptr(x), _ptr(weight), _ptr(bias), _ptr(residual), ldr, _ptr(gamma),
                                                     _ptr(beta), eps, out_ptr, ldc, _ptr(out16), out16.stride(0), M, N, K,
-                                                    flags, _stream()), 'ub_linear_tf32_dual')
+                                                    flags)
         return res
-    _cabi.check(_cabi.lib().ub_linear_tf32(_ptr(x), _ptr(weight), _ptr(bias), _ptr(residual), ldr, _ptr(gamma), _ptr(beta),
-                                           eps, out_ptr, ldc, _ptr(planes), planes_nv or 0, M, N, K, flags, _stream()),
-                'ub_linear_tf32')
+    _call('ub_linear_tf32', x, _ptr(x), _ptr(weight), _ptr(bias), _ptr(residual), ldr, _ptr(gamma), _ptr(beta),
+                                           eps, out_ptr, ldc, _ptr(planes), planes_nv or 0, M, N, K, flags)
+    return res
+
+
+def linear_simt(x, weight, bias=None, residual=None, relu=False, out=None):
+    """Generic fp32 (FFMA) projection ``x (M, K) @ weight (N, K)^T`` for shapes the tensor-core entry points reject."""
+    x, weight = _need(x, 'x'), _need(weight, 'weight')
+    M, K = x.shape
+    N = weight.shape[0]
+    if weight.shape[1] != K:
+        raise ValueError(f'linear_simt: x{tuple(x.shape)} vs weight{tuple(weight.shape)}')
+    bias = _need(bias, 'bias') if bias is not None else None
+    ldr = 0
+    if residual is not None:
+        if residual.shape != (M, N):
+            raise ValueError('linear_simt: residual shape mismatch')
+        if not (residual.is_cuda and residual.dtype == torch.float32 and residual.stride(1) == 1):
+            residual = _need(residual, 'residual')
+        ldr = residual.stride(0)
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    elif out.shape != (M, N) or out.stride(1) != 1 or out.dtype != torch.float32 or not out.is_cuda:
+        raise ValueError('linear_simt: `out` must be an fp32 CUDA (M, N) matrix with unit column stride')
+    _call('ub_linear_simt', x, _ptr(x), _ptr(weight), _ptr(bias), _ptr(residual), ldr, _ptr(out),
+                                           out.stride(0), M, N, K, int(relu))
+    return out
+
+
+def split_tf32(weight):
+    """weight fp32 -> (hi, lo): hi = what a TF32 MMA reads of weight (13 low mantissa bits cleared), lo = tf32(weight - hi)."""
+    weight = _need(weight, 'weight')
+    hi, lo = torch.empty_like(weight), torch.empty_like(weight)
+    _call('ub_split_tf32', weight, _ptr(weight), _ptr(hi), _ptr(lo), weight.numel())
+    return hi, lo
+
+
+def linear_tf32x3(x, w_split, bias=None, residual=None, relu=False, ln=None, out=None, planes_nv=None):
+    """fp32-grade ``x (M, K) @ W (N, K)^T`` on the tcgen05 tensor cores (three TF32 MMAs per product, see
+    ``ub_linear_tf32x3``); ``w_split = split_tf32(W)``.  Same fused epilogues as ``linear_tf32``; ``planes_nv``: return fp32
+    half-head planes (M // planes_nv, N // 16, planes_nv, 16) for the fp32 window-staged sampling kernels."""
+    x = _need(x, 'x')
+    w_hi, w_lo = _need(w_split[0], 'w_hi'), _need(w_split[1], 'w_lo')
+    M, K = x.shape
+    N = w_hi.shape[0]
+    if w_hi.shape != (N, K) or w_lo.shape != (N, K):
+        raise ValueError(f'linear_tf32x3: x{tuple(x.shape)} vs weight{tuple(w_hi.shape)}')
+    bias = _need(bias, 'bias') if bias is not None else None
+    flags = (1 if relu else 0) | (2 if ln is not None else 0)
+    gamma = beta = None
+    eps = 0.0
+    if ln is not None:
+        gamma, beta, eps = _need(ln[0], 'gamma'), _need(ln[1], 'beta'), float(ln[2])
+    ldr = 0
+    if residual is not None:
+        if residual.shape != (M, N):
+            raise ValueError('linear_tf32x3: residual shape mismatch')
+        if not (residual.is_cuda and residual.dtype == torch.float32 and residual.stride(1) == 1):
+            residual = _need(residual, 'residual')
+        ldr = residual.stride(0)
+    planes = None
+    if planes_nv is not None:
+        if M % planes_nv or N % 16:
+            raise ValueError('linear_tf32x3: planes need M % Nv == 0 and N % 16 == 0')
+        planes = out if out is not None else torch.empty(M // planes_nv, N // 16, planes_nv, 16, device=x.device,
+                                                         dtype=torch.float32)
+        res, out_ptr, ldc = planes, None, 0
+    else:
+        if out is None:
+            out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        elif out.shape != (M, N) or out.stride(1) != 1 or out.dtype != torch.float32 or not out.is_cuda:
+            raise ValueError('linear_tf32x3: `out` must be an fp32 CUDA (M, N) matrix with unit column stride')
+        res, out_ptr, ldc = out, _ptr(out), out.stride(0)
+    _call('ub_linear_tf32x3', x, _ptr(x), _ptr(w_hi), _ptr(w_lo), _ptr(bias), _ptr(residual), ldr, _ptr(gamma),
+                                             _ptr(beta), eps, out_ptr, ldc, _ptr(planes), planes_nv or 0, M, N, K, flags)
     return res
 
 
@@ -279,10 +363,10 @@ def linear_f16(x16, w16, bias=None, residual=None, relu=False, ln=None, out=None
         for t, dt in ((out, torch.float32), (out16, torch.float16)):
             if t is not None and (t.shape != (M, N) or t.stride(1) != 1 or t.dtype != dt or not t.is_cuda):
                 raise ValueError('linear_f16: outputs must be CUDA (M, N) matrices with unit column stride')
-    _cabi.check(_cabi.lib().ub_linear_f16(_ptr(x16), _ptr(w16), _ptr(bias), _ptr(residual), ldr, _ptr(gamma), _ptr(beta),
+    _call('ub_linear_f16', x16, _ptr(x16), _ptr(w16), _ptr(bias), _ptr(residual), ldr, _ptr(gamma), _ptr(beta),
                                           eps, _ptr(out), out.stride(0) if out is not None else 0, _ptr(out16),
                                           out16.stride(0) if out16 is not None else 0, _ptr(planes), planes_nv or 0,
-                                          M, N, K, flags, _stream()), 'ub_linear_f16')
+                                          M, N, K, flags)
     return planes if planes is not None else (out, out16)
 
 
@@ -300,11 +384,11 @@ def add_layernorm(x, gamma, beta, bias=None, residual=None, eps=1e-5, out=None, 
     if out16 is not None:
         if out16.shape != x.shape or out16.dtype != torch.float16 or not out16.is_cuda or not out16.is_contiguous():
             raise ValueError('add_layernorm: `out16` must be a contiguous fp16 CUDA tensor of the shape of x')
-        _cabi.check(_cabi.lib().ub_add_layernorm16(_ptr(x), _ptr(bias), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(out),
-                                                   _ptr(out16), rows, C, float(eps), _stream()), 'ub_add_layernorm16')
+        _call('ub_add_layernorm16', x, _ptr(x), _ptr(bias), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(out),
+                                                   _ptr(out16), rows, C, float(eps))
         return out
-    _cabi.check(_cabi.lib().ub_add_layernorm(_ptr(x), _ptr(bias), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(out),
-                                             rows, C, float(eps), _stream()), 'ub_add_layernorm')
+    _call('ub_add_layernorm', x, _ptr(x), _ptr(bias), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(out),
+                                             rows, C, float(eps))
     return out
 
 
@@ -318,8 +402,8 @@ def cnw_fuse(img, pts, w_img, w_pts, mode, c_flag, l_flag, s_img=None, s_pts=Non
     opt = [(_need(t, n) if t is not None else None) for t, n in
            ((w_img, 'w_img'), (w_pts, 'w_pts'), (s_img, 's_img'), (s_pts, 's_pts'), (modal_embed, 'modal_embed'))]
     out = torch.empty(B, Nq, C * (2 if mode == 'cat' else 1), device=ref.device, dtype=torch.float32)
-    _cabi.check(_cabi.lib().ub_cnw_fuse(_ptr(img), _ptr(pts), *[_ptr(t) for t in opt], _ptr(out), B * Nq, Nq, C,
-                                        FUSE_MODES[mode], int(c_flag), int(l_flag), _stream()), 'ub_cnw_fuse')
+    _call('ub_cnw_fuse', ref, _ptr(img), _ptr(pts), *[_ptr(t) for t in opt], _ptr(out), B * Nq, Nq, C,
+                                        FUSE_MODES[mode], int(c_flag), int(l_flag))
     return out
 
 
@@ -334,8 +418,8 @@ def flatten_feats(feat, embed_a=None, embed_b=None, fp32=True, fp16=False):
     n_a = embed_a.shape[0] if embed_a is not None else 0
     out = torch.empty(G, h * w, C, device=feat.device, dtype=torch.float32) if fp32 or not fp16 else None
     out16 = torch.empty(G, h * w, C, device=feat.device, dtype=torch.float16) if fp16 else None
-    _cabi.check(_cabi.lib().ub_flatten_feats16(_ptr(feat), _ptr(embed_a), n_a, _ptr(embed_b), _ptr(out), _ptr(out16), G, C,
-                                               h * w, _stream()), 'ub_flatten_feats16')
+    _call('ub_flatten_feats16', feat, _ptr(feat), _ptr(embed_a), n_a, _ptr(embed_b), _ptr(out), _ptr(out16), G, C,
+                                               h * w)
     return (out, out16) if fp16 else out
 
 
@@ -345,8 +429,7 @@ def broadcast_rows(src, B, fp32=True, fp16=True):
     rows, C = src.shape
     out32 = torch.empty(B, rows, C, device=src.device, dtype=torch.float32) if fp32 else None
     out16 = torch.empty(B, rows, C, device=src.device, dtype=torch.float16) if fp16 else None
-    _cabi.check(_cabi.lib().ub_broadcast_rows(_ptr(src), rows, C, B, _ptr(out32), _ptr(out16), _stream()),
-                'ub_broadcast_rows')
+    _call('ub_broadcast_rows', src, _ptr(src), rows, C, B, _ptr(out32), _ptr(out16))
     return out32, out16
 
 
@@ -373,15 +456,14 @@ def hard_voxelize(points, voxel_size, pc_range, max_points, max_voxels):
         return voxels, coors, num, voxel_num
     nbytes = ctypes.c_size_t(0)
     _cabi.check(_cabi.lib().ub_voxelize_workspace_bytes(N, ctypes.byref(nbytes)), 'ub_voxelize_workspace_bytes')
-    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _vox_ws.get(key)
     if ws is None or ws.numel() < nbytes.value:
         ws = _vox_ws[key] = torch.empty(nbytes.value, device=dev, dtype=torch.uint8)
     vs = (ctypes.c_float * 3)(*[float(v) for v in voxel_size])
     pr = (ctypes.c_float * 6)(*[float(v) for v in pc_range])
-    _cabi.check(_cabi.lib().ub_hard_voxelize(_ptr(points), N, C, vs, pr, int(max_points), int(max_voxels), _ptr(voxels),
-                                             _ptr(coors), _ptr(num), _ptr(voxel_num), _ptr(ws), ws.numel(), _stream()),
-                'ub_hard_voxelize')
+    _call('ub_hard_voxelize', points, _ptr(points), N, C, vs, pr, int(max_points), int(max_voxels), _ptr(voxels),
+                                             _ptr(coors), _ptr(num), _ptr(voxel_num), _ptr(ws), ws.numel())
     return voxels, coors, num, voxel_num
 
 
@@ -391,6 +473,5 @@ def voxel_mean(voxels, num_points, num_features):
     num_points = _need(num_points, 'num_points', torch.int32)
     M, T, C = voxels.shape
     out = torch.empty(M, num_features, device=voxels.device, dtype=torch.float32)
-    _cabi.check(_cabi.lib().ub_voxel_mean(_ptr(voxels), _ptr(num_points), M, T, C, int(num_features), _ptr(out),
-                                          _stream()), 'ub_voxel_mean')
+    _call('ub_voxel_mean', voxels, _ptr(voxels), _ptr(num_points), M, T, C, int(num_features), _ptr(out))
     return out

@@ -34,17 +34,34 @@ class GraphedEncoder:
             with torch.no_grad():
                 return model.encode([img_feat] if img_feat is not None else None,
                                     [pts_feat] if pts_feat is not None else None, bev_queries, bev_h, bev_w, **args)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                run()
-        torch.cuda.current_stream().wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = run()
+        self._run = run
+        self.out = None
+        self._capture()
+
+    def _capture(self):
+        from .plugin.fused import weights_signature
+        dev = (self.img_feat if self.img_feat is not None else self.pts_feat).device
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._run()
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                out = self._run()
+        self.out = out
+        # the graph reads derived weight copies (split / fp16 / concatenated) made at capture time
+        self._signature = weights_signature(self.model)
 
     def replay(self):
+        from .plugin.fused import weights_signature
+        if weights_signature(self.model) != self._signature:
+            # a parameter changed (optimizer step, load_state_dict, .to()): the captured copies are stale.  The new graph
+            # owns a new output buffer: use the tensor replay() returns, not one kept from an earlier call.
+            del self.graph
+            self._capture()
         self.graph.replay()
         return self.out
 

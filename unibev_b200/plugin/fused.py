@@ -5,30 +5,31 @@ encoder layer:
 
     self-attention   V  = x Wv^T + bv                     GEMM  (N = C)
                      QP = (x + pos) [Woff;Watt]^T + b     GEMM  (N = H*P*3), pos part precomputed per frame
-                     S  = ub_bev_sample_fwd(V, QP)        fused ref-point/softmax/gather/reduce
-                     x  = LN(S Wo^T + bo + x)             GEMM + ub_add_layernorm
+                     S  = sample(V, QP)                   fused ref-point/softmax/gather/reduce
+                     x  = LN(S Wo^T + bo + x)             GEMM with residual + LayerNorm epilogue
     cross-attention  QP = x [Woff;Watt]^T + b             GEMM  (N = H*P*3)
-                     S  = ub_img_sample_fwd | ub_bev_sample_fwd (value projected once per frame)
-                     x  = LN(S Wo^T + bo + x)             GEMM + ub_add_layernorm
+                     S  = img_sample | bev_sample         (value projected once per layer)
+                     x  = LN(S Wo^T + bo + x)
     FFN              x  = LN(relu(x W1^T + b1) W2^T + b2 + x)
 
-No sampling_locations / attention_weights / rebatch tensors exist, nothing syncs with
-the host, and all activations live in buffers allocated once per shape.  GEMMs are
-cuBLAS(Lt) through torch.  Two precision classes:
+No sampling_locations / attention_weights / rebatch tensors exist, nothing syncs with the host, and every GEMM and
+sampling step is a libunibev_b200 kernel (no torch / cuBLAS matmul anywhere in this file).  Two precision classes:
 
-* ``precision='tf32'`` (default): TF32 tensor-core GEMMs -- what torch 1.10, the reference's
-  stack, also defaulted to -- and the window-staged sampling kernels (``ub_*_sample_win_fwd``:
-  value maps staged as fp16 planes by TMA, fp32 accumulation) where the shape is covered
-  (head dim 32, 4 / 8 points); their rounding error is a fraction of the TF32 GEMMs'.
-* ``precision='fp32'``: strict fp32 GEMMs and the fp32 sampling kernels.
+* ``precision='fp32'`` (default): the arithmetic class of the reference (fp32 everywhere, no ``fp16`` key in any
+  UniBEV config).  Projections run on the tensor cores as 3xTF32 (``ub_linear_tf32x3``: three tcgen05 kind::tf32 MMAs
+  per product, ~2^-21 relative error, fp32 accumulation, residual / LayerNorm epilogues); sampling in fp32 (fp32 value
+  maps, fp32 bilinear x attention weights, exact softmax).  Meets rtol 1e-3 / atol 1e-4 against the oracle.
+* ``precision='fp16'`` (opt-in fast class): fp16 tensor-core operands (activations, weights and input tokens are
+  rounded to an 11-bit significand and must stay below 65504), fp16-staged value maps and sampling weights, fp32
+  accumulation / residual stream / LayerNorm.  max |err| ~3e-3 on O(1) outputs (tests use atol 5e-3).
+
+``gemm=`` / ``sampling=`` override one half of a class (ablation: tools/ablation.py):
+gemm in {'tf32x3', 'tf32', 'f16'}, sampling in {'fp32', 'win16'}.
 
 Reference lines reproduced: transformer_fusion.py:231-278,463-538;
 encoder_unibev_detr_img.py:189-289,413-479; encoder_unibev_detr_pts.py:129-209;
 spatial_cross_attention_img.py:141-215,381-419; spatial_cross_attention_pts.py:159-206.
 """
-import contextlib
-import os
-
 import numpy as np
 import torch
 
@@ -38,6 +39,7 @@ from .attention import (MSDeformableAttention3DImg, MSDeformableAttention3DPts, 
 from .encoder import anchor_heights
 
 _ORDER = ('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm')
+PRECISIONS = {'fp32': ('tf32x3', 'fp32'), 'fp16': ('f16', 'win16')}     # class -> (gemm, sampling)
 
 
 def _layer_ok(layer, cross_cls, inner_cls):
@@ -73,16 +75,6 @@ def fused_supported(model, img_feats, pts_feats):
     return True
 
 
-@contextlib.contextmanager
-def _matmul_precision(tf32):
-    old = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = tf32
-    try:
-        yield
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = old
-
-
 class _LayerWeights:
     """Per-layer weights in the layout the fused pipeline wants (concatenated offset|logit linears)."""
 
@@ -114,33 +106,61 @@ class _LayerWeights:
         return self._half
 
 
+def weights_signature(model):
+    """Identity + version of every parameter the fused pipeline derives copies from (concatenated / split / fp16
+    weights): an in-place update (optimizer step, load_state_dict) bumps ``_version``, a ``.to()`` / ``.cuda()`` or a
+    re-assignment changes ``data_ptr``.  Compared on every call; ~100 integers."""
+    return tuple((p.data_ptr(), p._version) for p in model.parameters())
+
+
 class FusedEncoder:
-    def __init__(self, model, precision='tf32'):
-        if precision not in ('tf32', 'fp32'):
-            raise ValueError("precision must be 'tf32' or 'fp32'")
+    def __init__(self, model, precision='fp32', gemm=None, sampling=None):
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)} (got {precision!r}); 'fp32' is the class of "
+                             "the reference, 'fp16' the opt-in fast class")
         self.m = model
         self.precision = precision
-        self.tf32 = precision == 'tf32'
-        self.fast_sampling = self.tf32      # window-staged fp16 sampling kernels where the shape is covered
-        self.tc_gemm = self.tf32            # hand-written tcgen05 GEMM with fused epilogues where the shape is covered
-        # residual + LayerNorm inside the GEMM (residual preloaded into the accumulator; else GEMM + one streaming LN pass)
-        self.fuse_ln = os.environ.get('UB_FUSE_LN', '1') == '1'
+        self.gemm, self.sampling = PRECISIONS[precision]
+        if gemm is not None:
+            if gemm not in ('tf32x3', 'tf32', 'f16'):
+                raise ValueError(f'unknown gemm class {gemm!r}')
+            self.gemm = gemm
+        if sampling is not None:
+            if sampling not in ('fp32', 'win16'):
+                raise ValueError(f'unknown sampling class {sampling!r}')
+            self.sampling = sampling
+        self.f16 = self.gemm == 'f16'
         # sampled rows leave the window kernels as fp16 (the A operand of the fp16 output projection)
-        self.half_samples = os.environ.get('UB_HALF_SAMPLES', '1') == '1'
-        # FFN1 as two launches over column halves, each with its weights resident, instead of one launch whose CTA pairs
-        # share a row range (whole step at 4 frames: 809 vs 798 frames/s)
-        self.ffn1_halves = os.environ.get('UB_FFN1_HALVES', '1') == '1'
-        self._w = {}
-        self._rn = {}
-        self._pos_w = {}
+        self.half_samples = self.f16 and self.sampling == 'win16'
+        self._signature = None
+        self._drop_caches()
+
+    # derived weight copies ---------------------------------------------------------------------------------
+    def _drop_caches(self):
+        self._w, self._split, self._rn, self._pos_w = {}, {}, {}, {}
+
+    def refresh(self):
+        """Drop every derived weight copy if any source parameter changed since they were built.  Returns True when
+        the caches were dropped (a CUDA graph captured over the old copies is stale then)."""
+        sig = weights_signature(self.m)
+        if sig != self._signature:
+            stale = self._signature is not None
+            self._signature = sig
+            self._drop_caches()
+            return stale
+        return False
 
     def _weights(self, name):
         if name not in self._w:
-            enc = getattr(self.m, name)
-            layers = [_LayerWeights(l) for l in enc.layers]
-            pos_w = torch.cat([lw.sa_wq for lw in layers], 0).contiguous()      # every layer's (offset|logit) rows
-            self._w[name] = (layers, pos_w)
+            self._w[name] = [_LayerWeights(l) for l in getattr(self.m, name).layers]
         return self._w[name]
+
+    def _hi_lo(self, w):
+        """(w_hi, w_lo) of the 3xTF32 projection (once per weight)."""
+        key = (w.data_ptr(), tuple(w.shape))
+        if key not in self._split:
+            self._split[key] = ops.split_tf32(w.contiguous())
+        return self._split[key]
 
     def _tf32(self, w):
         """Weight rounded to nearest TF32 (once): tcgen05 kind::tf32 truncates fp32 operands, which would bias every
@@ -152,53 +172,39 @@ class FusedEncoder:
         return self._rn[key]
 
     # dense projections ------------------------------------------------------------------------------
-    # An activation travels as a pair (fp32 rows, fp16 copy or None).  With precision='tf32' the LayerNorm epilogues
-    # emit the fp16 copy next to the fp32 rows, and the projections that read it run with fp16 operands (the
-    # significand of TF32 in half the bytes, weight tile resident in shared memory).
+    # An activation travels as a pair (fp32 rows, fp16 copy or None).  In the fp16 class the LayerNorm epilogues emit
+    # the fp16 copy next to the fp32 rows, and the projections read it as their A operand.
     def _lin(self, x, w, b, residual=None, relu=False, ln=None, out=None, w16=None, want16=False, only16=False):
         """epilogue(x @ w^T) -> (fp32 rows or None, fp16 copy or None).  x: fp32 rows or a (fp32, fp16) pair."""
         x32, x16 = x if isinstance(x, tuple) else (x, None)
-        if self.tc_gemm:
-            try:
-                if ln is not None and not self.fuse_ln:
-                    # projection (bias in the epilogue) + one streaming residual/LayerNorm pass that also emits the
-                    # fp16 copy: measured faster than the LayerNorm epilogue, whose residual reads are latency-bound
-                    o, _ = self._lin(x, w, b, w16=w16)
-                    o16 = torch.empty(o.shape, device=o.device, dtype=torch.float16) if want16 else None
-                    return ops.add_layernorm(o, ln[0], ln[1], residual=residual, eps=ln[2], out=o, out16=o16), o16
-                if x16 is not None and w16 is not None:
-                    N = w16.shape[0]
-                    if self.ffn1_halves and only16 and N == 512 and residual is None and ln is None and out is None:
-                        # two column halves, each with its weight tile resident in shared memory (a 512-row W does
-                        # not fit and would be re-streamed from L2 for every row tile)
-                        o16 = torch.empty(x16.shape[0], N, device=x16.device, dtype=torch.float16)
-                        for h0 in (0, 256):
-                            ops.linear_f16(x16, w16[h0:h0 + 256], b[h0:h0 + 256], relu=relu, fp32_out=False,
-                                           out16=o16[:, h0:h0 + 256])
-                        return None, o16
-                    return ops.linear_f16(x16, w16, b, residual=residual, relu=relu, ln=ln, out=out,
-                                          fp32_out=not only16, f16_out=want16 or only16)
-                if x32 is not None and not only16:
-                    o16 = torch.empty(x32.shape[0], w.shape[0], device=x32.device, dtype=torch.float16) if want16 else None
-                    return ops.linear_tf32(x32, self._tf32(w), b, residual=residual, relu=relu, ln=ln, out=out,
-                                           out16=o16), o16
-            except _cabi.UnsupportedShape:
-                pass
-        if x32 is None:
-            x32 = x16.float()
+        try:
+            if self.gemm == 'tf32x3':
+                return ops.linear_tf32x3(self._rows32(x), self._hi_lo(w), b, residual=residual, relu=relu, ln=ln, out=out), None
+            if self.f16 and x16 is not None and w16 is not None:
+                N = w16.shape[0]
+                if only16 and N == 512 and residual is None and ln is None and out is None:
+                    # two column halves, each with its weight tile resident in shared memory (a 512-row W does
+                    # not fit and would be re-streamed from L2 for every row tile)
+                    o16 = torch.empty(x16.shape[0], N, device=x16.device, dtype=torch.float16)
+                    for h0 in (0, 256):
+                        ops.linear_f16(x16, w16[h0:h0 + 256], b[h0:h0 + 256], relu=relu, fp32_out=False,
+                                       out16=o16[:, h0:h0 + 256])
+                    return None, o16
+                return ops.linear_f16(x16, w16, b, residual=residual, relu=relu, ln=ln, out=out,
+                                      fp32_out=not only16, f16_out=want16 or only16)
+            if self.gemm in ('tf32', 'f16') and x32 is not None and not only16:
+                o16 = torch.empty(x32.shape[0], w.shape[0], device=x32.device, dtype=torch.float16) if want16 else None
+                return ops.linear_tf32(x32, self._tf32(w), b, residual=residual, relu=relu, ln=ln, out=out,
+                                       out16=o16), o16
+        except _cabi.UnsupportedShape:
+            pass        # counted by the library (ub_unsupported_count); bench.py asserts the benchmarked shapes have none
+        # generic fp32 FFMA projection + (for 'norm' steps) one streaming residual / LayerNorm pass
+        x32 = self._rows32(x)
         if ln is not None:
-            o = torch.mm(x32, w.t())
-            o = ops.add_layernorm(o, ln[0], ln[1], bias=b, residual=residual, eps=ln[2], out=o)
+            o = ops.linear_simt(x32, w, b, out=out)
+            o = ops.add_layernorm(o, ln[0], ln[1], residual=residual, eps=ln[2], out=o)
         else:
-            if relu:
-                o = torch._addmm_activation(b, x32, w.t(), use_gelu=False)
-            else:
-                o = torch.addmm(b, x32, w.t()) if b is not None else torch.mm(x32, w.t())
-            if residual is not None:
-                o += residual
-        if out is not None:
-            out.copy_(o)
-            o = out
+            o = ops.linear_simt(x32, w, b, residual=residual, relu=relu, out=out)
         return o, None
 
     @staticmethod
@@ -208,22 +214,21 @@ class FusedEncoder:
         return (None, s) if s.dtype == torch.float16 else s
 
     def _project_value(self, x, w, b, G, Nv, H, P, w16=None):
-        """value_proj of the rows x (G*Nv, C) -> (fp16 head-major planes for the window kernels or None, fp32 rows or
-        None).  With the tcgen05 GEMM the planes come straight out of the epilogue."""
+        """value_proj of the rows x (G*Nv, C) -> (fp16 head-major planes for the fp16 window kernels or None, fp32 rows
+        or None).  With the fp16 / TF32 tensor-core GEMM the planes come straight out of the epilogue."""
         x32, x16 = x if isinstance(x, tuple) else (x, None)
         C = w.shape[0]
-        if self.fast_sampling and ops.window_supported(C // H, P):
-            if self.tc_gemm:
-                try:
-                    if x16 is not None and w16 is not None:
-                        return ops.linear_f16(x16, w16, b, planes_nv=Nv), None
-                    if x32 is not None:
-                        return ops.linear_tf32(x32, self._tf32(w), b, planes_nv=Nv), None
-                except _cabi.UnsupportedShape:
-                    pass
-            rows = torch.addmm(b, self._rows32(x), w.t())
+        if self.sampling == 'win16' and ops.window_supported(C // H, P):
+            try:
+                if self.f16 and x16 is not None and w16 is not None:
+                    return ops.linear_f16(x16, w16, b, planes_nv=Nv), None
+                if self.gemm == 'tf32' and x32 is not None:
+                    return ops.linear_tf32(x32, self._tf32(w), b, planes_nv=Nv), None
+            except _cabi.UnsupportedShape:
+                pass
+            rows, _ = self._lin(x, w, b, w16=w16)
             return ops.value_to_half(rows, G, Nv, H), rows
-        return None, torch.addmm(b, self._rows32(x), w.t())
+        return None, self._lin(x, w, b, w16=w16)[0]
 
     def _bev_sample(self, x, w, b, qp, B, bev_h, bev_w, fh, fw, H, P, w16=None):
         """value_proj + BEV-grid sampling: rows x (B*fh*fw, C) un-projected -> sampled (B, Nq, C)."""
@@ -231,35 +236,36 @@ class FusedEncoder:
         planes, rows = self._project_value(x, w, b, B, fh * fw, H, P, w16)
         if planes is not None and qp.shape[2] % 4 == 0:
             try:
-                if self.tc_gemm and self.half_samples and w16 is not None:
-                    return ops.bev_sample_win(planes, qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2, out_dtype=torch.float16)
-                # the sampled rows feed the TF32 output projection: have the kernel round them to nearest
-                _cabi.lib().ub_set_window_round_tf32(1 if self.tc_gemm else 0)
-                return ops.bev_sample_win(planes, qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2)
+                return ops.bev_sample_win(planes, qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2, workspace=self._counter(),
+                                          out_dtype=torch.float16 if self.half_samples else torch.float32,
+                                          # fp32 rows that feed a plain TF32 projection: round instead of truncating
+                                          round_tf32=self.gemm == 'tf32')
             except _cabi.UnsupportedShape:
                 pass
-            finally:
-                _cabi.lib().ub_set_window_round_tf32(0)
         if rows is None:
-            rows = torch.addmm(b, self._rows32(x), w.t())
+            rows = self._lin(x, w, b, w16=w16)[0]
         return ops.bev_sample(rows.view(B, fh * fw, C), qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2)
 
-    # one BEV encoder ------------------------------------------------------------------------------
-    def _use_f16(self, C):
-        return self.tc_gemm and C % 64 == 0
+    def _counter(self):
+        """The next 2-int work-counter slot of this call's workspace (zeroed once per call, re-armed by each kernel)."""
+        k = self._n_counters
+        self._n_counters += 1
+        if k >= self._counters.shape[0]:
+            return None        # more window launches than slots: the op allocates its own
+        return self._counters[k]
 
     def _pos_rows(self, names, pos, rows):
         """Positional part of every layer's self-attention offset|logit rows, once per frame and for all encoders
         together: -> {encoder name: [per-layer (rows, n_q) views]}.  pos: fp32 rows or a (fp32, fp16) pair."""
         if pos is None:
             return {n: None for n in names}
-        blocks = [(n, lw) for n in names for lw in self._weights(n)[0]]
+        blocks = [(n, lw) for n in names for lw in self._weights(n)]
         widths = [lw.sa_wq.shape[0] for _, lw in blocks]
         dev = (pos[1] if isinstance(pos, tuple) and pos[0] is None else (pos[0] if isinstance(pos, tuple) else pos)).device
         buf = torch.empty(rows, sum(widths), device=dev, dtype=torch.float32)
         views = buf.split(widths, dim=1)
         done = False
-        if isinstance(pos, tuple) and pos[1] is not None and all(w == widths[0] and w % 32 == 0 for w in widths):
+        if self.f16 and isinstance(pos, tuple) and pos[1] is not None and all(w == widths[0] and w % 32 == 0 for w in widths):
             # fp16 operands, as many layers per GEMM as fit one 256-column tile with its weights resident
             key = tuple(names)
             if key not in self._pos_w:
@@ -277,23 +283,27 @@ class FusedEncoder:
                 self._lin(pos, lw.sa_wq, None, out=dst)
         out, k = {}, 0
         for n in names:
-            nl = len(self._weights(n)[0])
+            nl = len(self._weights(n))
             out[n] = views[k:k + nl]
             k += nl
         return out
+
+    # one BEV encoder ------------------------------------------------------------------------------
+    def _use_f16(self, C):
+        return self.f16 and C % 64 == 0
 
     def _run_encoder(self, name, queries, B, pos_q, value_tokens, sample_cross, bev_h, bev_w):
         """queries (Nq, C) the BEV query table (every sample starts from it, transformer_fusion.py:493-498); pos_q: per-layer
         positional offset|logit rows or None; value_tokens: un-projected feature rows, fp32 or a (fp32 | None, fp16)
         pair; sample_cross(lw, value_tokens, qp) -> sampled (B, Nq, C)."""
-        layers, pos_w = self._weights(name)
+        layers = self._weights(name)
         Nq, C = queries.shape
         f16 = self._use_f16(C)
         if C % 8 == 0:
             x32, x16 = ops.broadcast_rows(queries.detach(), B, fp32=True, fp16=f16)
         else:
             x32 = queries.detach().unsqueeze(0).expand(B, Nq, C).contiguous()
-            x16 = x32.half() if f16 else None
+            x16 = None
         x = (x32.view(B * Nq, C), x16.view(B * Nq, C) if f16 else None)
         if f16 and not isinstance(value_tokens, tuple):
             value_tokens = (value_tokens, value_tokens.half())   # fp16 copy once per frame, read by every layer
@@ -328,6 +338,7 @@ class FusedEncoder:
         host->device copy of ``img_metas[i]['lidar2img']`` (encoder_unibev_detr_img.py:115-124) when the caller
         stages calibration itself (``unibev_b200.pipeline.FramePipeline``)."""
         m = self.m
+        self.refresh()
         ref = (img_feats or pts_feats)[0]
         B, dev = ref.size(0), ref.device
         Nq, C = bev_h * bev_w, m.embed_dims
@@ -336,13 +347,18 @@ class FusedEncoder:
         else:
             q_img = q_pts = bev_queries
         f16 = self._use_f16(C)
-        pos = None
-        if bev_pos is not None:
-            pos = ops.flatten_feats(bev_pos, fp32=not f16, fp16=f16)
-            pos = tuple(t.view(B * Nq, C) if t is not None else None for t in pos) if f16 else pos.view(B * Nq, C)
-        img = pts = None
         names = (['img_bev_encoder'] if img_feats is not None else []) + (['pts_bev_encoder'] if pts_feats is not None else [])
-        with torch.no_grad(), _matmul_precision(self.tf32):
+        with torch.no_grad(), torch.cuda.device(dev):
+            # work counters of this call's window-kernel launches: one memset per call, distinct memory per call
+            # (and so per captured CUDA graph)
+            n_win = sum(2 * len(self._weights(n)) for n in names) if self.sampling == 'win16' else 0
+            self._counters = torch.zeros(max(n_win, 1), 2, device=dev, dtype=torch.int32)
+            self._n_counters = 0
+            pos = None
+            if bev_pos is not None:
+                pos = ops.flatten_feats(bev_pos, fp32=not f16, fp16=f16)
+                pos = tuple(t.view(B * Nq, C) if t is not None else None for t in pos) if f16 else pos.view(B * Nq, C)
+            img = pts = None
             pos_q = self._pos_rows(names, pos, B * Nq)
             if img_feats is not None:
                 feat = img_feats[0]
@@ -368,21 +384,20 @@ class FusedEncoder:
                         if not hits:
                             hits.append(ops.build_hits(mask))
                         try:
-                            half = self.tc_gemm and self.half_samples and isinstance(tokens, tuple)
                             return ops.img_sample_win(planes.view(B, N, lw.H_c, fh * fw, -1), qp, ref_cam, hits[0], bev_h,
                                                       bev_w, fh, fw, lw.H_c, lw.P_c, 0, lw.H_c * lw.P_c * 2,
-                                                      out_dtype=torch.float16 if half else torch.float32)
+                                                      out_dtype=torch.float16 if self.half_samples else torch.float32)
                         except _cabi.UnsupportedShape:
                             pass
                     if rows is None:
-                        rows = torch.addmm(lw.ca_bv, self._rows32(tokens), lw.ca_wv.t())
+                        rows = self._lin(tokens, lw.ca_wv, lw.ca_bv,
+                                         w16=lw.half()['ca_wv'] if isinstance(tokens, tuple) else None)[0]
                     return ops.img_sample(rows.view(B, N, fh * fw, C), qp, ref_cam, mask, bev_h, bev_w, fh, fw,
                                           lw.H_c, lw.P_c, 0, lw.H_c * lw.P_c * 2)
                 img = self._run_encoder('img_bev_encoder', q_img, B, pos_q['img_bev_encoder'], tokens, cross, bev_h, bev_w)
             if pts_feats is not None:
                 feat = pts_feats[0]
                 _, _, fh, fw = feat.shape
-                enc = m.pts_bev_encoder
                 tokens = self._tokens(feat, None, m.pts_level_embeds[0], f16, B * fh * fw, C)
 
                 def cross(lw, tokens, qp, fh=fh, fw=fw):

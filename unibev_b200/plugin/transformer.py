@@ -86,7 +86,9 @@ class UniBEVTransformer(nn.Module):
         self.vis_output = vis_output
         self.l_flag = self.c_flag = 1
         self._fused = None
-        self.fused_precision = 'tf32'        # GEMM math of the fused eval pipeline: 'tf32' | 'fp32'
+        # arithmetic class of the fused eval pipeline: 'fp32' (the reference's class: 3xTF32 tensor-core projections, fp32
+        # sampling) or the opt-in 'fp16' (fp16 operands / value maps, ~3e-3 absolute error); see plugin/fused.py
+        self.fused_precision = 'fp32'
         self.init_layers()
 
     @property
@@ -303,8 +305,11 @@ class UniBEVTransformer(nn.Module):
             self.l_flag = int(flags[1]) if pts_mlvl_feats is not None else 0
         grad = torch.is_grad_enabled() and (self.training or any(p.requires_grad for p in self.parameters()))
         if not self.training and not grad and fused_supported(self, img_mlvl_feats, pts_mlvl_feats):
-            if self._fused is None or self._fused.precision != self.fused_precision:
-                self._fused = FusedEncoder(self, self.fused_precision)
+            over = getattr(self, 'fused_overrides', None) or {}     # ablation: {'gemm': ..., 'sampling': ...}
+            key = (self.fused_precision, over.get('gemm'), over.get('sampling'))
+            if self._fused is None or self._fused_key != key:
+                # (derived weight copies are re-built by FusedEncoder.refresh() whenever a parameter changes)
+                self._fused, self._fused_key = FusedEncoder(self, self.fused_precision, **over), key
             return self._fused(img_mlvl_feats, pts_mlvl_feats, bev_queries, bev_h, bev_w, bev_pos,
                                kwargs.get('img_metas'), kwargs.get('lidar2img'), kwargs.get('img_shape'))
         img, pts = self._encode_modules(img_mlvl_feats, pts_mlvl_feats, bev_queries, bev_h, bev_w, bev_pos, **kwargs)
