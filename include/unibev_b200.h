@@ -129,6 +129,12 @@ enum { UB_WIN_ROUND_TF32 = 1 };
 int ub_bev_sample_win_fwd(const void* value16, const float* qproj, void* out, int out_f16,
                           int B, int bev_h, int bev_w, int fH, int fW, int H, int Dh, int P,
                           int ld, int off_col, int logit_col, int* workspace, int flags, ub_stream_t stream);
+/* fp32 twin of ub_bev_sample_win_fwd (the default precision class): planes32 (B, 2 H, fH*fW, 16) fp32 half-head planes
+ * from ub_linear_tf32x3 (channel c of head h lives in plane 2 h + c / 16), fp32 weights, exact softmax; out (B, Nq, H*32)
+ * fp32.  Same shapes covered (head dim 32, 4 or 8 points), same workspace contract. */
+int ub_bev_sample_win32_fwd(const float* planes32, const float* qproj, float* out,
+                            int B, int bev_h, int bev_w, int fH, int fW, int H, int Dh, int P,
+                            int ld, int off_col, int logit_col, int* workspace, ub_stream_t stream);
 /* mask (B, Nq, N) from ub_project_points -> the queries batch item 0 sees in camera n
  * (spatial_cross_attention_img.py:141-152), split by rank: hit_idx (N + 1, Nq) int32, row n = the hits whose lowest
  * seeing camera is n ("first", ascending, from the front) and the other hits of camera n ("later", from the back:

@@ -1,0 +1,79 @@
+"""fp32 window-staged sampling kernels (win_sample32.cu) against the oracle's MSDA core: fp32 tolerance (the same
+rtol 1e-4 / atol 5e-5 as the fp32 tile kernels), slow path, ragged tiles, full size, caller-owned work counters."""
+import pytest
+import torch
+
+from oracle import mmcv_semantics as ms
+from tests.helpers import bev_loc_weights
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from unibev_b200 import ops as _ops
+    return _ops
+
+
+def _case(ops, B, bev_h, bev_w, fH, fW, H, P, off_scale, seed, halo=0):
+    from unibev_b200 import _cabi
+    g = torch.Generator().manual_seed(seed)
+    Nq, C = bev_h * bev_w, H * 32
+    value = torch.randn(B, fH * fW, C, generator=g)
+    qproj = torch.cat((torch.randn(B, Nq, H * P * 2, generator=g) * off_scale,
+                       torch.randn(B, Nq, H * P, generator=g)), -1)
+    loc, aw = bev_loc_weights(qproj, bev_h, bev_w, fH, fW, H, P)
+    want = ms.msda_core(value.view(B, fH * fW, H, 32), [(fH, fW)], loc.unsqueeze(3), aw.unsqueeze(3))
+    planes = ops.value_to_planes32(value.cuda().view(B * fH * fW, C), B, fH * fW, H)
+    assert planes.shape == (B, 2 * H, fH * fW, 16)
+    torch.testing.assert_close(ops.planes32_to_rows(planes).cpu(), value.view(-1, C), rtol=0, atol=0)
+    _cabi.check(_cabi.lib().ub_set_window_halo(halo), 'ub_set_window_halo')
+    try:
+        ws = torch.zeros(2, dtype=torch.int32).cuda()
+        got = ops.bev_sample_win32(planes, qproj.cuda(), bev_h, bev_w, fH, fW, H, P, 0, H * P * 2, workspace=ws).cpu()
+        got2 = ops.bev_sample_win32(planes, qproj.cuda(), bev_h, bev_w, fH, fW, H, P, 0, H * P * 2, workspace=ws).cpu()
+        assert ws.cpu().tolist() == [0, 0]
+    finally:
+        _cabi.lib().ub_set_window_halo(0)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=5e-5)
+    torch.testing.assert_close(got2, got, rtol=0, atol=1e-6)       # (far samples accumulate with red.add)
+    return got
+
+
+@pytest.mark.parametrize('B,bev,f,H,P,off_scale', [
+    (1, (32, 32), (32, 32), 8, 4, 1.5),        # self-attention geometry, offsets inside the halo
+    (2, (40, 24), (36, 20), 8, 8, 3.0),        # LiDAR-cross geometry (scale != 1), ragged tiles
+    (1, (16, 16), (12, 12), 2, 8, 40.0),       # huge offsets: most samples far or outside the map
+    (1, (50, 50), (45, 45), 4, 4, 6.0),        # offsets beyond the halo: slow path mixed with the window path
+    (3, (17, 33), (9, 29), 1, 8, 2.0),         # one head, odd sizes
+])
+def test_bev_sample_win32_vs_oracle(ops, B, bev, f, H, P, off_scale):
+    _case(ops, B, bev[0], bev[1], f[0], f[1], H, P, off_scale, seed=B * 100 + P)
+
+
+def test_bev_sample_win32_small_halo_forces_slow_path(ops):
+    _case(ops, 1, 32, 32, 32, 32, 8, 8, 4.0, seed=5, halo=1)
+
+
+def test_bev_sample_win32_matches_tile_kernel_at_full_size(ops):
+    """BASELINE sizes (200 x 200 queries, 180 x 180 LiDAR map, 8 heads x 8 points, and the P = 4 self-attention): equal to
+    the fp32 tile kernel (itself pinned to the oracle) to fp32 rounding."""
+    g = torch.Generator().manual_seed(0)
+    for fH, P, B in ((180, 8, 2), (200, 4, 1)):
+        H, C = 8, 256
+        value = torch.randn(B, fH * fH, C, generator=g).cuda()
+        qproj = torch.cat((torch.randn(B, 40000, H * P * 2, generator=g) * 2.5, torch.randn(B, 40000, H * P, generator=g)), -1).cuda()
+        planes = ops.value_to_planes32(value.view(B * fH * fH, C), B, fH * fH, H)
+        got = ops.bev_sample_win32(planes, qproj, 200, 200, fH, fH, H, P, 0, H * P * 2)
+        ref = ops.bev_sample(value, qproj, 200, 200, fH, fH, H, P, 0, H * P * 2)
+        torch.testing.assert_close(got, ref, rtol=1e-5, atol=2e-6)
+
+
+def test_bev_sample_win32_rejects_uncovered_shapes(ops):
+    from unibev_b200 import _cabi
+    planes = torch.zeros(1, 8, 81, 16).cuda()
+    qp = torch.zeros(1, 100, 4 * 2 * 3).cuda()
+    with pytest.raises(_cabi.UnsupportedShape):
+        ops.bev_sample_win32(planes, qp, 10, 10, 9, 9, 4, 2, 0, 16)       # 2 points: not covered
+    with pytest.raises(RuntimeError):
+        ops.bev_sample_win32(planes.cpu(), qp, 10, 10, 9, 9, 4, 8, 0, 64)

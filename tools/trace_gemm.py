@@ -24,12 +24,17 @@ def main():
     _cabi.lib().ub_set_gemm_cluster(cs)
 
     x16, w16 = x.half(), w.half()
+    ws = ops.split_tf32(w)
 
     def run():
         if mode == 'ln':
             return ops.linear_tf32(x, w, b, residual=r, ln=(g, g, 1e-5))
         if mode == 'f16':
             return ops.linear_f16(x16, w16, b)
+        if mode == 'x3':
+            return ops.linear_tf32x3(x, ws, b)
+        if mode == 'x3ln':
+            return ops.linear_tf32x3(x, ws, b, residual=r, ln=(g, g, 1e-5))
         if mode == 'f16ln':
             return ops.linear_f16(x16, w16, b, residual=r, ln=(g, g, 1e-5), f16_out=True)
         return ops.linear_tf32(x, w, b)
@@ -55,7 +60,8 @@ def main():
         epi = [rel(v) for v in row[81:121] if int(v)]
         print(f'CTA {cta}: start {rel(row[0]):.2f} us')
         print('  producer issued k-blocks at :', ' '.join('%.2f' % v for v in prod))
-        print('  mma saw k-blocks full at    :', ' '.join('%.2f' % v for v in mma))
+        print('  mma saw k-blocks full at    :', ' '.join('%.2f' % v for v in mma),
+              '   (x3 modes: four stamps per k-block = A landed, a_lo ready, W_hi landed, W_lo landed)')
         print('  epilogue (acc ready, done)  :', ' '.join('%.2f' % v for v in epi))
     ends = [max(int(v) for v in t[c] if int(v)) for c in range(148) if int(t[c, 0])]
     print('last event over CTAs: %.2f us after first start' % ((max(ends) - t0) / 1e3))

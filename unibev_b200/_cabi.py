@@ -28,6 +28,7 @@ PROTOTYPES = {
     'ub_img_sample_fwd': ([_p] * 5 + [_i] * 13 + [_p], _i),
     'ub_value_to_half': ([_p, _p] + [_i] * 4 + [_p], _i),
     'ub_bev_sample_win_fwd': ([_p] * 3 + [_i] * 12 + [_p, _i, _p], _i),
+    'ub_bev_sample_win32_fwd': ([_p] * 3 + [_i] * 11 + [_p, _p], _i),
     'ub_build_hits': ([_p] * 5 + [_i] * 3 + [_p], _i),
     'ub_img_sample_win_fwd': ([_p] * 8 + [_i] * 14 + [_p], _i),
     'ub_linear_tf32': ([_p] * 4 + [_i, _p, _p, _f, _p, _i, _p] + [_i] * 5 + [_p], _i),
@@ -90,6 +91,7 @@ def lib():
 
 
 UB_EUNSUPPORTED = -4
+unsupported_log = []      # messages of the last UB_EUNSUPPORTED answers (diagnostics: which call fell back, and why)
 
 
 class UnsupportedShape(UniBEVNativeError):
@@ -102,6 +104,8 @@ def check(rc, what):
         if rc == -1:
             raise ValueError(f'{what}: {msg}')
         if rc == UB_EUNSUPPORTED:
+            unsupported_log.append(f'{what}: {msg}')
+            del unsupported_log[:-32]
             raise UnsupportedShape(f'{what}: {msg}')
         raise UniBEVNativeError(f'{what} failed (code {rc}): {msg}')
 

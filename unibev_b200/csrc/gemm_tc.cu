@@ -294,7 +294,9 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
     if (a.ln) s_par[a.N + i] = a.gamma[i], s_par[2 * a.N + i] = a.beta[i];
   }
   if (tid == 0) {
-    for (int i = 0; i < SA; ++i) mbar_init(smem_u32(&s_fa[i]), 1), mbar_init(smem_u32(&s_ea[i]), 1);
+    // SPLIT: a slot is free again once the MMAs that read it have completed AND every converter warp has passed it
+    // (also the residual slots, which the converters do not touch): no waiter can then fall a whole phase behind
+    for (int i = 0; i < SA; ++i) mbar_init(smem_u32(&s_fa[i]), 1), mbar_init(smem_u32(&s_ea[i]), SPLIT ? 1 + kConvWarps : 1);
     for (int i = 0; i < SW; ++i) mbar_init(smem_u32(&s_fw[i]), 1), mbar_init(smem_u32(&s_ew[i]), cs);
     for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&s_tfull[i]), 1), mbar_init(smem_u32(&s_tempty[i]), kEpiWarps);
     for (int i = 0; i < SL; ++i) mbar_init(smem_u32(&s_fl[i]), kConvWarps), mbar_init(smem_u32(&s_el[i]), 1);
@@ -408,7 +410,9 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
         if (SPLIT) {
           for (int kb = 0; kb < k_blocks; ++kb) {
             mbar_wait(smem_u32(&s_fa[sa]), pa);
+            trace_event(a, 1, ev++);
             mbar_wait(smem_u32(&s_fl[sl]), pl);             // the converters have masked the A slot and filled the lo slot
+            trace_event(a, 1, ev++);
             mbar_wait(smem_u32(&s_fw[sw]), pw);             // W_hi k-block
             trace_event(a, 1, ev++);
             tc_fence_after();
@@ -426,6 +430,7 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
               mma_commit_multicast(smem_u32(&s_ew[sw]), cta_mask);
             if (++sw == SW) sw = 0, pw ^= 1u;
             mbar_wait(smem_u32(&s_fw[sw]), pw);             // W_lo k-block
+            trace_event(a, 1, ev++);
             tc_fence_after();
             bdesc = smem_desc_k128(sm_w + (uint32_t)sw * w_bytes);
 #pragma unroll
@@ -478,8 +483,11 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
     int sa = 0, sl = 0;
     uint32_t pa = 0, pl = 0;
     for (int it = 0; it < n_iter; ++it) {
-      for (int rc = 0; rc < a.res_chunks; ++rc)            // residual boxes pass through the ring untouched
+      for (int rc = 0; rc < a.res_chunks; ++rc) {          // residual boxes pass through the ring untouched
+        mbar_wait(smem_u32(&s_fa[sa]), pa);
+        if (lane == 0) mbar_arrive(smem_u32(&s_ea[sa]));
         if (++sa == SA) sa = 0, pa ^= 1u;
+      }
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(smem_u32(&s_fa[sa]), pa);
         mbar_wait(smem_u32(&s_el[sl]), pl ^ 1u);
@@ -499,7 +507,7 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
         }
         fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_fl[sl]));
+        if (lane == 0) mbar_arrive(smem_u32(&s_fl[sl])), mbar_arrive(smem_u32(&s_ea[sa]));
         if (++sa == SA) sa = 0, pa ^= 1u;
         if (++sl == SL) sl = 0, pl ^= 1u;
       }

@@ -37,18 +37,12 @@
 // use red.global.add.v4.f32 -- no zero-fill pass and no read-modify-write for the bulk of the pairs.
 #include <cuda_fp16.h>
 
-#include "ub_tma.cuh"
+#include "win_common.cuh"
 
 namespace ub {
 
-constexpr int kWorkerWarps = 16;                           // one query row / 16 hits of the unit each
-constexpr int kWarpItems = 16;                             // items (query, head) per worker warp and unit
-constexpr int kBevThreads = (kWorkerWarps + 1) * 32;       // + the scheduler warp
-constexpr int kImgThreads = kWorkerWarps * 32;
-constexpr int kTQ = 16;                                    // BEV tile: 16 x 16 queries
-constexpr int kUnitItems = kWorkerWarps * kWarpItems;      // items per unit
-
 static int g_bev_halo = 0;       // 0 = default (P + 1)
+int g_bev_halo_shared() { return g_bev_halo; }   // the fp32 twin (win_sample32.cu) honours the same knob
 static int g_img_two_win = 0;    // camera mode: double-buffer the plane windows when two fit
 static int g_img_vec_ref = 1;
 static int g_img_stage = 0;      // camera mode: P1 inputs through bulk async copies instead of register prefetch; off:
@@ -93,40 +87,9 @@ struct Desc {
   static constexpr int bytes = w_bytes + idx_bytes;
 };
 
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   const __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
-}
-
-// P1 works with two lanes per item, each owning PPL = P / 2 consecutive sampling points.
-// Softmax over the item's P logits: in-lane over the PPL own ones, one shuffle with the partner lane.
-template <int PPL>
-__device__ __forceinline__ void softmax_pair(const float (&lg)[PPL], bool ok, float scale, float (&aw)[PPL]) {
-  float mx = lg[0];
-#pragma unroll
-  for (int i = 1; i < PPL; ++i) mx = fmaxf(mx, lg[i]);
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < PPL; ++i) {
-    aw[i] = ex2_approx((lg[i] - mx) * 1.4426950408889634f);
-    sum += aw[i];
-  }
-  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-  const float inv = ok ? rcp_approx(sum) * scale : 0.f;
-#pragma unroll
-  for (int i = 0; i < PPL; ++i) aw[i] *= inv;
 }
 
 // One sample -> descriptor words (branch-free).  (h_im, w_im): pixel coordinates in the value map; aw: attention
@@ -163,17 +126,6 @@ __device__ __forceinline__ void store_descs(uint32_t sm_w, uint32_t sm_idx, int 
                  : "memory");
   else
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(ia), "r"(idx[0] | (idx[1] << 16)) : "memory");
-}
-
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
 }
 
 // acc[0..7] += fp16x8 (v) * one fp16 weight (low half of w when TOP, high half otherwise), fp32 accumulation
@@ -218,15 +170,6 @@ __device__ __forceinline__ void fhfma8(float (&acc)[8], const uint4& v, uint32_t
         : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]), "+f"(acc[6]), "+f"(acc[7])
         : "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(w));
   }
-}
-
-__device__ __forceinline__ float round_tf32(float x) {   // round to nearest (ties away) at 10 mantissa bits
-  uint32_t t;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
-  return __uint_as_float(t);
-}
-__device__ __forceinline__ void red_add4(float* p, const float4& v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // fp16 output rows: this lane's four channels as 8 bytes
@@ -315,10 +258,6 @@ struct BevWinArgs {
   int off_col, logit_col;
   float sx, sy;
   int round_tf32;
-};
-
-struct __align__(16) UnitInfo {
-  int u, b, h, tx0, ty0, wx0, wy0, pad;
 };
 
 template <int PP>
@@ -981,8 +920,6 @@ __global__ void __launch_bounds__(kImgThreads, 1)
 
 // ---------------------------------------------------------------------------------------------------------
 // host side
-
-constexpr size_t kSmemBudget = 232448 - 1024 - 64;  // 227 KB per CTA minus the static part
 
 template <int PP, int ROWB>
 static int launch_bev_win_v(BevWinArgs& a, const CUtensorMap& mv, const CUtensorMap& mo, const CUtensorMap& ml,

@@ -169,6 +169,36 @@ def bev_sample_win(value16, qproj, bev_h, bev_w, fH, fW, H, P, off_col, logit_co
     return out
 
 
+def bev_sample_win32(planes32, qproj, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out=None, workspace=None):
+    """fp32 twin of ``bev_sample_win``: planes32 (B, 2H, fH*fW, 16) fp32 half-head planes (``linear_tf32x3(planes_nv=)``
+    or ``value_to_planes32``); qproj (B, Nq, ld) -> (B, Nq, H*32) fp32."""
+    planes32, qproj = _need(planes32, 'planes32'), _need(qproj, 'qproj')
+    B, H2, Nv, Dh2 = planes32.shape
+    if H2 != 2 * H or Dh2 != 16 or Nv != fH * fW or qproj.shape[0] != B or qproj.shape[1] != bev_h * bev_w:
+        raise ValueError(f'bev_sample_win32: inconsistent shapes planes32{tuple(planes32.shape)} qproj{tuple(qproj.shape)}')
+    if out is None:
+        out = torch.empty(B, bev_h * bev_w, H * 32, device=qproj.device, dtype=torch.float32)
+    if workspace is None:
+        workspace = torch.zeros(2, device=qproj.device, dtype=torch.int32)
+    elif workspace.dtype != torch.int32 or workspace.numel() < 2 or workspace.device != qproj.device:
+        raise ValueError('bev_sample_win32: `workspace` must be 2 int32 on the device of the inputs')
+    _call('ub_bev_sample_win32_fwd', planes32, _ptr(planes32), _ptr(qproj), _ptr(out), B, bev_h, bev_w, fH, fW, H, 32, P,
+          qproj.shape[2], off_col, logit_col, _ptr(workspace))
+    return out
+
+
+def value_to_planes32(value, G, Nv, H):
+    """value (G*Nv, H*32) fp32 token-major rows -> (G, 2H, Nv, 16) half-head planes (torch glue for tests / ablations;
+    the product path gets the planes from the value projection's epilogue)."""
+    return value.view(G, Nv, 2 * H, 16).permute(0, 2, 1, 3).contiguous()
+
+
+def planes32_to_rows(planes32):
+    """(G, 2H, Nv, 16) half-head planes -> (G*Nv, H*32) token-major rows (torch glue; inverse of value_to_planes32)."""
+    G, H2, Nv, _ = planes32.shape
+    return planes32.permute(0, 2, 1, 3).reshape(G * Nv, H2 * 16)
+
+
 def build_hits(mask):
     """mask (B, Nq, N) uint8 -> hit_idx (N + 1, Nq) int32 (rank-split lists, row N = unseen queries), hit_cnt (2N + 1)
     int32 (first counts, later counts, unseen count), inv_cnt (B, Nq) fp32, hit_ic (B, N, Nq) fp32 = inv_cnt in hit-list

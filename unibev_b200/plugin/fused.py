@@ -30,6 +30,8 @@ Reference lines reproduced: transformer_fusion.py:231-278,463-538;
 encoder_unibev_detr_img.py:189-289,413-479; encoder_unibev_detr_pts.py:129-209;
 spatial_cross_attention_img.py:141-215,381-419; spatial_cross_attention_pts.py:159-206.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -131,6 +133,8 @@ class FusedEncoder:
             self.sampling = sampling
         self.f16 = self.gemm == 'f16'
         # sampled rows leave the window kernels as fp16 (the A operand of the fp16 output projection)
+        # fp32 sampling through the window-staged fp32 kernels where the shape is covered (UB_WIN32=0: tile kernels only)
+        self.win32 = os.environ.get('UB_WIN32', '1') == '1'
         self.half_samples = self.f16 and self.sampling == 'win16'
         self._signature = None
         self._drop_caches()
@@ -192,10 +196,12 @@ class FusedEncoder:
                     return None, o16
                 return ops.linear_f16(x16, w16, b, residual=residual, relu=relu, ln=ln, out=out,
                                       fp32_out=not only16, f16_out=want16 or only16)
-            if self.gemm in ('tf32', 'f16') and x32 is not None and not only16:
+            if self.gemm == 'tf32' and x32 is not None and not only16:      # ablation only: one TF32 pass
                 o16 = torch.empty(x32.shape[0], w.shape[0], device=x32.device, dtype=torch.float16) if want16 else None
                 return ops.linear_tf32(x32, self._tf32(w), b, residual=residual, relu=relu, ln=ln, out=out,
                                        out16=o16), o16
+            if self.f16:        # channel counts the fp16 GEMM does not take (C % 64 != 0): fp32-grade products instead
+                return ops.linear_tf32x3(self._rows32(x), self._hi_lo(w), b, residual=residual, relu=relu, ln=ln, out=out), None
         except _cabi.UnsupportedShape:
             pass        # counted by the library (ub_unsupported_count); bench.py asserts the benchmarked shapes have none
         # generic fp32 FFMA projection + (for 'norm' steps) one streaming residual / LayerNorm pass
@@ -213,11 +219,17 @@ class FusedEncoder:
         s = s.view(rows, C)
         return (None, s) if s.dtype == torch.float16 else s
 
-    def _project_value(self, x, w, b, G, Nv, H, P, w16=None):
-        """value_proj of the rows x (G*Nv, C) -> (fp16 head-major planes for the fp16 window kernels or None, fp32 rows
-        or None).  With the fp16 / TF32 tensor-core GEMM the planes come straight out of the epilogue."""
+    def _project_value(self, x, w, b, G, Nv, H, P, w16=None, planes32=False):
+        """value_proj of the rows x (G*Nv, C) -> (value planes for the window kernels or None, fp32 rows or None).
+        Planes are fp16 head-major (G, H, Nv, 32) in the 'win16' sampling class and, with ``planes32``, fp32 half-head
+        planes (G, 2H, Nv, 16) in the 'fp32' class; they come straight out of the projection's epilogue."""
         x32, x16 = x if isinstance(x, tuple) else (x, None)
         C = w.shape[0]
+        if planes32 and self.win32 and self.sampling == 'fp32' and ops.window_supported(C // H, P):
+            try:
+                return ops.linear_tf32x3(self._rows32(x), self._hi_lo(w), b, planes_nv=Nv), None
+            except _cabi.UnsupportedShape:
+                pass
         if self.sampling == 'win16' and ops.window_supported(C // H, P):
             try:
                 if self.f16 and x16 is not None and w16 is not None:
@@ -233,11 +245,17 @@ class FusedEncoder:
     def _bev_sample(self, x, w, b, qp, B, bev_h, bev_w, fh, fw, H, P, w16=None):
         """value_proj + BEV-grid sampling: rows x (B*fh*fw, C) un-projected -> sampled (B, Nq, C)."""
         C = w.shape[0]
-        planes, rows = self._project_value(x, w, b, B, fh * fw, H, P, w16)
-        if planes is not None and qp.shape[2] % 4 == 0:
+        planes, rows = self._project_value(x, w, b, B, fh * fw, H, P, w16, planes32=qp.shape[2] % 4 == 0)
+        if planes is not None and planes.dtype == torch.float32:
             try:
+                return ops.bev_sample_win32(planes, qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2, workspace=self._counter())
+            except _cabi.UnsupportedShape:
+                rows = ops.planes32_to_rows(planes)
+        elif planes is not None and qp.shape[2] % 4 == 0:
+            try:
+                half = self.half_samples and w16 is not None      # the output projection takes fp16 operands
                 return ops.bev_sample_win(planes, qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2, workspace=self._counter(),
-                                          out_dtype=torch.float16 if self.half_samples else torch.float32,
+                                          out_dtype=torch.float16 if half else torch.float32,
                                           # fp32 rows that feed a plain TF32 projection: round instead of truncating
                                           round_tf32=self.gemm == 'tf32')
             except _cabi.UnsupportedShape:
@@ -351,7 +369,7 @@ class FusedEncoder:
         with torch.no_grad(), torch.cuda.device(dev):
             # work counters of this call's window-kernel launches: one memset per call, distinct memory per call
             # (and so per captured CUDA graph)
-            n_win = sum(2 * len(self._weights(n)) for n in names) if self.sampling == 'win16' else 0
+            n_win = sum(2 * len(self._weights(n)) for n in names)
             self._counters = torch.zeros(max(n_win, 1), 2, device=dev, dtype=torch.int32)
             self._n_counters = 0
             pos = None
@@ -386,7 +404,8 @@ class FusedEncoder:
                         try:
                             return ops.img_sample_win(planes.view(B, N, lw.H_c, fh * fw, -1), qp, ref_cam, hits[0], bev_h,
                                                       bev_w, fh, fw, lw.H_c, lw.P_c, 0, lw.H_c * lw.P_c * 2,
-                                                      out_dtype=torch.float16 if self.half_samples else torch.float32)
+                                                      out_dtype=torch.float16 if self.half_samples and
+                                                      isinstance(tokens, tuple) else torch.float32)
                         except _cabi.UnsupportedShape:
                             pass
                     if rows is None:
