@@ -312,9 +312,10 @@ def main():
     #     inputs and outputs each, i.e. more than L2 between two uses of the same buffer) are replayed back to back from a
     #     CUDA graph and timed with CUDA events on the launching stream: no host gaps, no L2 reuse.
     records, calls = {}, {}
-    op_names = ('bev_sample', 'img_sample', 'bev_sample_win', 'img_sample_win', 'linear_tf32', 'linear_f16',
-                'linear_tf32x3', 'linear_simt', 'add_layernorm', 'value_to_half', 'flatten_feats', 'cnw_fuse', 'build_hits',
-                'project_points', 'broadcast_rows')
+    op_names = ('bev_sample', 'img_sample', 'bev_sample_win', 'img_sample_win', 'bev_sample_win32', 'img_sample_win32',
+                'linear_tf32', 'linear_f16', 'linear_tf32x3', 'linear_tf32x3_scatter', 'linear_simt', 'add_layernorm',
+                'value_to_half', 'flatten_feats', 'cnw_fuse', 'build_hits', 'hit_order', 'project_points', 'broadcast_rows')
+    used = set()
     real = {n: getattr(ops, n) for n in op_names}
 
     def clone_arg(v):
@@ -326,15 +327,16 @@ def main():
 
     def wrap(name):
         def inner(*a, **k):
-            if name in ('bev_sample', 'bev_sample_win'):
+            if name in ('bev_sample', 'bev_sample_win', 'bev_sample_win32'):
                 key = 'bev_self' if (a[7] == 4 and a[4] == a[2]) else 'pts_cross'
-            elif name in ('img_sample', 'img_sample_win'):
+            elif name in ('img_sample', 'img_sample_win', 'img_sample_win32'):
                 key = 'img_cross'
             else:
                 key = name
             if key in ('bev_self', 'pts_cross', 'img_cross'):
+                used.add((key, name))
                 r = real[name](*a, **k)
-                kk = {x: y for x, y in k.items() if x != 'out'}
+                kk = {x: y for x, y in k.items() if x not in ('out', 'workspace')}
                 calls.setdefault(key, []).append((name, tuple(clone_arg(v) for v in a), kk, torch.empty_like(r)))
                 return r
             records[key] = records.get(key, 0) + 1
@@ -393,7 +395,8 @@ def main():
            'img_cross': algorithmic_bytes('img', B, C, H, Nq, 6 * 1450, 8) + B * (pairs * 4 * 2 * 4 + 2 * Nq * 6)}
     kernels, other = {}, {}
     for key, (mean_us, per_step) in sample_us.items():
-        kernels[key] = {'launches_per_step': per_step, 'avg_us': mean_us, 'alg_bytes': alg[key],
+        kernels[key] = {'op': sorted(n for kk, n in used if kk == key), 'launches_per_step': per_step, 'avg_us': mean_us,
+                        'alg_bytes': alg[key],
                         'achieved_gbs': alg[key] / mean_us / 1e3, 'frac': alg[key] / mean_us / 1e3 / peak,
                         'timing': 'CUDA graph of the step\'s recorded launches replayed back to back, CUDA events'}
     for key, n in records.items():      # the other libunibev_b200 ops of a step: counts only (shares: profiles/ launch list)
@@ -408,10 +411,13 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(str(B), {}).get(dominant)
         except OSError:
             traffic = None
-        win = '_win' if args.precision == 'fp16' else ''      # fp32 class: the fp32 tile kernels of tile_sample.cu
-        roofline = {'bound': 'hbm', 'kernel': {'bev_self': f'bev_sample{win}_kernel (BEV self-attn, P=4)',
-                                               'pts_cross': f'bev_sample{win}_kernel (LiDAR cross-attn, P=8)',
-                                               'img_cross': f'img_sample{win}_kernel (camera cross-attn, P=8)'}[dominant],
+        kname = {'bev_sample': 'bev_sample_kernel (fp32 tile kernel)', 'bev_sample_win': 'bev_sample_win_kernel (fp16-staged windows)',
+                 'bev_sample_win32': 'bev_sample_win32_kernel (fp32 half-head windows)',
+                 'img_sample': 'img_sample_kernel (fp32 tile kernel)', 'img_sample_win': 'img_sample_win_kernel (fp16-staged planes)',
+                 'img_sample_win32': 'img_sample_win32_kernel (fp32 half-head planes)'}
+        what = {'bev_self': 'BEV self-attn, P=4', 'pts_cross': 'LiDAR cross-attn, P=8', 'img_cross': 'camera cross-attn, P=8'}
+        op_used = sorted(n for kk, n in used if kk == dominant)
+        roofline = {'bound': 'hbm', 'kernel': ' + '.join(kname[n] for n in op_used) + f' ({what[dominant]})',
                     'achieved': k['achieved_gbs'], 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
                     'frac': k['frac'], 'traffic': traffic, 'avg_us': k['avg_us'], 'alg_bytes_per_launch': k['alg_bytes']}
 

@@ -144,6 +144,20 @@ int ub_bev_sample_win32_fwd(const float* planes32, const float* qproj, float* ou
  * sampling kernel reads coalesced. */
 int ub_build_hits(const uint8_t* mask, int* hit_idx, int* hit_cnt, float* inv_cnt, float* hit_ic, int B, int N, int Nq,
                   ub_stream_t stream);
+/* Hit-list-ordered inputs of ub_img_sample_win32_fwd, once per frame: q_dst (Nq, N) int32 = for query q the rows
+ * n * Nq + pos (pos = its position in camera n's row of hit_idx) of every camera that sees it, -1 padded -- the scatter map of
+ * ub_linear_tf32x3_scatter; hit_ref (B, N, Nq, 2 D) = ref_cam (B, Nq, N, D, 2) gathered into hit-list order. */
+int ub_hit_order(const uint8_t* mask, const float* ref_cam, const int* hit_idx, const int* hit_cnt, int* q_dst,
+                 float* hit_ref, int B, int N, int Nq, int D, ub_stream_t stream);
+/* fp32 twin of ub_img_sample_win_fwd (the default precision class).  planes32 (B*N, 2 H, fH*fW, 16) fp32 half-head planes;
+ * qp_hit (B, N, Nq, ld) the offset|logit rows in hit-list order (ub_linear_tf32x3_scatter; rows that are no hit are never
+ * read as valid and may be uninitialised); hit_ref from ub_hit_order; hit_ic / hit_idx / hit_cnt from ub_build_hits.
+ * Every row of out (B, Nq, H*32) is written (zero rows for unseen queries, later hits accumulated with red.global.add).
+ * Head dim 32, 4 or 8 points, an even number of Z-anchors, Nq % 4 == 0. */
+int ub_img_sample_win32_fwd(const float* planes32, const float* qp_hit, const float* hit_ref, const float* hit_ic,
+                            const int* hit_idx, const int* hit_cnt, float* out, int B, int N, int bev_h, int bev_w,
+                            int fH, int fW, int H, int Dh, int P, int D, int ld, int off_col, int logit_col,
+                            ub_stream_t stream);
 /* value16 (B, N, H, fH*fW, 32) fp16; hit_idx / hit_cnt / inv_cnt from ub_build_hits.  Every row of out
  * (B, Nq, H*32) is written: first hits with plain stores (zero rows for unseen queries), later hits accumulated with
  * red.global.add on top (sums over more than three cameras are order-dependent in the last bit).  out_f16 as in
@@ -190,6 +204,14 @@ int ub_linear_f16(const void* A16, const void* W16, const float* bias, const flo
 int ub_linear_tf32x3(const float* A, const float* W_hi, const float* W_lo, const float* bias, const float* residual, int ldr,
                      const float* gamma, const float* beta, float eps, float* out, int ldc, float* planes32, int Nv,
                      int M, int N, int K, int flags, ub_stream_t stream);
+/* ub_linear_tf32x3 (bias only) whose result rows leave in another order: row b * rows_per_item + q of the product is
+ * written to the rows b * dst_rows_per_item + scatter[q * scatter_r + j] of `out` (row stride ldc), j = 0, 1, ... up to the
+ * first negative entry (none: the row is dropped).  With scatter = q_dst of ub_hit_order the camera cross-attention's
+ * offset|logit projection writes its rows in hit-list order (spatial_cross_attention_img.py:156-170 rebatches the queries
+ * per camera BEFORE the projection; the effect is the same). */
+int ub_linear_tf32x3_scatter(const float* A, const float* W_hi, const float* W_lo, const float* bias, float* out, int ldc,
+                             const int* scatter, int scatter_r, int rows_per_item, int dst_rows_per_item,
+                             int M, int N, int K, ub_stream_t stream);
 /* Generic fp32 (FFMA) projection for shapes the tensor-core entry points reject (UB_EUNSUPPORTED): any M, N, K.
  * out (M, N; row stride ldc) = [relu](A (M, K) @ W (N, K)^T + bias + residual (row stride ldr)); bias / residual may be NULL. */
 int ub_linear_simt(const float* A, const float* W, const float* bias, const float* residual, int ldr, float* out, int ldc,

@@ -77,3 +77,90 @@ def test_bev_sample_win32_rejects_uncovered_shapes(ops):
         ops.bev_sample_win32(planes, qp, 10, 10, 9, 9, 4, 2, 0, 16)       # 2 points: not covered
     with pytest.raises(RuntimeError):
         ops.bev_sample_win32(planes.cpu(), qp, 10, 10, 9, 9, 4, 8, 0, 64)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# camera mode: hit-list-ordered inputs (ub_hit_order), the row-scattering offset|logit projection and the fp32 window kernel
+def _camera(ops, B, bev, fhw, P, seed):
+    from tests.test_gpu_window import _camera_inputs
+    H = 8
+    l2i, value, qproj, zs = _camera_inputs(B, bev[0], bev[1], fhw[0], fhw[1], H, P, seed=seed)
+    ref_cam, mask = ops.project_points(l2i.cuda(), zs, [-54, -54, -5, 54, 54, 3], 928, 1600, bev[0], bev[1])
+    return H, value, qproj, ref_cam, mask
+
+
+def test_hit_order_exact(ops):
+    H, value, qproj, ref_cam, mask = _camera(ops, 2, (40, 36), (29, 50), 8, 3)
+    hits = ops.build_hits(mask)
+    q_dst, hit_ref = ops.hit_order(mask, ref_cam, hits)
+    hit_idx, hit_cnt = hits[0].cpu(), hits[1].cpu()
+    m, rc = mask.cpu(), ref_cam.cpu()
+    B, Nq, N = m.shape
+    q_dst, hit_ref = q_dst.cpu(), hit_ref.cpu()
+    n_pairs = 0
+    for q in range(Nq):
+        cams = (m[0, q] != 0).nonzero().squeeze(1).tolist()          # batch item 0's visibility (reference quirk)
+        row = q_dst[q].tolist()
+        assert row[len(cams):] == [-1] * (N - len(cams))
+        for j, n in enumerate(cams):
+            d = row[j]
+            assert d // Nq == n
+            pos = d % Nq
+            assert int(hit_idx[n, pos]) == q
+            assert pos < int(hit_cnt[n]) or pos >= Nq - int(hit_cnt[N + n])
+            for b in range(B):
+                assert torch.equal(hit_ref[b, n, pos], rc[b, q, n].reshape(-1))
+            n_pairs += 1
+    assert n_pairs == int(hit_cnt[:2 * N].sum())
+
+
+def test_linear_x3_scatter_rows(ops):
+    g = torch.Generator().manual_seed(1)
+    B, Nq, N, K, Nout = 2, 1000, 6, 256, 192
+    x = torch.randn(B * Nq, K, generator=g)
+    w, b = torch.randn(Nout, K, generator=g) / 16, torch.randn(Nout, generator=g)
+    q_dst = torch.full((Nq, N), -1, dtype=torch.int32)
+    perm = torch.randperm(N * Nq, generator=g)
+    k = 0
+    for q in range(Nq):                                              # 0 .. 3 distinct destination rows per query
+        c = q % 4
+        q_dst[q, :c] = perm[k:k + c].int()
+        k += c
+    out = torch.full((B, N * Nq, Nout), float('nan')).cuda()
+    ops.linear_tf32x3_scatter(x.cuda(), ops.split_tf32(w.cuda()), b.cuda(), q_dst.cuda(), Nq, out)
+    want = torch.nn.functional.linear(x.double(), w.double(), b.double()).float().view(B, Nq, Nout)
+    got = out.cpu()
+    written = torch.zeros(N * Nq, dtype=torch.bool)
+    for q in range(Nq):
+        for d in q_dst[q].tolist():
+            if d < 0:
+                break
+            written[d] = True
+            torch.testing.assert_close(got[:, d], want[:, q], rtol=1e-5, atol=5e-5)
+    assert bool(torch.isnan(got[:, ~written]).all())                 # no other row is touched
+
+
+@pytest.mark.parametrize('B,bev,fhw,P', [(1, (40, 36), (29, 50), 8), (2, (50, 50), (29, 50), 8), (2, (24, 24), (8, 22), 4)])
+def test_img_sample_win32_vs_fp32_kernel(ops, B, bev, fhw, P):
+    """Same result as the fp32 tile kernel (pinned to the oracle / the golden vectors in test_gpu_kernels.py) to fp32
+    rounding; every output row is written by the call (poisoned buffer); differing calibrations per batch item."""
+    H, value, qproj, ref_cam, mask = _camera(ops, B, bev, fhw, P, seed=B + P)
+    bev_h, bev_w = bev
+    fh, fw = fhw
+    Nq, N = bev_h * bev_w, 6
+    vg, qg = value.cuda(), qproj.cuda()
+    ref = ops.img_sample(vg, qg, ref_cam, mask, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2).cpu()
+    hits = ops.build_hits(mask)
+    q_dst, hit_ref = ops.hit_order(mask, ref_cam, hits)
+    planes = ops.value_to_planes32(vg.view(-1, H * 32), B * N, fh * fw, H)
+    # hit-ordered offset|logit rows by torch glue here (the product path: linear_tf32x3_scatter); other rows poisoned
+    qp_hit = torch.full((B, N * Nq, qproj.shape[2]), float('nan')).cuda()
+    for q_rows, d in ((q_dst[:, j] >= 0, q_dst[:, j]) for j in range(N)):
+        qp_hit[:, d[q_rows].long()] = qg[:, q_rows]
+    out = torch.full((B, Nq, H * 32), float('nan')).cuda()
+    got = ops.img_sample_win32(planes, qp_hit, hit_ref, hits, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2, out=out).cpu()
+    assert not bool(torch.isnan(got).any())
+    if bev == (40, 36):
+        assert int((got.abs().sum(-1) == 0).sum()) > 0              # this case has rows no camera sees
+    assert float(ref.abs().max()) > 0.1                            # the rig does see the grid
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=5e-6)

@@ -14,7 +14,9 @@ from tools.bench_gemm import timeit
 def main():
     dev = 'cuda'
     M = int(os.environ.get('M', 160000))
-    for cs in [int(c) for c in os.environ.get('CS', '4').split(',')]:
+    for opt in os.environ.get('OPTS', '1,0,4,0').split(';'):      # "inplace,direct,cluster,stagger_ns" variants of the 3xTF32 mode
+        inplace, direct, cs, stag = (int(v) for v in opt.split(','))
+        _cabi.check(_cabi.lib().ub_set_gemm_x3(inplace, direct, cs, stag), 'ub_set_gemm_x3')
         _cabi.lib().ub_set_gemm_cluster(cs)
         for name, N, K, ln in (('value 256x256', 256, 256, False), ('out+LN 256x256', 256, 256, True), ('qp 96', 96, 256, False),
                                ('qp 192', 192, 256, False), ('ffn1 512', 512, 256, False), ('ffn2+LN K512', 256, 512, True)):
@@ -35,8 +37,8 @@ def main():
             t1 = timeit(lambda: ops.linear_tf32(a, w, b, residual=r, ln=lnp, out=out))
             th = timeit(lambda: ops.linear_f16(a16, w16, b, residual=r, ln=lnp, out=out))
             bytes_ = 4 * (M * K + M * N * (2 if ln else 1))
-            print('cs=%d %-16s x3 %7.1f us (%5.1f TFLOP/s eff, %5.0f GB/s) | tf32 %7.1f us | f16 %7.1f us' %
-                  (cs, name, t3, 2.0 * M * N * K / t3 / 1e6, bytes_ / t3 / 1e3, t1, th), flush=True)
+            print('inplace=%d direct=%d cs=%d stagger=%d %-16s x3 %7.1f us (%5.1f TFLOP/s eff, %5.0f GB/s) | tf32 %7.1f us | f16 %7.1f us' %
+                  (inplace, direct, cs, stag, name, t3, 2.0 * M * N * K / t3 / 1e6, bytes_ / t3 / 1e3, t1, th), flush=True)
 
 
 if __name__ == '__main__':

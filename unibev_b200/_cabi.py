@@ -29,11 +29,14 @@ PROTOTYPES = {
     'ub_value_to_half': ([_p, _p] + [_i] * 4 + [_p], _i),
     'ub_bev_sample_win_fwd': ([_p] * 3 + [_i] * 12 + [_p, _i, _p], _i),
     'ub_bev_sample_win32_fwd': ([_p] * 3 + [_i] * 11 + [_p, _p], _i),
+    'ub_hit_order': ([_p] * 6 + [_i] * 4 + [_p], _i),
+    'ub_img_sample_win32_fwd': ([_p] * 7 + [_i] * 13 + [_p], _i),
     'ub_build_hits': ([_p] * 5 + [_i] * 3 + [_p], _i),
     'ub_img_sample_win_fwd': ([_p] * 8 + [_i] * 14 + [_p], _i),
     'ub_linear_tf32': ([_p] * 4 + [_i, _p, _p, _f, _p, _i, _p] + [_i] * 5 + [_p], _i),
     'ub_linear_tf32_dual': ([_p] * 4 + [_i, _p, _p, _f, _p, _i, _p] + [_i] * 5 + [_p], _i),
     'ub_linear_tf32x3': ([_p] * 5 + [_i, _p, _p, _f, _p, _i, _p] + [_i] * 5 + [_p], _i),
+    'ub_linear_tf32x3_scatter': ([_p] * 5 + [_i, _p] + [_i] * 6 + [_p], _i),
     'ub_linear_simt': ([_p] * 4 + [_i, _p] + [_i] * 5 + [_p], _i),
     'ub_split_tf32': ([_p, _p, _p, _i64, _p], _i),
     'ub_linear_f16': ([_p] * 4 + [_i, _p, _p, _f, _p, _i, _p, _i, _p] + [_i] * 5 + [_p], _i),
@@ -53,6 +56,7 @@ _PRIVATE = {
     'ub_set_tuning': ([_i] * 3, _i),
     'ub_set_window_halo': ([_i], _i),
     'ub_set_gemm_cluster': ([_i], _i),
+    'ub_set_gemm_x3': ([_i] * 4, _i),
     'ub_set_gemm_trace': ([_p], _i),
     'ub_set_pdl': ([_i], _i),
     'ub_set_img_two_windows': ([_i], _i),
@@ -87,6 +91,8 @@ def lib():
                         ('UB_IMG_VECREF', 'ub_set_img_vec_ref'), ('UB_PDL', 'ub_set_pdl')):
             if env in os.environ:
                 getattr(handle, fn)(int(os.environ[env]))
+        if 'UB_X3' in os.environ:       # "inplace,direct,cluster,stagger_ns"
+            handle.ub_set_gemm_x3(*[int(v) for v in os.environ['UB_X3'].split(',')])
     return _lib
 
 

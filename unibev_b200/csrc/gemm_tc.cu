@@ -69,6 +69,15 @@ struct GemmArgs {
   unsigned long long* trace;   // optional per-CTA event timestamps (tools/trace_gemm.py), else null
   int SL;               // 3xTF32 mode: depth of the A_lo ring
   float* planes32;      // fp32 half-head planes (G, N / 16, Nv, 16): the value-map layout of the fp32 window kernels, or null
+  // row scatter (camera cross-attention: offset|logit rows written in hit-list order): row r = b * sc_rows + q goes to the rows
+  // b * sc_dst_rows + scatter[q * sc_r + j], j = 0 .. until the first negative entry, of `out`; null: row r goes to row r
+  const int* scatter;
+  int sc_r, sc_rows, sc_dst_rows;
+  int x3_inplace;       // 3xTF32: the converters also write a_hi back (result independent of the tensor core's operand rounding)
+  int stagger_ns;       // every other cluster starts its first tile this much later: the CTAs' epilogue bursts (output stores)
+                        // then interleave with the others' operand loads instead of all hitting DRAM at once
+  int direct_store;     // fp32 result rows straight from registers (2 x 32 B per thread and chunk) instead of through the
+                        // per-warp staging buffers: fewer shared-memory wavefronts where the data pipe is the bottleneck
 };
 
 // trace slots per CTA: [0] start, [1 + 32 r + i]: role r (0 producer, 1 mma, 2 epilogue warp 0), event i
@@ -327,6 +336,13 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
       // A and the residual come from the predecessor kernel (and this kernel's outputs may alias buffers it still
       // reads): everything up to here -- barriers, TMEM, parameters, the resident weight tile -- overlapped its tail
       pdl_wait();
+      if (a.stagger_ns && (cluster_id & 1)) {
+        unsigned long long t0, t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        } while (t - t0 < (unsigned long long)a.stagger_ns);
+      }
       int stage = 0, ev = 0;
       uint32_t phase = 0;
       for (int i = 0; i < n_iter; ++i) {
@@ -502,7 +518,8 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
             const float lo = __uint_as_float(x[e]) - __uint_as_float(h[e]);    // exact
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l[e]) : "f"(lo));
           }
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(src + j), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+          if (a.x3_inplace)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(src + j), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + j), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
         }
         fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
@@ -529,7 +546,17 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
       const bool rows_live = row0 < r_end;                      // warp-uniform (and equal for the warps of the quarter)
 
       auto store_rows = [&](int c, const float (&f)[16]) {    // this thread's row chunk -> global
-        if (a.out) {                                          // fp32 rows, coalesced through the buffer
+        if (a.out && a.direct_store && !a.scatter) {          // fp32 rows: 64 contiguous bytes per thread, two 32-byte stores
+          if (row0 + lane < r_end) {
+            float* p = a.out + (size_t)(row0 + lane) * a.ldc + n0 + c * kChunk;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p + 8 * j), "f"(f[8 * j]),
+                           "f"(f[8 * j + 1]), "f"(f[8 * j + 2]), "f"(f[8 * j + 3]), "f"(f[8 * j + 4]), "f"(f[8 * j + 5]),
+                           "f"(f[8 * j + 6]), "f"(f[8 * j + 7])
+                           : "memory");
+          }
+        } else if (a.out) {                                   // fp32 rows, coalesced through the buffer
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(swz(buf, lane, j)), "f"(f[4 * j]), "f"(f[4 * j + 1]),
@@ -542,7 +569,19 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
             float4 o;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
                          : "r"(swz(buf, crow + 8 * i, ccol)));
-            if (row < r_end) st_stream4(a.out + (size_t)row * a.ldc + n0 + c * kChunk + ccol * 4, o);
+            if (row < r_end) {
+              if (!a.scatter) {
+                st_stream4(a.out + (size_t)row * a.ldc + n0 + c * kChunk + ccol * 4, o);
+              } else {
+                const int bi = row / a.sc_rows;
+                const int* dl = a.scatter + (size_t)(row - bi * a.sc_rows) * a.sc_r;
+                for (int j = 0; j < a.sc_r; ++j) {
+                  const int d = __ldg(dl + j);
+                  if (d < 0) break;
+                  st_stream4(a.out + ((size_t)bi * a.sc_dst_rows + d) * a.ldc + n0 + c * kChunk + ccol * 4, o);
+                }
+              }
+            }
           }
           __syncwarp();
         }
@@ -664,6 +703,15 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
 using namespace ub;
 
 static int g_gemm_cluster = 4;
+static int g_x3_inplace = 1, g_x3_direct = 0, g_x3_cluster = 4, g_x3_stagger_ns = 0;
+// A/B knobs of the 3xTF32 mode (tools/bench_gemm_x3.py): in-place a_hi write-back, direct result stores, cluster size,
+// start offset of every other cluster
+extern "C" int ub_set_gemm_x3(int inplace, int direct_store, int cluster, int stagger_ns) {
+  UB_REQUIRE(cluster == 1 || cluster == 2 || cluster == 4, "ub_set_gemm_x3: cluster size must be 1, 2 or 4");
+  UB_REQUIRE(stagger_ns >= 0 && stagger_ns <= 100000, "ub_set_gemm_x3: stagger must be in 0 .. 100 us");
+  g_x3_inplace = inplace ? 1 : 0, g_x3_direct = direct_store ? 1 : 0, g_x3_cluster = cluster, g_x3_stagger_ns = stagger_ns;
+  return UB_OK;
+}
 static int g_gemm_stream_w_res = 1;   // stream W (deeper A / residual ring) when a residual rides the ring: 103 vs 107 us
 extern "C" int ub_set_gemm_stream_w_with_residual(int on) {
   g_gemm_stream_w_res = on ? 1 : 0;
@@ -686,12 +734,16 @@ extern "C" int ub_set_gemm_cluster(int cs) {
 static int launch_linear(const char* fn, int f16, const void* A, const void* W, const float* W_lo, const float* bias,
                          const float* residual, int ldr, const float* gamma, const float* beta, float eps, float* out,
                          int ldc, void* out16, int ldc16, void* planes, float* planes32, int Nv, int M, int N, int K,
-                         int flags, ub_stream_t stream) {
+                         int flags, ub_stream_t stream, const int* scatter = nullptr, int sc_r = 0, int sc_rows = 0,
+                         int sc_dst_rows = 0) {
   const int relu = flags & 1, ln = (flags >> 1) & 1;
   const int kb_elems = f16 ? 64 : 32, esize = f16 ? 2 : 4;
   const bool split = W_lo != nullptr;
   UB_REQUIRE(A && W && (out || out16 || planes || planes32), "%s: null pointer", fn);
   UB_REQUIRE(!(split && f16), "%s: the 3xTF32 mode takes fp32 operands", fn);
+  UB_REQUIRE(!scatter || (out && !out16 && !planes && !planes32 && !ln && sc_r > 0 && sc_rows > 0 && M % sc_rows == 0 &&
+                          sc_dst_rows > 0),
+             "%s: a row scatter takes a plain fp32 output and M %% rows_per_item == 0", fn);
   UB_REQUIRE(M > 0 && N > 0 && K > 0, "%s: non-positive dimension", fn);
   UB_REQUIRE(!ln || (gamma && beta), "%s: layernorm needs gamma and beta", fn);
   UB_REQUIRE_ALIGNED16(A);
@@ -710,6 +762,9 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   GemmArgs a;
   a.bias = bias, a.gamma = gamma, a.beta = beta, a.planes = reinterpret_cast<__half*>(planes);
   a.planes32 = planes32, a.SL = split ? 2 : 0;
+  a.scatter = scatter, a.sc_r = sc_r, a.sc_rows = sc_rows, a.sc_dst_rows = sc_dst_rows;
+  a.x3_inplace = g_x3_inplace, a.stagger_ns = split ? g_x3_stagger_ns : 0;
+  a.direct_store = split && g_x3_direct && out && ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0;
   a.Nv = Nv, a.H = N / 32;
   a.M = M, a.N = N, a.K = K, a.BN = N > 256 ? 256 : N;
   a.n_tiles_m = (M + kBM - 1) / kBM, a.n_tiles_n = N / a.BN;
@@ -728,7 +783,7 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   a.w_res = !split && (a.n_tiles_n == 1 || split_ok) && k_blocks <= kMaxStages && !(residual && ln && g_gemm_stream_w_res) &&
             fixed + (size_t)k_blocks * a.BN * 128 + 3 * (size_t)kBM * 128 <= budget;
   // cluster size (streaming W only): the W k-block is split into `cs` slices of whole 8-row swizzle groups
-  a.cs = a.w_res ? 1 : g_gemm_cluster;
+  a.cs = a.w_res ? 1 : (split ? g_x3_cluster : g_gemm_cluster);
   while (a.cs > 1 && ((a.BN / a.cs) % 8 != 0 || a.BN % a.cs != 0 || a.n_tiles_m < a.cs)) a.cs >>= 1;
   CUtensorMap ma, mw, mr, mwl;
   const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
@@ -847,6 +902,17 @@ extern "C" int ub_linear_tf32x3(const float* A, const float* W_hi, const float* 
   UB_REQUIRE(W_lo, "ub_linear_tf32x3: null pointer");
   return launch_linear("ub_linear_tf32x3", 0, A, W_hi, W_lo, bias, residual, ldr, gamma, beta, eps, planes32 ? nullptr : out, ldc,
                        nullptr, 0, nullptr, planes32, Nv, M, N, K, flags, stream);
+}
+// ub_linear_tf32x3 whose result rows leave in another order: row b * rows_per_item + q of the product is written to the
+// rows b * dst_rows_per_item + scatter[q * scatter_r + j] of `out` for j = 0, 1, ... up to the first negative entry (none:
+// the row is dropped).  The camera cross-attention's offset|logit projection writes its rows in hit-list order this way
+// (scatter = q_dst of ub_hit_order), so that the sampling kernel reads them as TMA tiles.
+extern "C" int ub_linear_tf32x3_scatter(const float* A, const float* W_hi, const float* W_lo, const float* bias, float* out,
+                                        int ldc, const int* scatter, int scatter_r, int rows_per_item, int dst_rows_per_item,
+                                        int M, int N, int K, ub_stream_t stream) {
+  UB_REQUIRE(W_lo && scatter, "ub_linear_tf32x3_scatter: null pointer");
+  return launch_linear("ub_linear_tf32x3_scatter", 0, A, W_hi, W_lo, bias, nullptr, 0, nullptr, nullptr, 0.f, out, ldc, nullptr,
+                       0, nullptr, nullptr, 0, M, N, K, 0, stream, scatter, scatter_r, rows_per_item, dst_rows_per_item);
 }
 
 namespace ub {

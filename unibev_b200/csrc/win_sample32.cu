@@ -488,3 +488,357 @@ extern "C" int ub_bev_sample_win32_fwd(const float* planes32, const float* qproj
   return P == 8 ? launch_bev_win32<8>(a, planes32, qproj, ld, (cudaStream_t)stream)
                 : launch_bev_win32<4>(a, planes32, qproj, ld, (cudaStream_t)stream);
 }
+
+namespace ub {
+
+// =========================================================================================================
+// Camera mode (fp32).
+//
+// The camera kernels take their per-hit inputs in HIT-LIST ORDER, so that a worker warp's 16 hits are 16 consecutive
+// rows that one TMA box copy per tensor brings into its shared-memory slice (no scattered loads in the sampling kernel):
+//   qp_hit  (B, N, Nq, ld)   offset|logit rows: written in that order by the projection's epilogue (ub_linear_tf32x3 with
+//                            the scatter map q_dst)
+//   hit_ref (B, N, Nq, 2 D)  projected anchors              } ub_hit_order, once per frame (they do not depend on the layer)
+//   hit_ic  (B, N, Nq)       1 / #cameras                   } ub_build_hits
+//   hit_idx (N + 1, Nq)      the query of each hit          } ub_build_hits
+// Position p of camera n's row holds a FIRST hit when p < cnt_first[n] and a LATER hit when p >= Nq - cnt_later[n]
+// (ub_build_hits' rank-split layout); rows in between are never read as valid.
+
+// q_dst (Nq, N): for query q the destination rows n * Nq + pos of its offset|logit row, one per camera that sees it
+// (batch item 0's visibility, the reference's quirk), -1 padded.  hit_ref: anchors gathered into hit-list order.
+__global__ void __launch_bounds__(256) hit_order_kernel(const uint8_t* __restrict__ mask, const float* __restrict__ ref_cam,
+                                                        const int* __restrict__ hit_idx, const int* __restrict__ hit_cnt,
+                                                        int* __restrict__ q_dst, float* __restrict__ hit_ref, int B, int N,
+                                                        int Nq, int D2) {
+  pdl_trigger();
+  const int64_t total = (int64_t)B * N * Nq;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t % Nq), n = (int)((t / Nq) % N), b = (int)(t / ((int64_t)Nq * N));
+    const bool valid = i < hit_cnt[n] || i >= Nq - hit_cnt[N + n];      // i as a position of camera n's row
+    if (valid) {
+      const int q = hit_idx[(int64_t)n * Nq + i];
+      const float* src = ref_cam + (((int64_t)b * Nq + q) * N + n) * D2;
+      float* dst = hit_ref + (((int64_t)b * N + n) * Nq + i) * D2;
+      for (int e = 0; e < D2; ++e) dst[e] = src[e];
+      if (b == 0) {
+        int slot = 0;
+        for (int m = 0; m < n; ++m) slot += mask[(int64_t)q * N + m] != 0 ? 1 : 0;
+        q_dst[(int64_t)q * N + slot] = n * Nq + i;
+      }
+    }
+    if (b == 0) {                                                      // i as a query, n as a slot: pad the unused slots
+      int cnt = 0;
+      for (int m = 0; m < N; ++m) cnt += mask[(int64_t)i * N + m] != 0 ? 1 : 0;
+      if (n >= cnt) q_dst[(int64_t)i * N + n] = -1;
+    }
+  }
+}
+
+struct ImgWin32Args {
+  const int* hit_idx;     // (N + 1, Nq): row N = unseen queries
+  const int* hit_cnt;     // (2 N + 1): first counts, later counts, unseen count
+  float* out;             // (B, Nq, H*32)
+  int B, N, Nq, fH, fW, H, D, off_col, logit_col;
+  int WW, WH;
+  int part;               // 0: first hits (plain stores) + zero rows of the unseen queries; 1: later hits (red.add)
+};
+
+template <int PP>
+struct ImgSmem32 {
+  // per warp: staged P1 inputs of its 16 hits, then the descriptors
+  static constexpr int sl_off = kWarpItems * PP * 8, sl_lg = kWarpItems * PP * 4, sl_ref = kWarpItems * 64, sl_ic = 128, sl_q = 128;   // (TMA destinations: 128-byte aligned)
+  static constexpr int slice_bytes = sl_off + sl_lg + sl_ref + sl_ic + sl_q;
+  static constexpr int warp_bytes = ((slice_bytes + 127) & ~127) + ((Desc32<PP>::bytes + 127) & ~127);
+  static size_t total(int win_bytes) { return (size_t)win_bytes + (size_t)kWorkerWarps * warp_bytes; }
+};
+
+// CTAs are grouped by 2 H: the 2 H CTAs of a group walk the same contiguous range of units (b, camera, chunk of 256 hits),
+// one HALF-HEAD each -- the window is that half-head's whole camera plane plus a one-pixel zero halo (reloaded when the
+// range crosses into another camera) -- so a hit's input rows come from DRAM once and from L2 for the other CTAs of the
+// group.  Warp w owns hits 16 w .. 16 w + 15 of the chunk: P1 from its TMA-staged slice (issued one unit ahead), P2
+// gathers its 16 items from the window and writes / accumulates 64 bytes (16 channels) per hit.
+template <int PP, int ROWB>
+__global__ void __launch_bounds__(kImgThreads, 1)
+    img_sample_win32_kernel(const ImgWin32Args a, const __grid_constant__ CUtensorMap map_val,
+                            const __grid_constant__ CUtensorMap map_off, const __grid_constant__ CUtensorMap map_lg,
+                            const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_ic,
+                            const __grid_constant__ CUtensorMap map_q) {
+  using D = Desc32<PP>;
+  using SM = ImgSmem32<PP>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t s_bar, s_qp[kWorkerWarps];
+
+  const int win_bytes = (a.WW * a.WH * 64 + 127) & ~127;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sm_win = smem_u32(smem), bar = smem_u32(&s_bar);
+  const uint32_t sl_off = sm_win + (uint32_t)win_bytes + (uint32_t)warp * SM::warp_bytes;
+  const uint32_t sl_lg = sl_off + SM::sl_off, sl_ref = sl_lg + SM::sl_lg, sl_ic = sl_ref + SM::sl_ref, sl_q = sl_ic + SM::sl_ic;
+  const uint32_t sm_w = sl_off + ((SM::slice_bytes + 127) & ~127), sm_idx = sm_w + D::w_bytes;
+  const uint32_t bar_qp = smem_u32(&s_qp[warp]);
+  const int C = a.H * 32;
+
+  pdl_trigger();
+  pdl_wait();   // hit lists, planes, offset|logit rows come from the predecessor kernels; `out` may alias their inputs
+  const int* cnt_p = a.hit_cnt + a.part * a.N;
+  if (a.part == 0) {   // rows of the queries no camera sees
+    const int n_zero = __ldg(a.hit_cnt + 2 * a.N);
+    const int per_row = C / 4;
+    for (int64_t e = (int64_t)blockIdx.x * kImgThreads + tid; e < (int64_t)a.B * n_zero * per_row;
+         e += (int64_t)gridDim.x * kImgThreads) {
+      const int c4 = (int)(e % per_row);
+      const int64_t r = e / per_row;
+      const int q = __ldg(a.hit_idx + (int64_t)a.N * a.Nq + (int)(r % n_zero));
+      st_stream4(a.out + ((r / n_zero) * a.Nq + q) * C + c4 * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+  }
+  int chunks_tot = 0;
+  for (int n = 0; n < a.N; ++n) chunks_tot += (__ldg(cnt_p + n) + kUnitItems - 1) / kUnitItems;
+  const int G = 2 * a.H;
+  const int n_grp = (int)gridDim.x / G, cgrp = (int)blockIdx.x / G, my_hs = (int)blockIdx.x % G;
+  if (cgrp >= n_grp) return;
+  const int my_h = my_hs >> 1, my_s = my_hs & 1;
+  const int total = chunks_tot * a.B;
+  const int per = total / n_grp, rem = total % n_grp;
+  const int u_beg = cgrp * per + min(cgrp, rem);
+  const int u_end = u_beg + per + (cgrp < rem ? 1 : 0);
+  if (u_beg >= u_end) return;   // uniform per CTA
+
+  struct Unit {
+    int b, n, pos0, limit, plane;   // pos0: first hit-list position of the chunk; positions < limit are valid
+  };
+  auto decode = [&](int uu) {
+    Unit w;
+    w.b = uu / chunks_tot;
+    int r = uu % chunks_tot;
+    w.n = 0, w.pos0 = 0, w.limit = 0;
+    for (int n = 0; n < a.N; ++n) {
+      const int cnt = __ldg(cnt_p + n), ch = (cnt + kUnitItems - 1) / kUnitItems;
+      if (r < ch) {
+        w.n = n;
+        w.pos0 = (a.part ? a.Nq - cnt : 0) + r * kUnitItems;
+        w.limit = a.part ? a.Nq : cnt;
+        break;
+      }
+      r -= ch;
+    }
+    w.plane = ((w.b * a.N + w.n) * a.H + my_h) * 2 + my_s;
+    return w;
+  };
+  auto load_plane = [&](int plane) {   // one thread
+    mbar_arrive_expect_tx(bar, (uint32_t)(a.WW * a.WH * 64));
+    tma_load_4d(sm_win, &map_val, bar, 0, -1, -1, plane);
+  };
+  Unit w = decode(u_beg);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    for (int i = 0; i < kWorkerWarps; ++i) mbar_init(smem_u32(&s_qp[i]), 1);
+    mbar_init_fence();
+    tma_prefetch_desc(&map_val);
+    load_plane(w.plane);
+  }
+  __syncthreads();
+
+  constexpr int PPL = PP / 2;                // sampling points per lane in P1 (two lanes per item)
+  const int item_l = lane >> 1, p0 = (lane & 1) * PPL;
+  const int grp = lane >> 3, sub = lane & 7, side = sub >> 2, cq = sub & 3;
+  const uint32_t ref_bytes = (uint32_t)a.D * 8u;
+
+  // lane 0: the warp's 16 consecutive hit-list rows of unit wu -> its slice (five box copies on one barrier)
+  auto issue = [&](const Unit& wu) {
+    const int p = wu.pos0 + warp * kWarpItems;
+    mbar_arrive_expect_tx(bar_qp, (uint32_t)(SM::sl_off + SM::sl_lg + kWarpItems * ref_bytes + 2 * kWarpItems * 4));
+    tma_load_4d(sl_off, &map_off, bar_qp, a.off_col + my_h * PP * 2, p, wu.n, wu.b);
+    tma_load_4d(sl_lg, &map_lg, bar_qp, a.logit_col + my_h * PP, p, wu.n, wu.b);
+    tma_load_4d(sl_ref, &map_ref, bar_qp, 0, p, wu.n, wu.b);
+    tma_load_3d(sl_ic, &map_ic, bar_qp, p, wu.n, wu.b);
+    tma_load_2d(sl_q, &map_q, bar_qp, p, wu.n);
+  };
+  if (lane == 0) issue(w);
+
+  int loaded = w.plane;
+  uint32_t win_phase = 0u;
+  bool fresh = true;
+  for (int u = u_beg; u < u_end; ++u) {
+    // ---- P1 from the staged slice
+    mbar_wait(bar_qp, (uint32_t)((u - u_beg) & 1));
+    const int pos = w.pos0 + warp * kWarpItems + item_l;
+    const bool ok = pos < w.limit;
+    float off[PPL * 2], lg[PPL], ref[PPL * 2], ic;
+    int qq;
+    {
+      const uint32_t oa = sl_off + (uint32_t)(item_l * PP + p0) * 8u, la = sl_lg + (uint32_t)(item_l * PP + p0) * 4u;
+#pragma unroll
+      for (int i = 0; i < PPL / 2; ++i)
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(off[4 * i]), "=f"(off[4 * i + 1]), "=f"(off[4 * i + 2]), "=f"(off[4 * i + 3])
+                     : "r"(oa + i * 16));
+      if (PPL == 4)
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(lg[0]), "=f"(lg[1]), "=f"(lg[2]), "=f"(lg[PPL - 1]) : "r"(la));
+      else
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(lg[0]), "=f"(lg[1]) : "r"(la));
+      const uint32_t ra = sl_ref + (uint32_t)item_l * ref_bytes;
+#pragma unroll
+      for (int i = 0; i < PPL; ++i)
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(ref[2 * i]), "=f"(ref[2 * i + 1])
+                     : "r"(ra + (uint32_t)((p0 + i) % a.D) * 8u));
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ic) : "r"(sl_ic + (uint32_t)item_l * 4u));
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(qq) : "r"(sl_q + (uint32_t)item_l * 4u));
+      if (!ok) {   // rows beyond the list hold other hits or uninitialised memory
+        ic = 0.f;
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) off[2 * i] = off[2 * i + 1] = ref[2 * i] = ref[2 * i + 1] = lg[i] = 0.f;
+      }
+    }
+    {
+      float aw[PPL];
+      softmax_pair32<PPL>(lg, ok, ic, aw);
+      float4 w4[PPL];
+      uint32_t idx[PPL];
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) {
+        const float w_im = fmaf(ref[2 * i], (float)a.fW, off[2 * i] - 0.5f);
+        const float h_im = fmaf(ref[2 * i + 1], (float)a.fH, off[2 * i + 1] - 0.5f);
+        // the window is the whole plane plus a one-pixel zero halo (origin (-1, -1)): nothing is ever far
+        make_desc32(ok, h_im, w_im, aw[i], a.fH, a.fW, -1, -1, a.WW, a.WH, w4[i], idx[i]);
+      }
+      store_descs32<PP>(sm_w, sm_idx, item_l, p0, w4, idx);
+    }
+    // the items this lane writes in P2: (grp + 4 m) for m = 2 side, 2 side + 1 -> their queries (-1: not a hit)
+    int qm[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int item = grp + 4 * (2 * side + j);
+      const int q_it = __shfl_sync(0xffffffffu, qq, item * 2);
+      const bool ok_it = w.pos0 + warp * kWarpItems + item < w.limit;
+      qm[j] = ok_it ? q_it : -1;
+    }
+    __syncwarp();   // descriptors visible to the whole warp; the slice has been consumed
+    const Unit w_cur = w;
+    if (u + 1 < u_end) {
+      w = decode(u + 1);
+      if (lane == 0) issue(w);
+    }
+    // ---- P2
+    if (fresh) {
+      mbar_wait(bar, win_phase);
+      win_phase ^= 1u;
+      fresh = false;
+    }
+    float4 res[4];
+    gather_warp32<PP, ROWB>(sm_w, sm_idx, sm_win + sub * 16u, (uint32_t)a.WW * 64u, grp, side, res);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (qm[j] >= 0) {
+        float* dst = a.out + ((int64_t)w_cur.b * a.Nq + qm[j]) * C + my_h * 32 + my_s * 16 + cq * 4;
+        const float4 o = side ? res[2 + j] : res[j];
+        if (a.part)
+          red_add4(dst, o);
+        else
+          st_stream4(dst, o);
+      }
+    }
+    __syncwarp();
+    if (u + 1 < u_end && w.plane != loaded) {   // uniform per CTA: every warp leaves the old plane first
+      __syncthreads();
+      if (tid == 0) load_plane(w.plane);
+      loaded = w.plane;
+      fresh = true;
+    }
+  }
+}
+
+template <int PP, int ROWB>
+static int launch_img_win32_v(ImgWin32Args& a, const CUtensorMap* m, size_t smem, cudaStream_t s) {
+  const char* fn = "ub_img_sample_win32_fwd";
+  if (int rc = ensure_smem(img_sample_win32_kernel<PP, ROWB>, smem, fn)) return rc;
+  for (int part = 0; part < 2; ++part) {   // later hits (~12 % of the pairs on the nuScenes rig) accumulate on top
+    a.part = part;
+    launch_pdl(img_sample_win32_kernel<PP, ROWB>, dim3(sm_count()), dim3(kImgThreads), smem, s, a, m[0], m[1], m[2], m[3],
+               m[4], m[5]);
+    if (int rc = check_launch(fn)) return rc;
+  }
+  return UB_OK;
+}
+
+}  // namespace ub
+
+extern "C" int ub_hit_order(const uint8_t* mask, const float* ref_cam, const int* hit_idx, const int* hit_cnt, int* q_dst,
+                            float* hit_ref, int B, int N, int Nq, int D, ub_stream_t stream) {
+  UB_REQUIRE(mask && ref_cam && hit_idx && hit_cnt && q_dst && hit_ref, "ub_hit_order: null pointer");
+  UB_REQUIRE(B > 0 && N > 0 && N <= 32 && Nq > 0 && D > 0 && D <= 8, "ub_hit_order: bad dimension (B=%d N=%d Nq=%d D=%d)", B, N,
+             Nq, D);
+  int blocks = (int)(((int64_t)B * N * Nq + 255) / 256);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  hit_order_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mask, ref_cam, hit_idx, hit_cnt, q_dst, hit_ref, B, N, Nq, 2 * D);
+  return check_launch("ub_hit_order");
+}
+
+extern "C" int ub_img_sample_win32_fwd(const float* planes32, const float* qp_hit, const float* hit_ref, const float* hit_ic,
+                                       const int* hit_idx, const int* hit_cnt, float* out, int B, int N, int bev_h, int bev_w,
+                                       int fH, int fW, int H, int Dh, int P, int D, int ld, int off_col, int logit_col,
+                                       ub_stream_t stream) {
+  const char* fn = "ub_img_sample_win32_fwd";
+  UB_REQUIRE(planes32 && qp_hit && hit_ref && hit_ic && hit_idx && hit_cnt && out, "%s: null pointer", fn);
+  UB_REQUIRE(B > 0 && N > 0 && N <= 32 && bev_h > 0 && bev_w > 0 && fH >= 2 && fW >= 2 && H > 0 && D > 0 && D <= 8,
+             "%s: bad dimension (B=%d N=%d D=%d)", fn, B, N, D);
+  UB_REQUIRE(P % D == 0, "%s: num_points %d must be a multiple of the %d Z-anchors", fn, P, D);
+  UB_REQUIRE(off_col >= 0 && logit_col >= 0 && ld >= off_col + H * P * 2 && ld >= logit_col + H * P,
+             "%s: qproj row stride %d too small", fn, ld);
+  UB_REQUIRE_ALIGNED16(planes32);
+  UB_REQUIRE_ALIGNED16(qp_hit);
+  UB_REQUIRE_ALIGNED16(hit_ref);
+  UB_REQUIRE_ALIGNED16(hit_ic);
+  UB_REQUIRE_ALIGNED16(hit_idx);
+  UB_REQUIRE_ALIGNED16(out);
+  const int Nq = bev_h * bev_w;
+  const int win_bytes = ((fW + 2) * (fH + 2) * 64 + 127) & ~127;
+  if (Dh != 32 || (P != 4 && P != 8) || ld % 4 != 0 || off_col % 4 != 0 || logit_col % 4 != 0 || D % 2 != 0 || Nq % 4 != 0 ||
+      fW + 2 > 256 || fH + 2 > 256 || (int64_t)(fH + 2) * (fW + 2) > 65535 || (int64_t)B * N * H * 2 > (1 << 20) ||
+      2 * H > sm_count() || ImgSmem32<8>::total(win_bytes) > kSmemBudget) {
+    set_error("%s: shape not covered by the window kernels (Dh=%d P=%d D=%d fH=%d fW=%d Nq=%d)", fn, Dh, P, D, fH, fW, Nq);
+    return ub::unsupported();
+  }
+  ImgWin32Args a;
+  a.hit_idx = hit_idx, a.hit_cnt = hit_cnt, a.out = out;
+  a.B = B, a.N = N, a.Nq = Nq, a.fH = fH, a.fW = fW, a.H = H, a.D = D, a.off_col = off_col, a.logit_col = logit_col;
+  a.WW = fW + 2, a.WH = fH + 2, a.part = 0;
+  CUtensorMap m[6];
+  const CUtensorMapDataType f32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  {
+    const uint64_t dims[4] = {16, (uint64_t)fW, (uint64_t)fH, (uint64_t)B * N * H * 2};
+    const uint64_t str[3] = {64, (uint64_t)fW * 64, (uint64_t)fH * fW * 64};
+    const uint32_t box[4] = {16, (uint32_t)a.WW, (uint32_t)a.WH, 1};
+    if (int rc = make_tensor_map(&m[0], f32, 4, planes32, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)ld, (uint64_t)Nq, (uint64_t)N, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)ld * 4, (uint64_t)Nq * ld * 4, (uint64_t)N * Nq * ld * 4};
+    const uint32_t box_o[4] = {(uint32_t)(2 * P), kWarpItems, 1, 1}, box_l[4] = {(uint32_t)P, kWarpItems, 1, 1};
+    if (int rc = make_tensor_map(&m[1], f32, 4, qp_hit, dims, str, box_o, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+    if (int rc = make_tensor_map(&m[2], f32, 4, qp_hit, dims, str, box_l, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)(2 * D), (uint64_t)Nq, (uint64_t)N, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)D * 8, (uint64_t)Nq * D * 8, (uint64_t)N * Nq * D * 8};
+    const uint32_t box[4] = {(uint32_t)(2 * D), kWarpItems, 1, 1};
+    if (int rc = make_tensor_map(&m[3], f32, 4, hit_ref, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)Nq, (uint64_t)N, (uint64_t)B};
+    const uint64_t str[2] = {(uint64_t)Nq * 4, (uint64_t)N * Nq * 4};
+    const uint32_t box[3] = {kWarpItems, 1, 1};
+    if (int rc = make_tensor_map(&m[4], f32, 3, hit_ic, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)Nq, (uint64_t)N + 1};
+    const uint64_t str[1] = {(uint64_t)Nq * 4};
+    const uint32_t box[2] = {kWarpItems, 1};
+    if (int rc = make_tensor_map(&m[5], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, hit_idx, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))
+      return rc;
+  }
+  const size_t smem = P == 8 ? ImgSmem32<8>::total(win_bytes) : ImgSmem32<4>::total(win_bytes);
+  const cudaStream_t s = (cudaStream_t)stream;
+  if (a.WW == 52)   // nuScenes 1600 x 928 / 32 -> 50 + 2
+    return P == 8 ? launch_img_win32_v<8, 52 * 64>(a, m, smem, s) : launch_img_win32_v<4, 52 * 64>(a, m, smem, s);
+  return P == 8 ? launch_img_win32_v<8, 0>(a, m, smem, s) : launch_img_win32_v<4, 0>(a, m, smem, s);
+}

@@ -193,6 +193,52 @@ def value_to_planes32(value, G, Nv, H):
     return value.view(G, Nv, 2 * H, 16).permute(0, 2, 1, 3).contiguous()
 
 
+def hit_order(mask, ref_cam, hits):
+    """-> q_dst (Nq, N) int32 (scatter map of ``linear_tf32x3_scatter``), hit_ref (B, N, Nq, 2 D) fp32: the hit-list-ordered
+    inputs of ``img_sample_win32``; once per frame."""
+    mask, ref_cam = _need(mask, 'mask', torch.uint8), _need(ref_cam, 'ref_cam')
+    B, Nq, N = mask.shape
+    D = ref_cam.shape[3]
+    hit_idx, hit_cnt = hits[0], hits[1]
+    q_dst = torch.empty(Nq, N, device=mask.device, dtype=torch.int32)
+    hit_ref = torch.empty(B, N, Nq, 2 * D, device=mask.device, dtype=torch.float32)
+    _call('ub_hit_order', mask, _ptr(mask), _ptr(ref_cam), _ptr(hit_idx), _ptr(hit_cnt), _ptr(q_dst), _ptr(hit_ref), B, N, Nq, D)
+    return q_dst, hit_ref
+
+
+def linear_tf32x3_scatter(x, w_split, bias, q_dst, rows_per_item, out):
+    """``linear_tf32x3`` whose row b * rows_per_item + q is written to the rows b * out.shape[1] + q_dst[q, j] (j up to the
+    first negative entry) of ``out`` (B, rows, N): the offset|logit rows in hit-list order."""
+    x = _need(x, 'x')
+    w_hi, w_lo = _need(w_split[0], 'w_hi'), _need(w_split[1], 'w_lo')
+    q_dst = _need(q_dst, 'q_dst', torch.int32)
+    M, K = x.shape
+    N = w_hi.shape[0]
+    bias = _need(bias, 'bias') if bias is not None else None
+    if (w_hi.shape != (N, K) or out.dim() != 3 or out.shape[2] != N or not out.is_contiguous() or out.dtype != torch.float32
+            or M % rows_per_item or out.shape[0] != M // rows_per_item or q_dst.shape[0] != rows_per_item):
+        raise ValueError('linear_tf32x3_scatter: inconsistent shapes')
+    _call('ub_linear_tf32x3_scatter', x, _ptr(x), _ptr(w_hi), _ptr(w_lo), _ptr(bias), _ptr(out), N, _ptr(q_dst), q_dst.shape[1],
+          rows_per_item, out.shape[1], M, N, K)
+    return out
+
+
+def img_sample_win32(planes32, qp_hit, hit_ref, hits, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out=None):
+    """fp32 twin of ``img_sample_win``: planes32 (B*N, 2H, fH*fW, 16); qp_hit (B, N*Nq, ld) offset|logit rows in hit-list
+    order; hit_ref from ``hit_order``; hits = build_hits(mask) -> (B, Nq, H*32) fp32."""
+    planes32, qp_hit, hit_ref = _need(planes32, 'planes32'), _need(qp_hit, 'qp_hit'), _need(hit_ref, 'hit_ref')
+    hit_idx, hit_cnt, _, hit_ic = hits
+    B, N, Nq, D2 = hit_ref.shape
+    if (planes32.shape != (B * N, 2 * H, fH * fW, 16) or Nq != bev_h * bev_w or qp_hit.shape[:2] != (B, N * Nq)
+            or hit_idx.shape != (N + 1, Nq) or hit_ic.shape != (B, N, Nq)):
+        raise ValueError('img_sample_win32: inconsistent shapes')
+    if out is None:
+        out = torch.empty(B, Nq, H * 32, device=qp_hit.device, dtype=torch.float32)
+    _call('ub_img_sample_win32_fwd', planes32, _ptr(planes32), _ptr(qp_hit), _ptr(hit_ref), _ptr(hit_ic), _ptr(hit_idx),
+          _ptr(hit_cnt), _ptr(out), B, N, bev_h, bev_w, fH, fW, H, 32, P, D2 // 2, qp_hit.shape[2], off_col, logit_col)
+    return out
+
+
 def planes32_to_rows(planes32):
     """(G, 2H, Nv, 16) half-head planes -> (G*Nv, H*32) token-major rows (torch glue; inverse of value_to_planes32)."""
     G, H2, Nv, _ = planes32.shape

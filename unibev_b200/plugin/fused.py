@@ -313,7 +313,8 @@ class FusedEncoder:
     def _run_encoder(self, name, queries, B, pos_q, value_tokens, sample_cross, bev_h, bev_w):
         """queries (Nq, C) the BEV query table (every sample starts from it, transformer_fusion.py:493-498); pos_q: per-layer
         positional offset|logit rows or None; value_tokens: un-projected feature rows, fp32 or a (fp32 | None, fp16)
-        pair; sample_cross(lw, value_tokens, qp) -> sampled (B, Nq, C)."""
+        pair; sample_cross(lw, value_tokens, x, w16) -> sampled (B, Nq, C) (it runs the offset|logit projection of the
+        query rows x itself)."""
         layers = self._weights(name)
         Nq, C = queries.shape
         f16 = self._use_f16(C)
@@ -337,8 +338,7 @@ class FusedEncoder:
             if f16 and x[1] is None:
                 x = (x[0], x[0].half())
             # --- spatial cross-attention (query_pos is None for attentions[1])
-            qp, _ = self._lin(x, lw.ca_wq, lw.ca_bq, w16=h and h['ca_wq'])
-            s = sample_cross(lw, value_tokens, qp.view(B, Nq, -1))
+            s = sample_cross(lw, value_tokens, x, h and h['ca_wq'])
             x = self._lin(self._rows(s, B * Nq, C), lw.ca_wo, lw.ca_bo, residual=x[0], ln=lw.ln[1], want16=f16,
                           w16=h and h['ca_wo'])
             if f16 and x[1] is None:
@@ -393,9 +393,27 @@ class FusedEncoder:
                 D = enc.num_points_in_pillar
                 zs = anchor_heights(enc.pc_range[5] - enc.pc_range[2], D).tolist()
                 ref_cam, mask = ops.project_points(l2i, zs, enc.pc_range, ih, iw, bev_h, bev_w)
-                hits = []
+                hits, order = [], []
 
-                def cross(lw, tokens, qp):
+                def cross(lw, tokens, x, wq16):
+                    if (self.win32 and self.sampling == 'fp32' and self.gemm == 'tf32x3' and D % 2 == 0 and Nq % 4 == 0
+                            and ops.window_supported(C // lw.H_c, lw.P_c)):
+                        # fp32 window kernel: value planes from the projection's epilogue, offset|logit rows written
+                        # in hit-list order by theirs
+                        if not hits:
+                            hits.append(ops.build_hits(mask))
+                        if not order:
+                            order.append(ops.hit_order(mask, ref_cam, hits[0]))
+                        q_dst, hit_ref = order[0]
+                        try:
+                            planes = ops.linear_tf32x3(self._rows32(tokens), self._hi_lo(lw.ca_wv), lw.ca_bv, planes_nv=fh * fw)
+                            qp_hit = torch.empty(B, N * Nq, lw.ca_wq.shape[0], device=dev, dtype=torch.float32)
+                            ops.linear_tf32x3_scatter(self._rows32(x), self._hi_lo(lw.ca_wq), lw.ca_bq, q_dst, Nq, qp_hit)
+                            return ops.img_sample_win32(planes, qp_hit, hit_ref, hits[0], bev_h, bev_w, fh, fw, lw.H_c,
+                                                        lw.P_c, 0, lw.H_c * lw.P_c * 2)
+                        except _cabi.UnsupportedShape:
+                            pass
+                    qp = self._lin(x, lw.ca_wq, lw.ca_bq, w16=wq16)[0].view(B, Nq, -1)
                     planes, rows = self._project_value(tokens, lw.ca_wv, lw.ca_bv, B * N, fh * fw, lw.H_c, lw.P_c,
                                                        w16=lw.half()['ca_wv'] if isinstance(tokens, tuple) else None)
                     if planes is not None and (fh + 2) * (fw + 2) * 64 <= 150 * 1024 and qp.shape[2] % 4 == 0:
@@ -419,7 +437,8 @@ class FusedEncoder:
                 _, _, fh, fw = feat.shape
                 tokens = self._tokens(feat, None, m.pts_level_embeds[0], f16, B * fh * fw, C)
 
-                def cross(lw, tokens, qp, fh=fh, fw=fw):
+                def cross(lw, tokens, x, wq16, fh=fh, fw=fw):
+                    qp = self._lin(x, lw.ca_wq, lw.ca_bq, w16=wq16)[0].view(B, Nq, -1)
                     return self._bev_sample(tokens, lw.ca_wv, lw.ca_bv, qp, B, bev_h, bev_w, fh, fw, lw.H_c, lw.P_c,
                                             w16=lw.half()['ca_wv'] if isinstance(tokens, tuple) else None)
                 pts = self._run_encoder('pts_bev_encoder', q_pts, B, pos_q['pts_bev_encoder'], tokens, cross, bev_h, bev_w)
