@@ -144,17 +144,18 @@ int ub_bev_sample_win32_fwd(const float* planes32, const float* qproj, float* ou
  * sampling kernel reads coalesced. */
 int ub_build_hits(const uint8_t* mask, int* hit_idx, int* hit_cnt, float* inv_cnt, float* hit_ic, int B, int N, int Nq,
                   ub_stream_t stream);
-/* Hit-list-ordered inputs of ub_img_sample_win32_fwd, once per frame: q_dst (Nq, N) int32 = for query q the rows
- * n * Nq + pos (pos = its position in camera n's row of hit_idx) of every camera that sees it, -1 padded -- the scatter map of
- * ub_linear_tf32x3_scatter; hit_ref (B, N, Nq, 2 D) = ref_cam (B, Nq, N, D, 2) gathered into hit-list order. */
-int ub_hit_order(const uint8_t* mask, const float* ref_cam, const int* hit_idx, const int* hit_cnt, int* q_dst,
-                 float* hit_ref, int B, int N, int Nq, int D, ub_stream_t stream);
+/* Hit-list-ordered inputs of ub_img_sample_win32_fwd, once per frame (hit_idx / hit_cnt / inv_cnt from ub_build_hits):
+ * q_dst (Nq, N) int32 = for query q the rows n * Nq + pos (pos = its position in camera n's row of hit_idx) of every camera
+ * that sees it, -1 padded -- the scatter map of ub_linear_tf32x3_scatter; hit_ref (B, N, Nq, 2 D) = ref_cam (B, Nq, N, D, 2)
+ * gathered into hit-list order; hit_meta (B, N, Nq, 4) fp32 records {query index (int bits), 1 / #cameras, 0, 0}. */
+int ub_hit_order(const uint8_t* mask, const float* ref_cam, const int* hit_idx, const int* hit_cnt, const float* inv_cnt,
+                 int* q_dst, float* hit_ref, float* hit_meta, int B, int N, int Nq, int D, ub_stream_t stream);
 /* fp32 twin of ub_img_sample_win_fwd (the default precision class).  planes32 (B*N, 2 H, fH*fW, 16) fp32 half-head planes;
  * qp_hit (B, N, Nq, ld) the offset|logit rows in hit-list order (ub_linear_tf32x3_scatter; rows that are no hit are never
- * read as valid and may be uninitialised); hit_ref from ub_hit_order; hit_ic / hit_idx / hit_cnt from ub_build_hits.
+ * read as valid and may be uninitialised); hit_ref / hit_meta from ub_hit_order; hit_idx / hit_cnt from ub_build_hits.
  * Every row of out (B, Nq, H*32) is written (zero rows for unseen queries, later hits accumulated with red.global.add).
- * Head dim 32, 4 or 8 points, an even number of Z-anchors, Nq % 4 == 0. */
-int ub_img_sample_win32_fwd(const float* planes32, const float* qp_hit, const float* hit_ref, const float* hit_ic,
+ * Head dim 32, 4 or 8 points, an even number of Z-anchors. */
+int ub_img_sample_win32_fwd(const float* planes32, const float* qp_hit, const float* hit_ref, const float* hit_meta,
                             const int* hit_idx, const int* hit_cnt, float* out, int B, int N, int bev_h, int bev_w,
                             int fH, int fW, int H, int Dh, int P, int D, int ld, int off_col, int logit_col,
                             ub_stream_t stream);

@@ -92,11 +92,10 @@ def _camera(ops, B, bev, fhw, P, seed):
 def test_hit_order_exact(ops):
     H, value, qproj, ref_cam, mask = _camera(ops, 2, (40, 36), (29, 50), 8, 3)
     hits = ops.build_hits(mask)
-    q_dst, hit_ref = ops.hit_order(mask, ref_cam, hits)
-    hit_idx, hit_cnt = hits[0].cpu(), hits[1].cpu()
+    q_dst, hit_ref, hit_meta = (t.cpu() for t in ops.hit_order(mask, ref_cam, hits))
+    hit_idx, hit_cnt, inv_cnt = hits[0].cpu(), hits[1].cpu(), hits[2].cpu()
     m, rc = mask.cpu(), ref_cam.cpu()
     B, Nq, N = m.shape
-    q_dst, hit_ref = q_dst.cpu(), hit_ref.cpu()
     n_pairs = 0
     for q in range(Nq):
         cams = (m[0, q] != 0).nonzero().squeeze(1).tolist()          # batch item 0's visibility (reference quirk)
@@ -110,6 +109,8 @@ def test_hit_order_exact(ops):
             assert pos < int(hit_cnt[n]) or pos >= Nq - int(hit_cnt[N + n])
             for b in range(B):
                 assert torch.equal(hit_ref[b, n, pos], rc[b, q, n].reshape(-1))
+                assert int(hit_meta[b, n, pos, :1].view(torch.int32)) == q
+                assert float(hit_meta[b, n, pos, 1]) == float(inv_cnt[b, q])
             n_pairs += 1
     assert n_pairs == int(hit_cnt[:2 * N].sum())
 
@@ -151,14 +152,15 @@ def test_img_sample_win32_vs_fp32_kernel(ops, B, bev, fhw, P):
     vg, qg = value.cuda(), qproj.cuda()
     ref = ops.img_sample(vg, qg, ref_cam, mask, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2).cpu()
     hits = ops.build_hits(mask)
-    q_dst, hit_ref = ops.hit_order(mask, ref_cam, hits)
+    order = ops.hit_order(mask, ref_cam, hits)
+    q_dst = order[0]
     planes = ops.value_to_planes32(vg.view(-1, H * 32), B * N, fh * fw, H)
     # hit-ordered offset|logit rows by torch glue here (the product path: linear_tf32x3_scatter); other rows poisoned
     qp_hit = torch.full((B, N * Nq, qproj.shape[2]), float('nan')).cuda()
     for q_rows, d in ((q_dst[:, j] >= 0, q_dst[:, j]) for j in range(N)):
         qp_hit[:, d[q_rows].long()] = qg[:, q_rows]
     out = torch.full((B, Nq, H * 32), float('nan')).cuda()
-    got = ops.img_sample_win32(planes, qp_hit, hit_ref, hits, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2, out=out).cpu()
+    got = ops.img_sample_win32(planes, qp_hit, order, hits, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2, out=out).cpu()
     assert not bool(torch.isnan(got).any())
     if bev == (40, 36):
         assert int((got.abs().sum(-1) == 0).sum()) > 0              # this case has rows no camera sees

@@ -29,7 +29,7 @@ PROTOTYPES = {
     'ub_value_to_half': ([_p, _p] + [_i] * 4 + [_p], _i),
     'ub_bev_sample_win_fwd': ([_p] * 3 + [_i] * 12 + [_p, _i, _p], _i),
     'ub_bev_sample_win32_fwd': ([_p] * 3 + [_i] * 11 + [_p, _p], _i),
-    'ub_hit_order': ([_p] * 6 + [_i] * 4 + [_p], _i),
+    'ub_hit_order': ([_p] * 8 + [_i] * 4 + [_p], _i),
     'ub_img_sample_win32_fwd': ([_p] * 7 + [_i] * 13 + [_p], _i),
     'ub_build_hits': ([_p] * 5 + [_i] * 3 + [_p], _i),
     'ub_img_sample_win_fwd': ([_p] * 8 + [_i] * 14 + [_p], _i),

@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
 using namespace ub;
 
 static int g_gemm_cluster = 4;
-static int g_x3_inplace = 1, g_x3_direct = 0, g_x3_cluster = 4, g_x3_stagger_ns = 0;
+static int g_x3_inplace = 1, g_x3_direct = 1, g_x3_cluster = 2, g_x3_stagger_ns = 0;   // measured best (profiles/r2_gemm_x3.txt)
 // A/B knobs of the 3xTF32 mode (tools/bench_gemm_x3.py): in-place a_hi write-back, direct result stores, cluster size,
 // start offset of every other cluster
 extern "C" int ub_set_gemm_x3(int inplace, int direct_store, int cluster, int stagger_ns) {

@@ -498,9 +498,9 @@ namespace ub {
 // rows that one TMA box copy per tensor brings into its shared-memory slice (no scattered loads in the sampling kernel):
 //   qp_hit  (B, N, Nq, ld)   offset|logit rows: written in that order by the projection's epilogue (ub_linear_tf32x3 with
 //                            the scatter map q_dst)
-//   hit_ref (B, N, Nq, 2 D)  projected anchors              } ub_hit_order, once per frame (they do not depend on the layer)
-//   hit_ic  (B, N, Nq)       1 / #cameras                   } ub_build_hits
-//   hit_idx (N + 1, Nq)      the query of each hit          } ub_build_hits
+//   hit_ref  (B, N, Nq, 2 D)  projected anchors                                   } ub_hit_order, once per frame (they do
+//   hit_meta (B, N, Nq, 4)    {query index (int bits), 1 / #cameras, 0, 0}        } not depend on the layer)
+// (16-byte records: the hit position is then never the innermost TMA coordinate, whose byte offset must be 16-byte aligned)
 // Position p of camera n's row holds a FIRST hit when p < cnt_first[n] and a LATER hit when p >= Nq - cnt_later[n]
 // (ub_build_hits' rank-split layout); rows in between are never read as valid.
 
@@ -508,7 +508,8 @@ namespace ub {
 // (batch item 0's visibility, the reference's quirk), -1 padded.  hit_ref: anchors gathered into hit-list order.
 __global__ void __launch_bounds__(256) hit_order_kernel(const uint8_t* __restrict__ mask, const float* __restrict__ ref_cam,
                                                         const int* __restrict__ hit_idx, const int* __restrict__ hit_cnt,
-                                                        int* __restrict__ q_dst, float* __restrict__ hit_ref, int B, int N,
+                                                        const float* __restrict__ inv_cnt, int* __restrict__ q_dst,
+                                                        float* __restrict__ hit_ref, float4* __restrict__ hit_meta, int B, int N,
                                                         int Nq, int D2) {
   pdl_trigger();
   const int64_t total = (int64_t)B * N * Nq;
@@ -520,6 +521,7 @@ __global__ void __launch_bounds__(256) hit_order_kernel(const uint8_t* __restric
       const float* src = ref_cam + (((int64_t)b * Nq + q) * N + n) * D2;
       float* dst = hit_ref + (((int64_t)b * N + n) * Nq + i) * D2;
       for (int e = 0; e < D2; ++e) dst[e] = src[e];
+      hit_meta[((int64_t)b * N + n) * Nq + i] = make_float4(__int_as_float(q), inv_cnt[(int64_t)b * Nq + q], 0.f, 0.f);
       if (b == 0) {
         int slot = 0;
         for (int m = 0; m < n; ++m) slot += mask[(int64_t)q * N + m] != 0 ? 1 : 0;
@@ -546,8 +548,8 @@ struct ImgWin32Args {
 template <int PP>
 struct ImgSmem32 {
   // per warp: staged P1 inputs of its 16 hits, then the descriptors
-  static constexpr int sl_off = kWarpItems * PP * 8, sl_lg = kWarpItems * PP * 4, sl_ref = kWarpItems * 64, sl_ic = 128, sl_q = 128;   // (TMA destinations: 128-byte aligned)
-  static constexpr int slice_bytes = sl_off + sl_lg + sl_ref + sl_ic + sl_q;
+  static constexpr int sl_off = kWarpItems * PP * 8, sl_lg = kWarpItems * PP * 4, sl_ref = kWarpItems * 64, sl_meta = kWarpItems * 16;
+  static constexpr int slice_bytes = sl_off + sl_lg + sl_ref + sl_meta;
   static constexpr int warp_bytes = ((slice_bytes + 127) & ~127) + ((Desc32<PP>::bytes + 127) & ~127);
   static size_t total(int win_bytes) { return (size_t)win_bytes + (size_t)kWorkerWarps * warp_bytes; }
 };
@@ -561,8 +563,7 @@ template <int PP, int ROWB>
 __global__ void __launch_bounds__(kImgThreads, 1)
     img_sample_win32_kernel(const ImgWin32Args a, const __grid_constant__ CUtensorMap map_val,
                             const __grid_constant__ CUtensorMap map_off, const __grid_constant__ CUtensorMap map_lg,
-                            const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_ic,
-                            const __grid_constant__ CUtensorMap map_q) {
+                            const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_meta) {
   using D = Desc32<PP>;
   using SM = ImgSmem32<PP>;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -572,7 +573,7 @@ __global__ void __launch_bounds__(kImgThreads, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sm_win = smem_u32(smem), bar = smem_u32(&s_bar);
   const uint32_t sl_off = sm_win + (uint32_t)win_bytes + (uint32_t)warp * SM::warp_bytes;
-  const uint32_t sl_lg = sl_off + SM::sl_off, sl_ref = sl_lg + SM::sl_lg, sl_ic = sl_ref + SM::sl_ref, sl_q = sl_ic + SM::sl_ic;
+  const uint32_t sl_lg = sl_off + SM::sl_off, sl_ref = sl_lg + SM::sl_lg, sl_meta = sl_ref + SM::sl_ref;
   const uint32_t sm_w = sl_off + ((SM::slice_bytes + 127) & ~127), sm_idx = sm_w + D::w_bytes;
   const uint32_t bar_qp = smem_u32(&s_qp[warp]);
   const int C = a.H * 32;
@@ -643,15 +644,14 @@ __global__ void __launch_bounds__(kImgThreads, 1)
   const int grp = lane >> 3, sub = lane & 7, side = sub >> 2, cq = sub & 3;
   const uint32_t ref_bytes = (uint32_t)a.D * 8u;
 
-  // lane 0: the warp's 16 consecutive hit-list rows of unit wu -> its slice (five box copies on one barrier)
+  // lane 0: the warp's 16 consecutive hit-list rows of unit wu -> its slice (four box copies on one barrier)
   auto issue = [&](const Unit& wu) {
     const int p = wu.pos0 + warp * kWarpItems;
-    mbar_arrive_expect_tx(bar_qp, (uint32_t)(SM::sl_off + SM::sl_lg + kWarpItems * ref_bytes + 2 * kWarpItems * 4));
+    mbar_arrive_expect_tx(bar_qp, (uint32_t)(SM::sl_off + SM::sl_lg + kWarpItems * ref_bytes + SM::sl_meta));
     tma_load_4d(sl_off, &map_off, bar_qp, a.off_col + my_h * PP * 2, p, wu.n, wu.b);
     tma_load_4d(sl_lg, &map_lg, bar_qp, a.logit_col + my_h * PP, p, wu.n, wu.b);
     tma_load_4d(sl_ref, &map_ref, bar_qp, 0, p, wu.n, wu.b);
-    tma_load_3d(sl_ic, &map_ic, bar_qp, p, wu.n, wu.b);
-    tma_load_2d(sl_q, &map_q, bar_qp, p, wu.n);
+    tma_load_4d(sl_meta, &map_meta, bar_qp, 0, p, wu.n, wu.b);
   };
   if (lane == 0) issue(w);
 
@@ -681,8 +681,7 @@ __global__ void __launch_bounds__(kImgThreads, 1)
       for (int i = 0; i < PPL; ++i)
         asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(ref[2 * i]), "=f"(ref[2 * i + 1])
                      : "r"(ra + (uint32_t)((p0 + i) % a.D) * 8u));
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ic) : "r"(sl_ic + (uint32_t)item_l * 4u));
-      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(qq) : "r"(sl_q + (uint32_t)item_l * 4u));
+      asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(qq), "=f"(ic) : "r"(sl_meta + (uint32_t)item_l * 16u));
       if (!ok) {   // rows beyond the list hold other hits or uninitialised memory
         ic = 0.f;
 #pragma unroll
@@ -753,8 +752,7 @@ static int launch_img_win32_v(ImgWin32Args& a, const CUtensorMap* m, size_t smem
   if (int rc = ensure_smem(img_sample_win32_kernel<PP, ROWB>, smem, fn)) return rc;
   for (int part = 0; part < 2; ++part) {   // later hits (~12 % of the pairs on the nuScenes rig) accumulate on top
     a.part = part;
-    launch_pdl(img_sample_win32_kernel<PP, ROWB>, dim3(sm_count()), dim3(kImgThreads), smem, s, a, m[0], m[1], m[2], m[3],
-               m[4], m[5]);
+    launch_pdl(img_sample_win32_kernel<PP, ROWB>, dim3(sm_count()), dim3(kImgThreads), smem, s, a, m[0], m[1], m[2], m[3], m[4]);
     if (int rc = check_launch(fn)) return rc;
   }
   return UB_OK;
@@ -762,23 +760,26 @@ static int launch_img_win32_v(ImgWin32Args& a, const CUtensorMap* m, size_t smem
 
 }  // namespace ub
 
-extern "C" int ub_hit_order(const uint8_t* mask, const float* ref_cam, const int* hit_idx, const int* hit_cnt, int* q_dst,
-                            float* hit_ref, int B, int N, int Nq, int D, ub_stream_t stream) {
-  UB_REQUIRE(mask && ref_cam && hit_idx && hit_cnt && q_dst && hit_ref, "ub_hit_order: null pointer");
+extern "C" int ub_hit_order(const uint8_t* mask, const float* ref_cam, const int* hit_idx, const int* hit_cnt,
+                            const float* inv_cnt, int* q_dst, float* hit_ref, float* hit_meta, int B, int N, int Nq, int D,
+                            ub_stream_t stream) {
+  UB_REQUIRE(mask && ref_cam && hit_idx && hit_cnt && inv_cnt && q_dst && hit_ref && hit_meta, "ub_hit_order: null pointer");
+  UB_REQUIRE_ALIGNED16(hit_meta);
   UB_REQUIRE(B > 0 && N > 0 && N <= 32 && Nq > 0 && D > 0 && D <= 8, "ub_hit_order: bad dimension (B=%d N=%d Nq=%d D=%d)", B, N,
              Nq, D);
   int blocks = (int)(((int64_t)B * N * Nq + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  hit_order_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mask, ref_cam, hit_idx, hit_cnt, q_dst, hit_ref, B, N, Nq, 2 * D);
+  hit_order_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mask, ref_cam, hit_idx, hit_cnt, inv_cnt, q_dst, hit_ref,
+                                                             reinterpret_cast<float4*>(hit_meta), B, N, Nq, 2 * D);
   return check_launch("ub_hit_order");
 }
 
-extern "C" int ub_img_sample_win32_fwd(const float* planes32, const float* qp_hit, const float* hit_ref, const float* hit_ic,
+extern "C" int ub_img_sample_win32_fwd(const float* planes32, const float* qp_hit, const float* hit_ref, const float* hit_meta,
                                        const int* hit_idx, const int* hit_cnt, float* out, int B, int N, int bev_h, int bev_w,
                                        int fH, int fW, int H, int Dh, int P, int D, int ld, int off_col, int logit_col,
                                        ub_stream_t stream) {
   const char* fn = "ub_img_sample_win32_fwd";
-  UB_REQUIRE(planes32 && qp_hit && hit_ref && hit_ic && hit_idx && hit_cnt && out, "%s: null pointer", fn);
+  UB_REQUIRE(planes32 && qp_hit && hit_ref && hit_meta && hit_idx && hit_cnt && out, "%s: null pointer", fn);
   UB_REQUIRE(B > 0 && N > 0 && N <= 32 && bev_h > 0 && bev_w > 0 && fH >= 2 && fW >= 2 && H > 0 && D > 0 && D <= 8,
              "%s: bad dimension (B=%d N=%d D=%d)", fn, B, N, D);
   UB_REQUIRE(P % D == 0, "%s: num_points %d must be a multiple of the %d Z-anchors", fn, P, D);
@@ -787,12 +788,11 @@ extern "C" int ub_img_sample_win32_fwd(const float* planes32, const float* qp_hi
   UB_REQUIRE_ALIGNED16(planes32);
   UB_REQUIRE_ALIGNED16(qp_hit);
   UB_REQUIRE_ALIGNED16(hit_ref);
-  UB_REQUIRE_ALIGNED16(hit_ic);
-  UB_REQUIRE_ALIGNED16(hit_idx);
+  UB_REQUIRE_ALIGNED16(hit_meta);
   UB_REQUIRE_ALIGNED16(out);
   const int Nq = bev_h * bev_w;
   const int win_bytes = ((fW + 2) * (fH + 2) * 64 + 127) & ~127;
-  if (Dh != 32 || (P != 4 && P != 8) || ld % 4 != 0 || off_col % 4 != 0 || logit_col % 4 != 0 || D % 2 != 0 || Nq % 4 != 0 ||
+  if (Dh != 32 || (P != 4 && P != 8) || ld % 4 != 0 || off_col % 4 != 0 || logit_col % 4 != 0 || D % 2 != 0 ||
       fW + 2 > 256 || fH + 2 > 256 || (int64_t)(fH + 2) * (fW + 2) > 65535 || (int64_t)B * N * H * 2 > (1 << 20) ||
       2 * H > sm_count() || ImgSmem32<8>::total(win_bytes) > kSmemBudget) {
     set_error("%s: shape not covered by the window kernels (Dh=%d P=%d D=%d fH=%d fW=%d Nq=%d)", fn, Dh, P, D, fH, fW, Nq);
@@ -802,7 +802,7 @@ extern "C" int ub_img_sample_win32_fwd(const float* planes32, const float* qp_hi
   a.hit_idx = hit_idx, a.hit_cnt = hit_cnt, a.out = out;
   a.B = B, a.N = N, a.Nq = Nq, a.fH = fH, a.fW = fW, a.H = H, a.D = D, a.off_col = off_col, a.logit_col = logit_col;
   a.WW = fW + 2, a.WH = fH + 2, a.part = 0;
-  CUtensorMap m[6];
+  CUtensorMap m[5];
   const CUtensorMapDataType f32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   {
     const uint64_t dims[4] = {16, (uint64_t)fW, (uint64_t)fH, (uint64_t)B * N * H * 2};
@@ -824,17 +824,10 @@ extern "C" int ub_img_sample_win32_fwd(const float* planes32, const float* qp_hi
     if (int rc = make_tensor_map(&m[3], f32, 4, hit_ref, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
   }
   {
-    const uint64_t dims[3] = {(uint64_t)Nq, (uint64_t)N, (uint64_t)B};
-    const uint64_t str[2] = {(uint64_t)Nq * 4, (uint64_t)N * Nq * 4};
-    const uint32_t box[3] = {kWarpItems, 1, 1};
-    if (int rc = make_tensor_map(&m[4], f32, 3, hit_ic, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
-  }
-  {
-    const uint64_t dims[2] = {(uint64_t)Nq, (uint64_t)N + 1};
-    const uint64_t str[1] = {(uint64_t)Nq * 4};
-    const uint32_t box[2] = {kWarpItems, 1};
-    if (int rc = make_tensor_map(&m[5], CU_TENSOR_MAP_DATA_TYPE_INT32, 2, hit_idx, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))
-      return rc;
+    const uint64_t dims[4] = {4, (uint64_t)Nq, (uint64_t)N, (uint64_t)B};
+    const uint64_t str[3] = {16, (uint64_t)Nq * 16, (uint64_t)N * Nq * 16};
+    const uint32_t box[4] = {4, kWarpItems, 1, 1};
+    if (int rc = make_tensor_map(&m[4], f32, 4, hit_meta, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
   }
   const size_t smem = P == 8 ? ImgSmem32<8>::total(win_bytes) : ImgSmem32<4>::total(win_bytes);
   const cudaStream_t s = (cudaStream_t)stream;

@@ -194,16 +194,18 @@ def value_to_planes32(value, G, Nv, H):
 
 
 def hit_order(mask, ref_cam, hits):
-    """-> q_dst (Nq, N) int32 (scatter map of ``linear_tf32x3_scatter``), hit_ref (B, N, Nq, 2 D) fp32: the hit-list-ordered
-    inputs of ``img_sample_win32``; once per frame."""
+    """-> q_dst (Nq, N) int32 (scatter map of ``linear_tf32x3_scatter``), hit_ref (B, N, Nq, 2 D) fp32, hit_meta (B, N, Nq, 4)
+    fp32 records {query index bits, 1 / #cameras, 0, 0}: the hit-list-ordered inputs of ``img_sample_win32``; once per frame."""
     mask, ref_cam = _need(mask, 'mask', torch.uint8), _need(ref_cam, 'ref_cam')
     B, Nq, N = mask.shape
     D = ref_cam.shape[3]
-    hit_idx, hit_cnt = hits[0], hits[1]
+    hit_idx, hit_cnt, inv_cnt = hits[0], hits[1], hits[2]
     q_dst = torch.empty(Nq, N, device=mask.device, dtype=torch.int32)
     hit_ref = torch.empty(B, N, Nq, 2 * D, device=mask.device, dtype=torch.float32)
-    _call('ub_hit_order', mask, _ptr(mask), _ptr(ref_cam), _ptr(hit_idx), _ptr(hit_cnt), _ptr(q_dst), _ptr(hit_ref), B, N, Nq, D)
-    return q_dst, hit_ref
+    hit_meta = torch.empty(B, N, Nq, 4, device=mask.device, dtype=torch.float32)
+    _call('ub_hit_order', mask, _ptr(mask), _ptr(ref_cam), _ptr(hit_idx), _ptr(hit_cnt), _ptr(inv_cnt), _ptr(q_dst),
+          _ptr(hit_ref), _ptr(hit_meta), B, N, Nq, D)
+    return q_dst, hit_ref, hit_meta
 
 
 def linear_tf32x3_scatter(x, w_split, bias, q_dst, rows_per_item, out):
@@ -223,18 +225,19 @@ def linear_tf32x3_scatter(x, w_split, bias, q_dst, rows_per_item, out):
     return out
 
 
-def img_sample_win32(planes32, qp_hit, hit_ref, hits, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out=None):
+def img_sample_win32(planes32, qp_hit, order, hits, bev_h, bev_w, fH, fW, H, P, off_col, logit_col, out=None):
     """fp32 twin of ``img_sample_win``: planes32 (B*N, 2H, fH*fW, 16); qp_hit (B, N*Nq, ld) offset|logit rows in hit-list
-    order; hit_ref from ``hit_order``; hits = build_hits(mask) -> (B, Nq, H*32) fp32."""
-    planes32, qp_hit, hit_ref = _need(planes32, 'planes32'), _need(qp_hit, 'qp_hit'), _need(hit_ref, 'hit_ref')
-    hit_idx, hit_cnt, _, hit_ic = hits
+    order; order = hit_order(mask, ref_cam, hits); hits = build_hits(mask) -> (B, Nq, H*32) fp32."""
+    planes32, qp_hit = _need(planes32, 'planes32'), _need(qp_hit, 'qp_hit')
+    hit_ref, hit_meta = _need(order[1], 'hit_ref'), _need(order[2], 'hit_meta')
+    hit_idx, hit_cnt = hits[0], hits[1]
     B, N, Nq, D2 = hit_ref.shape
     if (planes32.shape != (B * N, 2 * H, fH * fW, 16) or Nq != bev_h * bev_w or qp_hit.shape[:2] != (B, N * Nq)
-            or hit_idx.shape != (N + 1, Nq) or hit_ic.shape != (B, N, Nq)):
+            or hit_idx.shape != (N + 1, Nq) or hit_meta.shape != (B, N, Nq, 4)):
         raise ValueError('img_sample_win32: inconsistent shapes')
     if out is None:
         out = torch.empty(B, Nq, H * 32, device=qp_hit.device, dtype=torch.float32)
-    _call('ub_img_sample_win32_fwd', planes32, _ptr(planes32), _ptr(qp_hit), _ptr(hit_ref), _ptr(hit_ic), _ptr(hit_idx),
+    _call('ub_img_sample_win32_fwd', planes32, _ptr(planes32), _ptr(qp_hit), _ptr(hit_ref), _ptr(hit_meta), _ptr(hit_idx),
           _ptr(hit_cnt), _ptr(out), B, N, bev_h, bev_w, fH, fW, H, 32, P, D2 // 2, qp_hit.shape[2], off_col, logit_col)
     return out
 

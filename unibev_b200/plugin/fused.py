@@ -396,7 +396,7 @@ class FusedEncoder:
                 hits, order = [], []
 
                 def cross(lw, tokens, x, wq16):
-                    if (self.win32 and self.sampling == 'fp32' and self.gemm == 'tf32x3' and D % 2 == 0 and Nq % 4 == 0
+                    if (self.win32 and self.sampling == 'fp32' and self.gemm == 'tf32x3' and D % 2 == 0
                             and ops.window_supported(C // lw.H_c, lw.P_c)):
                         # fp32 window kernel: value planes from the projection's epilogue, offset|logit rows written
                         # in hit-list order by theirs
@@ -404,12 +404,12 @@ class FusedEncoder:
                             hits.append(ops.build_hits(mask))
                         if not order:
                             order.append(ops.hit_order(mask, ref_cam, hits[0]))
-                        q_dst, hit_ref = order[0]
+                        q_dst = order[0][0]
                         try:
                             planes = ops.linear_tf32x3(self._rows32(tokens), self._hi_lo(lw.ca_wv), lw.ca_bv, planes_nv=fh * fw)
                             qp_hit = torch.empty(B, N * Nq, lw.ca_wq.shape[0], device=dev, dtype=torch.float32)
                             ops.linear_tf32x3_scatter(self._rows32(x), self._hi_lo(lw.ca_wq), lw.ca_bq, q_dst, Nq, qp_hit)
-                            return ops.img_sample_win32(planes, qp_hit, hit_ref, hits[0], bev_h, bev_w, fh, fw, lw.H_c,
+                            return ops.img_sample_win32(planes, qp_hit, order[0], hits[0], bev_h, bev_w, fh, fw, lw.H_c,
                                                         lw.P_c, 0, lw.H_c * lw.P_c * 2)
                         except _cabi.UnsupportedShape:
                             pass
