@@ -213,7 +213,8 @@ r, w = dist.get_rank(), dist.get_world_size()
 torch.manual_seed(0)                                   # same weights on every rank (the reference seeds ranks alike)
 net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 4), torch.nn.Linear(4, 3))
 unused = torch.nn.Linear(3, 3)                         # never part of rank 1's graph: contributes zeros there
-params = list(net.parameters()) + list(unused.parameters())
+never = torch.nn.Linear(2, 2)                          # no rank uses it: its grad must stay None (ADVICE r1)
+params = list(net.parameters()) + list(unused.parameters()) + list(never.parameters())
 buckets = GradBuckets(params, bucket_bytes=64)         # tiny buckets: several collectives, launched during backward
 assert len(buckets.buckets) > 2
 xs = [torch.randn(7, 6, generator=torch.Generator().manual_seed(10 + k)) for k in range(w)]
@@ -227,13 +228,27 @@ for step in range(2):                                  # hooks re-arm after fini
         p.grad = None
     loss_of(r, with_unused=(r == 0)).backward()
     buckets.finish()
-    got = [p.grad.clone() for p in params]
-    for p in params:
-        p.grad = None
+    got = [p.grad.clone() if p.grad is not None else None for p in params]
     want_loss = sum(loss_of(k, with_unused=(k == 0)) for k in range(w)) / w
-    want_loss.backward()
-    for p, g in zip(params, got):
-        torch.testing.assert_close(g, p.grad, rtol=1e-6, atol=1e-7)
+    want = torch.autograd.grad(want_loss, params, allow_unused=True)      # (no .grad accumulation: the hooks stay quiet)
+    for p, g, wg in zip(params, got, want):
+        if wg is None:
+            assert g is None
+        else:
+            torch.testing.assert_close(g, wg, rtol=1e-6, atol=1e-7)
+    assert all(p.grad is None for p in never.parameters())
+# two backward passes before finish(): no bucket is on the wire yet (bucket 0 holds the never-used parameters and waits for
+# finish()), so the accumulated gradients are exchanged -- never a stale first-pass copy (ADVICE r1); had a bucket already
+# been all-reduced, the second pass would raise instead
+for p in params:
+    p.grad = None
+loss_of(r, with_unused=True).backward()
+loss_of(r, with_unused=True).backward()
+buckets.finish()
+want = torch.autograd.grad(2 * sum(loss_of(k, with_unused=True) for k in range(w)) / w, params, allow_unused=True)
+for p, wg in zip(params, want):
+    if wg is not None:
+        torch.testing.assert_close(p.grad, wg, rtol=1e-6, atol=1e-7)
 dist.barrier()
 if r == 0:
     print('GRAD_OK', len(buckets.buckets), buckets.nbytes())

@@ -11,6 +11,7 @@ torch linears, the deformable sampling itself is ``MultiScaleDeformableAttnFunct
 (``unibev_b200/plugin/fused.py``), reading the parameters held here.
 """
 import math
+import os
 import warnings
 
 import torch
@@ -86,7 +87,13 @@ class _DeformAttnBase(nn.Module):
         return v, off, aw
 
 
-@ATTENTION.register_module(force=HAVE_MMCV)
+# With mmcv installed its own ``MultiScaleDeformableAttention`` already owns that registry name (and serves other models,
+# CPU fallback included): take the name over only when the deployment asks for it, otherwise register ours
+# as ``UBMultiScaleDeformableAttention`` and leave mmcv's entry alone.
+_TAKE_OVER = HAVE_MMCV and os.environ.get('UNIBEV_B200_OVERRIDE_MMCV_MSDA') == '1'
+
+
+@ATTENTION.register_module(name=None if (not HAVE_MMCV or _TAKE_OVER) else 'UBMultiScaleDeformableAttention', force=_TAKE_OVER)
 class MultiScaleDeformableAttention(_DeformAttnBase):
     """mmcv's module of the same name (BEV self-attention of every encoder layer,
     config ``attn_cfgs[0]``), backed by libunibev_b200."""

@@ -296,6 +296,21 @@ class FusedEncoder:
                 done = True
             except _cabi.UnsupportedShape:
                 pass
+        if not done and self.gemm == 'tf32x3' and all(w == widths[0] and w % 32 == 0 for w in widths):
+            # as many layers per launch as fit one 256-column tile: the A side of the 3xTF32 projection (TMA, hi / lo
+            # split, operand reads) is paid once per launch
+            key = ('x3',) + tuple(names)
+            per = max(1, 256 // widths[0])
+            if key not in self._pos_w:
+                self._pos_w[key] = [ops.split_tf32(torch.cat([lw.sa_wq for _, lw in blocks[b0:b0 + per]], 0).contiguous())
+                                    for b0 in range(0, len(blocks), per)]
+            try:
+                for k, b0 in enumerate(range(0, len(blocks), per)):
+                    c0, c1 = b0 * widths[0], min(len(blocks), b0 + per) * widths[0]
+                    ops.linear_tf32x3(self._rows32(pos), self._pos_w[key][k], None, out=buf[:, c0:c1])
+                done = True
+            except _cabi.UnsupportedShape:
+                pass
         if not done:
             for (_, lw), dst in zip(blocks, views):
                 self._lin(pos, lw.sa_wq, None, out=dst)

@@ -2,9 +2,9 @@
 
 Registered name, constructor keywords, parameter names and the ``forward`` signature /
 return tuple follow transformer_fusion.py:49-118,416-426,586.  The object-query decoder
-(transformer_fusion.py:540-586) is out of scope for this library: if its ``type`` resolves
-in the active registry (mmcv/mmdet3d installed) it is built and run exactly as the
-reference does, otherwise ``forward`` returns ``(bev_embed, None, init_reference, None)``.
+(transformer_fusion.py:540-586; ``plugin/decoder.py``) is built from the ``decoder`` config like the
+encoders; only when its top-level ``type`` is not registered does ``forward`` return
+``(bev_embed, None, init_reference, None)``.
 
 Eval-mode forwards run the fused B200 pipeline (``fused.FusedEncoder``); training-mode
 forwards run the autograd-capable module path.
@@ -72,8 +72,12 @@ class UniBEVTransformer(nn.Module):
         if decoder is not None:
             try:
                 self.decoder = build_transformer_layer_sequence(decoder)
-            except KeyError:
-                self.decoder = None        # decoder type not available without mmcv/mmdet3d: encoder half only
+            except KeyError as e:
+                # only a missing TOP-LEVEL decoder type (registry without the decoder classes) means "encoder half only";
+                # a typo in a nested `type=` must not silently turn the model into one without a decoder
+                if str(decoder.get('type')) not in str(e):
+                    raise
+                self.decoder = None
         self.dual_queries, self.embed_dims = dual_queries, embed_dims
         self.num_feature_levels, self.num_cams = num_feature_levels, num_cams
         self.fp16_enabled = False
@@ -320,8 +324,12 @@ class UniBEVTransformer(nn.Module):
     def _modal_embed(self):
         if self.use_modal_embeds != 'Fixed':
             return None
-        e = self.c_flag * self.modal_embbeding_C + self.l_flag * self.modal_embbeding_L
-        return torch.cat((e, e)) if self.fusion_method == 'cat' else e
+        if self.fusion_method == 'cat':
+            # the reference adds the C-wide embedding to the 2C-wide concatenation and fails (transformer_fusion.py:310-312);
+            # the module path fails the same way -- keep the two paths in agreement
+            raise ValueError("use_modal_embeds='Fixed' cannot be combined with fusion_method='cat' (C-wide embedding, "
+                             "2C-wide features; transformer_fusion.py:310-312)")
+        return self.c_flag * self.modal_embbeding_C + self.l_flag * self.modal_embbeding_L
 
     def forward(self, img_mlvl_feats, pts_mlvl_feats, bev_queries, object_query_embed, bev_h, bev_w, bev_pos=None,
                 reg_branches=None, cls_branches=None, **kwargs):

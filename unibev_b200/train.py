@@ -59,10 +59,19 @@ class GradBuckets:
 
     # ---- backward-time side ---------------------------------------------------------------------------------
     def _on_grad(self, p):
+        """One backward pass per ``finish()``: a second gradient for a parameter whose bucket is already on the wire cannot
+        be exchanged any more and raises; before that (gradient accumulation inside one backward graph, shared
+        parameters) the accumulated ``p.grad`` is simply copied again."""
+        if self.world == 1:
+            return                                     # single process: gradients stay where autograd left them
+        bi, off, n = self._where[p]
         if p in self._seen:
+            if bi < self._next:
+                raise RuntimeError('GradBuckets: a parameter received another gradient after its bucket was all-reduced; '
+                                   'call finish() after every backward pass (no gradient accumulation across passes)')
+            self.buckets[bi][0][off:off + n].copy_(p.grad.reshape(-1))
             return
         self._seen.add(p)
-        bi, off, n = self._where[p]
         flat = self.buckets[bi][0]
         flat[off:off + n].copy_(p.grad.reshape(-1))
         self._pending[bi] -= 1
@@ -74,8 +83,6 @@ class GradBuckets:
 
     def _launch(self, bi):
         flat = self.buckets[bi][0]
-        if self.world == 1:
-            return
         if self._stream is not None:
             self._stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._stream):
@@ -86,11 +93,10 @@ class GradBuckets:
     # ---- after backward -------------------------------------------------------------------------------------
     def finish(self):
         """Completes the exchange: buckets whose parameters got no gradient this step are reduced too (zeros), in bucket
-        order, so all ranks run identical collectives; then p.grad <- average over ranks."""
-        if self.world == 1:           # single process: gradients stay where autograd left them
-            self._next = 0
-            self._seen.clear()
-            self._pending = [len(items) for _, items in self.buckets]
+        order, so all ranks run identical collectives; then p.grad <- average over ranks.  A parameter no rank used keeps
+        ``p.grad = None`` (one small all-reduce of per-parameter "touched" flags decides), so weight decay / Adam leave it
+        alone exactly as in a single-process run."""
+        if self.world == 1:
             return
         for bi in range(self._next, len(self.buckets)):
             flat, items = self.buckets[bi]
@@ -99,16 +105,23 @@ class GradBuckets:
                     flat[off:off + n].zero_()
             self._launch(bi)
         self._next = 0
+        dev = self.buckets[0][0].device
+        touched = torch.tensor([1.0 if p in self._seen else 0.0 for p in self.params], device=dev)
+        dist.all_reduce(touched, group=self.group)
         for w in self._works:
             w.wait()
         if self._stream is not None:
             torch.cuda.current_stream().wait_stream(self._stream)
+        used = dict(zip(self.params, touched.tolist()))
         inv = 1.0 / self.world
         for flat, items in self.buckets:
             flat.mul_(inv)
             for p, off, n in items:
+                if used[p] == 0.0:
+                    p.grad = None
+                    continue
                 g = flat[off:off + n].view_as(p)
-                if p.grad is None:        # unused on this rank (same convention as DDP find_unused_parameters: zeros / average)
+                if p.grad is None:        # unused on this rank, used on another: the average over ranks
                     p.grad = g.clone()
                 else:
                     p.grad.copy_(g)
