@@ -751,6 +751,139 @@ def golden_decoder(seed=700, C=32, heads=4, layers=3, nq=37, bs=2, bev_hw=(10, 1
     save('decoder', **arrays)
 
 
+def golden_head(fusion_mod, tag, seed, fusion='linear', dual_queries=False, bs=2, C=32, heads=4, cams=3, bev_hw=(6, 8),
+                num_query=12, dec_layers=2, img_fhw=(5, 8), pts_fhw=(7, 7), max_num=9, score_threshold=None):
+    """The reference's own UniBEV_Head.forward / get_bboxes (unibev_head.py, unmodified) and NMSFreeCoder.decode
+    (nms_free_coder.py, unmodified) around the reference transformer (encoders + DetectionTransformerDecoder).  Third-party
+    pieces are stubbed by their published behaviour: mmdet's DETRHead.__init__ (stores the arguments, builds the transformer
+    and the positional encoding, calls _init_layers), LearnedPositionalEncoding, inverse_sigmoid, BaseBBoxCoder."""
+    import json
+    import types
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class LearnedPositionalEncoding(BaseModule):          # mmdet 2.19 (SURVEY.md appendix B)
+        def __init__(self, num_feats, row_num_embed=50, col_num_embed=50, init_cfg=None):
+            super().__init__(init_cfg)
+            self.row_embed = nn.Embedding(row_num_embed, num_feats)
+            self.col_embed = nn.Embedding(col_num_embed, num_feats)
+
+        def forward(self, mask):
+            h, w = mask.shape[-2:]
+            x, y = torch.arange(w), torch.arange(h)
+            x_embed, y_embed = self.col_embed(x), self.row_embed(y)
+            pos = torch.cat((x_embed.unsqueeze(0).repeat(h, 1, 1), y_embed.unsqueeze(1).repeat(1, w, 1)), dim=-1)
+            return pos.permute(2, 0, 1).unsqueeze(0).repeat(mask.shape[0], 1, 1, 1)
+
+    def inverse_sigmoid(x, eps=1e-5):                      # mmdet.models.utils.transformer
+        x = x.clamp(min=0, max=1)
+        return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+    BBOX_CODERS, HEADS = Registry('bbox_coder'), Registry('head')
+
+    class DETRHead(BaseModule):                            # the part of mmdet's DETRHead.__init__ the subclass relies on
+        def __init__(self, num_classes, in_channels, num_query=100, num_reg_fcs=2, transformer=None,
+                     sync_cls_avg_factor=False, positional_encoding=None, loss_cls=None, loss_bbox=None, loss_iou=None,
+                     train_cfg=None, test_cfg=None, init_cfg=None, **kwargs):
+            super().__init__(init_cfg)
+            self.num_classes, self.in_channels, self.num_query, self.num_reg_fcs = num_classes, in_channels, num_query, num_reg_fcs
+            self.loss_cls = types.SimpleNamespace(use_sigmoid=loss_cls.get('use_sigmoid', False))
+            self.cls_out_channels = num_classes if self.loss_cls.use_sigmoid else num_classes + 1
+            pe = dict(positional_encoding)
+            pe.pop('type')
+            self.positional_encoding = LearnedPositionalEncoding(**pe)
+            self.transformer = TRANSFORMER.build(transformer)
+            self.embed_dims = self.transformer.embed_dims
+            self._init_layers()
+
+    core = types.ModuleType('refcore')
+    core.__path__ = [os.path.join(REF_MODULES, '..', '..', 'core')]
+    sys.modules['refcore'] = core
+    for sub in ('bbox', 'bbox.coders'):
+        m = types.ModuleType('refcore.' + sub)
+        m.__path__ = [os.path.join(REF_MODULES, '..', '..', 'core', *sub.split('.'))]
+        sys.modules['refcore.' + sub] = m
+    mod('mmdet.core.bbox.builder', BBOX_CODERS=BBOX_CODERS)
+    mod('mmdet.core.bbox', BaseBBoxCoder=object, builder=sys.modules['mmdet.core.bbox.builder'])
+    mod('mmdet.core', multi_apply=None, reduce_mean=None, bbox=sys.modules['mmdet.core.bbox'])
+    sys.modules['mmdet'].core = sys.modules['mmdet.core']
+    util = importlib.import_module('refcore.bbox.util')
+    coder_mod = importlib.import_module('refcore.bbox.coders.nms_free_coder')
+    mod('mmdet.models.utils.transformer', inverse_sigmoid=inverse_sigmoid)
+    sys.modules['mmdet.models'].HEADS = HEADS
+    mod('mmdet.models.dense_heads', DETRHead=DETRHead)
+    mod('mmdet3d.core.bbox.coders', build_bbox_coder=BBOX_CODERS.build)
+    mod('mmdet3d.core.bbox', coders=sys.modules['mmdet3d.core.bbox.coders'])
+    mod('mmdet3d.core', bbox=sys.modules['mmdet3d.core.bbox'])
+    mod('mmdet3d.unibev_plugin.core.bbox.util', normalize_bbox=util.normalize_bbox)
+    mod('mmdet3d.unibev_plugin.core.bbox')
+    mod('mmdet3d.unibev_plugin.core')
+    mod('mmdet3d.unibev_plugin')
+    mod('mmdet3d', core=sys.modules['mmdet3d.core'])
+    sys.modules['mmcv.cnn'].Linear = nn.Linear
+    sys.modules['mmcv.cnn'].bias_init_with_prob = lambda p: float(-np.log((1 - p) / p))
+    heads_pkg = types.ModuleType('refheads')
+    heads_pkg.__path__ = [os.path.join(REF_MODULES, '..', 'dense_heads')]
+    sys.modules['refheads'] = heads_pkg
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        importlib.import_module('refmods.decoder')
+        head_mod = importlib.import_module('refheads.unibev_head')
+
+    tcfg = transformer_cfg(C=C, heads=heads, layers=1, cams=cams, fusion=fusion, feature_norm='ChannelNormWeights' if fusion != 'cat' else None,
+                           dual_queries=dual_queries, bev_h=bev_hw[0], bev_w=bev_hw[1])
+    Cd = C * (2 if fusion == 'cat' else 1)
+    tcfg['decoder'] = dict(type='DetectionTransformerDecoder', num_layers=dec_layers, return_intermediate=True,
+                           transformerlayers=dict(
+                               type='DetrTransformerDecoderLayer',
+                               attn_cfgs=[dict(type='MultiheadAttention', embed_dims=Cd, num_heads=heads, dropout=0.0),
+                                          dict(type='CustomMSDeformableAttention', embed_dims=Cd, num_heads=heads,
+                                               num_levels=1, dropout=0.0)],
+                               ffn_cfgs=dict(type='FFN', embed_dims=Cd), feedforward_channels=2 * Cd, ffn_dropout=0.0,
+                               operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm')))
+    pc_range = list(tcfg['img_encoder']['pc_range'])
+    hcfg = dict(type='UniBEV_Head', bev_h=bev_hw[0], bev_w=bev_hw[1], num_query=num_query, num_classes=10, in_channels=C,
+                sync_cls_avg_factor=True, with_box_refine=True, as_two_stage=False, transformer=tcfg,
+                bbox_coder=dict(type='NMSFreeCoder', post_center_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0],
+                                pc_range=pc_range, max_num=max_num, num_classes=10, score_threshold=score_threshold),
+                positional_encoding=dict(type='LearnedPositionalEncoding', num_feats=C // 2, row_num_embed=bev_hw[0],
+                                         col_num_embed=bev_hw[1]),
+                loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=2.0),
+                loss_bbox=dict(type='L1Loss', loss_weight=0.25), loss_iou=dict(type='GIoULoss', loss_weight=0.0))
+    build = copy.deepcopy(hcfg)
+    build.pop('type')
+    torch.manual_seed(seed)
+    head = head_mod.UniBEV_Head(**build)
+    assert type(head.bbox_coder) is coder_mod.NMSFreeCoder
+    head.init_weights()
+    randomize_(head, seed + 1)
+    with torch.no_grad():                                  # spread the boxes over the range so the centre mask bites
+        for br in head.reg_branches:
+            br[-1].bias.copy_(torch.tensor([0.0, 0.0, 0.3, 0.5, 0.0, 0.2, 0.1, 0.9, 0.0, 0.0]))
+    head.eval()
+    g = torch.Generator().manual_seed(seed + 2)
+    img_hw = (96, 160)
+    img_feats = [torch.randn(bs, cams, C, *img_fhw, generator=g)]
+    pts_feats = [torch.randn(bs, C, *pts_fhw, generator=g)]
+    metas = [dict(lidar2img=camera_rig(cams, img_hw, seed=seed + s, jitter=0.1 * s),
+                  img_shape=[(img_hw[0], img_hw[1], 3)] * cams, box_type_3d=lambda b, code_size: b) for s in range(bs)]
+    with torch.no_grad():
+        outs = head(img_feats, pts_feats, metas)
+        boxes = head.get_bboxes({k: (v.clone() if torch.is_tensor(v) else v) for k, v in outs.items()}, metas)
+    arrays = dict(img_feats=img_feats[0], pts_feats=pts_feats[0], img_hw=np.array(img_hw),
+                  lidar2img=np.asarray([m['lidar2img'] for m in metas]), bev_embed=outs['bev_embed'],
+                  all_cls_scores=outs['all_cls_scores'], all_bbox_preds=outs['all_bbox_preds'],
+                  cfg_json=np.array(json.dumps(hcfg)))
+    for i, (b, sc, lb) in enumerate(boxes):
+        arrays.update({f'det{i}_bboxes': b, f'det{i}_scores': sc, f'det{i}_labels': lb})
+    arrays.update({'p.' + k: t for k, t in head.state_dict().items()})
+    save('head_' + tag, **arrays)
+
+
 def main():
     torch.set_num_threads(1)
     fusion_mod, enc_img, sca_img, sca_pts = import_reference()
@@ -774,6 +907,8 @@ def main():
                         train_flags=True, drop_modality=dict(dropout_prob=1.0, lidar_prob=1.0))
     golden_encoder_half(fusion_mod, 'lc_cnw_modal_mlp', 614, use_modal_embeds='MLP')
     golden_decoder()
+    golden_head(fusion_mod, 'linear', 800)
+    golden_head(fusion_mod, 'cat_dual_thresh', 810, fusion='cat', dual_queries=True, score_threshold=0.6095)
 
 
 if __name__ == '__main__':

@@ -9,7 +9,10 @@ Same constructor keywords and parameter names (``row_embed.weight``, ``col_embed
 import torch
 import torch.nn as nn
 
+from ..registry import HAVE_MMDET, POSITIONAL_ENCODING
 
+
+@POSITIONAL_ENCODING.register_module(name=None if not HAVE_MMDET else 'UBLearnedPositionalEncoding')
 class LearnedPositionalEncoding(nn.Module):
     def __init__(self, num_feats, row_num_embed=50, col_num_embed=50, init_cfg=None):
         super().__init__()

@@ -54,6 +54,17 @@ except Exception:  # noqa: BLE001
     TRANSFORMER = _Registry('Transformer')
     HAVE_MMCV = False
 
+try:  # pragma: no cover - mmdet is absent from the build image
+    from mmdet.core.bbox.builder import BBOX_CODERS
+    from mmdet.models import HEADS
+    from mmdet.models.utils.builder import POSITIONAL_ENCODING
+    HAVE_MMDET = True
+except Exception:  # noqa: BLE001
+    BBOX_CODERS = _Registry('bbox_coder')
+    HEADS = _Registry('head')
+    POSITIONAL_ENCODING = _Registry('position encoding')
+    HAVE_MMDET = False
+
 
 def build_attention(cfg):
     return ATTENTION.build(cfg)
@@ -73,3 +84,15 @@ def build_transformer_layer_sequence(cfg):
 
 def build_transformer(cfg):
     return TRANSFORMER.build(cfg)
+
+
+def build_bbox_coder(cfg):
+    return BBOX_CODERS.build(cfg)
+
+
+def build_positional_encoding(cfg):
+    return POSITIONAL_ENCODING.build(cfg)
+
+
+def build_head(cfg):
+    return HEADS.build(cfg)
