@@ -46,6 +46,10 @@ def parse():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
+                    help='infer (default): BASELINE.json metric, configs[2]/[3].  train: configs[4], the data-parallel '
+                         'training step of unibev_nus_LC_cat_128 (2 samples per GPU, NCCL gradient all-reduce, AdamW)')
+    ap.add_argument('--bucket-mb', type=float, default=8.0, help='train mode: gradient bucket size')
     ap.add_argument('--batch', type=int, default=4, help='frames per GPU per step (BASELINE configs[3]: 32 frames over 8 GPUs)')
     ap.add_argument('--no-graphs', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'fp16'],
@@ -183,9 +187,15 @@ def main():
                                                'depend on the batch on the CPU), all host threads, rank 0 only'},
                 'cpu_baseline': {k: ref[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
                 'e2e': {'value': ref['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-                'gpu_launches': 0}
+                'gpu_launches': 0,
+                # under torchrun only rank 0 runs the CPU arm (the other ranks exit): the N-GPU / reference ratio of a
+                # scaling run divides N GPUs by ONE host-wide CPU run, not by N of them
+                'reference_ranks': 1}
         print(json.dumps(line), flush=True)
         return
+
+    if args.mode == 'train':
+        return train_main(args, rank, world, local)
 
     import torch
     import torch.distributed as dist
@@ -304,6 +314,37 @@ def main():
     e2e_ms, _ = e2e_run(args.steps)
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+
+    # the host's copy ceiling with every rank copying at once (both directions, pinned memory, this step's byte counts and no
+    # kernels): what the e2e figure can reach at most on this box whatever the GPUs do
+    def host_ceiling(reps=6):
+        a_in = torch.empty(h2d, dtype=torch.uint8).pin_memory()
+        a_out = torch.empty(d2h, dtype=torch.uint8).pin_memory()
+        d_in, d_out = torch.empty(h2d, dtype=torch.uint8, device=dev), torch.empty(d2h, dtype=torch.uint8, device=dev)
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        best = None
+        for trial in range(2):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s1.wait_event(e0)
+            s2.wait_event(e0)
+            for _ in range(reps):
+                with torch.cuda.stream(s1):
+                    d_in.copy_(a_in, non_blocking=True)
+                with torch.cuda.stream(s2):
+                    a_out.copy_(d_out, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(s1)
+            torch.cuda.current_stream().wait_stream(s2)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            best = float(ms.item()) if best is None else min(best, float(ms.item()))
+        barrier()
+        return world * B * reps / (best / 1e3), world * (h2d + d2h) * reps / (best / 1e3) / 1e9
+    ceil_fps, ceil_gbs = host_ceiling()
 
     # ---- per-kernel timing ---------------------------------------------------------------------------------
     # (1) one instrumented eager step: the sampling launches are RECORDED (arguments cloned, so every recorded call owns
@@ -446,10 +487,105 @@ def main():
                                      f'(tests/test_gpu_encoder.py::test_full_size_vs_oracle_{args.precision})'},
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'result_dtype': args.e2e_result_dtype,
-                        'ms_per_step': e2e_ms / args.steps},
+                        'ms_per_step': e2e_ms / args.steps,
+                        # copy-only ceiling of this host with all ranks copying at once (no kernels): e2e cannot exceed it
+                        'host_ceiling_frames_s': ceil_fps, 'host_ceiling_gbs': ceil_gbs,
+                        'frac_of_host_ceiling': e2e_value / ceil_fps},
                 'gpu_launches': launches, 'clocks': clk.summary(), 'roofline': roofline, 'kernels': kernels,
                 'other_kernels': other, 'cpu_baseline': cpu}
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def train_main(args, rank, world, local):
+    """BASELINE configs[4]: unibev_nus_LC_cat_128 training step, `--batch` samples per GPU (default 2: 16 over 8 GPUs),
+    modality dropout 0.5 with the same numpy seed on every rank (train_UniBEV.py:200-204), synthetic scalar loss on
+    fused_bev_embed, backward through ub_msda_bwd, bucketed NCCL all-reduce overlapped with backward
+    (unibev_b200.train.GradBuckets), AdamW.  value: inputs resident in HBM; e2e: per step H2D of the step's feature
+    tensors from pinned memory + the loss read back."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from unibev_b200 import _cabi, synth
+    from unibev_b200.train import GradBuckets, train_step
+    wl = 'unibev_nus_LC_cat_128'
+    B = 2 if args.batch == 4 else args.batch            # (--batch defaults to the inference value)
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = True          # module path: torch linears (what torch 1.10, the reference's stack, did)
+    np.random.seed(0)
+    model, cfg = synth.build_model(wl, drop_modality=0.5)
+    model = model.to(dev).train()
+    host = [synth.make_inputs(wl, batch=B, seed=1 + rank * 100 + i, pin=True) for i in range(N_INPUT_SETS)]
+    dev_sets = [dict(h, img_feats=[h['img_feats'][0].to(dev)], pts_feats=[h['pts_feats'][0].to(dev)], bev_pos=h['bev_pos'].to(dev))
+                for h in host]
+    g = torch.Generator().manual_seed(7)
+    bev_embedding = torch.nn.Parameter(torch.randn(host[0]['bev_queries'].shape, generator=g).to(dev))
+    params = list(model.parameters()) + [bev_embedding]
+    opt = torch.optim.AdamW(params, lr=2e-4, weight_decay=0.01)
+    buckets = GradBuckets(params, bucket_bytes=int(args.bucket_mb * (1 << 20)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(steps, from_host):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss_sum = 0.0
+        for i in range(steps):
+            if from_host:
+                h = host[i % N_INPUT_SETS]
+                inp = dict(h, img_feats=[h['img_feats'][0].to(dev, non_blocking=True)],
+                           pts_feats=[h['pts_feats'][0].to(dev, non_blocking=True)], bev_pos=h['bev_pos'].to(dev, non_blocking=True))
+            else:
+                inp = dev_sets[i % N_INPUT_SETS]
+            loss = train_step(model, bev_embedding, inp, opt, buckets)
+            if from_host:
+                loss_sum += float(loss)                    # D2H read of the step's result
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item()), float(loss)
+    run(max(args.warmup, 3), False)
+    _cabi.reset_launch_count()
+    clk = ClockSampler(local)
+    clk.__enter__()
+    ms, loss = run(args.steps, False)
+    launches = _cabi.launch_count()
+    run(2, True)
+    e2e_ms, _ = run(args.steps, True)
+    clk.__exit__(None, None, None)
+    check = torch.stack([p.detach().double().sum() for p in params]).sum().reshape(1)
+    in_sync = True
+    if world > 1:
+        lo, hi = check.clone(), check.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool(torch.allclose(lo, hi, rtol=1e-9, atol=0))
+    h2d = sum(t.numel() * 4 for t in (host[0]['img_feats'][0], host[0]['pts_feats'][0], host[0]['bev_pos']))
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'nuScenes frames/sec train step (L+C cat-128, modality dropout 0.5; BASELINE configs[4])', 'unit': UNIT,
+            'value': world * B * args.steps / (ms / 1e3), 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 (TF32 torch linears in the module path, fp32 ub_msda_fwd / ub_msda_bwd)', 'data': 'synthetic',
+            'config': {'workload': f'{wl} training step, {B} samples per GPU, {world} GPU(s), synthetic loss (mean square of '
+                                   'fused_bev_embed), AdamW',
+                       'collective': f'nccl all_reduce, {buckets.nbytes() / 1e6:.1f} MB per step in {len(buckets.buckets)} buckets, '
+                                     'overlapped with backward' if world > 1 else 'none (1 GPU)',
+                       'params_in_sync_across_ranks': in_sync, 'loss': loss},
+            'e2e': {'value': world * B * args.steps / (e2e_ms / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / args.steps},
+            'gpu_launches': launches, 'clocks': clk.summary(), 'roofline': None, 'cpu_baseline': None}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
