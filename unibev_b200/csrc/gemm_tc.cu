@@ -550,9 +550,20 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
 
 }  // namespace ub
 
+namespace ub {
+int launch_x3_pair(const char* fn, const float* A, const float* W_hi, const float* W_lo, const float* bias, const float* residual,
+                   int ldr, const float* gamma, const float* beta, float eps, float* out, int ldc, float* planes32, int Nv,
+                   int M, int N, int K, int relu, int ln, cudaStream_t stream);   // gemm_pair.cu
+}
+
 using namespace ub;
 
 static int g_gemm_cluster = 4;
+static int g_x3_pair = 0;   // 3xTF32 on CTA pairs (tcgen05.mma.cta_group::2, gemm_pair.cu) where the shape is covered
+extern "C" int ub_set_gemm_x3_pair(int on) {
+  g_x3_pair = on ? 1 : 0;
+  return UB_OK;
+}
 static int g_x3_inplace = 1, g_x3_direct = 1, g_x3_cluster = 2, g_x3_stagger_ns = 0;   // measured best (profiles/r2_gemm_x3.txt)
 // A/B knobs of the 3xTF32 mode (tools/bench_gemm_x3.py): in-place a_hi write-back, direct result stores, cluster size,
 // start offset of every other cluster
@@ -608,6 +619,11 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
       (residual && (ldr % 4 != 0 || (reinterpret_cast<uintptr_t>(residual) & 15u))) || N > 1024) {
     set_error("%s: shape not covered (M=%d N=%d K=%d flags=%d)", fn, M, N, K, flags);
     return ub::unsupported();
+  }
+  if (split && g_x3_pair && !scatter && !out16 && !planes && M >= 2 * kBM * 16) {
+    const int rc = launch_x3_pair(fn, reinterpret_cast<const float*>(A), reinterpret_cast<const float*>(W), W_lo, bias, residual,
+                                  ldr, gamma, beta, eps, out, ldc, planes32, Nv, M, N, K, relu, ln, (cudaStream_t)stream);
+    if (rc != UB_EUNSUPPORTED) return rc;   // (not covered: the single-CTA kernel below; not a generic fallback)
   }
   GemmArgs a;
   a.bias = bias, a.gamma = gamma, a.beta = beta, a.planes = reinterpret_cast<__half*>(planes);
