@@ -267,3 +267,84 @@ def test_unsupported_shapes_are_counted(ops):
     assert _cabi.unsupported_count() == 1
     _cabi.reset_launch_count()
     assert _cabi.unsupported_count() == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ub_linear_f16x3: the same three-product scheme on kind::f16 MMAs (operands bounded below the fp16 range by the caller)
+def _h3(ops, x, w, b=None, **kw):
+    return ops.linear_f16x3(x.cuda(), ops.split_f16(w.cuda()), b.cuda() if b is not None else None, **kw).cpu()
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 256, 256), (1000, 256, 256), (40000, 256, 256), (333, 96, 256),
+                                   (700, 192, 256), (513, 512, 256), (260, 256, 512), (129, 128, 128), (64, 32, 64)])
+@pytest.mark.parametrize('relu', [False, True])
+def test_linear_f16x3_gaussian(ops, M, N, K, relu):
+    g = torch.Generator().manual_seed(M + N + K)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    want = F.linear(x.double(), w.double(), b.double())
+    want = (want.relu() if relu else want).float()
+    got = _h3(ops, x, w, b, relu=relu)
+    err = (got - want).abs()
+    # the same precision class as the 3xTF32 mode (2 x 11 significand bits per operand), half as many accumulation steps
+    assert float(err.max()) < 4e-5 and float(err.mean()) < 5e-6, (float(err.max()), float(err.mean()))
+    x3 = (_x3(ops, x, w, b, relu=relu) - want).abs()
+    assert float(err.mean()) < 2 * float(x3.mean()) + 1e-7
+
+
+def test_linear_f16x3_operand_range(ops):
+    """Operands from 1e-4 to 1e3 (inside the fp16 range the caller must guarantee): absolute error stays at the fp32 level
+    relative to sum |a||w|; tiny elements keep their absolute precision."""
+    g = torch.Generator().manual_seed(4)
+    M, N, K = 777, 256, 256
+    x = torch.randn(M, K, generator=g) * torch.logspace(-4, 3, K)
+    w = torch.randn(N, K, generator=g) * torch.logspace(-4, 0, N)[:, None]
+    want = F.linear(x.double(), w.double()).float()
+    got = _h3(ops, x, w)
+    scale = F.linear(x.double().abs(), w.double().abs()).float()
+    assert float(((got - want).abs() / scale).max()) < 5e-6
+
+
+def test_linear_f16x3_residual_layernorm_planes_scatter(ops):
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 1777, 256, 512
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    r = torch.randn(M, N, generator=g)
+    gam, bet = torch.randn(N, generator=g), torch.randn(N, generator=g)
+    pre = F.linear(x.double(), w.double(), b.double()) + r.double()
+    torch.testing.assert_close(_h3(ops, x, w, b, residual=r.cuda()), pre.float(), rtol=1e-5, atol=5e-5)
+    want = F.layer_norm(pre, (N,), gam.double(), bet.double(), 1e-5).float()
+    torch.testing.assert_close(_h3(ops, x, w, b, residual=r.cuda(), ln=(gam.cuda(), bet.cuda(), 1e-5)), want, rtol=1e-5, atol=5e-5)
+    # strided output view
+    wide = torch.zeros(M, 3 * N).cuda()
+    ops.linear_f16x3(x.cuda(), ops.split_f16(w.cuda()), b.cuda(), out=wide[:, N:2 * N])
+    torch.testing.assert_close(wide[:, N:2 * N].cpu(), F.linear(x.double(), w.double(), b.double()).float(), rtol=1e-5, atol=5e-5)
+    assert float(wide[:, :N].abs().max()) == 0 and float(wide[:, 2 * N:].abs().max()) == 0
+    # fp32 half-head planes
+    G, Nv = 3, 500
+    xp = torch.randn(G * Nv, 256, generator=g)
+    wp = torch.randn(256, 256, generator=g) / 16
+    wantp = F.linear(xp.double(), wp.double(), b.double()).float().view(G, Nv, 16, 16).permute(0, 2, 1, 3).contiguous()
+    torch.testing.assert_close(_h3(ops, xp, wp, b, planes_nv=Nv), wantp, rtol=1e-5, atol=5e-5)
+    # row scatter
+    B, Nq, Ncam, Nout = 2, 1000, 6, 192
+    xs = torch.randn(B * Nq, 256, generator=g)
+    ws, bs = torch.randn(Nout, 256, generator=g) / 16, torch.randn(Nout, generator=g)
+    q_dst = torch.full((Nq, Ncam), -1, dtype=torch.int32)
+    perm = torch.randperm(Ncam * Nq, generator=g)
+    k = 0
+    for q in range(Nq):
+        c = q % 4
+        q_dst[q, :c] = perm[k:k + c].int()
+        k += c
+    out = torch.full((B, Ncam * Nq, Nout), float('nan')).cuda()
+    ops.linear_f16x3(xs.cuda(), ops.split_f16(ws.cuda()), bs.cuda(), out=out, scatter=(q_dst.cuda(), Nq))
+    wants = F.linear(xs.double(), ws.double(), bs.double()).float().view(B, Nq, Nout)
+    got = out.cpu()
+    written = torch.zeros(Ncam * Nq, dtype=torch.bool)
+    for q in range(Nq):
+        for d in q_dst[q].tolist():
+            if d < 0:
+                break
+            written[d] = True
+            torch.testing.assert_close(got[:, d], wants[:, q], rtol=1e-5, atol=5e-5)
+    assert bool(torch.isnan(got[:, ~written]).all())

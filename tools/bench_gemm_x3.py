@@ -34,11 +34,13 @@ def main():
                 torch.cuda.synchronize()
                 continue
             t3 = timeit(lambda: ops.linear_tf32x3(a, ws, b, residual=r, ln=lnp, out=out))
+            wh = ops.split_f16(w)
+            t6 = timeit(lambda: ops.linear_f16x3(a, wh, b, residual=r, ln=lnp, out=out))
             t1 = timeit(lambda: ops.linear_tf32(a, w, b, residual=r, ln=lnp, out=out))
             th = timeit(lambda: ops.linear_f16(a16, w16, b, residual=r, ln=lnp, out=out))
             bytes_ = 4 * (M * K + M * N * (2 if ln else 1))
-            print('inplace=%d direct=%d cs=%d stagger=%d %-16s x3 %7.1f us (%5.1f TFLOP/s eff, %5.0f GB/s) | tf32 %7.1f us | f16 %7.1f us' %
-                  (inplace, direct, cs, stag, name, t3, 2.0 * M * N * K / t3 / 1e6, bytes_ / t3 / 1e3, t1, th), flush=True)
+            print('inplace=%d direct=%d cs=%d stagger=%d %-16s x3 %7.1f us (%5.1f TFLOP/s eff, %5.0f GB/s) | f16x3 %7.1f us | tf32 %7.1f us | f16 %7.1f us' %
+                  (inplace, direct, cs, stag, name, t3, 2.0 * M * N * K / t3 / 1e6, bytes_ / t3 / 1e3, t6, t1, th), flush=True)
 
 
 if __name__ == '__main__':

@@ -100,8 +100,15 @@ __device__ __forceinline__ void trace_event(const GemmArgs& a, int role, int i) 
 // the tensor core rounds its operands) and write a_lo into a second, identically laid out (swizzle and all: the
 // transform is element-wise) ring, which the MMA lane consumes through the same kind of descriptors.  All three products
 // accumulate into the same TMEM columns, so residual-via-tcgen05.cp and the epilogues are unchanged.
-template <bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
+//
+// MODE 2 (fp16 x3, ub_linear_f16x3): the same three-product scheme on kind::f16 MMAs, which run at twice the TF32 rate and
+// move half the operand bytes: a = a_hi + a_lo with a_hi = fp16(a), a_lo = fp16(a - a_hi) (2 x 11 significand bits, the same
+// as the TF32 split) -- valid where the caller can BOUND the operands below the fp16 range (plugin/fused.py derives the
+// bounds from the weights; everything else stays on MODE 1).  W_hi / W_lo arrive as fp16 tensors (64-element k-blocks); the
+// converters turn every two fp32 A k-blocks into one 64-element fp16 operand slot {a_hi tile, a_lo tile}, writing the
+// 128-byte swizzle themselves (the element size changes, so the layout does); the MMA lane never reads the A ring.
+template <int MODE>
+__global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
     gemm_tf32_kernel(const GemmArgs a, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_wl) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -110,14 +117,18 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
   __shared__ uint32_t s_tmem;
   __shared__ float2 s_stat[4][kBM];   // LayerNorm partial (sum, sum of squares) per epilogue warp of a lane quarter
 
+  constexpr bool SPLIT = MODE == 1, F16S = MODE == 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int SA = a.SA, SW = a.SW;
   const uint32_t a_bytes = kBM * 128, w_bytes = (uint32_t)a.BN * 128;
-  const int SL = SPLIT ? a.SL : 0;
-  const uint32_t sm_a = smem_u32(smem), sm_l = sm_a + (uint32_t)SA * a_bytes, sm_w = sm_l + (uint32_t)SL * a_bytes;
-  const uint32_t sm_stage_buf = sm_w + (uint32_t)SW * w_bytes;                  // [16 warps] x 2 KB
-  float* s_par = reinterpret_cast<float*>(smem + (size_t)(SA + SL) * a_bytes + (size_t)SW * w_bytes + kEpiWarps * kStageBuf);
-  const int k_blocks = a.K / a.kb_elems;
+  const int SL = MODE ? a.SL : 0;
+  const uint32_t l_bytes = F16S ? 2u * a_bytes : a_bytes;      // MODE 2: an operand slot = {a_hi tile, a_lo tile} of 64 k
+  const uint32_t sm_a = smem_u32(smem), sm_l = sm_a + (uint32_t)SA * a_bytes, sm_w = sm_l + (uint32_t)SL * l_bytes;
+  const uint32_t sm_stage_buf = sm_w + (uint32_t)SW * w_bytes;                  // [16 warps] x 2 KB (none in MODE 2)
+  float* s_par = reinterpret_cast<float*>(smem + (size_t)SA * a_bytes + (size_t)SL * l_bytes + (size_t)SW * w_bytes +
+                                          (F16S ? 0 : kEpiWarps * kStageBuf));
+  const int k_blocks = a.K / a.kb_elems;                       // A k-blocks (MODE 2: 32 fp32 each, two per W k-block)
+  const int w_blocks = F16S ? a.K / 64 : k_blocks, w_elems = F16S ? 64 : a.kb_elems;
   // Work = groups of `cs` consecutive row tiles of one column tile; cluster c takes groups c, c + n_clusters, ...
   // and CTA rank r of the cluster the r-th row tile of the group (possibly past M: loads zero-fill, nothing is stored).
   const int cs = a.cs, rank = (int)blockIdx.x % cs, cluster_id = (int)blockIdx.x / cs, n_clusters = (int)gridDim.x / cs;
@@ -155,7 +166,7 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
   if (tid == 0) {
     // SPLIT: a slot is free again once the MMAs that read it have completed AND every converter warp has passed it
     // (also the residual slots, which the converters do not touch): no waiter can then fall a whole phase behind
-    for (int i = 0; i < SA; ++i) mbar_init(smem_u32(&s_fa[i]), 1), mbar_init(smem_u32(&s_ea[i]), SPLIT ? 1 + kConvWarps : 1);
+    for (int i = 0; i < SA; ++i) mbar_init(smem_u32(&s_fa[i]), 1), mbar_init(smem_u32(&s_ea[i]), MODE ? 1 + kConvWarps : 1);
     for (int i = 0; i < SW; ++i) mbar_init(smem_u32(&s_fw[i]), 1), mbar_init(smem_u32(&s_ew[i]), cs);
     for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&s_tfull[i]), 1), mbar_init(smem_u32(&s_tempty[i]), kEpiWarps);
     for (int i = 0; i < SL; ++i) mbar_init(smem_u32(&s_fl[i]), kConvWarps), mbar_init(smem_u32(&s_el[i]), 1);
@@ -229,21 +240,21 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
       } else {
         int stage = 0;
         uint32_t phase = 0;
-        if (SPLIT) tma_prefetch_desc(&map_wl);
+        if (MODE) tma_prefetch_desc(&map_wl);
         for (int i = 0; i < n_iter; ++i) {
           const int n0 = tile_n0(i);
-          for (int kb = 0; kb < k_blocks; ++kb) {
+          for (int kb = 0; kb < w_blocks; ++kb) {
 #pragma unroll
-            for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {   // SPLIT: the hi k-block, then the lo k-block
+            for (int part = 0; part < (MODE ? 2 : 1); ++part) {   // split modes: the hi k-block, then the lo k-block
               const CUtensorMap* mw = part ? &map_wl : &map_w;
               mbar_wait(smem_u32(&s_ew[stage]), phase ^ 1u);   // every CTA of the cluster has consumed the slot
               const uint32_t bar = smem_u32(&s_fw[stage]);
               const uint32_t dst = sm_w + (uint32_t)stage * w_bytes;
               mbar_arrive_expect_tx(bar, w_bytes);             // all `cs` slices of the W k-block
               if (cs == 1)
-                tma_load_2d(dst, mw, bar, kb * a.kb_elems, n0);
+                tma_load_2d(dst, mw, bar, kb * w_elems, n0);
               else
-                tma_load_2d_multicast(dst + (uint32_t)rank * w_slice_bytes, mw, bar, kb * a.kb_elems,
+                tma_load_2d_multicast(dst + (uint32_t)rank * w_slice_bytes, mw, bar, kb * w_elems,
                                       n0 + rank * (int)w_slice_rows, cta_mask);
               if (++stage == SW) stage = 0, phase ^= 1u;
             }
@@ -254,7 +265,7 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = a.f16 ? idesc_f16(a.BN) : idesc_tf32(a.BN);
+      const uint32_t idesc = (a.f16 || F16S) ? idesc_f16(a.BN) : idesc_tf32(a.BN);
       int sa = 0, sw = 0, sl = 0, ev = 0;
       uint32_t pa = 0, pw = 0, pl = 0;
       for (int it = 0; it < n_iter; ++it) {
@@ -273,7 +284,43 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
           if (++sa == SA) sa = 0, pa ^= 1u;
         }
         const uint32_t acc0 = a.res_chunks ? 1u : 0u;       // accumulate on top of the preloaded residual
-        if (SPLIT) {
+        if (F16S) {
+          for (int kb = 0; kb < w_blocks; ++kb) {
+            mbar_wait(smem_u32(&s_fl[sl]), pl);             // operand slot: both A k-blocks converted
+            // the two A slots were only read by the converters: this lane's arrival is the one the MMA commit is elsewhere
+            mbar_arrive(smem_u32(&s_ea[sa]));
+            if (++sa == SA) sa = 0, pa ^= 1u;
+            mbar_arrive(smem_u32(&s_ea[sa]));
+            if (++sa == SA) sa = 0, pa ^= 1u;
+            mbar_wait(smem_u32(&s_fw[sw]), pw);             // W_hi k-block
+            tc_fence_after();
+            const uint64_t hdesc = smem_desc_k128(sm_l + (uint32_t)sl * l_bytes);
+            const uint64_t ldesc = smem_desc_k128(sm_l + (uint32_t)sl * l_bytes + a_bytes);
+            uint64_t bdesc = smem_desc_k128(sm_w + (uint32_t)sw * w_bytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_f16(tmem_d, hdesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : acc0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_f16(tmem_d, ldesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+            if (cs == 1)
+              mma_commit(smem_u32(&s_ew[sw]));
+            else
+              mma_commit_multicast(smem_u32(&s_ew[sw]), cta_mask);
+            if (++sw == SW) sw = 0, pw ^= 1u;
+            mbar_wait(smem_u32(&s_fw[sw]), pw);             // W_lo k-block
+            tc_fence_after();
+            bdesc = smem_desc_k128(sm_w + (uint32_t)sw * w_bytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_f16(tmem_d, hdesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+            if (cs == 1)
+              mma_commit(smem_u32(&s_ew[sw]));
+            else
+              mma_commit_multicast(smem_u32(&s_ew[sw]), cta_mask);
+            if (++sw == SW) sw = 0, pw ^= 1u;
+            mma_commit(smem_u32(&s_el[sl]));
+            if (++sl == SL) sl = 0, pl ^= 1u;
+          }
+        } else if (SPLIT) {
           for (int kb = 0; kb < k_blocks; ++kb) {
             mbar_wait(smem_u32(&s_fa[sa]), pa);
             trace_event(a, 1, ev++);
@@ -343,6 +390,55 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
         mma_commit(smem_u32(&s_tfull[acc]));
       }
     }
+  } else if (F16S && (warp == 2 || warp >= 4 + kEpiWarps)) {
+    // ------------------------------------------------------------------ fp16 x3: two fp32 A k-blocks -> {a_hi, a_lo} fp16 tiles
+    const int ct = (warp == 2 ? 0 : warp - (4 + kEpiWarps) + 1) * 32 + lane;   // 0 .. 32 kConvWarps - 1
+    int sa = 0, sl = 0;
+    uint32_t pa = 0, pl = 0;
+    for (int it = 0; it < n_iter; ++it) {
+      for (int rc = 0; rc < a.res_chunks; ++rc) {          // residual boxes pass through the ring untouched
+        mbar_wait(smem_u32(&s_fa[sa]), pa);
+        if (lane == 0) mbar_arrive(smem_u32(&s_ea[sa]));
+        if (++sa == SA) sa = 0, pa ^= 1u;
+      }
+      for (int kb = 0; kb < w_blocks; ++kb) {
+        mbar_wait(smem_u32(&s_el[sl]), pl ^ 1u);
+        const uint32_t hi_t = sm_l + (uint32_t)sl * l_bytes, lo_t = hi_t + a_bytes;
+#pragma unroll
+        for (int hsel = 0; hsel < 2; ++hsel) {              // the two 32-float k-blocks of this 64-element operand slot
+          mbar_wait(smem_u32(&s_fa[sa]), pa);
+          const uint32_t src = sm_a + (uint32_t)sa * a_bytes;
+#pragma unroll 4
+          for (uint32_t s = (uint32_t)ct; s < 1024u; s += 32u * kConvWarps) {
+            // source chunk s: 16 bytes (4 floats) at stored position s & 7 of row `row`; the rows of one warp instruction
+            // are permuted so that their fp16 stores fall into both 64-byte halves of the shared-memory banks
+            const uint32_t rr = s >> 3, row = (rr & ~7u) | ((rr & 1u) << 2) | ((rr & 6u) >> 1), cp = s & 7u;
+            const uint32_t c = cp ^ (row & 7u);              // logical 16-byte chunk: floats 4 c .. 4 c + 3 of the k-block
+            float x[4];
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3])
+                         : "r"(src + row * 128u + cp * 16u));
+            __half2 h01 = __floats2half2_rn(x[0], x[1]), h23 = __floats2half2_rn(x[2], x[3]);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            __half2 l01 = __floats2half2_rn(x[0] - f01.x, x[1] - f01.y), l23 = __floats2half2_rn(x[2] - f23.x, x[3] - f23.y);
+            // fp16 element 32 hsel + 4 c + i -> 16-byte chunk 4 hsel + c / 2 (XOR-swizzled with the row), half c & 1 of it
+            const uint32_t off = row * 128u + (((4u * hsel + (c >> 1)) ^ (row & 7u)) << 4) + ((c & 1u) << 3);
+            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(hi_t + off), "r"(*reinterpret_cast<uint32_t*>(&h01)),
+                         "r"(*reinterpret_cast<uint32_t*>(&h23))
+                         : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(lo_t + off), "r"(*reinterpret_cast<uint32_t*>(&l01)),
+                         "r"(*reinterpret_cast<uint32_t*>(&l23))
+                         : "memory");
+          }
+          __syncwarp();                                      // every lane has read the A slot
+          if (lane == 0) mbar_arrive(smem_u32(&s_ea[sa]));
+          if (++sa == SA) sa = 0, pa ^= 1u;
+        }
+        fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_fl[sl]));
+        if (++sl == SL) sl = 0, pl ^= 1u;
+      }
+    }
   } else if (SPLIT && (warp == 2 || warp >= 4 + kEpiWarps)) {
     // ------------------------------------------------------------------ 3xTF32: A k-block -> (a_hi in place, a_lo slot)
     const int ct = (warp == 2 ? 0 : warp - (4 + kEpiWarps) + 1) * 32 + lane;   // 0 .. 32 kConvWarps - 1
@@ -396,15 +492,28 @@ __global__ void __launch_bounds__(SPLIT ? kGemmThreadsSplit : kGemmThreads, 1)
       const bool rows_live = row0 < r_end;                      // warp-uniform (and equal for the warps of the quarter)
 
       auto store_rows = [&](int c, const float (&f)[16]) {    // this thread's row chunk -> global
-        if (a.out && a.direct_store && !a.scatter) {          // fp32 rows: 64 contiguous bytes per thread, two 32-byte stores
-          if (row0 + lane < r_end) {
-            float* p = a.out + (size_t)(row0 + lane) * a.ldc + n0 + c * kChunk;
+        if (a.out && a.direct_store) {          // fp32 rows: 64 contiguous bytes per thread, two 32-byte stores
+          const int row = row0 + lane;
+          if (row < r_end) {
+            auto put = [&](float* p) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p + 8 * j), "f"(f[8 * j]),
-                           "f"(f[8 * j + 1]), "f"(f[8 * j + 2]), "f"(f[8 * j + 3]), "f"(f[8 * j + 4]), "f"(f[8 * j + 5]),
-                           "f"(f[8 * j + 6]), "f"(f[8 * j + 7])
-                           : "memory");
+              for (int j = 0; j < 2; ++j)
+                asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p + 8 * j), "f"(f[8 * j]),
+                             "f"(f[8 * j + 1]), "f"(f[8 * j + 2]), "f"(f[8 * j + 3]), "f"(f[8 * j + 4]), "f"(f[8 * j + 5]),
+                             "f"(f[8 * j + 6]), "f"(f[8 * j + 7])
+                             : "memory");
+            };
+            if (!a.scatter) {
+              put(a.out + (size_t)row * a.ldc + n0 + c * kChunk);
+            } else {
+              const int bi = row / a.sc_rows;
+              const int* dl = a.scatter + (size_t)(row - bi * a.sc_rows) * a.sc_r;
+              for (int j = 0; j < a.sc_r; ++j) {
+                const int d = __ldg(dl + j);
+                if (d < 0) break;
+                put(a.out + ((size_t)bi * a.sc_dst_rows + d) * a.ldc + n0 + c * kChunk);
+              }
+            }
           }
         } else if (a.out) {                                   // fp32 rows, coalesced through the buffer
 #pragma unroll
@@ -596,10 +705,11 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
                          const float* residual, int ldr, const float* gamma, const float* beta, float eps, float* out,
                          int ldc, void* out16, int ldc16, void* planes, float* planes32, int Nv, int M, int N, int K,
                          int flags, ub_stream_t stream, const int* scatter = nullptr, int sc_r = 0, int sc_rows = 0,
-                         int sc_dst_rows = 0) {
+                         int sc_dst_rows = 0, bool f16s = false) {
+  // f16s: fp16 x3 (kernel MODE 2): A fp32, W / W_lo fp16 (64-element k-blocks)
   const int relu = flags & 1, ln = (flags >> 1) & 1;
   const int kb_elems = f16 ? 64 : 32, esize = f16 ? 2 : 4;
-  const bool split = W_lo != nullptr;
+  const bool split = W_lo != nullptr && !f16s;
   UB_REQUIRE(A && W && (out || out16 || planes || planes32), "%s: null pointer", fn);
   UB_REQUIRE(!(split && f16), "%s: the 3xTF32 mode takes fp32 operands", fn);
   UB_REQUIRE(!scatter || (out && !out16 && !planes && !planes32 && !ln && sc_r > 0 && sc_rows > 0 && M % sc_rows == 0 &&
@@ -609,10 +719,11 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   UB_REQUIRE(!ln || (gamma && beta), "%s: layernorm needs gamma and beta", fn);
   UB_REQUIRE_ALIGNED16(A);
   UB_REQUIRE_ALIGNED16(W);
-  if (K % kb_elems != 0 || N % 32 != 0 || (N > 256 && N % 256 != 0) || (ln && N > 256) ||
+  if (K % (f16s ? 64 : kb_elems) != 0 || N % 32 != 0 || (N > 256 && N % 256 != 0) || (ln && N > 256) ||
       (planes && (ln || relu || residual || out16 || planes32)) || ((planes || planes32) && (Nv <= 0 || M % Nv != 0)) ||
       (planes32 && (ln || relu || residual || out16 || out || (reinterpret_cast<uintptr_t>(planes32) & 31u))) ||
-      (split && (reinterpret_cast<uintptr_t>(W_lo) & 15u)) ||
+      ((split || f16s) && (reinterpret_cast<uintptr_t>(W_lo) & 15u)) ||
+      (f16s && (out16 || planes || (out && (ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 31u))))) ||
       (out && (ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(out) & 15u))) ||
       (out16 && (ldc16 % 16 != 0 || (reinterpret_cast<uintptr_t>(out16) & 31u))) ||
       (planes && (reinterpret_cast<uintptr_t>(planes) & 31u)) ||
@@ -627,10 +738,10 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   }
   GemmArgs a;
   a.bias = bias, a.gamma = gamma, a.beta = beta, a.planes = reinterpret_cast<__half*>(planes);
-  a.planes32 = planes32, a.SL = split ? 2 : 0;
+  a.planes32 = planes32, a.SL = (split || f16s) ? 2 : 0;
   a.scatter = scatter, a.sc_r = sc_r, a.sc_rows = sc_rows, a.sc_dst_rows = sc_dst_rows;
   a.x3_inplace = g_x3_inplace, a.stagger_ns = split ? g_x3_stagger_ns : 0;
-  a.direct_store = split && g_x3_direct && out && ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0;
+  a.direct_store = f16s || (split && !scatter && g_x3_direct && out && ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0);
   a.Nv = Nv, a.H = N / 32;
   a.M = M, a.N = N, a.K = K, a.BN = N > 256 ? 256 : N;
   a.n_tiles_m = (M + kBM - 1) / kBM, a.n_tiles_n = N / a.BN;
@@ -640,16 +751,16 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   a.f16 = f16, a.kb_elems = kb_elems;
   a.trace = g_gemm_trace;
   const int k_blocks = K / kb_elems;
-  const size_t fixed = kEpiWarps * kStageBuf + (size_t)3 * N * sizeof(float);
+  const size_t fixed = (f16s ? 0 : kEpiWarps * kStageBuf) + (size_t)3 * N * sizeof(float);   // (MODE 2 stores straight from registers)
   const size_t budget = 232448 - 5120 - 1024;   // minus static shared memory and slack
   // W resident: every k-block of the (single) W tile stays in shared memory, with at least 3 A stages next to it
   // (with several column tiles: one CTA per column tile and row range, see n_split in the kernel)
   const int n_sms = sm_count();
   const bool split_ok = a.n_tiles_n > 1 && n_sms % a.n_tiles_n == 0 && M >= 4 * n_sms;
-  a.w_res = !split && (a.n_tiles_n == 1 || split_ok) && k_blocks <= kMaxStages && !(residual && ln && g_gemm_stream_w_res) &&
+  a.w_res = !split && !f16s && (a.n_tiles_n == 1 || split_ok) && k_blocks <= kMaxStages && !(residual && ln && g_gemm_stream_w_res) &&
             fixed + (size_t)k_blocks * a.BN * 128 + 3 * (size_t)kBM * 128 <= budget;
   // cluster size (streaming W only): the W k-block is split into `cs` slices of whole 8-row swizzle groups
-  a.cs = a.w_res ? 1 : (split ? g_x3_cluster : g_gemm_cluster);
+  a.cs = a.w_res ? 1 : ((split || f16s) ? g_x3_cluster : g_gemm_cluster);
   while (a.cs > 1 && ((a.BN / a.cs) % 8 != 0 || a.BN % a.cs != 0 || a.n_tiles_m < a.cs)) a.cs >>= 1;
   CUtensorMap ma, mw, mr, mwl;
   const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
@@ -659,12 +770,13 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
     if (int rc = make_tensor_map(&ma, dt, 2, A, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)K * esize};
-    const uint32_t box[2] = {(uint32_t)kb_elems, (uint32_t)(a.BN / a.cs)};
-    if (int rc = make_tensor_map(&mw, dt, 2, W, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[1] = {(uint64_t)K * (f16s ? 2 : esize)};
+    const uint32_t box[2] = {(uint32_t)(f16s ? 64 : kb_elems), (uint32_t)(a.BN / a.cs)};
+    const CUtensorMapDataType wdt = f16s ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : dt;
+    if (int rc = make_tensor_map(&mw, wdt, 2, W, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     mwl = mw;
-    if (split)
-      if (int rc = make_tensor_map(&mwl, dt, 2, W_lo, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    if (split || f16s)
+      if (int rc = make_tensor_map(&mwl, wdt, 2, W_lo, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   }
   a.res_chunks = 0;
   mr = ma;
@@ -679,10 +791,10 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   a.n_split = a.balanced ? a.n_tiles_n : 1;
   // ring depths: W resident or shallow, A as deep as the 227 KB of shared memory allow (up to 8)
   a.SW = a.w_res ? k_blocks : (a.BN > 128 ? 3 : 4);
-  if (split) {
+  if (split || f16s) {
     // W slots alternate hi / lo k-blocks: as many as fit next to three A stages and the A_lo ring (at least three:
-    // one k-block in use, half of the next in flight)
-    const size_t rest = budget - fixed - (size_t)(3 + a.SL) * kBM * 128;
+    // one k-block in use, half of the next in flight); MODE 2: the SL operand slots are twice as large
+    const size_t rest = budget - fixed - (size_t)(3 + a.SL * (f16s ? 2 : 1)) * kBM * 128;
     a.SW = (int)(rest / ((size_t)a.BN * 128));
     if (a.SW > 6) a.SW = 6;
     if (a.SW < 3) {
@@ -690,19 +802,20 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
       return ub::unsupported();
     }
   }
-  a.SA = (int)((budget - fixed - (size_t)a.SW * a.BN * 128) / (kBM * 128)) - a.SL;
+  a.SA = (int)((budget - fixed - (size_t)a.SW * a.BN * 128) / (kBM * 128)) - a.SL * (f16s ? 2 : 1);
   if (a.SA > kMaxStages) a.SA = kMaxStages;
-  if (split && a.SA > 4) a.SA = 4;   // a k-block lasts three MMA groups: a shallow ring already covers the DRAM latency
+  if ((split || f16s) && a.SA > 4) a.SA = 4;   // a k-block lasts three MMA groups: a shallow ring already covers the DRAM latency
   if (a.SA < 2) {
     set_error("%s: no room for the operand rings (N=%d)", fn, N);
     return ub::unsupported();
   }
-  const size_t smem = (size_t)(a.SA + a.SL) * kBM * 128 + (size_t)a.SW * a.BN * 128 + fixed;
-  auto kernel = split ? gemm_tf32_kernel<true> : gemm_tf32_kernel<false>;
+  const size_t smem = (size_t)(a.SA + a.SL * (f16s ? 2 : 1)) * kBM * 128 + (size_t)a.SW * a.BN * 128 + fixed;
+  const int mode = f16s ? 2 : (split ? 1 : 0);
+  auto kernel = f16s ? gemm_tf32_kernel<2> : (split ? gemm_tf32_kernel<1> : gemm_tf32_kernel<0>);
   if (int rc = ensure_smem(kernel, smem, fn)) return rc;
   const int n_groups = ((a.n_tiles_m + a.cs - 1) / a.cs) * a.n_tiles_n;
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(split ? kGemmThreadsSplit : kGemmThreads);
+  cfg.blockDim = dim3(mode ? kGemmThreadsSplit : kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[2];
@@ -713,18 +826,18 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 2 : 1;
   // persistent grid: as many clusters as can be resident at once (one CTA per SM; clusters do not span GPCs)
   // (a property of the kernel variant, cluster size and shared-memory size; every B200 answers the same)
-  static std::atomic<int> max_clusters[2][5] = {};
-  static std::atomic<size_t> max_clusters_smem[2][5] = {};
-  if (max_clusters[split][a.cs].load() == 0 || max_clusters_smem[split][a.cs].load() != smem) {
+  static std::atomic<int> max_clusters[3][5] = {};
+  static std::atomic<size_t> max_clusters_smem[3][5] = {};
+  if (max_clusters[mode][a.cs].load() == 0 || max_clusters_smem[mode][a.cs].load() != smem) {
     cfg.gridDim = dim3(n_sms / a.cs * a.cs);
     int n = 0;
     if (a.cs == 1 || cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
       cudaGetLastError();
       n = a.cs == 1 ? n_sms : (n_sms / a.cs) * 3 / 4;
     }
-    max_clusters[split][a.cs].store(n), max_clusters_smem[split][a.cs].store(smem);
+    max_clusters[mode][a.cs].store(n), max_clusters_smem[mode][a.cs].store(smem);
   }
-  int clusters = max_clusters[split][a.cs].load();
+  int clusters = max_clusters[mode][a.cs].load();
   if (clusters > n_groups && !a.balanced) clusters = n_groups;
   cfg.gridDim = dim3(clusters * a.cs);
   if (cudaLaunchKernelEx(&cfg, kernel, a, ma, mw, mr, mwl) != cudaSuccess) {
@@ -781,7 +894,31 @@ extern "C" int ub_linear_tf32x3_scatter(const float* A, const float* W_hi, const
                        0, nullptr, nullptr, 0, M, N, K, 0, stream, scatter, scatter_r, rows_per_item, dst_rows_per_item);
 }
 
+// The same on kind::f16 MMAs (fp16 x3): every product as a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with x_hi = fp16(x), x_lo =
+// fp16(x - x_hi) -- two 11-bit significands, the precision class of ub_linear_tf32x3, at twice the tensor-core rate.
+// VALID ONLY where every |A| element (and |W| element) is below the fp16 range (65504): the caller guarantees that bound
+// (unibev_b200/plugin/fused.py derives it from the weights); values below 2^-14 x 2^11 lose relative (not absolute) precision.
+// A (M, K) fp32; W16_hi / W16_lo (N, K) fp16 from ub_split_f16; K % 64 == 0; epilogues as ub_linear_tf32x3 (+ optional row
+// scatter as ub_linear_tf32x3_scatter when scatter != NULL).
+extern "C" int ub_linear_f16x3(const float* A, const void* W16_hi, const void* W16_lo, const float* bias, const float* residual,
+                               int ldr, const float* gamma, const float* beta, float eps, float* out, int ldc, float* planes32,
+                               int Nv, const int* scatter, int scatter_r, int rows_per_item, int dst_rows_per_item, int M, int N,
+                               int K, int flags, ub_stream_t stream) {
+  UB_REQUIRE(W16_lo, "ub_linear_f16x3: null pointer");
+  return launch_linear("ub_linear_f16x3", 0, A, W16_hi, reinterpret_cast<const float*>(W16_lo), bias, residual, ldr, gamma, beta,
+                       eps, planes32 ? nullptr : out, ldc, nullptr, 0, nullptr, planes32, Nv, M, N, K, flags, stream, scatter,
+                       scatter_r, rows_per_item, dst_rows_per_item, true);
+}
+
 namespace ub {
+__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ w, __half* __restrict__ hi,
+                                                        __half* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = w[i];
+    const __half h = __float2half_rn(x);
+    hi[i] = h, lo[i] = __float2half_rn(x - __half2float(h));
+  }
+}
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi,
                                                          float* __restrict__ lo, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -793,6 +930,15 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   }
 }
 }  // namespace ub
+
+// w (n) fp32 -> hi = fp16(w), lo = fp16(w - hi)
+extern "C" int ub_split_f16(const float* w, void* hi16, void* lo16, int64_t n, ub_stream_t stream) {
+  UB_REQUIRE(w && hi16 && lo16 && n > 0, "ub_split_f16: bad argument");
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  split_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<__half*>(hi16), reinterpret_cast<__half*>(lo16), n);
+  return check_launch("ub_split_f16");
+}
 
 // w (n) -> hi = w with the 13 low mantissa bits cleared (exactly what a TF32 MMA reads of w), lo = tf32(w - hi)
 extern "C" int ub_split_tf32(const float* w, float* hi, float* lo, int64_t n, ub_stream_t stream) {

@@ -406,6 +406,63 @@ def linear_tf32x3(x, w_split, bias=None, residual=None, relu=False, ln=None, out
     return res
 
 
+def split_f16(weight):
+    """weight fp32 -> (hi16, lo16) fp16: hi = fp16(weight), lo = fp16(weight - hi) (operands of ``linear_f16x3``)."""
+    weight = _need(weight, 'weight')
+    hi = torch.empty(weight.shape, device=weight.device, dtype=torch.float16)
+    lo = torch.empty(weight.shape, device=weight.device, dtype=torch.float16)
+    _call('ub_split_f16', weight, _ptr(weight), _ptr(hi), _ptr(lo), weight.numel())
+    return hi, lo
+
+
+def linear_f16x3(x, w16_split, bias=None, residual=None, relu=False, ln=None, out=None, planes_nv=None, scatter=None):
+    """``linear_tf32x3`` on fp16 tensor-core passes (``ub_linear_f16x3``): same precision class, twice the rate -- ONLY for
+    operands the caller has bounded below the fp16 range.  ``w16_split = split_f16(W)``.  ``scatter=(q_dst, rows_per_item)``
+    with a 3-D ``out`` (B, rows, N): rows leave in hit-list order as in ``linear_tf32x3_scatter``."""
+    x = _need(x, 'x')
+    w_hi, w_lo = _need(w16_split[0], 'w16_hi', torch.float16), _need(w16_split[1], 'w16_lo', torch.float16)
+    M, K = x.shape
+    N = w_hi.shape[0]
+    if w_hi.shape != (N, K) or w_lo.shape != (N, K):
+        raise ValueError(f'linear_f16x3: x{tuple(x.shape)} vs weight{tuple(w_hi.shape)}')
+    bias = _need(bias, 'bias') if bias is not None else None
+    flags = (1 if relu else 0) | (2 if ln is not None else 0)
+    gamma = beta = None
+    eps = 0.0
+    if ln is not None:
+        gamma, beta, eps = _need(ln[0], 'gamma'), _need(ln[1], 'beta'), float(ln[2])
+    ldr = 0
+    if residual is not None:
+        if residual.shape != (M, N):
+            raise ValueError('linear_f16x3: residual shape mismatch')
+        if not (residual.is_cuda and residual.dtype == torch.float32 and residual.stride(1) == 1):
+            residual = _need(residual, 'residual')
+        ldr = residual.stride(0)
+    planes, sc, sc_r, sc_rows, sc_dst = None, None, 0, 0, 0
+    if planes_nv is not None:
+        if M % planes_nv or N % 16:
+            raise ValueError('linear_f16x3: planes need M % Nv == 0 and N % 16 == 0')
+        planes = out if out is not None else torch.empty(M // planes_nv, N // 16, planes_nv, 16, device=x.device,
+                                                         dtype=torch.float32)
+        res, out_ptr, ldc = planes, None, 0
+    elif scatter is not None:
+        sc, sc_rows = _need(scatter[0], 'q_dst', torch.int32), int(scatter[1])
+        if (out is None or out.dim() != 3 or out.shape[2] != N or not out.is_contiguous() or out.dtype != torch.float32
+                or M % sc_rows or out.shape[0] != M // sc_rows or sc.shape[0] != sc_rows):
+            raise ValueError('linear_f16x3: scatter needs a contiguous fp32 `out` (B, rows, N) and q_dst (rows_per_item, R)')
+        sc_r, sc_dst = sc.shape[1], out.shape[1]
+        res, out_ptr, ldc = out, _ptr(out), N
+    else:
+        if out is None:
+            out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        elif out.shape != (M, N) or out.stride(1) != 1 or out.dtype != torch.float32 or not out.is_cuda:
+            raise ValueError('linear_f16x3: `out` must be an fp32 CUDA (M, N) matrix with unit column stride')
+        res, out_ptr, ldc = out, _ptr(out), out.stride(0)
+    _call('ub_linear_f16x3', x, _ptr(x), _ptr(w_hi), _ptr(w_lo), _ptr(bias), _ptr(residual), ldr, _ptr(gamma), _ptr(beta), eps,
+          out_ptr, ldc, _ptr(planes), planes_nv or 0, _ptr(sc), sc_r, sc_rows, sc_dst, M, N, K, flags)
+    return res
+
+
 def linear_f16(x16, w16, bias=None, residual=None, relu=False, ln=None, out=None, out16=None, fp32_out=True,
                f16_out=False, planes_nv=None):
     """fp16-operand variant of ``linear_tf32``: x16 (M, K) fp16 @ w16 (N, K)^T fp16, fp32 accumulation and epilogue.
