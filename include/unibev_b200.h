@@ -214,18 +214,20 @@ int ub_linear_tf32x3_scatter(const float* A, const float* W_hi, const float* W_l
                              const int* scatter, int scatter_r, int rows_per_item, int dst_rows_per_item,
                              int M, int N, int K, ub_stream_t stream);
 /* "fp16 x3": the three-product scheme of ub_linear_tf32x3 on kind::f16 MMAs (x_hi = fp16(x), x_lo = fp16(x - x_hi): two 11-bit
- * significands, the same precision class, twice the tensor-core rate, half the operand bytes).  VALID ONLY where every element
- * of A and W is below the fp16 range (65504) in magnitude -- the caller guarantees the bound (unibev_b200/plugin/fused.py derives
- * it from the LayerNorm / projection weights; operands it cannot bound go through ub_linear_tf32x3); elements below ~0.1 keep
- * their ABSOLUTE precision (2^-25) but not the relative one.  A (M, K) fp32 is split on chip; W16_hi / W16_lo (N, K) fp16 from
- * ub_split_f16.  K % 64 == 0; out 32-byte aligned with ldc % 8 == 0.  Epilogues as ub_linear_tf32x3; scatter != NULL: rows leave
- * as in ub_linear_tf32x3_scatter. */
-int ub_linear_f16x3(const float* A, const void* W16_hi, const void* W16_lo, const float* bias, const float* residual, int ldr,
-                    const float* gamma, const float* beta, float eps, float* out, int ldc, float* planes32, int Nv,
-                    const int* scatter, int scatter_r, int rows_per_item, int dst_rows_per_item, int M, int N, int K, int flags,
-                    ub_stream_t stream);
-/* w (n) fp32 -> hi16 (n) = fp16(w), lo16 (n) = fp16(w - hi16). */
-int ub_split_f16(const float* w, void* hi16, void* lo16, int64_t n, ub_stream_t stream);
+ * significands, the same precision class, twice the tensor-core rate, half the operand bytes).  VALID ONLY where the caller can
+ * bound |A|: every element of A times a_scale must stay below the fp16 range (65504) -- unibev_b200/plugin/fused.py derives the
+ * bound from the LayerNorm / projection weights and picks a_scale (a power of two) from it; operands it cannot bound go through
+ * ub_linear_tf32x3.  W16_hi / W16_lo (N, K) fp16 and col_scale (N) from ub_split_f16 (row-wise power-of-two scaling, undone
+ * exactly in the epilogue).  A (M, K) fp32 is scaled and split on chip.  K % 64 == 0; out / residual 32-byte aligned with
+ * row strides % 8 == 0.  Epilogues as ub_linear_tf32x3; scatter != NULL: rows leave as in ub_linear_tf32x3_scatter. */
+int ub_linear_f16x3(const float* A, float a_scale, const void* W16_hi, const void* W16_lo, const float* col_scale,
+                    const float* bias, const float* residual, int ldr, const float* gamma, const float* beta, float eps,
+                    float* out, int ldc, float* planes32, int Nv, const int* scatter, int scatter_r, int rows_per_item,
+                    int dst_rows_per_item, int M, int N, int K, int flags, ub_stream_t stream);
+/* w (rows, cols) fp32 -> hi16 / lo16 (rows, cols) fp16 of w[n, :] * s_n (s_n: the power of two that brings the row's largest
+ * magnitude into [4096, 8192)), col_scale (rows) = 1 / (s_n a_scale); col_scale == NULL: no scaling. */
+int ub_split_f16(const float* w, void* hi16, void* lo16, float* col_scale, int rows, int cols, float a_scale,
+                 ub_stream_t stream);
 /* Generic fp32 (FFMA) projection for shapes the tensor-core entry points reject (UB_EUNSUPPORTED): any M, N, K.
  * out (M, N; row stride ldc) = [relu](A (M, K) @ W (N, K)^T + bias + residual (row stride ldr)); bias / residual may be NULL. */
 int ub_linear_simt(const float* A, const float* W, const float* bias, const float* residual, int ldr, float* out, int ldc,

@@ -34,7 +34,7 @@ def main():
                 torch.cuda.synchronize()
                 continue
             t3 = timeit(lambda: ops.linear_tf32x3(a, ws, b, residual=r, ln=lnp, out=out))
-            wh = ops.split_f16(w)
+            wh = ops.split_f16(w, 64.0)
             t6 = timeit(lambda: ops.linear_f16x3(a, wh, b, residual=r, ln=lnp, out=out))
             t1 = timeit(lambda: ops.linear_tf32(a, w, b, residual=r, ln=lnp, out=out))
             th = timeit(lambda: ops.linear_f16(a16, w16, b, residual=r, ln=lnp, out=out))

@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 240 python -m pytest tests/test_gpu_gemm.py -q -x -k "f16x3" > gpurun_out/j_gemm_f16x3.log 2>&1; echo "f16x3 rc=$?" | tee gpurun_out/j_rc.txt
-OPTS='1,1,2,0;1,1,1,0' timeout 240 python tools/bench_gemm_x3.py > gpurun_out/j_gemm_bench.log 2>&1; echo "bench rc=$?" | tee -a gpurun_out/j_rc.txt
-tail -n 25 gpurun_out/j_gemm_f16x3.log; cat gpurun_out/j_gemm_bench.log
+timeout 300 python -m pytest tests/test_gpu_gemm.py -q > gpurun_out/j_gemm.log 2>&1; echo "gemm rc=$?" | tee gpurun_out/j_rc.txt
+OPTS='1,1,2,0' timeout 240 python tools/bench_gemm_x3.py > gpurun_out/j_gemm_bench.log 2>&1; echo "bench rc=$?" | tee -a gpurun_out/j_rc.txt
+UB_X3_PAIR=1 OPTS='1,1,2,0' timeout 240 python tools/bench_gemm_x3.py > gpurun_out/j_gemm_bench_pair.log 2>&1
+tail -n 25 gpurun_out/j_gemm.log; cat gpurun_out/j_gemm_bench.log gpurun_out/j_gemm_bench_pair.log

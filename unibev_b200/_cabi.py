@@ -37,8 +37,8 @@ PROTOTYPES = {
     'ub_linear_tf32_dual': ([_p] * 4 + [_i, _p, _p, _f, _p, _i, _p] + [_i] * 5 + [_p], _i),
     'ub_linear_tf32x3': ([_p] * 5 + [_i, _p, _p, _f, _p, _i, _p] + [_i] * 5 + [_p], _i),
     'ub_linear_tf32x3_scatter': ([_p] * 5 + [_i, _p] + [_i] * 6 + [_p], _i),
-    'ub_linear_f16x3': ([_p] * 5 + [_i, _p, _p, _f, _p, _i, _p, _i, _p] + [_i] * 7 + [_p], _i),
-    'ub_split_f16': ([_p, _p, _p, _i64, _p], _i),
+    'ub_linear_f16x3': ([_p, _f] + [_p] * 5 + [_i, _p, _p, _f, _p, _i, _p, _i, _p] + [_i] * 7 + [_p], _i),
+    'ub_split_f16': ([_p, _p, _p, _p, _i, _i, _f, _p], _i),
     'ub_linear_simt': ([_p] * 4 + [_i, _p] + [_i] * 5 + [_p], _i),
     'ub_split_tf32': ([_p, _p, _p, _i64, _p], _i),
     'ub_linear_f16': ([_p] * 4 + [_i, _p, _p, _f, _p, _i, _p, _i, _p] + [_i] * 5 + [_p], _i),

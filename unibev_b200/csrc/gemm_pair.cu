@@ -258,19 +258,31 @@ __global__ void __launch_bounds__(kPairThreads, 1)
       for (int kb = 0; kb < k_blocks; ++kb) {
         // (the LO slot of this index is free: its last readers completed before the A slot was refilled)
         mbar_wait(smem_u32(&s_fa[sa]), pa);
-        const uint32_t src = sm_a + (uint32_t)sa * a_bytes, dst = sm_l + (uint32_t)sa * a_bytes;
-#pragma unroll 4
-        for (uint32_t j = (uint32_t)ct * 16u; j < a_bytes; j += 32u * kConvWarps * 16u) {
-          uint32_t x[4], h[4], l[4];
-          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(src + j));
+        // all of a thread's loads first (plain C++ accesses: the compiler keeps them in flight together), then the splits
+        constexpr int kPer = (1024 + 32 * kConvWarps - 1) / (32 * kConvWarps);
+        unsigned char* a_slot = smem + (size_t)sa * a_bytes;
+        unsigned char* l_slot = smem + (size_t)(SA + sa) * a_bytes;
+        uint4 xs[kPer];
+#pragma unroll
+        for (int m = 0; m < kPer; ++m) {
+          const uint32_t j = ((uint32_t)ct + 32u * kConvWarps * m) * 16u;
+          xs[m] = j < a_bytes ? *reinterpret_cast<const uint4*>(a_slot + j) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int m = 0; m < kPer; ++m) {
+          const uint32_t j = ((uint32_t)ct + 32u * kConvWarps * m) * 16u;
+          const uint32_t x[4] = {xs[m].x, xs[m].y, xs[m].z, xs[m].w};
+          uint32_t h[4], l[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             h[e] = x[e] & 0xffffe000u;
             const float lo = __uint_as_float(x[e]) - __uint_as_float(h[e]);    // exact
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l[e]) : "f"(lo));
           }
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(src + j), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + j), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+          if (j < a_bytes) {
+            *reinterpret_cast<uint4*>(a_slot + j) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(l_slot + j) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
         }
         fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
         __syncwarp();

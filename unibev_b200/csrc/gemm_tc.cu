@@ -70,6 +70,12 @@ struct GemmArgs {
   // b * sc_dst_rows + scatter[q * sc_r + j], j = 0 .. until the first negative entry, of `out`; null: row r goes to row r
   const int* scatter;
   int sc_r, sc_rows, sc_dst_rows;
+  // MODE 2 (fp16 x3): A is multiplied by a_scale (a power of two chosen from the caller's bound) before the split, W row n
+  // arrives multiplied by a power of two s_n; cscale[n] = 1 / (a_scale s_n) undoes both in the epilogue (exact).  The residual
+  // is added in the epilogue (it cannot ride in the scaled accumulator).
+  float a_scale;
+  const float* cscale;  // (N) or null (= 1 / a_scale)
+  int epi_res;
   int x3_inplace;       // 3xTF32: the converters also write a_hi back (result independent of the tensor core's operand rounding)
   int stagger_ns;       // every other cluster starts its first tile this much later: the CTAs' epilogue bursts (output stores)
                         // then interleave with the others' operand loads instead of all hitting DRAM at once
@@ -162,6 +168,7 @@ __global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
   for (int i = tid; i < a.N; i += (int)blockDim.x) {
     s_par[i] = a.bias ? a.bias[i] : 0.f;
     if (a.ln) s_par[a.N + i] = a.gamma[i], s_par[2 * a.N + i] = a.beta[i];
+    if (F16S) s_par[3 * a.N + i] = a.cscale ? a.cscale[i] : 1.f / a.a_scale;
   }
   if (tid == 0) {
     // SPLIT: a slot is free again once the MMAs that read it have completed AND every converter warp has passed it
@@ -403,31 +410,40 @@ __global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
       }
       for (int kb = 0; kb < w_blocks; ++kb) {
         mbar_wait(smem_u32(&s_el[sl]), pl ^ 1u);
-        const uint32_t hi_t = sm_l + (uint32_t)sl * l_bytes, lo_t = hi_t + a_bytes;
 #pragma unroll
         for (int hsel = 0; hsel < 2; ++hsel) {              // the two 32-float k-blocks of this 64-element operand slot
           mbar_wait(smem_u32(&s_fa[sa]), pa);
-          const uint32_t src = sm_a + (uint32_t)sa * a_bytes;
-#pragma unroll 4
-          for (uint32_t s = (uint32_t)ct; s < 1024u; s += 32u * kConvWarps) {
-            // source chunk s: 16 bytes (4 floats) at stored position s & 7 of row `row`; the rows of one warp instruction
-            // are permuted so that their fp16 stores fall into both 64-byte halves of the shared-memory banks
-            const uint32_t rr = s >> 3, row = (rr & ~7u) | ((rr & 1u) << 2) | ((rr & 6u) >> 1), cp = s & 7u;
+          // 1024 16-byte chunks over the 96 converter threads: all of a thread's loads first (plain C++ accesses, so the
+          // compiler keeps them in flight together), then the conversions and stores
+          constexpr int kPer = (1024 + 32 * kConvWarps - 1) / (32 * kConvWarps);
+          const unsigned char* a_slot = smem + (size_t)sa * a_bytes;
+          unsigned char* hi_p = smem + (size_t)SA * a_bytes + (size_t)sl * l_bytes;
+          float4 xs[kPer];
+#pragma unroll
+          for (int m = 0; m < kPer; ++m) {
+            const uint32_t sidx = (uint32_t)ct + 32u * kConvWarps * m;
+            // source chunk sidx: stored position sidx & 7 of row `row`; the rows of one warp instruction are permuted so
+            // that their fp16 stores fall into both 64-byte halves of the shared-memory banks
+            const uint32_t rr = sidx >> 3, row = (rr & ~7u) | ((rr & 1u) << 2) | ((rr & 6u) >> 1), cp = sidx & 7u;
+            xs[m] = sidx < 1024u ? *reinterpret_cast<const float4*>(a_slot + row * 128u + cp * 16u) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int m = 0; m < kPer; ++m) {
+            const uint32_t sidx = (uint32_t)ct + 32u * kConvWarps * m;
+            const uint32_t rr = sidx >> 3, row = (rr & ~7u) | ((rr & 1u) << 2) | ((rr & 6u) >> 1), cp = sidx & 7u;
             const uint32_t c = cp ^ (row & 7u);              // logical 16-byte chunk: floats 4 c .. 4 c + 3 of the k-block
-            float x[4];
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3])
-                         : "r"(src + row * 128u + cp * 16u));
-            __half2 h01 = __floats2half2_rn(x[0], x[1]), h23 = __floats2half2_rn(x[2], x[3]);
+            const float4 x = make_float4(xs[m].x * a.a_scale, xs[m].y * a.a_scale, xs[m].z * a.a_scale, xs[m].w * a.a_scale);
+            const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-            __half2 l01 = __floats2half2_rn(x[0] - f01.x, x[1] - f01.y), l23 = __floats2half2_rn(x[2] - f23.x, x[3] - f23.y);
+            const __half2 l01 = __floats2half2_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2half2_rn(x.z - f23.x, x.w - f23.y);
             // fp16 element 32 hsel + 4 c + i -> 16-byte chunk 4 hsel + c / 2 (XOR-swizzled with the row), half c & 1 of it
             const uint32_t off = row * 128u + (((4u * hsel + (c >> 1)) ^ (row & 7u)) << 4) + ((c & 1u) << 3);
-            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(hi_t + off), "r"(*reinterpret_cast<uint32_t*>(&h01)),
-                         "r"(*reinterpret_cast<uint32_t*>(&h23))
-                         : "memory");
-            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(lo_t + off), "r"(*reinterpret_cast<uint32_t*>(&l01)),
-                         "r"(*reinterpret_cast<uint32_t*>(&l23))
-                         : "memory");
+            if (sidx < 1024u) {
+              *reinterpret_cast<uint2*>(hi_p + off) =
+                  make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+              *reinterpret_cast<uint2*>(hi_p + a_bytes + off) =
+                  make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+            }
           }
           __syncwarp();                                      // every lane has read the A slot
           if (lane == 0) mbar_arrive(smem_u32(&s_ea[sa]));
@@ -453,20 +469,32 @@ __global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(smem_u32(&s_fa[sa]), pa);
         mbar_wait(smem_u32(&s_el[sl]), pl ^ 1u);
-        const uint32_t src = sm_a + (uint32_t)sa * a_bytes, dst = sm_l + (uint32_t)sl * a_bytes;
-#pragma unroll 4
-        for (uint32_t j = (uint32_t)ct * 16u; j < a_bytes; j += 32u * kConvWarps * 16u) {
-          uint32_t x[4], h[4], l[4];
-          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(src + j));
+        // 1024 16-byte chunks over the 96 converter threads: all of a thread's loads first (plain C++ accesses, so the
+        // compiler keeps them in flight together), then the splits and stores
+        constexpr int kPer = (1024 + 32 * kConvWarps - 1) / (32 * kConvWarps);
+        unsigned char* a_slot = smem + (size_t)sa * a_bytes;
+        unsigned char* l_slot = smem + (size_t)SA * a_bytes + (size_t)sl * a_bytes;
+        uint4 xs[kPer];
+#pragma unroll
+        for (int m = 0; m < kPer; ++m) {
+          const uint32_t j = ((uint32_t)ct + 32u * kConvWarps * m) * 16u;
+          xs[m] = j < a_bytes ? *reinterpret_cast<const uint4*>(a_slot + j) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int m = 0; m < kPer; ++m) {
+          const uint32_t j = ((uint32_t)ct + 32u * kConvWarps * m) * 16u;
+          const uint32_t x[4] = {xs[m].x, xs[m].y, xs[m].z, xs[m].w};
+          uint32_t h[4], l[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             h[e] = x[e] & 0xffffe000u;
             const float lo = __uint_as_float(x[e]) - __uint_as_float(h[e]);    // exact
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l[e]) : "f"(lo));
           }
-          if (a.x3_inplace)
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(src + j), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + j), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+          if (j < a_bytes) {
+            if (a.x3_inplace) *reinterpret_cast<uint4*>(a_slot + j) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(l_slot + j) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
         }
         fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
         __syncwarp();
@@ -567,14 +595,36 @@ __global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 b4 = params4(bias, j);
-          f[4 * j] = __uint_as_float(v[4 * j]) + b4.x, f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z, f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+          if (F16S) {   // undo the operand scaling (exact powers of two)
+            const float4 s4 = params4(s_par + 3 * a.N + n0 + c * kChunk, j);
+            f[4 * j] = fmaf(__uint_as_float(v[4 * j]), s4.x, b4.x), f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), s4.y, b4.y);
+            f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), s4.z, b4.z), f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), s4.w, b4.w);
+          } else {
+            f[4 * j] = __uint_as_float(v[4 * j]) + b4.x, f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z, f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+          }
+        }
+        if (F16S && a.epi_res && row0 + lane < r_end) {   // residual: 64 contiguous bytes of this thread's row
+          const float* rp = a.residual + (size_t)(row0 + lane) * a.ldr + n0 + c * kChunk;
+          float r8[8];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            ld_stream8(rp + 8 * j, r8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[8 * j + e] += r8[e];
+          }
         }
         if (a.ln) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             sum += f[j];
             sumsq = fmaf(f[j], f[j], sumsq);
+          }
+          if (F16S) {   // park the unscaled pre-LayerNorm values for pass B
+            uint32_t w16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w16[j] = __float_as_uint(f[j]);
+            tmem_st16(tbase + (uint32_t)(c * kChunk), w16);
           }
         } else if (a.planes) {
           // fp16 head-major planes: chunk c of the row is half (c & 1) of head (n0 / 32 + c / 2) of token (row % Nv)
@@ -630,7 +680,8 @@ __global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
             const float* bet = s_par + 2 * a.N + n0 + c * kChunk;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 g4 = params4(gam, j), b4 = params4(bet, j), c4 = params4(bias, j);
+              const float4 g4 = params4(gam, j), b4 = params4(bet, j);
+              const float4 c4 = F16S ? make_float4(0.f, 0.f, 0.f, 0.f) : params4(bias, j);   // (MODE 2: already added in pass A)
               f[4 * j] = (__uint_as_float(v[4 * j]) + c4.x - mean) * rstd * g4.x + b4.x;
               f[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) + c4.y - mean) * rstd * g4.y + b4.y;
               f[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) + c4.z - mean) * rstd * g4.z + b4.z;
@@ -705,7 +756,7 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
                          const float* residual, int ldr, const float* gamma, const float* beta, float eps, float* out,
                          int ldc, void* out16, int ldc16, void* planes, float* planes32, int Nv, int M, int N, int K,
                          int flags, ub_stream_t stream, const int* scatter = nullptr, int sc_r = 0, int sc_rows = 0,
-                         int sc_dst_rows = 0, bool f16s = false) {
+                         int sc_dst_rows = 0, bool f16s = false, float a_scale = 1.f, const float* col_scale = nullptr) {
   // f16s: fp16 x3 (kernel MODE 2): A fp32, W / W_lo fp16 (64-element k-blocks)
   const int relu = flags & 1, ln = (flags >> 1) & 1;
   const int kb_elems = f16 ? 64 : 32, esize = f16 ? 2 : 4;
@@ -723,7 +774,8 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
       (planes && (ln || relu || residual || out16 || planes32)) || ((planes || planes32) && (Nv <= 0 || M % Nv != 0)) ||
       (planes32 && (ln || relu || residual || out16 || out || (reinterpret_cast<uintptr_t>(planes32) & 31u))) ||
       ((split || f16s) && (reinterpret_cast<uintptr_t>(W_lo) & 15u)) ||
-      (f16s && (out16 || planes || (out && (ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 31u))))) ||
+      (f16s && (out16 || planes || (out && (ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 31u))) ||
+                (residual && (ldr % 8 != 0 || (reinterpret_cast<uintptr_t>(residual) & 31u))) || !(a_scale > 0.f))) ||
       (out && (ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(out) & 15u))) ||
       (out16 && (ldc16 % 16 != 0 || (reinterpret_cast<uintptr_t>(out16) & 31u))) ||
       (planes && (reinterpret_cast<uintptr_t>(planes) & 31u)) ||
@@ -740,6 +792,7 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   a.bias = bias, a.gamma = gamma, a.beta = beta, a.planes = reinterpret_cast<__half*>(planes);
   a.planes32 = planes32, a.SL = (split || f16s) ? 2 : 0;
   a.scatter = scatter, a.sc_r = sc_r, a.sc_rows = sc_rows, a.sc_dst_rows = sc_dst_rows;
+  a.a_scale = a_scale, a.cscale = col_scale, a.epi_res = 0;
   a.x3_inplace = g_x3_inplace, a.stagger_ns = split ? g_x3_stagger_ns : 0;
   a.direct_store = f16s || (split && !scatter && g_x3_direct && out && ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0);
   a.Nv = Nv, a.H = N / 32;
@@ -751,7 +804,7 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   a.f16 = f16, a.kb_elems = kb_elems;
   a.trace = g_gemm_trace;
   const int k_blocks = K / kb_elems;
-  const size_t fixed = (f16s ? 0 : kEpiWarps * kStageBuf) + (size_t)3 * N * sizeof(float);   // (MODE 2 stores straight from registers)
+  const size_t fixed = (f16s ? 0 : kEpiWarps * kStageBuf) + (size_t)(f16s ? 4 : 3) * N * sizeof(float);   // (MODE 2 stores straight from registers)
   const size_t budget = 232448 - 5120 - 1024;   // minus static shared memory and slack
   // W resident: every k-block of the (single) W tile stays in shared memory, with at least 3 A stages next to it
   // (with several column tiles: one CTA per column tile and row range, see n_split in the kernel)
@@ -780,7 +833,9 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   }
   a.res_chunks = 0;
   mr = ma;
-  if (residual) {   // fp32 boxes of 32 columns x 128 rows, laid out in shared memory like a TF32 A k-block
+  if (residual && f16s) {
+    a.epi_res = 1;   // added in the epilogue
+  } else if (residual) {   // fp32 boxes of 32 columns x 128 rows, laid out in shared memory like a TF32 A k-block
     const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, str[1] = {(uint64_t)ldr * 4};
     const uint32_t box[2] = {32, kBM};
     if (int rc = make_tensor_map(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, residual, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
@@ -900,24 +955,40 @@ extern "C" int ub_linear_tf32x3_scatter(const float* A, const float* W_hi, const
 // (unibev_b200/plugin/fused.py derives it from the weights); values below 2^-14 x 2^11 lose relative (not absolute) precision.
 // A (M, K) fp32; W16_hi / W16_lo (N, K) fp16 from ub_split_f16; K % 64 == 0; epilogues as ub_linear_tf32x3 (+ optional row
 // scatter as ub_linear_tf32x3_scatter when scatter != NULL).
-extern "C" int ub_linear_f16x3(const float* A, const void* W16_hi, const void* W16_lo, const float* bias, const float* residual,
-                               int ldr, const float* gamma, const float* beta, float eps, float* out, int ldc, float* planes32,
-                               int Nv, const int* scatter, int scatter_r, int rows_per_item, int dst_rows_per_item, int M, int N,
-                               int K, int flags, ub_stream_t stream) {
+extern "C" int ub_linear_f16x3(const float* A, float a_scale, const void* W16_hi, const void* W16_lo, const float* col_scale,
+                               const float* bias, const float* residual, int ldr, const float* gamma, const float* beta,
+                               float eps, float* out, int ldc, float* planes32, int Nv, const int* scatter, int scatter_r,
+                               int rows_per_item, int dst_rows_per_item, int M, int N, int K, int flags, ub_stream_t stream) {
   UB_REQUIRE(W16_lo, "ub_linear_f16x3: null pointer");
   return launch_linear("ub_linear_f16x3", 0, A, W16_hi, reinterpret_cast<const float*>(W16_lo), bias, residual, ldr, gamma, beta,
                        eps, planes32 ? nullptr : out, ldc, nullptr, 0, nullptr, planes32, Nv, M, N, K, flags, stream, scatter,
-                       scatter_r, rows_per_item, dst_rows_per_item, true);
+                       scatter_r, rows_per_item, dst_rows_per_item, true, a_scale, col_scale);
 }
 
 namespace ub {
-__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ w, __half* __restrict__ hi,
-                                                        __half* __restrict__ lo, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float x = w[i];
+// one CTA per weight row: s = the power of two that brings the row's largest magnitude into [4096, 8192), hi = fp16(w s),
+// lo = fp16(w s - hi), col_scale = 1 / (s a_scale)
+__global__ void __launch_bounds__(128) split_f16_kernel(const float* __restrict__ w, __half* __restrict__ hi,
+                                                        __half* __restrict__ lo, float* __restrict__ col_scale, int cols,
+                                                        float a_scale) {
+  __shared__ float s_max[4];
+  const float* row = w + (size_t)blockIdx.x * cols;
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < cols; i += 128) mx = fmaxf(mx, fabsf(row[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(s_max[0], s_max[1]), fmaxf(s_max[2], s_max[3]));
+  int e = 0;
+  if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &e);          // mx = m 2^e, m in [0.5, 1)
+  const float s = col_scale ? ldexpf(1.f, 13 - e) : 1.f;  // mx s in [4096, 8192)
+  for (int i = threadIdx.x; i < cols; i += 128) {
+    const float x = row[i] * s;
     const __half h = __float2half_rn(x);
-    hi[i] = h, lo[i] = __float2half_rn(x - __half2float(h));
+    hi[(size_t)blockIdx.x * cols + i] = h, lo[(size_t)blockIdx.x * cols + i] = __float2half_rn(x - __half2float(h));
   }
+  if (col_scale && threadIdx.x == 0) col_scale[blockIdx.x] = 1.f / (s * a_scale);
 }
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi,
                                                          float* __restrict__ lo, int64_t n) {
@@ -931,12 +1002,14 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
 }
 }  // namespace ub
 
-// w (n) fp32 -> hi = fp16(w), lo = fp16(w - hi)
-extern "C" int ub_split_f16(const float* w, void* hi16, void* lo16, int64_t n, ub_stream_t stream) {
-  UB_REQUIRE(w && hi16 && lo16 && n > 0, "ub_split_f16: bad argument");
-  int blocks = (int)((n + 255) / 256);
-  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  split_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<__half*>(hi16), reinterpret_cast<__half*>(lo16), n);
+// w (rows, cols) fp32 -> hi16 / lo16 (rows, cols) fp16 of w[n, :] s_n with s_n the power of two that brings the row's largest
+// magnitude into [4096, 8192) (hi = fp16, lo = fp16 of the remainder: both normal numbers for every element within 2^-16 of
+// the row maximum), col_scale (rows) = 1 / (s_n a_scale): the epilogue factor of ub_linear_f16x3.  col_scale == NULL: s_n = 1.
+extern "C" int ub_split_f16(const float* w, void* hi16, void* lo16, float* col_scale, int rows, int cols, float a_scale,
+                            ub_stream_t stream) {
+  UB_REQUIRE(w && hi16 && lo16 && rows > 0 && cols > 0 && a_scale > 0.f, "ub_split_f16: bad argument");
+  split_f16_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<__half*>(hi16), reinterpret_cast<__half*>(lo16),
+                                                           col_scale, cols, a_scale);
   return check_launch("ub_split_f16");
 }
 

@@ -406,13 +406,18 @@ def linear_tf32x3(x, w_split, bias=None, residual=None, relu=False, ln=None, out
     return res
 
 
-def split_f16(weight):
-    """weight fp32 -> (hi16, lo16) fp16: hi = fp16(weight), lo = fp16(weight - hi) (operands of ``linear_f16x3``)."""
+def split_f16(weight, a_scale=1.0):
+    """weight (N, K) fp32 -> (hi16, lo16, col_scale, a_scale): fp16 hi / lo parts of the row-scaled weight and the epilogue
+    factors 1 / (s_n a_scale) -- the weight operand of ``linear_f16x3`` for activations that are multiplied by ``a_scale``
+    (a power of two chosen so that |activation| * a_scale stays below the fp16 range) before their own split."""
     weight = _need(weight, 'weight')
+    if weight.dim() != 2:
+        raise ValueError('split_f16: weight must be (N, K)')
     hi = torch.empty(weight.shape, device=weight.device, dtype=torch.float16)
     lo = torch.empty(weight.shape, device=weight.device, dtype=torch.float16)
-    _call('ub_split_f16', weight, _ptr(weight), _ptr(hi), _ptr(lo), weight.numel())
-    return hi, lo
+    cs = torch.empty(weight.shape[0], device=weight.device, dtype=torch.float32)
+    _call('ub_split_f16', weight, _ptr(weight), _ptr(hi), _ptr(lo), _ptr(cs), weight.shape[0], weight.shape[1], float(a_scale))
+    return hi, lo, cs, float(a_scale)
 
 
 def linear_f16x3(x, w16_split, bias=None, residual=None, relu=False, ln=None, out=None, planes_nv=None, scatter=None):
@@ -421,6 +426,7 @@ def linear_f16x3(x, w16_split, bias=None, residual=None, relu=False, ln=None, ou
     with a 3-D ``out`` (B, rows, N): rows leave in hit-list order as in ``linear_tf32x3_scatter``."""
     x = _need(x, 'x')
     w_hi, w_lo = _need(w16_split[0], 'w16_hi', torch.float16), _need(w16_split[1], 'w16_lo', torch.float16)
+    col_scale, a_scale = _need(w16_split[2], 'col_scale'), float(w16_split[3])
     M, K = x.shape
     N = w_hi.shape[0]
     if w_hi.shape != (N, K) or w_lo.shape != (N, K):
@@ -458,7 +464,8 @@ def linear_f16x3(x, w16_split, bias=None, residual=None, relu=False, ln=None, ou
         elif out.shape != (M, N) or out.stride(1) != 1 or out.dtype != torch.float32 or not out.is_cuda:
             raise ValueError('linear_f16x3: `out` must be an fp32 CUDA (M, N) matrix with unit column stride')
         res, out_ptr, ldc = out, _ptr(out), out.stride(0)
-    _call('ub_linear_f16x3', x, _ptr(x), _ptr(w_hi), _ptr(w_lo), _ptr(bias), _ptr(residual), ldr, _ptr(gamma), _ptr(beta), eps,
+    _call('ub_linear_f16x3', x, _ptr(x), a_scale, _ptr(w_hi), _ptr(w_lo), _ptr(col_scale), _ptr(bias), _ptr(residual), ldr,
+          _ptr(gamma), _ptr(beta), eps,
           out_ptr, ldc, _ptr(planes), planes_nv or 0, _ptr(sc), sc_r, sc_rows, sc_dst, M, N, K, flags)
     return res
 
