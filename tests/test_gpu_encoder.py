@@ -209,3 +209,65 @@ def test_batch_items_are_independent_at_full_size():
                            inp['bev_queries'].cuda(), 200, 200, bev_pos=inp['bev_pos'][1:2].cuda(),
                            img_metas=inp['img_metas'][1:2])
     torch.testing.assert_close(both[1:2], one, rtol=1e-5, atol=1e-5)
+
+
+def test_fp16x3_bounds_hold_and_path_is_taken():
+    """The fp16 x3 projections of the default class run only on operands with a proven bound: (1) the bounds derived from
+    the weights really dominate the activations they describe (hooks on the module path), (2) the fused pipeline takes the
+    fp16 x3 path for them (launch counter of a UB_F16X3=0 run differs only in kernel flavour, results agree to fp32 noise)."""
+    from unibev_b200 import synth
+    from unibev_b200.plugin.fused import FusedEncoder
+    wl = 'unibev_nus_LC_cnw_256'
+    model, cfg = synth.build_model(wl, num_layers=2)
+    model = model.cuda().eval()
+    inp = synth.make_inputs(wl, batch=1, bev_hw=(40, 40))
+    fe = FusedEncoder(model, 'fp32')
+    fe.refresh()
+    seen = {}
+
+    def hook(name):
+        def fn(mod, args, out):
+            seen[name] = max(seen.get(name, 0.0), float(args[0].abs().max()))
+        return fn
+    for enc in ('img_bev_encoder', 'pts_bev_encoder'):
+        layers = getattr(model, enc).layers
+        x_bound = None
+        for i, (layer, lw) in enumerate(zip(layers, fe._weights(enc))):
+            bd = lw.bounds(x_bound)
+            assert all(bd[k] is not None and bd[k] < 3e4 for k in ('x1', 'x2', 'hid', 'out'))
+            assert (bd['x'] is None) == (i == 0)
+            layer.attentions[1].deformable_attention.sampling_offsets.register_forward_hook(hook((enc, i, 'x1')))
+            layer.ffns[0].layers[0][0].register_forward_hook(hook((enc, i, 'x2')))
+            layer.ffns[0].layers[1].register_forward_hook(hook((enc, i, 'hid')))
+            layer.attentions[0].output_proj.register_forward_hook(hook((enc, i, 'sa_s')))
+            x_bound = bd['out']
+    model.train()                           # module path (torch linears: the hooks fire); dropout is irrelevant to magnitudes
+    model.drop_modality = None
+    with torch.no_grad():
+        model.encode(_cuda(inp['img_feats']), _cuda(inp['pts_feats']), inp['bev_queries'].cuda(), 40, 40,
+                     bev_pos=inp['bev_pos'].cuda(), img_metas=inp['img_metas'])
+    model.eval()
+    checked = 0
+    for (enc, i, key), observed in seen.items():
+        x_bound = None
+        for j, lw in enumerate(fe._weights(enc)):
+            bd = lw.bounds(x_bound)
+            if j == i and bd[key] is not None:
+                assert observed <= bd[key] * (1 + 1e-5), (enc, i, key, observed, bd[key])
+                checked += 1
+            x_bound = bd['out']
+    assert checked >= 12
+    import os
+    outs = {}
+    for flag in ('1', '0'):
+        os.environ['UB_F16X3'] = flag
+        try:
+            model._fused = None
+            with torch.no_grad():
+                outs[flag] = model.encode(_cuda(inp['img_feats']), _cuda(inp['pts_feats']), inp['bev_queries'].cuda(), 40, 40,
+                                          bev_pos=inp['bev_pos'].cuda(), img_metas=inp['img_metas']).clone()
+            assert model._fused.f16x3 == (flag == '1')
+        finally:
+            os.environ.pop('UB_F16X3', None)
+    assert len(model._fused._split16) == 0 and float((outs['1'] - outs['0']).abs().max()) > 0     # different kernels ...
+    torch.testing.assert_close(outs['1'], outs['0'], rtol=1e-4, atol=5e-5)                           # ... same numbers

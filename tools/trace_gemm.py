@@ -25,6 +25,7 @@ def main():
 
     x16, w16 = x.half(), w.half()
     ws = ops.split_tf32(w)
+    wh = ops.split_f16(w, 64.0)
 
     def run():
         if mode == 'ln':
@@ -33,6 +34,10 @@ def main():
             return ops.linear_f16(x16, w16, b)
         if mode == 'x3':
             return ops.linear_tf32x3(x, ws, b)
+        if mode == 'h3':
+            return ops.linear_f16x3(x, wh, b)
+        if mode == 'h3ln':
+            return ops.linear_f16x3(x, wh, b, residual=r, ln=(g, g, 1e-5))
         if mode == 'x3ln':
             return ops.linear_tf32x3(x, ws, b, residual=r, ln=(g, g, 1e-5))
         if mode == 'f16ln':
@@ -61,7 +66,7 @@ def main():
         print(f'CTA {cta}: start {rel(row[0]):.2f} us')
         print('  producer issued k-blocks at :', ' '.join('%.2f' % v for v in prod))
         print('  mma saw k-blocks full at    :', ' '.join('%.2f' % v for v in mma),
-              '   (x3 modes: four stamps per k-block = A landed, a_lo ready, W_hi landed, W_lo landed)')
+              '   (x3: four stamps per k-block = A landed, a_lo ready, W_hi landed, W_lo landed; h3: four per 64-k block = start, operand slot ready, W_hi landed, W_lo landed)')
         print('  epilogue (acc ready, done)  :', ' '.join('%.2f' % v for v in epi))
     ends = [max(int(v) for v in t[c] if int(v)) for c in range(148) if int(t[c, 0])]
     print('last event over CTAs: %.2f us after first start' % ((max(ends) - t0) / 1e3))

@@ -60,6 +60,7 @@ _PRIVATE = {
     'ub_set_gemm_cluster': ([_i], _i),
     'ub_set_gemm_x3': ([_i] * 4, _i),
     'ub_set_gemm_x3_pair': ([_i], _i),
+    'ub_set_gemm_x3_prefetch': ([_i], _i),
     'ub_set_gemm_trace': ([_p], _i),
     'ub_set_pdl': ([_i], _i),
     'ub_set_img_two_windows': ([_i], _i),
@@ -94,6 +95,8 @@ def lib():
                         ('UB_IMG_VECREF', 'ub_set_img_vec_ref'), ('UB_PDL', 'ub_set_pdl')):
             if env in os.environ:
                 getattr(handle, fn)(int(os.environ[env]))
+        if 'UB_X3_PREFETCH' in os.environ:
+            handle.ub_set_gemm_x3_prefetch(int(os.environ['UB_X3_PREFETCH']))
         if 'UB_X3_PAIR' in os.environ:
             handle.ub_set_gemm_x3_pair(int(os.environ['UB_X3_PAIR']))
         if 'UB_X3' in os.environ:       # "inplace,direct,cluster,stagger_ns"

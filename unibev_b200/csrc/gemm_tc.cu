@@ -37,6 +37,8 @@ namespace ub {
 
 constexpr int kGemmThreads = 640;                 // 4 control warps + 16 epilogue warps
 constexpr int kGemmThreadsSplit = kGemmThreads + 32 * kConvExtraWarps;
+constexpr int kConvWarpsF16 = 6;                  // fp16 x3 mode: its converters do more work per chunk (scale, two roundings, swizzle)
+constexpr int kGemmThreadsF16S = kGemmThreads + 32 * (kConvWarpsF16 - 1);   // 800 threads x 80 registers still fit the SM
 constexpr int kMaxStages = 8;
 constexpr int kStageBuf = kChunk * 32 * 4;         // one warp's 32 rows x 16 columns staging buffer (2 KB)
 
@@ -73,6 +75,7 @@ struct GemmArgs {
   // MODE 2 (fp16 x3): A is multiplied by a_scale (a power of two chosen from the caller's bound) before the split, W row n
   // arrives multiplied by a power of two s_n; cscale[n] = 1 / (a_scale s_n) undoes both in the epilogue (exact).  The residual
   // is added in the epilogue (it cannot ride in the scaled accumulator).
+  int no_staging;       // no per-warp staging buffers in shared memory (results leave straight from registers)
   float a_scale;
   const float* cscale;  // (N) or null (= 1 / a_scale)
   int epi_res;
@@ -114,7 +117,7 @@ __device__ __forceinline__ void trace_event(const GemmArgs& a, int role, int i) 
 // converters turn every two fp32 A k-blocks into one 64-element fp16 operand slot {a_hi tile, a_lo tile}, writing the
 // 128-byte swizzle themselves (the element size changes, so the layout does); the MMA lane never reads the A ring.
 template <int MODE>
-__global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
+__global__ void __launch_bounds__(MODE == 2 ? kGemmThreadsF16S : (MODE ? kGemmThreadsSplit : kGemmThreads), 1)
     gemm_tf32_kernel(const GemmArgs a, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_wl) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
   __shared__ float2 s_stat[4][kBM];   // LayerNorm partial (sum, sum of squares) per epilogue warp of a lane quarter
 
   constexpr bool SPLIT = MODE == 1, F16S = MODE == 2;
+  constexpr int CW = F16S ? kConvWarpsF16 : kConvWarps;   // converter warps: warp 2 and the warps after the epilogue warps
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int SA = a.SA, SW = a.SW;
   const uint32_t a_bytes = kBM * 128, w_bytes = (uint32_t)a.BN * 128;
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
   const uint32_t sm_a = smem_u32(smem), sm_l = sm_a + (uint32_t)SA * a_bytes, sm_w = sm_l + (uint32_t)SL * l_bytes;
   const uint32_t sm_stage_buf = sm_w + (uint32_t)SW * w_bytes;                  // [16 warps] x 2 KB (none in MODE 2)
   float* s_par = reinterpret_cast<float*>(smem + (size_t)SA * a_bytes + (size_t)SL * l_bytes + (size_t)SW * w_bytes +
-                                          (F16S ? 0 : kEpiWarps * kStageBuf));
+                                          (a.no_staging ? 0 : kEpiWarps * kStageBuf));
   const int k_blocks = a.K / a.kb_elems;                       // A k-blocks (MODE 2: 32 fp32 each, two per W k-block)
   const int w_blocks = F16S ? a.K / 64 : k_blocks, w_elems = F16S ? 64 : a.kb_elems;
   // Work = groups of `cs` consecutive row tiles of one column tile; cluster c takes groups c, c + n_clusters, ...
@@ -173,10 +177,10 @@ __global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
   if (tid == 0) {
     // SPLIT: a slot is free again once the MMAs that read it have completed AND every converter warp has passed it
     // (also the residual slots, which the converters do not touch): no waiter can then fall a whole phase behind
-    for (int i = 0; i < SA; ++i) mbar_init(smem_u32(&s_fa[i]), 1), mbar_init(smem_u32(&s_ea[i]), MODE ? 1 + kConvWarps : 1);
+    for (int i = 0; i < SA; ++i) mbar_init(smem_u32(&s_fa[i]), 1), mbar_init(smem_u32(&s_ea[i]), MODE ? 1 + CW : 1);
     for (int i = 0; i < SW; ++i) mbar_init(smem_u32(&s_fw[i]), 1), mbar_init(smem_u32(&s_ew[i]), cs);
     for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&s_tfull[i]), 1), mbar_init(smem_u32(&s_tempty[i]), kEpiWarps);
-    for (int i = 0; i < SL; ++i) mbar_init(smem_u32(&s_fl[i]), kConvWarps), mbar_init(smem_u32(&s_el[i]), 1);
+    for (int i = 0; i < SL; ++i) mbar_init(smem_u32(&s_fl[i]), CW), mbar_init(smem_u32(&s_el[i]), 1);
     mbar_init_fence();
   }
   if (warp == 2) {
@@ -211,6 +215,27 @@ __global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         } while (t - t0 < (unsigned long long)a.stagger_ns);
       }
+      // Split modes hold few A k-blocks in flight (the W_hi / W_lo and a_lo rings take the shared memory), too few to cover the
+      // DRAM latency: a tile's 128 rows (contiguous in A, and in the residual when its rows are dense) are pulled into L2 as
+      // one sequential stream a whole tile ahead, so the k-block loads only see L2 latency
+      // (issued in k_blocks slices next to the k-block loads: a tile-sized prefetch in one go would sit in front of them in
+      // the copy engine's queue)
+      auto prefetch_slice = [&](int i, int kb) {
+        if (!MODE || !a.A || i >= n_iter) return;
+        const int m0 = tile_m0(i);
+        if (m0 >= a.M) return;
+        const size_t rows = (size_t)min(kBM, a.M - m0);
+        const char* p = reinterpret_cast<const char*>(a.A) + (size_t)m0 * a.K * 4 + (size_t)kb * rows * 128;
+        bulk_prefetch_l2(p, (uint32_t)(rows * 128));
+        if (a.residual && a.ldr == a.N && a.N == a.BN && kb * 4 < a.N / 8) {   // residual tile: N * 4 / 128 slices of rows x 128 B
+          const char* r = reinterpret_cast<const char*>(a.residual) + (size_t)m0 * a.N * 4 + (size_t)kb * rows * 128;
+          if ((size_t)(kb + 1) * 128 <= (size_t)a.N * 4) bulk_prefetch_l2(r, (uint32_t)(rows * 128));
+        }
+      };
+      auto prefetch_tile = [&](int i) {
+        for (int kb = 0; kb < k_blocks; ++kb) prefetch_slice(i, kb);
+      };
+      prefetch_tile(0);
       int stage = 0, ev = 0;
       uint32_t phase = 0;
       for (int i = 0; i < n_iter; ++i) {
@@ -227,6 +252,7 @@ __global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
           const uint32_t bar = smem_u32(&s_fa[stage]);
           mbar_arrive_expect_tx(bar, a_bytes);
           tma_load_2d(sm_a + (uint32_t)stage * a_bytes, &map_a, bar, kb * a.kb_elems, m0);
+          prefetch_slice(i + 1, kb);
           trace_event(a, 0, ev++);
           if (++stage == SA) stage = 0, phase ^= 1u;
         }
@@ -293,13 +319,16 @@ __global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
         const uint32_t acc0 = a.res_chunks ? 1u : 0u;       // accumulate on top of the preloaded residual
         if (F16S) {
           for (int kb = 0; kb < w_blocks; ++kb) {
+            trace_event(a, 1, ev++);
             mbar_wait(smem_u32(&s_fl[sl]), pl);             // operand slot: both A k-blocks converted
+            trace_event(a, 1, ev++);
             // the two A slots were only read by the converters: this lane's arrival is the one the MMA commit is elsewhere
             mbar_arrive(smem_u32(&s_ea[sa]));
             if (++sa == SA) sa = 0, pa ^= 1u;
             mbar_arrive(smem_u32(&s_ea[sa]));
             if (++sa == SA) sa = 0, pa ^= 1u;
             mbar_wait(smem_u32(&s_fw[sw]), pw);             // W_hi k-block
+            trace_event(a, 1, ev++);
             tc_fence_after();
             const uint64_t hdesc = smem_desc_k128(sm_l + (uint32_t)sl * l_bytes);
             const uint64_t ldesc = smem_desc_k128(sm_l + (uint32_t)sl * l_bytes + a_bytes);
@@ -315,6 +344,7 @@ __global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
               mma_commit_multicast(smem_u32(&s_ew[sw]), cta_mask);
             if (++sw == SW) sw = 0, pw ^= 1u;
             mbar_wait(smem_u32(&s_fw[sw]), pw);             // W_lo k-block
+            trace_event(a, 1, ev++);
             tc_fence_after();
             bdesc = smem_desc_k128(sm_w + (uint32_t)sw * w_bytes);
 #pragma unroll
@@ -399,7 +429,24 @@ __global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
     }
   } else if (F16S && (warp == 2 || warp >= 4 + kEpiWarps)) {
     // ------------------------------------------------------------------ fp16 x3: two fp32 A k-blocks -> {a_hi, a_lo} fp16 tiles
-    const int ct = (warp == 2 ? 0 : warp - (4 + kEpiWarps) + 1) * 32 + lane;   // 0 .. 32 kConvWarps - 1
+    const int ct = (warp == 2 ? 0 : warp - (4 + kEpiWarps) + 1) * 32 + lane;   // 0 .. 32 CW - 1
+    // A k-block = 1024 16-byte chunks (4 floats) over the 32 CW converter threads.  Chunk sidx sits at stored position sidx & 7
+    // of row `row` (128-byte swizzle: logical chunk c = position ^ (row & 7)); its four fp16 values go to 16-byte chunk
+    // 4 hsel + c / 2 (XOR-swizzled with the row) of the operand tile's row, half c & 1 of it.  The rows of one warp
+    // instruction are permuted so that their fp16 stores fall into both 64-byte halves of the shared-memory banks.  Source
+    // and destination offsets do not depend on the k-block: computed once, packed into one register per chunk
+    // (destination for hsel = 1: XOR 64).
+    constexpr int kPer = (1024 + 32 * CW - 1) / (32 * CW);
+    uint32_t offs[kPer];
+#pragma unroll
+    for (int m = 0; m < kPer; ++m) {
+      const uint32_t sidx = min((uint32_t)ct + 32u * CW * m, 1023u);
+      const uint32_t rr = sidx >> 3, row = (rr & ~7u) | ((rr & 1u) << 2) | ((rr & 6u) >> 1), cp = sidx & 7u;
+      const uint32_t c = cp ^ (row & 7u);
+      offs[m] = (row * 128u + cp * 16u) | ((row * 128u + (((c >> 1) ^ (row & 7u)) << 4) + ((c & 1u) << 3)) << 16);
+    }
+    const int n_mine = ((uint32_t)ct + 32u * CW * (kPer - 1) < 1024u) ? kPer : kPer - 1;
+    const float a_scale = a.a_scale;
     int sa = 0, sl = 0;
     uint32_t pa = 0, pl = 0;
     for (int it = 0; it < n_iter; ++it) {
@@ -410,35 +457,23 @@ __global__ void __launch_bounds__(MODE ? kGemmThreadsSplit : kGemmThreads, 1)
       }
       for (int kb = 0; kb < w_blocks; ++kb) {
         mbar_wait(smem_u32(&s_el[sl]), pl ^ 1u);
+        unsigned char* hi_p = smem + (size_t)SA * a_bytes + (size_t)sl * l_bytes;
 #pragma unroll
         for (int hsel = 0; hsel < 2; ++hsel) {              // the two 32-float k-blocks of this 64-element operand slot
           mbar_wait(smem_u32(&s_fa[sa]), pa);
-          // 1024 16-byte chunks over the 96 converter threads: all of a thread's loads first (plain C++ accesses, so the
-          // compiler keeps them in flight together), then the conversions and stores
-          constexpr int kPer = (1024 + 32 * kConvWarps - 1) / (32 * kConvWarps);
           const unsigned char* a_slot = smem + (size_t)sa * a_bytes;
-          unsigned char* hi_p = smem + (size_t)SA * a_bytes + (size_t)sl * l_bytes;
+          // all of a thread's loads first (plain C++ accesses: they stay in flight together), then conversions and stores
           float4 xs[kPer];
 #pragma unroll
-          for (int m = 0; m < kPer; ++m) {
-            const uint32_t sidx = (uint32_t)ct + 32u * kConvWarps * m;
-            // source chunk sidx: stored position sidx & 7 of row `row`; the rows of one warp instruction are permuted so
-            // that their fp16 stores fall into both 64-byte halves of the shared-memory banks
-            const uint32_t rr = sidx >> 3, row = (rr & ~7u) | ((rr & 1u) << 2) | ((rr & 6u) >> 1), cp = sidx & 7u;
-            xs[m] = sidx < 1024u ? *reinterpret_cast<const float4*>(a_slot + row * 128u + cp * 16u) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int m = 0; m < kPer; ++m) xs[m] = *reinterpret_cast<const float4*>(a_slot + (offs[m] & 0xffffu));
 #pragma unroll
           for (int m = 0; m < kPer; ++m) {
-            const uint32_t sidx = (uint32_t)ct + 32u * kConvWarps * m;
-            const uint32_t rr = sidx >> 3, row = (rr & ~7u) | ((rr & 1u) << 2) | ((rr & 6u) >> 1), cp = sidx & 7u;
-            const uint32_t c = cp ^ (row & 7u);              // logical 16-byte chunk: floats 4 c .. 4 c + 3 of the k-block
-            const float4 x = make_float4(xs[m].x * a.a_scale, xs[m].y * a.a_scale, xs[m].z * a.a_scale, xs[m].w * a.a_scale);
+            const float4 x = make_float4(xs[m].x * a_scale, xs[m].y * a_scale, xs[m].z * a_scale, xs[m].w * a_scale);
             const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
             const __half2 l01 = __floats2half2_rn(x.x - f01.x, x.y - f01.y), l23 = __floats2half2_rn(x.z - f23.x, x.w - f23.y);
-            // fp16 element 32 hsel + 4 c + i -> 16-byte chunk 4 hsel + c / 2 (XOR-swizzled with the row), half c & 1 of it
-            const uint32_t off = row * 128u + (((4u * hsel + (c >> 1)) ^ (row & 7u)) << 4) + ((c & 1u) << 3);
-            if (sidx < 1024u) {
+            const uint32_t off = (offs[m] >> 16) ^ (hsel ? 64u : 0u);
+            if (m < n_mine) {
               *reinterpret_cast<uint2*>(hi_p + off) =
                   make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
               *reinterpret_cast<uint2*>(hi_p + a_bytes + off) =
@@ -719,6 +754,11 @@ int launch_x3_pair(const char* fn, const float* A, const float* W_hi, const floa
 using namespace ub;
 
 static int g_gemm_cluster = 4;
+static int g_x3_prefetch = 0;   // split modes: L2 prefetch of the next row tile (A and residual); measured neutral: off
+extern "C" int ub_set_gemm_x3_prefetch(int on) {
+  g_x3_prefetch = on ? 1 : 0;
+  return UB_OK;
+}
 static int g_x3_pair = 0;   // 3xTF32 on CTA pairs (tcgen05.mma.cta_group::2, gemm_pair.cu) where the shape is covered
 extern "C" int ub_set_gemm_x3_pair(int on) {
   g_x3_pair = on ? 1 : 0;
@@ -794,17 +834,21 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   a.scatter = scatter, a.sc_r = sc_r, a.sc_rows = sc_rows, a.sc_dst_rows = sc_dst_rows;
   a.a_scale = a_scale, a.cscale = col_scale, a.epi_res = 0;
   a.x3_inplace = g_x3_inplace, a.stagger_ns = split ? g_x3_stagger_ns : 0;
-  a.direct_store = f16s || (split && !scatter && g_x3_direct && out && ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0);
+  a.direct_store = f16s || (split && g_x3_direct && out && ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0);
   a.Nv = Nv, a.H = N / 32;
   a.M = M, a.N = N, a.K = K, a.BN = N > 256 ? 256 : N;
   a.n_tiles_m = (M + kBM - 1) / kBM, a.n_tiles_n = N / a.BN;
   a.eps = eps, a.relu = relu, a.ln = ln;
-  a.A = nullptr, a.residual = residual, a.out = out, a.ldr = ldr, a.ldc = ldc;
+  a.A = (split || f16s) && g_x3_prefetch ? reinterpret_cast<const float*>(A) : nullptr;
+  a.residual = residual, a.out = out, a.ldr = ldr, a.ldc = ldc;
   a.out16 = reinterpret_cast<__half*>(out16), a.ldc16 = ldc16;
   a.f16 = f16, a.kb_elems = kb_elems;
   a.trace = g_gemm_trace;
   const int k_blocks = K / kb_elems;
-  const size_t fixed = (f16s ? 0 : kEpiWarps * kStageBuf) + (size_t)(f16s ? 4 : 3) * N * sizeof(float);   // (MODE 2 stores straight from registers)
+  const bool direct_ok = out && ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0;
+  const bool stage_free = f16s || (split && ((g_x3_direct && direct_ok) || planes32));   // results leave straight from registers
+  a.no_staging = stage_free;
+  const size_t fixed = (stage_free ? 0 : kEpiWarps * kStageBuf) + (size_t)(f16s ? 4 : 3) * N * sizeof(float);   // (MODE 2 stores straight from registers)
   const size_t budget = 232448 - 5120 - 1024;   // minus static shared memory and slack
   // W resident: every k-block of the (single) W tile stays in shared memory, with at least 3 A stages next to it
   // (with several column tiles: one CTA per column tile and row range, see n_split in the kernel)
@@ -870,7 +914,7 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   if (int rc = ensure_smem(kernel, smem, fn)) return rc;
   const int n_groups = ((a.n_tiles_m + a.cs - 1) / a.cs) * a.n_tiles_n;
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(mode ? kGemmThreadsSplit : kGemmThreads);
+  cfg.blockDim = dim3(mode == 2 ? kGemmThreadsF16S : (mode ? kGemmThreadsSplit : kGemmThreads));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[2];

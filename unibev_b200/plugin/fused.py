@@ -16,9 +16,13 @@ No sampling_locations / attention_weights / rebatch tensors exist, nothing syncs
 sampling step is a libunibev_b200 kernel (no torch / cuBLAS matmul anywhere in this file).  Two precision classes:
 
 * ``precision='fp32'`` (default): the arithmetic class of the reference (fp32 everywhere, no ``fp16`` key in any
-  UniBEV config).  Projections run on the tensor cores as 3xTF32 (``ub_linear_tf32x3``: three tcgen05 kind::tf32 MMAs
-  per product, ~2^-21 relative error, fp32 accumulation, residual / LayerNorm epilogues); sampling in fp32 (fp32 value
-  maps, fp32 bilinear x attention weights, exact softmax).  Meets rtol 1e-3 / atol 1e-4 against the oracle.
+  UniBEV config).  Projections run on the tensor cores with fp32-grade products: every a*w is evaluated as
+  a_hi*w_hi + a_lo*w_hi + a_hi*w_lo over hi / lo splits with 2 x 11 significand bits, fp32 accumulation, residual /
+  LayerNorm epilogues -- as three kind::tf32 passes (``ub_linear_tf32x3``) in general, and as three kind::f16 passes
+  (``ub_linear_f16x3``, twice the tensor-core rate) where the activation operand has a PROVEN magnitude bound derived from
+  the weights (LayerNorm outputs and what is computed from them: ``_LayerWeights.bounds``), so that the power-of-two
+  scaled operand stays inside the fp16 range.  Sampling in fp32 (fp32 value maps, fp32 bilinear x attention weights,
+  expf / true division softmax).  Meets rtol 1e-3 / atol 1e-4 against the oracle.
 * ``precision='fp16'`` (opt-in fast class): fp16 tensor-core operands (activations, weights and input tokens are
   rounded to an 11-bit significand and must stay below 65504), fp16-staged value maps and sampling weights, fp32
   accumulation / residual stream / LayerNorm.  max |err| ~3e-3 on O(1) outputs (tests use atol 5e-3).
@@ -99,6 +103,27 @@ class _LayerWeights:
         self.w2, self.b2 = f.layers[1].weight.detach(), f.layers[1].bias.detach()
         self.ln = [(n.weight.detach(), n.bias.detach(), n.eps) for n in layer.norms]
         self._half = None
+        self._bounds = None
+
+    def bounds(self, x_in):
+        """Proven magnitude bounds of the activations this layer feeds to its projections, given the bound ``x_in`` of the
+        layer input (None = unknown): what lets a projection run as fp16 x3 (``ub_linear_f16x3``) instead of 3xTF32.
+        LayerNorm output: |y_i| <= sqrt(C - 1) |gamma_i| + |beta_i|; a projection: |x W^T + b| <= |x|_max max_n sum_k |W_nk| +
+        |b|_max; sampled rows are convex combinations of value rows (softmax x bilinear weights sum to at most 1); ReLU
+        shrinks.  One host read per weight version (the values are cached with the derived weights)."""
+        if self._bounds is None or self._bounds[0] != x_in:
+            C = self.ln[0][0].numel()
+
+            def ln_bound(k):
+                g, b, _ = self.ln[k]
+                return float(((C - 1) ** 0.5 * g.abs() + b.abs()).max())
+
+            def through(bound, w, b):
+                return None if bound is None else bound * float(w.abs().sum(1).max()) + float(b.abs().max())
+            b1, b2 = ln_bound(0), ln_bound(1)
+            self._bounds = (x_in, dict(x=x_in, sa_s=through(x_in, self.sa_wv, self.sa_bv), x1=b1, x2=b2,
+                                       hid=through(b2, self.w1, self.b1), out=ln_bound(2)))
+        return self._bounds[1]
 
     def half(self):
         """fp16 copies of the projection weights read with fp16 operands (built once)."""
@@ -135,13 +160,15 @@ class FusedEncoder:
         # sampled rows leave the window kernels as fp16 (the A operand of the fp16 output projection)
         # fp32 sampling through the window-staged fp32 kernels where the shape is covered (UB_WIN32=0: tile kernels only)
         self.win32 = os.environ.get('UB_WIN32', '1') == '1'
+        # fp32-grade projections whose activation operand has a proven bound run as fp16 x3 (UB_F16X3=0: 3xTF32 everywhere)
+        self.f16x3 = os.environ.get('UB_F16X3', '1') == '1'
         self.half_samples = self.f16 and self.sampling == 'win16'
         self._signature = None
         self._drop_caches()
 
     # derived weight copies ---------------------------------------------------------------------------------
     def _drop_caches(self):
-        self._w, self._split, self._rn, self._pos_w = {}, {}, {}, {}
+        self._w, self._split, self._split16, self._rn, self._pos_w = {}, {}, {}, {}, {}
 
     def refresh(self):
         """Drop every derived weight copy if any source parameter changed since they were built.  Returns True when
@@ -166,6 +193,22 @@ class FusedEncoder:
             self._split[key] = ops.split_tf32(w.contiguous())
         return self._split[key]
 
+    @staticmethod
+    def _a_scale(bound):
+        """Power of two that brings activations bounded by ``bound`` just below 2^15 (half the fp16 range), or None when the
+        operand cannot go through the fp16 split."""
+        if bound is None or not (0.0 < bound < 3.0e7):
+            return None
+        import math
+        return 2.0 ** max(-10, min(10, math.floor(math.log2(32768.0 / bound))))
+
+    def _hi_lo16(self, w, a_scale):
+        """(w16_hi, w16_lo, col_scale, a_scale) of the fp16 x3 projection (once per weight and activation scale)."""
+        key = (w.data_ptr(), tuple(w.shape), a_scale)
+        if key not in self._split16:
+            self._split16[key] = ops.split_f16(w.contiguous(), a_scale)
+        return self._split16[key]
+
     def _tf32(self, w):
         """Weight rounded to nearest TF32 (once): tcgen05 kind::tf32 truncates fp32 operands, which would bias every
         product low; a pre-rounded weight is read exactly."""
@@ -178,10 +221,17 @@ class FusedEncoder:
     # dense projections ------------------------------------------------------------------------------
     # An activation travels as a pair (fp32 rows, fp16 copy or None).  In the fp16 class the LayerNorm epilogues emit
     # the fp16 copy next to the fp32 rows, and the projections read it as their A operand.
-    def _lin(self, x, w, b, residual=None, relu=False, ln=None, out=None, w16=None, want16=False, only16=False):
-        """epilogue(x @ w^T) -> (fp32 rows or None, fp16 copy or None).  x: fp32 rows or a (fp32, fp16) pair."""
+    def _lin(self, x, w, b, residual=None, relu=False, ln=None, out=None, w16=None, want16=False, only16=False, bound=None):
+        """epilogue(x @ w^T) -> (fp32 rows or None, fp16 copy or None).  x: fp32 rows or a (fp32, fp16) pair.  ``bound``: a
+        proven bound of |x| (``_LayerWeights.bounds``): the fp32-grade projection then runs as fp16 x3 instead of 3xTF32."""
         x32, x16 = x if isinstance(x, tuple) else (x, None)
         try:
+            if self.gemm == 'tf32x3' and self.f16x3 and w.shape[1] % 64 == 0 and self._a_scale(bound) is not None:
+                try:
+                    return ops.linear_f16x3(self._rows32(x), self._hi_lo16(w, self._a_scale(bound)), b, residual=residual,
+                                            relu=relu, ln=ln, out=out), None
+                except _cabi.UnsupportedShape:
+                    pass
             if self.gemm == 'tf32x3':
                 return ops.linear_tf32x3(self._rows32(x), self._hi_lo(w), b, residual=residual, relu=relu, ln=ln, out=out), None
             if self.f16 and x16 is not None and w16 is not None:
@@ -219,7 +269,7 @@ class FusedEncoder:
         s = s.view(rows, C)
         return (None, s) if s.dtype == torch.float16 else s
 
-    def _project_value(self, x, w, b, G, Nv, H, P, w16=None, planes32=False):
+    def _project_value(self, x, w, b, G, Nv, H, P, w16=None, planes32=False, bound=None):
         """value_proj of the rows x (G*Nv, C) -> (value planes for the window kernels or None, fp32 rows or None).
         Planes are fp16 head-major (G, H, Nv, 32) in the 'win16' sampling class and, with ``planes32``, fp32 half-head
         planes (G, 2H, Nv, 16) in the 'fp32' class; they come straight out of the projection's epilogue."""
@@ -227,6 +277,8 @@ class FusedEncoder:
         C = w.shape[0]
         if planes32 and self.win32 and self.sampling == 'fp32' and ops.window_supported(C // H, P):
             try:
+                if self.f16x3 and w.shape[1] % 64 == 0 and self._a_scale(bound) is not None:
+                    return ops.linear_f16x3(self._rows32(x), self._hi_lo16(w, self._a_scale(bound)), b, planes_nv=Nv), None
                 return ops.linear_tf32x3(self._rows32(x), self._hi_lo(w), b, planes_nv=Nv), None
             except _cabi.UnsupportedShape:
                 pass
@@ -238,14 +290,14 @@ class FusedEncoder:
                     return ops.linear_tf32(x32, self._tf32(w), b, planes_nv=Nv), None
             except _cabi.UnsupportedShape:
                 pass
-            rows, _ = self._lin(x, w, b, w16=w16)
+            rows, _ = self._lin(x, w, b, w16=w16, bound=bound)
             return ops.value_to_half(rows, G, Nv, H), rows
-        return None, self._lin(x, w, b, w16=w16)[0]
+        return None, self._lin(x, w, b, w16=w16, bound=bound)[0]
 
-    def _bev_sample(self, x, w, b, qp, B, bev_h, bev_w, fh, fw, H, P, w16=None):
+    def _bev_sample(self, x, w, b, qp, B, bev_h, bev_w, fh, fw, H, P, w16=None, bound=None):
         """value_proj + BEV-grid sampling: rows x (B*fh*fw, C) un-projected -> sampled (B, Nq, C)."""
         C = w.shape[0]
-        planes, rows = self._project_value(x, w, b, B, fh * fw, H, P, w16, planes32=qp.shape[2] % 4 == 0)
+        planes, rows = self._project_value(x, w, b, B, fh * fw, H, P, w16, planes32=qp.shape[2] % 4 == 0, bound=bound)
         if planes is not None and planes.dtype == torch.float32:
             try:
                 return ops.bev_sample_win32(planes, qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2, workspace=self._counter())
@@ -261,7 +313,7 @@ class FusedEncoder:
             except _cabi.UnsupportedShape:
                 pass
         if rows is None:
-            rows = self._lin(x, w, b, w16=w16)[0]
+            rows = self._lin(x, w, b, w16=w16, bound=bound)[0]
         return ops.bev_sample(rows.view(B, fh * fw, C), qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2)
 
     def _counter(self):
@@ -328,8 +380,8 @@ class FusedEncoder:
     def _run_encoder(self, name, queries, B, pos_q, value_tokens, sample_cross, bev_h, bev_w):
         """queries (Nq, C) the BEV query table (every sample starts from it, transformer_fusion.py:493-498); pos_q: per-layer
         positional offset|logit rows or None; value_tokens: un-projected feature rows, fp32 or a (fp32 | None, fp16)
-        pair; sample_cross(lw, value_tokens, x, w16) -> sampled (B, Nq, C) (it runs the offset|logit projection of the
-        query rows x itself)."""
+        pair; sample_cross(lw, value_tokens, x, w16, x_bound) -> sampled (B, Nq, C) (it runs the offset|logit projection of
+        the query rows x, whose proven magnitude bound is x_bound, itself)."""
         layers = self._weights(name)
         Nq, C = queries.shape
         f16 = self._use_f16(C)
@@ -341,26 +393,30 @@ class FusedEncoder:
         x = (x32.view(B * Nq, C), x16.view(B * Nq, C) if f16 else None)
         if f16 and not isinstance(value_tokens, tuple):
             value_tokens = (value_tokens, value_tokens.half())   # fp16 copy once per frame, read by every layer
+        x_bound = None          # the query table is an input: no proven bound for the first layer's self-attention operands
         for i, lw in enumerate(layers):
             h = lw.half() if f16 else None
+            bd = lw.bounds(x_bound) if (self.gemm == 'tf32x3' and self.f16x3) else dict.fromkeys(('x', 'sa_s', 'x1', 'x2', 'hid', 'out'))
             # --- BEV self-attention (mmcv MultiScaleDeformableAttention, value = query, 1 level)
             qp, _ = self._lin(x, lw.sa_wq, lw.sa_bq, residual=pos_q[i] if pos_q is not None else None,
-                              w16=h and h['sa_wq'])
+                              w16=h and h['sa_wq'], bound=bd['x'])
             s = self._bev_sample(x, lw.sa_wv, lw.sa_bv, qp.view(B, Nq, -1), B, bev_h, bev_w, bev_h, bev_w, lw.H_s, lw.P_s,
-                                 w16=h and h['sa_wv'])
+                                 w16=h and h['sa_wv'], bound=bd['x'])
             x = self._lin(self._rows(s, B * Nq, C), lw.sa_wo, lw.sa_bo, residual=x[0], ln=lw.ln[0], want16=f16,
-                          w16=h and h['sa_wo'])
+                          w16=h and h['sa_wo'], bound=bd['sa_s'])
             if f16 and x[1] is None:
                 x = (x[0], x[0].half())
             # --- spatial cross-attention (query_pos is None for attentions[1])
-            s = sample_cross(lw, value_tokens, x, h and h['ca_wq'])
+            s = sample_cross(lw, value_tokens, x, h and h['ca_wq'], bd['x1'])
             x = self._lin(self._rows(s, B * Nq, C), lw.ca_wo, lw.ca_bo, residual=x[0], ln=lw.ln[1], want16=f16,
                           w16=h and h['ca_wo'])
             if f16 and x[1] is None:
                 x = (x[0], x[0].half())
             # --- FFN
-            hid = self._lin(x, lw.w1, lw.b1, relu=True, w16=h and h['w1'], only16=f16)
-            x = self._lin(hid, lw.w2, lw.b2, residual=x[0], ln=lw.ln[2], w16=h and h['w2'], want16=f16 and i + 1 < len(layers))
+            hid = self._lin(x, lw.w1, lw.b1, relu=True, w16=h and h['w1'], only16=f16, bound=bd['x2'])
+            x = self._lin(hid, lw.w2, lw.b2, residual=x[0], ln=lw.ln[2], w16=h and h['w2'], want16=f16 and i + 1 < len(layers),
+                          bound=bd['hid'])
+            x_bound = bd['out']
             if f16 and x[1] is None and i + 1 < len(layers):
                 x = (x[0], x[0].half())
         return x[0].view(B, Nq, C)
@@ -410,7 +466,7 @@ class FusedEncoder:
                 ref_cam, mask = ops.project_points(l2i, zs, enc.pc_range, ih, iw, bev_h, bev_w)
                 hits, order = [], []
 
-                def cross(lw, tokens, x, wq16):
+                def cross(lw, tokens, x, wq16, x_bound):
                     if (self.win32 and self.sampling == 'fp32' and self.gemm == 'tf32x3' and D % 2 == 0
                             and ops.window_supported(C // lw.H_c, lw.P_c)):
                         # fp32 window kernel: value planes from the projection's epilogue, offset|logit rows written
@@ -423,12 +479,16 @@ class FusedEncoder:
                         try:
                             planes = ops.linear_tf32x3(self._rows32(tokens), self._hi_lo(lw.ca_wv), lw.ca_bv, planes_nv=fh * fw)
                             qp_hit = torch.empty(B, N * Nq, lw.ca_wq.shape[0], device=dev, dtype=torch.float32)
-                            ops.linear_tf32x3_scatter(self._rows32(x), self._hi_lo(lw.ca_wq), lw.ca_bq, q_dst, Nq, qp_hit)
+                            if self.f16x3 and lw.ca_wq.shape[1] % 64 == 0 and self._a_scale(x_bound) is not None:
+                                ops.linear_f16x3(self._rows32(x), self._hi_lo16(lw.ca_wq, self._a_scale(x_bound)), lw.ca_bq,
+                                                 out=qp_hit, scatter=(q_dst, Nq))
+                            else:
+                                ops.linear_tf32x3_scatter(self._rows32(x), self._hi_lo(lw.ca_wq), lw.ca_bq, q_dst, Nq, qp_hit)
                             return ops.img_sample_win32(planes, qp_hit, order[0], hits[0], bev_h, bev_w, fh, fw, lw.H_c,
                                                         lw.P_c, 0, lw.H_c * lw.P_c * 2)
                         except _cabi.UnsupportedShape:
                             pass
-                    qp = self._lin(x, lw.ca_wq, lw.ca_bq, w16=wq16)[0].view(B, Nq, -1)
+                    qp = self._lin(x, lw.ca_wq, lw.ca_bq, w16=wq16, bound=x_bound)[0].view(B, Nq, -1)
                     planes, rows = self._project_value(tokens, lw.ca_wv, lw.ca_bv, B * N, fh * fw, lw.H_c, lw.P_c,
                                                        w16=lw.half()['ca_wv'] if isinstance(tokens, tuple) else None)
                     if planes is not None and (fh + 2) * (fw + 2) * 64 <= 150 * 1024 and qp.shape[2] % 4 == 0:
@@ -452,8 +512,8 @@ class FusedEncoder:
                 _, _, fh, fw = feat.shape
                 tokens = self._tokens(feat, None, m.pts_level_embeds[0], f16, B * fh * fw, C)
 
-                def cross(lw, tokens, x, wq16, fh=fh, fw=fw):
-                    qp = self._lin(x, lw.ca_wq, lw.ca_bq, w16=wq16)[0].view(B, Nq, -1)
+                def cross(lw, tokens, x, wq16, x_bound, fh=fh, fw=fw):
+                    qp = self._lin(x, lw.ca_wq, lw.ca_bq, w16=wq16, bound=x_bound)[0].view(B, Nq, -1)
                     return self._bev_sample(tokens, lw.ca_wv, lw.ca_bv, qp, B, bev_h, bev_w, fh, fw, lw.H_c, lw.P_c,
                                             w16=lw.half()['ca_wv'] if isinstance(tokens, tuple) else None)
                 pts = self._run_encoder('pts_bev_encoder', q_pts, B, pos_q['pts_bev_encoder'], tokens, cross, bev_h, bev_w)
