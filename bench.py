@@ -215,7 +215,8 @@ def main():
     host_sets = [synth.make_inputs(WORKLOAD, batch=B, seed=1 + rank * 100 + i, pin=True) for i in range(N_INPUT_SETS)]
     dev_sets = [dict(s, img_feats=[s['img_feats'][0].to(dev)], pts_feats=[s['pts_feats'][0].to(dev)],
                      bev_pos=s['bev_pos'].to(dev)) for s in host_sets]
-    bev_q = host_sets[0]['bev_queries'].to(dev)
+    # the BEV query table is the head's bev_embedding.weight (unibev_head.py:126-133): a Parameter, as in the real model
+    bev_q = torch.nn.Parameter(host_sets[0]['bev_queries'].to(dev), requires_grad=False)
     import numpy as np
     img_hw = tuple(host_sets[0]['img_metas'][0]['img_shape'][0][:2])
     for s in dev_sets:
@@ -354,7 +355,7 @@ def main():
     #     CUDA graph and timed with CUDA events on the launching stream: no host gaps, no L2 reuse.
     records, calls = {}, {}
     op_names = ('bev_sample', 'img_sample', 'bev_sample_win', 'img_sample_win', 'bev_sample_win32', 'img_sample_win32',
-                'linear_tf32', 'linear_f16', 'linear_tf32x3', 'linear_tf32x3_scatter', 'linear_simt', 'add_layernorm',
+                'linear_tf32', 'linear_f16', 'linear_tf32x3', 'linear_f16x3', 'linear_tf32x3_scatter', 'linear_simt', 'add_layernorm',
                 'value_to_half', 'flatten_feats', 'cnw_fuse', 'build_hits', 'hit_order', 'project_points', 'broadcast_rows')
     used = set()
     real = {n: getattr(ops, n) for n in op_names}
@@ -472,13 +473,14 @@ def main():
                 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None,
                 # the arithmetic type the path computes in (see unibev_b200/plugin/fused.py)
-                'dtype': 'f32 (3xTF32 tensor-core products, fp32 accumulate / sampling)' if args.precision == 'fp32' else 'fp16/fp32acc',
+                'dtype': 'f32 (split-operand tensor-core products at fp32 accuracy, fp32 accumulate / sampling)' if args.precision == 'fp32' else 'fp16/fp32acc',
                 'data': 'synthetic',
                 'config': {'workload': workload_string(B, world), 'precision_class': args.precision,
                            'frames_per_step': world * B, 'shapes': 'BEV 200x200 queries, 256 channels, 3 encoder layers per modality, '
                                                                     '6 cameras x 29x50 tokens, LiDAR map 180x180',
                            'l2_policy': f'rotating over {N_INPUT_SETS} input sets (> L2) + >1 GB of intermediates per frame',
-                           'gemm_math': ('tcgen05 kind::tf32 x3 (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo), fp32 accumulate in TMEM'
+                           'gemm_math': ('three tcgen05 passes per product (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, 2 x 11-bit splits), fp32 '
+                                         'accumulate in TMEM: kind::f16 where the activation operand has a proven bound, kind::tf32 elsewhere'
                                          if args.precision == 'fp32' else 'tcgen05 kind::f16 (fp16 operands), fp32 accumulate in TMEM'),
                            'sampling_math': ('fp32 value maps and weights, exact softmax' if args.precision == 'fp32' else
                                              'fp16-staged value maps and weights, fp32 accumulate'),

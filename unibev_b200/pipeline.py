@@ -35,11 +35,11 @@ class GraphedEncoder:
                 return model.encode([img_feat] if img_feat is not None else None,
                                     [pts_feat] if pts_feat is not None else None, bev_queries, bev_h, bev_w, **args)
         self._run = run
+        self._queries = bev_queries if isinstance(bev_queries, (list, tuple)) else [bev_queries]
         self.out = None
         self._capture()
 
     def _capture(self):
-        from .plugin.fused import weights_signature
         dev = (self.img_feat if self.img_feat is not None else self.pts_feat).device
         with torch.cuda.device(dev):
             side = torch.cuda.Stream()
@@ -53,11 +53,15 @@ class GraphedEncoder:
                 out = self._run()
         self.out = out
         # the graph reads derived weight copies (split / fp16 / concatenated) made at capture time
-        self._signature = weights_signature(self.model)
+        self._signature = self._sig()
+
+    def _sig(self):
+        from .plugin.fused import weights_signature
+        # (+ the query table: a Parameter of the head whose magnitude bound is baked into the captured launches)
+        return weights_signature(self.model) + tuple((q.data_ptr(), q._version) for q in self._queries)
 
     def replay(self):
-        from .plugin.fused import weights_signature
-        if weights_signature(self.model) != self._signature:
+        if self._sig() != self._signature:
             # a parameter changed (optimizer step, load_state_dict, .to()): the captured copies are stale.  The new graph
             # owns a new output buffer: use the tensor replay() returns, not one kept from an earlier call.
             del self.graph

@@ -164,6 +164,7 @@ class FusedEncoder:
         self.f16x3 = os.environ.get('UB_F16X3', '1') == '1'
         self.half_samples = self.f16 and self.sampling == 'win16'
         self._signature = None
+        self._qbound = None
         self._drop_caches()
 
     # derived weight copies ---------------------------------------------------------------------------------
@@ -192,6 +193,14 @@ class FusedEncoder:
         if key not in self._split:
             self._split[key] = ops.split_tf32(w.contiguous())
         return self._split[key]
+
+    def _param_bound(self, t):
+        if not isinstance(t, torch.nn.Parameter):
+            return None
+        key = (t.data_ptr(), t._version, tuple(t.shape))
+        if self._qbound is None or self._qbound[0] != key:
+            self._qbound = (key, float(t.detach().abs().max()))
+        return self._qbound[1]
 
     @staticmethod
     def _a_scale(bound):
@@ -393,7 +402,9 @@ class FusedEncoder:
         x = (x32.view(B * Nq, C), x16.view(B * Nq, C) if f16 else None)
         if f16 and not isinstance(value_tokens, tuple):
             value_tokens = (value_tokens, value_tokens.half())   # fp16 copy once per frame, read by every layer
-        x_bound = None          # the query table is an input: no proven bound for the first layer's self-attention operands
+        # the query table is an input: its bound is its own largest magnitude, read once per version when it is a Parameter
+        # (the head's bev_embedding.weight, unibev_head.py:126-133,172-177); a plain tensor stays unbounded (no host sync per call)
+        x_bound = self._param_bound(queries) if (self.gemm == 'tf32x3' and self.f16x3) else None
         for i, lw in enumerate(layers):
             h = lw.half() if f16 else None
             bd = lw.bounds(x_bound) if (self.gemm == 'tf32x3' and self.f16x3) else dict.fromkeys(('x', 'sa_s', 'x1', 'x2', 'hid', 'out'))
