@@ -449,8 +449,8 @@ def main():
         k = kernels[dominant]
         try:
             # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
-            # the same kernel at the same batch (profiles/ncu_traffic.json, keyed by frames per step)
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(str(B), {}).get(dominant)
+            # the same kernel at the same batch and precision class (profiles/ncu_traffic.json)
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(f'{B}_{args.precision}', {}).get(dominant)
         except OSError:
             traffic = None
         kname = {'bev_sample': 'bev_sample_kernel (fp32 tile kernel)', 'bev_sample_win': 'bev_sample_win_kernel (fp16-staged windows)',

@@ -29,8 +29,9 @@ def main():
             out = torch.empty(M, N, device=dev)
             ws = ops.split_tf32(w)
             a16, w16 = a.half(), w.half()
-            if os.environ.get('ONCE') == '1':      # under ncu: one x3 launch per shape
+            if os.environ.get('ONCE') == '1':      # under ncu: one launch per shape and split mode
                 ops.linear_tf32x3(a, ws, b, residual=r, ln=lnp, out=out)
+                ops.linear_f16x3(a, ops.split_f16(w, 64.0), b, residual=r, ln=lnp, out=out)
                 torch.cuda.synchronize()
                 continue
             t3 = timeit(lambda: ops.linear_tf32x3(a, ws, b, residual=r, ln=lnp, out=out))

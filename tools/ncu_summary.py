@@ -11,6 +11,11 @@ WANT = [
     ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram %peak'),
     ('l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed', 'L1 data-pipe wavefronts %peak'),
     ('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'L1 wavefronts shared'),
+    ('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed', 'shared LSU wavefronts %peak'),
+    ('l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed', 'tensor-core operand wavefronts %peak'),
+    ('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'shared bank conflicts'),
+    ('sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'tensor pipe active %'),
+    ('sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 'tensor operand fetch active %'),
     ('l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'global ld requests'),
     ('l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'global ld sectors'),
     ('l1tex__t_sector_hit_rate.pct', 'L1 hit %'),

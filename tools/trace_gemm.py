@@ -64,7 +64,7 @@ def main():
         mma = [rel(v) for v in row[41:81] if int(v)]
         epi = [rel(v) for v in row[81:121] if int(v)]
         print(f'CTA {cta}: start {rel(row[0]):.2f} us')
-        print('  producer issued k-blocks at :', ' '.join('%.2f' % v for v in prod))
+        print('  producer issued k-blocks at :', ' '.join('%.2f' % v for v in prod), '  (h3: converter warp 0, four stamps per 64-k block = operand slot free, A k-block 0 landed, A k-block 1 landed, slot published)')
         print('  mma saw k-blocks full at    :', ' '.join('%.2f' % v for v in mma),
               '   (x3: four stamps per k-block = A landed, a_lo ready, W_hi landed, W_lo landed; h3: four per 64-k block = start, operand slot ready, W_hi landed, W_lo landed)')
         print('  epilogue (acc ready, done)  :', ' '.join('%.2f' % v for v in epi))

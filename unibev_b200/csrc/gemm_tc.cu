@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kGemmThreadsF16S : (MODE ? kGemmTh
           mbar_arrive_expect_tx(bar, a_bytes);
           tma_load_2d(sm_a + (uint32_t)stage * a_bytes, &map_a, bar, kb * a.kb_elems, m0);
           prefetch_slice(i + 1, kb);
-          trace_event(a, 0, ev++);
+          if (!F16S) trace_event(a, 0, ev++);
           if (++stage == SA) stage = 0, phase ^= 1u;
         }
       }
@@ -447,6 +447,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kGemmThreadsF16S : (MODE ? kGemmTh
     }
     const int n_mine = ((uint32_t)ct + 32u * CW * (kPer - 1) < 1024u) ? kPer : kPer - 1;
     const float a_scale = a.a_scale;
+    int cev = 0;
     int sa = 0, sl = 0;
     uint32_t pa = 0, pl = 0;
     for (int it = 0; it < n_iter; ++it) {
@@ -457,10 +458,12 @@ __global__ void __launch_bounds__(MODE == 2 ? kGemmThreadsF16S : (MODE ? kGemmTh
       }
       for (int kb = 0; kb < w_blocks; ++kb) {
         mbar_wait(smem_u32(&s_el[sl]), pl ^ 1u);
+        if (ct == 0) trace_event(a, 0, cev++);               // (MODE 2 traces its first converter warp in the producer's slots)
         unsigned char* hi_p = smem + (size_t)SA * a_bytes + (size_t)sl * l_bytes;
 #pragma unroll
         for (int hsel = 0; hsel < 2; ++hsel) {              // the two 32-float k-blocks of this 64-element operand slot
           mbar_wait(smem_u32(&s_fa[sa]), pa);
+          if (ct == 0) trace_event(a, 0, cev++);
           const unsigned char* a_slot = smem + (size_t)sa * a_bytes;
           // all of a thread's loads first (plain C++ accesses: they stay in flight together), then conversions and stores
           float4 xs[kPer];
@@ -487,6 +490,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kGemmThreadsF16S : (MODE ? kGemmTh
         fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s_fl[sl]));
+        if (ct == 0) trace_event(a, 0, cev++);
         if (++sl == SL) sl = 0, pl ^= 1u;
       }
     }
