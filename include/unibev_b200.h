@@ -224,6 +224,14 @@ int ub_linear_f16x3(const float* A, float a_scale, const void* W16_hi, const voi
                     const float* bias, const float* residual, int ldr, const float* gamma, const float* beta, float eps,
                     float* out, int ldc, float* planes32, int Nv, const int* scatter, int scatter_r, int rows_per_item,
                     int dst_rows_per_item, int M, int N, int K, int flags, ub_stream_t stream);
+/* ub_linear_f16x3 whose activation bound is only known on the device: |A| <= *bound_dev * bound_mul + bound_add, bound_dev a
+ * device float written by an earlier kernel on the stream (ub_flatten_feats_max: the largest magnitude of an input tensor),
+ * bound_mul / bound_add what the caller proves about the path from there (row sums / bias magnitudes of a projection in
+ * between).  The kernel derives a_scale from it; col_scale = 1 / s_n from ub_split_f16 with a_scale = 1. */
+int ub_linear_f16x3_dyn(const float* A, const float* bound_dev, float bound_mul, float bound_add, const void* W16_hi,
+                        const void* W16_lo, const float* col_scale, const float* bias, const float* residual, int ldr,
+                        const float* gamma, const float* beta, float eps, float* out, int ldc, float* planes32, int Nv,
+                        int M, int N, int K, int flags, ub_stream_t stream);
 /* w (rows, cols) fp32 -> hi16 / lo16 (rows, cols) fp16 of w[n, :] * s_n (s_n: the power of two that brings the row's largest
  * magnitude into [4096, 8192)), col_scale (rows) = 1 / (s_n a_scale); col_scale == NULL: no scaling. */
 int ub_split_f16(const float* w, void* hi16, void* lo16, float* col_scale, int rows, int cols, float a_scale,
@@ -256,6 +264,9 @@ int ub_cnw_fuse(const float* img, const float* pts, const float* w_img, const fl
  * embed_a / embed_b may be NULL. */
 int ub_flatten_feats(const float* in, const float* embed_a, int n_a, const float* embed_b, float* out,
                      int G, int C, int HW, ub_stream_t stream);
+/* ub_flatten_feats that also raises *absmax (a device float the caller zeroed) to the largest magnitude it wrote. */
+int ub_flatten_feats_max(const float* in, const float* embed_a, int n_a, const float* embed_b, float* out, float* absmax,
+                         int G, int C, int HW, ub_stream_t stream);
 /* The same with an fp16 copy out16 (G, HW, C) next to / instead of the fp32 `out` (either may be NULL): the A operand
  * of the fp16 value projection (ub_linear_f16). */
 int ub_flatten_feats16(const float* in, const float* embed_a, int n_a, const float* embed_b, float* out, void* out16,

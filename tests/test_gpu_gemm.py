@@ -348,3 +348,28 @@ def test_linear_f16x3_residual_layernorm_planes_scatter(ops):
             written[d] = True
             torch.testing.assert_close(got[:, d], wants[:, q], rtol=1e-5, atol=5e-5)
     assert bool(torch.isnan(got[:, ~written]).all())
+
+
+def test_linear_f16x3_device_side_bound(ops):
+    """ub_flatten_feats_max records the largest magnitude of the rows it writes; ub_linear_f16x3_dyn derives the activation
+    scale from that device float (times the caller's proven factors) -- same result as the host-scaled call, at any
+    input magnitude the bound covers (1e-3 .. 3e4 here)."""
+    g = torch.Generator().manual_seed(8)
+    G, C, H, W, N = 3, 256, 9, 11, 192
+    for mag in (1e-3, 1.0, 3e4):
+        feat = (torch.randn(G, C, H, W, generator=g) * mag / 4).clamp(-mag, mag)
+        ea, eb = torch.randn(G, C, generator=g) * mag * 0.01, torch.randn(C, generator=g) * mag * 0.01
+        mx = torch.zeros(1).cuda()
+        rows = ops.flatten_feats_max(feat.cuda(), mx, ea.cuda(), eb.cuda())
+        want_rows = feat.flatten(2).transpose(1, 2) + ea[:, None, :] + eb
+        torch.testing.assert_close(rows.cpu(), want_rows, rtol=0, atol=0)
+        assert float(mx) == float(want_rows.abs().max())
+        w, b = torch.randn(N, C, generator=g) / 16, torch.randn(N, generator=g) * mag
+        x = rows.view(-1, C)
+        got = ops.linear_f16x3_dyn(x, (mx, 1.0, 0.0), ops.split_f16(w.cuda(), 1.0), b.cuda()).cpu()
+        want = F.linear(want_rows.reshape(-1, C).double(), w.double(), b.double()).float()
+        scale = F.linear(want_rows.reshape(-1, C).double().abs(), w.double().abs()).float() + b.abs()
+        assert float(((got - want).abs() / scale).max()) < 5e-6
+        # a looser (but still valid) bound -- what a projection's row sums give -- changes the scale, not the result class
+        got2 = ops.linear_f16x3_dyn(x, (mx, 3.7, 0.5 * mag), ops.split_f16(w.cuda(), 1.0), b.cuda()).cpu()
+        assert float(((got2 - want).abs() / scale).max()) < 5e-6

@@ -38,6 +38,7 @@ PROTOTYPES = {
     'ub_linear_tf32x3': ([_p] * 5 + [_i, _p, _p, _f, _p, _i, _p] + [_i] * 5 + [_p], _i),
     'ub_linear_tf32x3_scatter': ([_p] * 5 + [_i, _p] + [_i] * 6 + [_p], _i),
     'ub_linear_f16x3': ([_p, _f] + [_p] * 5 + [_i, _p, _p, _f, _p, _i, _p, _i, _p] + [_i] * 7 + [_p], _i),
+    'ub_linear_f16x3_dyn': ([_p, _p, _f, _f] + [_p] * 5 + [_i, _p, _p, _f, _p, _i, _p] + [_i] * 5 + [_p], _i),
     'ub_split_f16': ([_p, _p, _p, _p, _i, _i, _f, _p], _i),
     'ub_linear_simt': ([_p] * 4 + [_i, _p] + [_i] * 5 + [_p], _i),
     'ub_split_tf32': ([_p, _p, _p, _i64, _p], _i),
@@ -46,6 +47,7 @@ PROTOTYPES = {
     'ub_add_layernorm16': ([_p] * 7 + [_i64, _i, _f, _p], _i),
     'ub_cnw_fuse': ([_p] * 8 + [_i64, _i, _i, _i, _i, _i, _p], _i),
     'ub_flatten_feats': ([_p, _p, _i, _p, _p, _i, _i, _i, _p], _i),
+    'ub_flatten_feats_max': ([_p, _p, _i, _p, _p, _p, _i, _i, _i, _p], _i),
     'ub_flatten_feats16': ([_p, _p, _i, _p, _p, _p, _i, _i, _i, _p], _i),
     'ub_broadcast_rows': ([_p, _i64, _i, _i, _p, _p, _p], _i),
     'ub_voxelize_workspace_bytes': ([_i, ctypes.POINTER(ctypes.c_size_t)], _i),

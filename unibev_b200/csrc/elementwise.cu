@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(1024) cnw_fuse_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) flatten_feats_kernel(const float* __restrict__ in,
                                                             const float* __restrict__ embed_a, int n_a,
                                                             const float* __restrict__ embed_b, float* __restrict__ out,
-                                                            __half* __restrict__ out16, int C, int HW) {
+                                                            __half* __restrict__ out16, int C, int HW,
+                                                            float* __restrict__ absmax) {
   __shared__ float tile[32][33];
   pdl_trigger();
   const int g = blockIdx.z;
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(256) flatten_feats_kernel(const float* __restr
     if (embed_a) e1 = __ldg(embed_a + (int64_t)(g % n_a) * C + c);
     if (embed_b) e2 = __ldg(embed_b + c);
   }
+  float mx = 0.f;
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int p = p0 + ty + j;
@@ -179,9 +181,15 @@ __global__ void __launch_bounds__(256) flatten_feats_kernel(const float* __restr
       float v = tile[tx][ty + j];
       if (embed_a) v = __fadd_rn(v, e1);
       if (embed_b) v = __fadd_rn(v, e2);
+      mx = fmaxf(mx, fabsf(v));
       if (out) out[dst0 + (int64_t)p * C + c] = v;
       if (out16) out16[dst0 + (int64_t)p * C + c] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
     }
+  }
+  if (absmax) {   // largest magnitude written (non-negative floats order like their bit patterns)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (tx == 0 && mx > 0.f) atomicMax(reinterpret_cast<int*>(absmax), __float_as_int(mx));
   }
 }
 
@@ -324,8 +332,21 @@ extern "C" int ub_flatten_feats16(const float* in, const float* embed_a, int n_a
   }
   dim3 grid((HW + 31) / 32, (C + 31) / 32, G);
   flatten_feats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, embed_a, n_a > 0 ? n_a : 1, embed_b, out,
-                                                               reinterpret_cast<__half*>(out16), C, HW);
+                                                               reinterpret_cast<__half*>(out16), C, HW, nullptr);
   return check_launch("ub_flatten_feats");
+}
+
+// ub_flatten_feats that also raises *absmax (a device float the caller zeroed) to the largest magnitude it wrote: the
+// device-side operand bound of ub_linear_f16x3 for rows that come straight from an input tensor.
+extern "C" int ub_flatten_feats_max(const float* in, const float* embed_a, int n_a, const float* embed_b, float* out,
+                                    float* absmax, int G, int C, int HW, ub_stream_t stream) {
+  UB_REQUIRE(in && out && absmax, "ub_flatten_feats_max: null pointer");
+  UB_REQUIRE(G > 0 && G <= 65535 && C > 0 && HW > 0, "ub_flatten_feats_max: bad shape (G=%d C=%d HW=%d)", G, C, HW);
+  UB_REQUIRE(embed_a == nullptr || n_a > 0, "ub_flatten_feats_max: embed_a given with n_a=%d", n_a);
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, G);
+  flatten_feats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, embed_a, n_a > 0 ? n_a : 1, embed_b, out, nullptr, C, HW,
+                                                               absmax);
+  return check_launch("ub_flatten_feats_max");
 }
 
 extern "C" int ub_flatten_feats(const float* in, const float* embed_a, int n_a, const float* embed_b, float* out, int G,

@@ -78,6 +78,11 @@ struct GemmArgs {
   int no_staging;       // no per-warp staging buffers in shared memory (results leave straight from registers)
   float a_scale;
   const float* cscale;  // (N) or null (= 1 / a_scale)
+  // bound_ptr != null: the bound of |A| lives on the device (|A| <= *bound_ptr * bound_mul + bound_add, e.g. the largest input
+  // token found by ub_flatten_feats_max, pushed through a projection's row sums); the kernel derives a_scale from it and
+  // cscale[n] is 1 / s_n only
+  const float* bound_ptr;
+  float bound_mul, bound_add;
   int epi_res;
   int x3_inplace;       // 3xTF32: the converters also write a_hi back (result independent of the tensor core's operand rounding)
   int stagger_ns;       // every other cluster starts its first tile this much later: the CTAs' epilogue bursts (output stores)
@@ -169,10 +174,18 @@ __global__ void __launch_bounds__(MODE == 2 ? kGemmThreadsF16S : (MODE ? kGemmTh
   };
   auto tile_n0 = [&](int i) { return a.balanced ? my_n0 : ((cluster_id + i * n_clusters) / groups_m) * a.BN; };
 
+  float a_scale = a.a_scale;
+  if (F16S && a.bound_ptr) {
+    pdl_wait();   // the bound comes from a predecessor kernel
+    const float bnd = fmaf(__ldg(a.bound_ptr), a.bound_mul, a.bound_add);
+    int e = 11;   // a_scale = the power of two that brings the bound just below 2^15 (clamped to 2^-10 .. 2^10)
+    if (bnd > 0.f) frexpf(32768.f / bnd, &e);
+    a_scale = ldexpf(1.f, max(-10, min(10, e - 1)));
+  }
   for (int i = tid; i < a.N; i += (int)blockDim.x) {
     s_par[i] = a.bias ? a.bias[i] : 0.f;
     if (a.ln) s_par[a.N + i] = a.gamma[i], s_par[2 * a.N + i] = a.beta[i];
-    if (F16S) s_par[3 * a.N + i] = a.cscale ? a.cscale[i] : 1.f / a.a_scale;
+    if (F16S) s_par[3 * a.N + i] = a.bound_ptr ? a.cscale[i] / a_scale : (a.cscale ? a.cscale[i] : 1.f / a_scale);
   }
   if (tid == 0) {
     // SPLIT: a slot is free again once the MMAs that read it have completed AND every converter warp has passed it
@@ -446,7 +459,6 @@ __global__ void __launch_bounds__(MODE == 2 ? kGemmThreadsF16S : (MODE ? kGemmTh
       offs[m] = (row * 128u + cp * 16u) | ((row * 128u + (((c >> 1) ^ (row & 7u)) << 4) + ((c & 1u) << 3)) << 16);
     }
     const int n_mine = ((uint32_t)ct + 32u * CW * (kPer - 1) < 1024u) ? kPer : kPer - 1;
-    const float a_scale = a.a_scale;
     int cev = 0;
     int sa = 0, sl = 0;
     uint32_t pa = 0, pl = 0;
@@ -800,7 +812,9 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
                          const float* residual, int ldr, const float* gamma, const float* beta, float eps, float* out,
                          int ldc, void* out16, int ldc16, void* planes, float* planes32, int Nv, int M, int N, int K,
                          int flags, ub_stream_t stream, const int* scatter = nullptr, int sc_r = 0, int sc_rows = 0,
-                         int sc_dst_rows = 0, bool f16s = false, float a_scale = 1.f, const float* col_scale = nullptr) {
+                         int sc_dst_rows = 0, bool f16s = false, float a_scale = 1.f, const float* col_scale = nullptr,
+                         const float* bound_dev = nullptr, float bound_mul = 1.f, float bound_add = 0.f) {
+  UB_REQUIRE(!bound_dev || (f16s && col_scale), "%s: a device-side bound needs the fp16 x3 mode and col_scale", fn);
   // f16s: fp16 x3 (kernel MODE 2): A fp32, W / W_lo fp16 (64-element k-blocks)
   const int relu = flags & 1, ln = (flags >> 1) & 1;
   const int kb_elems = f16 ? 64 : 32, esize = f16 ? 2 : 4;
@@ -837,6 +851,7 @@ static int launch_linear(const char* fn, int f16, const void* A, const void* W, 
   a.planes32 = planes32, a.SL = (split || f16s) ? 2 : 0;
   a.scatter = scatter, a.sc_r = sc_r, a.sc_rows = sc_rows, a.sc_dst_rows = sc_dst_rows;
   a.a_scale = a_scale, a.cscale = col_scale, a.epi_res = 0;
+  a.bound_ptr = bound_dev, a.bound_mul = bound_mul, a.bound_add = bound_add;
   a.x3_inplace = g_x3_inplace, a.stagger_ns = split ? g_x3_stagger_ns : 0;
   a.direct_store = f16s || (split && g_x3_direct && out && ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0);
   a.Nv = Nv, a.H = N / 32;
@@ -1011,6 +1026,19 @@ extern "C" int ub_linear_f16x3(const float* A, float a_scale, const void* W16_hi
   return launch_linear("ub_linear_f16x3", 0, A, W16_hi, reinterpret_cast<const float*>(W16_lo), bias, residual, ldr, gamma, beta,
                        eps, planes32 ? nullptr : out, ldc, nullptr, 0, nullptr, planes32, Nv, M, N, K, flags, stream, scatter,
                        scatter_r, rows_per_item, dst_rows_per_item, true, a_scale, col_scale);
+}
+// ub_linear_f16x3 whose activation bound is only known on the device: |A| <= *bound_dev * bound_mul + bound_add (bound_dev: a
+// device float written by an earlier kernel on the stream, e.g. ub_flatten_feats_max).  The kernel derives a_scale from it;
+// col_scale = 1 / s_n from ub_split_f16 with a_scale = 1.  No ReLU / scatter variants needed by the encoder here.
+extern "C" int ub_linear_f16x3_dyn(const float* A, const float* bound_dev, float bound_mul, float bound_add, const void* W16_hi,
+                                   const void* W16_lo, const float* col_scale, const float* bias, const float* residual, int ldr,
+                                   const float* gamma, const float* beta, float eps, float* out, int ldc, float* planes32,
+                                   int Nv, int M, int N, int K, int flags, ub_stream_t stream) {
+  UB_REQUIRE(W16_lo && bound_dev && col_scale, "ub_linear_f16x3_dyn: null pointer");
+  UB_REQUIRE(bound_mul >= 0.f && bound_add >= 0.f, "ub_linear_f16x3_dyn: negative bound terms");
+  return launch_linear("ub_linear_f16x3_dyn", 0, A, W16_hi, reinterpret_cast<const float*>(W16_lo), bias, residual, ldr, gamma,
+                       beta, eps, planes32 ? nullptr : out, ldc, nullptr, 0, nullptr, planes32, Nv, M, N, K, flags, stream,
+                       nullptr, 0, 0, 0, true, 1.f, col_scale, bound_dev, bound_mul, bound_add);
 }
 
 namespace ub {

@@ -470,6 +470,50 @@ def linear_f16x3(x, w16_split, bias=None, residual=None, relu=False, ln=None, ou
     return res
 
 
+def linear_f16x3_dyn(x, bound, w16_split, bias=None, residual=None, ln=None, out=None, planes_nv=None):
+    """``linear_f16x3`` whose activation bound lives on the device: ``bound = (tensor with one float, mul, add)`` states
+    |x| <= tensor[0] * mul + add; ``w16_split = split_f16(W, 1.0)``."""
+    x = _need(x, 'x')
+    bt, mul, add = _need(bound[0], 'bound'), float(bound[1]), float(bound[2])
+    w_hi, w_lo = _need(w16_split[0], 'w16_hi', torch.float16), _need(w16_split[1], 'w16_lo', torch.float16)
+    col_scale = _need(w16_split[2], 'col_scale')
+    if float(w16_split[3]) != 1.0:
+        raise ValueError('linear_f16x3_dyn: the weight split must be made with a_scale = 1')
+    M, K = x.shape
+    N = w_hi.shape[0]
+    if w_hi.shape != (N, K) or w_lo.shape != (N, K):
+        raise ValueError(f'linear_f16x3_dyn: x{tuple(x.shape)} vs weight{tuple(w_hi.shape)}')
+    bias = _need(bias, 'bias') if bias is not None else None
+    flags = 2 if ln is not None else 0
+    gamma = beta = None
+    eps = 0.0
+    if ln is not None:
+        gamma, beta, eps = _need(ln[0], 'gamma'), _need(ln[1], 'beta'), float(ln[2])
+    ldr = 0
+    if residual is not None:
+        if residual.shape != (M, N):
+            raise ValueError('linear_f16x3_dyn: residual shape mismatch')
+        if not (residual.is_cuda and residual.dtype == torch.float32 and residual.stride(1) == 1):
+            residual = _need(residual, 'residual')
+        ldr = residual.stride(0)
+    planes = None
+    if planes_nv is not None:
+        if M % planes_nv or N % 16:
+            raise ValueError('linear_f16x3_dyn: planes need M % Nv == 0 and N % 16 == 0')
+        planes = out if out is not None else torch.empty(M // planes_nv, N // 16, planes_nv, 16, device=x.device,
+                                                         dtype=torch.float32)
+        res, out_ptr, ldc = planes, None, 0
+    else:
+        if out is None:
+            out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        elif out.shape != (M, N) or out.stride(1) != 1 or out.dtype != torch.float32 or not out.is_cuda:
+            raise ValueError('linear_f16x3_dyn: `out` must be an fp32 CUDA (M, N) matrix with unit column stride')
+        res, out_ptr, ldc = out, _ptr(out), out.stride(0)
+    _call('ub_linear_f16x3_dyn', x, _ptr(x), _ptr(bt), mul, add, _ptr(w_hi), _ptr(w_lo), _ptr(col_scale), _ptr(bias),
+          _ptr(residual), ldr, _ptr(gamma), _ptr(beta), eps, out_ptr, ldc, _ptr(planes), planes_nv or 0, M, N, K, flags)
+    return res
+
+
 def linear_f16(x16, w16, bias=None, residual=None, relu=False, ln=None, out=None, out16=None, fp32_out=True,
                f16_out=False, planes_nv=None):
     """fp16-operand variant of ``linear_tf32``: x16 (M, K) fp16 @ w16 (N, K)^T fp16, fp32 accumulation and epilogue.
@@ -564,6 +608,21 @@ def flatten_feats(feat, embed_a=None, embed_b=None, fp32=True, fp16=False):
     _call('ub_flatten_feats16', feat, _ptr(feat), _ptr(embed_a), n_a, _ptr(embed_b), _ptr(out), _ptr(out16), G, C,
                                                h * w)
     return (out, out16) if fp16 else out
+
+
+def flatten_feats_max(feat, absmax, embed_a=None, embed_b=None):
+    """``flatten_feats`` (fp32 rows) that also raises ``absmax`` (one zeroed fp32 on the device) to the largest magnitude it
+    wrote: the device-side operand bound of ``linear_f16x3_dyn``."""
+    feat = _need(feat, 'feat')
+    absmax = _need(absmax, 'absmax')
+    C, h, w = feat.shape[-3:]
+    G = feat.numel() // (C * h * w)
+    embed_a = _need(embed_a, 'embed_a') if embed_a is not None else None
+    embed_b = _need(embed_b, 'embed_b') if embed_b is not None else None
+    out = torch.empty(G, h * w, C, device=feat.device, dtype=torch.float32)
+    _call('ub_flatten_feats_max', feat, _ptr(feat), _ptr(embed_a), embed_a.shape[0] if embed_a is not None else 0,
+          _ptr(embed_b), _ptr(out), _ptr(absmax), G, C, h * w)
+    return out
 
 
 def broadcast_rows(src, B, fp32=True, fp16=True):

@@ -121,8 +121,11 @@ class _LayerWeights:
             def through(bound, w, b):
                 return None if bound is None else bound * float(w.abs().sum(1).max()) + float(b.abs().max())
             b1, b2 = ln_bound(0), ln_bound(1)
+            # cross-attention rows are sampled from value rows tokens Wv^T + bv: |.| <= |tokens|_max ca_mul + ca_add, with the
+            # largest token only known on the device (FusedEncoder._tokens)
             self._bounds = (x_in, dict(x=x_in, sa_s=through(x_in, self.sa_wv, self.sa_bv), x1=b1, x2=b2,
-                                       hid=through(b2, self.w1, self.b1), out=ln_bound(2)))
+                                       hid=through(b2, self.w1, self.b1), out=ln_bound(2),
+                                       ca_mul=float(self.ca_wv.abs().sum(1).max()), ca_add=float(self.ca_bv.abs().max())))
         return self._bounds[1]
 
     def half(self):
@@ -165,6 +168,7 @@ class FusedEncoder:
         self.half_samples = self.f16 and self.sampling == 'win16'
         self._signature = None
         self._qbound = None
+        self._dyn, self._pos_dyn = {}, None
         self._drop_caches()
 
     # derived weight copies ---------------------------------------------------------------------------------
@@ -230,11 +234,19 @@ class FusedEncoder:
     # dense projections ------------------------------------------------------------------------------
     # An activation travels as a pair (fp32 rows, fp16 copy or None).  In the fp16 class the LayerNorm epilogues emit
     # the fp16 copy next to the fp32 rows, and the projections read it as their A operand.
-    def _lin(self, x, w, b, residual=None, relu=False, ln=None, out=None, w16=None, want16=False, only16=False, bound=None):
+    def _lin(self, x, w, b, residual=None, relu=False, ln=None, out=None, w16=None, want16=False, only16=False, bound=None,
+             dyn=None):
         """epilogue(x @ w^T) -> (fp32 rows or None, fp16 copy or None).  x: fp32 rows or a (fp32, fp16) pair.  ``bound``: a
         proven bound of |x| (``_LayerWeights.bounds``): the fp32-grade projection then runs as fp16 x3 instead of 3xTF32."""
         x32, x16 = x if isinstance(x, tuple) else (x, None)
         try:
+            if self.gemm == 'tf32x3' and self.f16x3 and w.shape[1] % 64 == 0 and dyn is not None and not relu:
+                # the operand's bound lives on the device: (one-float tensor, mul, add) states |x| <= t * mul + add
+                try:
+                    return ops.linear_f16x3_dyn(self._rows32(x), dyn, self._hi_lo16(w, 1.0), b, residual=residual, ln=ln,
+                                                out=out), None
+                except _cabi.UnsupportedShape:
+                    pass
             if self.gemm == 'tf32x3' and self.f16x3 and w.shape[1] % 64 == 0 and self._a_scale(bound) is not None:
                 try:
                     return ops.linear_f16x3(self._rows32(x), self._hi_lo16(w, self._a_scale(bound)), b, residual=residual,
@@ -278,7 +290,7 @@ class FusedEncoder:
         s = s.view(rows, C)
         return (None, s) if s.dtype == torch.float16 else s
 
-    def _project_value(self, x, w, b, G, Nv, H, P, w16=None, planes32=False, bound=None):
+    def _project_value(self, x, w, b, G, Nv, H, P, w16=None, planes32=False, bound=None, dyn=None):
         """value_proj of the rows x (G*Nv, C) -> (value planes for the window kernels or None, fp32 rows or None).
         Planes are fp16 head-major (G, H, Nv, 32) in the 'win16' sampling class and, with ``planes32``, fp32 half-head
         planes (G, 2H, Nv, 16) in the 'fp32' class; they come straight out of the projection's epilogue."""
@@ -286,6 +298,8 @@ class FusedEncoder:
         C = w.shape[0]
         if planes32 and self.win32 and self.sampling == 'fp32' and ops.window_supported(C // H, P):
             try:
+                if self.f16x3 and w.shape[1] % 64 == 0 and dyn is not None:
+                    return ops.linear_f16x3_dyn(self._rows32(x), dyn, self._hi_lo16(w, 1.0), b, planes_nv=Nv), None
                 if self.f16x3 and w.shape[1] % 64 == 0 and self._a_scale(bound) is not None:
                     return ops.linear_f16x3(self._rows32(x), self._hi_lo16(w, self._a_scale(bound)), b, planes_nv=Nv), None
                 return ops.linear_tf32x3(self._rows32(x), self._hi_lo(w), b, planes_nv=Nv), None
@@ -299,14 +313,14 @@ class FusedEncoder:
                     return ops.linear_tf32(x32, self._tf32(w), b, planes_nv=Nv), None
             except _cabi.UnsupportedShape:
                 pass
-            rows, _ = self._lin(x, w, b, w16=w16, bound=bound)
+            rows, _ = self._lin(x, w, b, w16=w16, bound=bound, dyn=dyn)
             return ops.value_to_half(rows, G, Nv, H), rows
-        return None, self._lin(x, w, b, w16=w16, bound=bound)[0]
+        return None, self._lin(x, w, b, w16=w16, bound=bound, dyn=dyn)[0]
 
-    def _bev_sample(self, x, w, b, qp, B, bev_h, bev_w, fh, fw, H, P, w16=None, bound=None):
+    def _bev_sample(self, x, w, b, qp, B, bev_h, bev_w, fh, fw, H, P, w16=None, bound=None, dyn=None):
         """value_proj + BEV-grid sampling: rows x (B*fh*fw, C) un-projected -> sampled (B, Nq, C)."""
         C = w.shape[0]
-        planes, rows = self._project_value(x, w, b, B, fh * fw, H, P, w16, planes32=qp.shape[2] % 4 == 0, bound=bound)
+        planes, rows = self._project_value(x, w, b, B, fh * fw, H, P, w16, planes32=qp.shape[2] % 4 == 0, bound=bound, dyn=dyn)
         if planes is not None and planes.dtype == torch.float32:
             try:
                 return ops.bev_sample_win32(planes, qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2, workspace=self._counter())
@@ -322,7 +336,7 @@ class FusedEncoder:
             except _cabi.UnsupportedShape:
                 pass
         if rows is None:
-            rows = self._lin(x, w, b, w16=w16, bound=bound)[0]
+            rows = self._lin(x, w, b, w16=w16, bound=bound, dyn=dyn)[0]
         return ops.bev_sample(rows.view(B, fh * fw, C), qp, bev_h, bev_w, fh, fw, H, P, 0, H * P * 2)
 
     def _counter(self):
@@ -354,6 +368,20 @@ class FusedEncoder:
                 for b0 in range(0, len(blocks), per):
                     c0, c1 = b0 * widths[0], min(len(blocks), b0 + per) * widths[0]
                     ops.linear_f16(pos[1], w_all[c0:c1], None, out=buf[:, c0:c1])
+                done = True
+            except _cabi.UnsupportedShape:
+                pass
+        if not done and self.gemm == 'tf32x3' and self._pos_dyn is not None and all(w == widths[0] and w % 32 == 0 for w in widths):
+            # bev_pos is an input: its largest magnitude was found on the device while flattening it
+            key = ('h3',) + tuple(names)
+            per = max(1, 256 // widths[0])
+            if key not in self._pos_w:
+                self._pos_w[key] = [ops.split_f16(torch.cat([lw.sa_wq for _, lw in blocks[b0:b0 + per]], 0).contiguous(), 1.0)
+                                    for b0 in range(0, len(blocks), per)]
+            try:
+                for k, b0 in enumerate(range(0, len(blocks), per)):
+                    c0, c1 = b0 * widths[0], min(len(blocks), b0 + per) * widths[0]
+                    ops.linear_f16x3_dyn(self._rows32(pos), self._pos_dyn, self._pos_w[key][k], None, out=buf[:, c0:c1])
                 done = True
             except _cabi.UnsupportedShape:
                 pass
@@ -407,7 +435,8 @@ class FusedEncoder:
         x_bound = self._param_bound(queries) if (self.gemm == 'tf32x3' and self.f16x3) else None
         for i, lw in enumerate(layers):
             h = lw.half() if f16 else None
-            bd = lw.bounds(x_bound) if (self.gemm == 'tf32x3' and self.f16x3) else dict.fromkeys(('x', 'sa_s', 'x1', 'x2', 'hid', 'out'))
+            bd = (lw.bounds(x_bound) if (self.gemm == 'tf32x3' and self.f16x3) else
+                  dict.fromkeys(('x', 'sa_s', 'x1', 'x2', 'hid', 'out', 'ca_mul', 'ca_add')))
             # --- BEV self-attention (mmcv MultiScaleDeformableAttention, value = query, 1 level)
             qp, _ = self._lin(x, lw.sa_wq, lw.sa_bq, residual=pos_q[i] if pos_q is not None else None,
                               w16=h and h['sa_wq'], bound=bd['x'])
@@ -419,8 +448,9 @@ class FusedEncoder:
                 x = (x[0], x[0].half())
             # --- spatial cross-attention (query_pos is None for attentions[1])
             s = sample_cross(lw, value_tokens, x, h and h['ca_wq'], bd['x1'])
+            tok_max = self._dyn.get(id(value_tokens))      # largest input token (device): sampled rows <= max * ca_mul + ca_add
             x = self._lin(self._rows(s, B * Nq, C), lw.ca_wo, lw.ca_bo, residual=x[0], ln=lw.ln[1], want16=f16,
-                          w16=h and h['ca_wo'])
+                          w16=h and h['ca_wo'], dyn=(tok_max, bd['ca_mul'], bd['ca_add']) if tok_max is not None else None)
             if f16 and x[1] is None:
                 x = (x[0], x[0].half())
             # --- FFN
@@ -452,10 +482,17 @@ class FusedEncoder:
             # work counters of this call's window-kernel launches: one memset per call, distinct memory per call
             # (and so per captured CUDA graph)
             n_win = sum(2 * len(self._weights(n)) for n in names)
-            self._counters = torch.zeros(max(n_win, 1), 2, device=dev, dtype=torch.int32)
-            self._n_counters = 0
+            ws = torch.zeros(max(n_win, 1) + 2, 2, device=dev, dtype=torch.int32)
+            self._counters, self._n_counters = ws[:-2], 0
+            # ... and of the device-side operand bounds (largest magnitudes of bev_pos / image tokens / LiDAR tokens)
+            maxes = ws[-2:].view(torch.float32).reshape(-1)
+            dyn_ok = self.gemm == 'tf32x3' and self.f16x3
+            self._dyn, self._pos_dyn = {}, None
             pos = None
-            if bev_pos is not None:
+            if bev_pos is not None and dyn_ok:
+                pos = ops.flatten_feats_max(bev_pos, maxes[0:1]).view(B * Nq, C)
+                self._pos_dyn = (maxes[0:1], 1.0, 0.0)
+            elif bev_pos is not None:
                 pos = ops.flatten_feats(bev_pos, fp32=not f16, fp16=f16)
                 pos = tuple(t.view(B * Nq, C) if t is not None else None for t in pos) if f16 else pos.view(B * Nq, C)
             img = pts = None
@@ -465,7 +502,7 @@ class FusedEncoder:
                 _, N, _, fh, fw = feat.shape
                 enc = m.img_bev_encoder
                 tokens = self._tokens(feat, m.cams_embeds if m.use_cams_embeds else None, m.img_level_embeds[0], f16,
-                                      B * N * fh * fw, C)
+                                      B * N * fh * fw, C, maxes[1:2] if dyn_ok else None)
                 if lidar2img is not None:
                     l2i = lidar2img
                     ih, iw = img_shape
@@ -488,7 +525,12 @@ class FusedEncoder:
                             order.append(ops.hit_order(mask, ref_cam, hits[0]))
                         q_dst = order[0][0]
                         try:
-                            planes = ops.linear_tf32x3(self._rows32(tokens), self._hi_lo(lw.ca_wv), lw.ca_bv, planes_nv=fh * fw)
+                            tmax = self._dyn.get(id(tokens))
+                            if self.f16x3 and tmax is not None and lw.ca_wv.shape[1] % 64 == 0:
+                                planes = ops.linear_f16x3_dyn(self._rows32(tokens), (tmax, 1.0, 0.0), self._hi_lo16(lw.ca_wv, 1.0),
+                                                              lw.ca_bv, planes_nv=fh * fw)
+                            else:
+                                planes = ops.linear_tf32x3(self._rows32(tokens), self._hi_lo(lw.ca_wv), lw.ca_bv, planes_nv=fh * fw)
                             qp_hit = torch.empty(B, N * Nq, lw.ca_wq.shape[0], device=dev, dtype=torch.float32)
                             if self.f16x3 and lw.ca_wq.shape[1] % 64 == 0 and self._a_scale(x_bound) is not None:
                                 ops.linear_f16x3(self._rows32(x), self._hi_lo16(lw.ca_wq, self._a_scale(x_bound)), lw.ca_bq,
@@ -521,21 +563,28 @@ class FusedEncoder:
             if pts_feats is not None:
                 feat = pts_feats[0]
                 _, _, fh, fw = feat.shape
-                tokens = self._tokens(feat, None, m.pts_level_embeds[0], f16, B * fh * fw, C)
+                tokens = self._tokens(feat, None, m.pts_level_embeds[0], f16, B * fh * fw, C, maxes[2:3] if dyn_ok else None)
 
                 def cross(lw, tokens, x, wq16, x_bound, fh=fh, fw=fw):
                     qp = self._lin(x, lw.ca_wq, lw.ca_bq, w16=wq16, bound=x_bound)[0].view(B, Nq, -1)
+                    tmax = self._dyn.get(id(tokens)) if not isinstance(tokens, tuple) else None
                     return self._bev_sample(tokens, lw.ca_wv, lw.ca_bv, qp, B, bev_h, bev_w, fh, fw, lw.H_c, lw.P_c,
-                                            w16=lw.half()['ca_wv'] if isinstance(tokens, tuple) else None)
+                                            w16=lw.half()['ca_wv'] if isinstance(tokens, tuple) else None,
+                                            dyn=(tmax, 1.0, 0.0) if tmax is not None else None)
                 pts = self._run_encoder('pts_bev_encoder', q_pts, B, pos_q['pts_bev_encoder'], tokens, cross, bev_h, bev_w)
             return m.fuse(img, pts)
 
-    @staticmethod
-    def _tokens(feat, embed_a, embed_b, f16, rows, C):
-        """backbone map -> token rows: fp32, or (None, fp16) when every reader takes fp16 operands"""
+    def _tokens(self, feat, embed_a, embed_b, f16, rows, C, absmax=None):
+        """backbone map -> token rows: fp32, or (None, fp16) when every reader takes fp16 operands.  With ``absmax`` (one
+        zeroed device float) the flatten kernel also records the largest token magnitude: the device-side operand bound
+        that lets the value projection (and, through its row sums, the output projection) run as fp16 x3."""
         if f16:
             _, t16 = ops.flatten_feats(feat, embed_a, embed_b, fp32=False, fp16=True)
             return (None, t16.view(rows, C))
+        if absmax is not None:
+            t = ops.flatten_feats_max(feat, absmax, embed_a, embed_b).view(rows, C)
+            self._dyn[id(t)] = absmax
+            return t
         return ops.flatten_feats(feat, embed_a, embed_b).view(rows, C)
 
     @staticmethod
