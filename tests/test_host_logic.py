@@ -237,6 +237,32 @@ for step in range(2):                                  # hooks re-arm after fini
         else:
             torch.testing.assert_close(g, wg, rtol=1e-6, atol=1e-7)
     assert all(p.grad is None for p in never.parameters())
+# gradient views: prepare() points every p.grad at its bucket slot, autograd accumulates in place, finish() copies nothing
+for step in range(2):
+    buckets.prepare()
+    flat_ptrs = {p: p.grad.data_ptr() for p in params}
+    loss_of(r, with_unused=(r == 0)).backward()
+    buckets.finish()
+    want_loss = sum(loss_of(k, with_unused=(k == 0)) for k in range(w)) / w
+    want = torch.autograd.grad(want_loss, params, allow_unused=True)
+    for p, wg in zip(params, want):
+        if wg is None:
+            assert p.grad is None
+        else:
+            assert p.grad.data_ptr() == flat_ptrs[p]           # still the bucket slot: no copy back
+            torch.testing.assert_close(p.grad, wg, rtol=1e-6, atol=1e-7)
+# uniform_usage=True (ranks seeded alike, every rank touches the same parameters): no flag exchange, same result
+ub = GradBuckets(list(net.parameters()) + list(never.parameters()), bucket_bytes=64, uniform_usage=True)
+buckets.remove()
+ub.prepare()
+loss_of(r, with_unused=False).backward()
+ub.finish()
+want = torch.autograd.grad(sum(loss_of(k, with_unused=False) for k in range(w)) / w, list(net.parameters()))
+for p, wg in zip(net.parameters(), want):
+    torch.testing.assert_close(p.grad, wg, rtol=1e-6, atol=1e-7)
+assert all(p.grad is None for p in never.parameters())
+ub.remove()
+buckets = GradBuckets(params, bucket_bytes=64)
 # two backward passes before finish(): no bucket is on the wire yet (bucket 0 holds the never-used parameters and waits for
 # finish()), so the accumulated gradients are exchanged -- never a stale first-pass copy (ADVICE r1); had a bucket already
 # been all-reduced, the second pass would raise instead

@@ -50,7 +50,7 @@ def main():
     bev_embedding = torch.nn.Parameter(torch.randn(inp['bev_queries'].shape, generator=g).to(dev))
     params = list(model.parameters()) + [bev_embedding]
     opt = torch.optim.AdamW(params, lr=2e-4, weight_decay=0.01)
-    buckets = GradBuckets(params, bucket_bytes=int(args.bucket_mb * (1 << 20)))
+    buckets = GradBuckets(params, bucket_bytes=int(args.bucket_mb * (1 << 20)), uniform_usage=True)   # ranks seeded alike
 
     def step():
         return train_step(model, bev_embedding, inp, opt, buckets)
