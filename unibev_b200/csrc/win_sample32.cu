@@ -21,14 +21,19 @@
 namespace ub {
 
 // Per-warp descriptor buffer of the warp's 16 items: per sample four fp32 weights {left top, left bottom, right top,
-// right bottom} (attention weight folded in; item stride padded by four words so the four items a warp reads in one
-// instruction fall into different banks), then 16-bit window pixel indices.
+// right bottom} (attention weight folded in), then 16-bit window pixel indices.  The weights are stored per pixel SIDE and
+// per PAIR of sampling points -- {top, bottom} of point 2 j, {top, bottom} of point 2 j + 1 -- so that a gathering lane
+// (which owns one side) fetches two points' weights with one 16-byte load.  Item stride and side offset are chosen so
+// that the 4 items x 2 sides x 16 bytes one warp instruction reads fall into 32 different banks (one wavefront):
+//   P = 8: [side][pair] (side offset 16 words), item stride 36 words;  P = 4: [pair][side] (side offset 4), stride 24.
 template <int PP>
 struct Desc32 {
-  static constexpr int w_stride = PP * 4 + 4;  // words per item
+  static constexpr int w_stride = PP == 8 ? 36 : PP * 4 + 8;  // words per item
   static constexpr int w_bytes = kWarpItems * w_stride * 4;
   static constexpr int idx_bytes = kWarpItems * PP * 2;
   static constexpr int bytes = w_bytes + idx_bytes;
+  // word offset of the float4 {w_top(2 j), w_bot(2 j), w_top(2 j + 1), w_bot(2 j + 1)} of pixel side `side`
+  __device__ static constexpr int pair_off(int side, int j) { return PP == 8 ? side * 16 + j * 4 : j * 8 + side * 4; }
 };
 
 // softmax over the item's P logits (two lanes per item, PPL points each): expf and a true division
@@ -72,12 +77,17 @@ template <int PP>
 __device__ __forceinline__ void store_descs32(uint32_t sm_w, uint32_t sm_idx, int item, int p0, const float4 (&w4)[PP / 2],
                                               const uint32_t (&idx)[PP / 2]) {
   constexpr int PPL = PP / 2;
-  const uint32_t wa = sm_w + (uint32_t)(item * Desc32<PP>::w_stride + p0 * 4) * 4u;
+  const uint32_t wa = sm_w + (uint32_t)(item * Desc32<PP>::w_stride) * 4u;
 #pragma unroll
-  for (int i = 0; i < PPL; ++i)
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(wa + i * 16), "f"(w4[i].x), "f"(w4[i].y), "f"(w4[i].z),
-                 "f"(w4[i].w)
+  for (int i = 0; i < PPL; i += 2) {   // this lane's point pairs p0 / 2 + i / 2
+    const int j = p0 / 2 + i / 2;
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(wa + (uint32_t)Desc32<PP>::pair_off(0, j) * 4u), "f"(w4[i].x),
+                 "f"(w4[i].y), "f"(w4[i + 1].x), "f"(w4[i + 1].y)
                  : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(wa + (uint32_t)Desc32<PP>::pair_off(1, j) * 4u), "f"(w4[i].z),
+                 "f"(w4[i].w), "f"(w4[i + 1].z), "f"(w4[i + 1].w)
+                 : "memory");
+  }
   const uint32_t ia = sm_idx + (uint32_t)(item * PP + p0) * 2u;
   if (PPL == 4)
     asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(ia), "r"(idx[0] | (idx[1] << 16)), "r"(idx[2] | (idx[PPL - 1] << 16))
@@ -100,17 +110,20 @@ __device__ __forceinline__ float2 lds64f(uint32_t addr) {
 // The gather of one warp's 16 items from ONE half-head window: lane group `grp` (8 lanes) reduces items grp, grp + 4,
 // grp + 8, grp + 12, two at a time; lanes 0-3 of a group own the left pixel, 4-7 the right one, four channels each.
 // res[m] = this lane's four channels (cq * 4 ...) of item grp + 4 m, both pixel sides summed (held by both side lanes).
+// n_live (warp-uniform): only items < n_live are real (tile columns beyond the BEV grid / list positions beyond the hit
+// list); a pair of item quads with no real item is skipped (res left untouched).
 template <int PP, int ROWB>
 __device__ __forceinline__ void gather_warp32(uint32_t sm_w, uint32_t sm_idx, uint32_t win, uint32_t row_rt, int grp,
-                                              int side, float4 (&res)[4]) {
+                                              int side, int n_live, float4 (&res)[4]) {
   const uint32_t row_b = ROWB > 0 ? (uint32_t)ROWB : row_rt;
 #pragma unroll
   for (int k = 0; k < 4; k += 2) {
+    if (k * 4 >= n_live) break;
     const int item[2] = {grp + k * 4, grp + (k + 1) * 4};
     uint32_t ix[2][4], wa[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      wa[j] = sm_w + (uint32_t)(item[j] * Desc32<PP>::w_stride + side * 2) * 4u;
+      wa[j] = sm_w + (uint32_t)(item[j] * Desc32<PP>::w_stride + side * Desc32<PP>::pair_off(1, 0)) * 4u;
       if (PP == 8) {
         const uint4 t = lds128(sm_idx + item[j] * 16);
         ix[j][0] = t.x, ix[j][1] = t.y, ix[j][2] = t.z, ix[j][3] = t.w;
@@ -122,22 +135,27 @@ __device__ __forceinline__ void gather_warp32(uint32_t sm_w, uint32_t sm_idx, ui
     }
     float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
 #pragma unroll
-    for (int p = 0; p < PP; ++p) {
-      float4 top[2], bot[2];
-      float2 w[2];
+    for (int pp = 0; pp < PP / 2; ++pp) {
+      float4 w[2];   // {top, bottom} of point 2 pp, {top, bottom} of point 2 pp + 1, this lane's pixel side
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t word = ix[j][p >> 1];
-        const uint32_t id = (p & 1) ? (word >> 16) : (word & 0xffffu);
-        const uint32_t a = win + id * 64u;
-        w[j] = lds64f(wa[j] + p * 16);
-        top[j] = lds128f(a);
-        bot[j] = lds128f(a + row_b);
-      }
+      for (int j = 0; j < 2; ++j)
+        w[j] = lds128f(wa[j] + (uint32_t)Desc32<PP>::pair_off(0, pp) * 4u);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        fma4(acc[j], w[j].x, top[j]);
-        fma4(acc[j], w[j].y, bot[j]);
+      for (int q = 0; q < 2; ++q) {
+        float4 top[2], bot[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t word = ix[j][pp];
+          const uint32_t id = q ? (word >> 16) : (word & 0xffffu);
+          const uint32_t a = win + id * 64u;
+          top[j] = lds128f(a);
+          bot[j] = lds128f(a + row_b);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          fma4(acc[j], q ? w[j].z : w[j].x, top[j]);
+          fma4(acc[j], q ? w[j].w : w[j].y, bot[j]);
+        }
       }
     }
 #pragma unroll
@@ -362,12 +380,14 @@ __global__ void __launch_bounds__(kBevThreads, 1)
     // ---- P2: the two half-head windows of the unit
     float4 r0[4], r1[4];
     const uint32_t ph = (uint32_t)(k & 1);
+    // real items of this warp's query row: none below the grid, 16 or fewer in the last tile column
+    const int n_live = row_ok ? min(kWarpItems, a.bev_w - w.tx0) : 0;
     mbar_wait(bar_full, ph);
-    gather_warp32<PP, ROWB>(sm_w, sm_idx, sm_win + sub * 16u, (uint32_t)a.WW * 64u, grp, side, r0);
+    gather_warp32<PP, ROWB>(sm_w, sm_idx, sm_win + sub * 16u, (uint32_t)a.WW * 64u, grp, side, n_live, r0);
     __syncwarp();   // every lane is done with window 0
     if (lane == 0) mbar_arrive(bar_empty);
     mbar_wait(bar_full + 8u, ph);
-    gather_warp32<PP, ROWB>(sm_w, sm_idx, sm_win + (uint32_t)win_bytes + sub * 16u, (uint32_t)a.WW * 64u, grp, side, r1);
+    gather_warp32<PP, ROWB>(sm_w, sm_idx, sm_win + (uint32_t)win_bytes + sub * 16u, (uint32_t)a.WW * 64u, grp, side, n_live, r1);
     __syncwarp();   // ... and with window 1 and the descriptors
     if (lane == 0) mbar_arrive(bar_empty + 8u);
     // rows: lanes of pixel side 0 write the first half-head's channels, side 1 the second's: 128 B per item and store
@@ -724,7 +744,8 @@ __global__ void __launch_bounds__(kImgThreads, 1)
       fresh = false;
     }
     float4 res[4];
-    gather_warp32<PP, ROWB>(sm_w, sm_idx, sm_win + sub * 16u, (uint32_t)a.WW * 64u, grp, side, res);
+    const int n_live = max(0, min(kWarpItems, w_cur.limit - (w_cur.pos0 + warp * kWarpItems)));
+    gather_warp32<PP, ROWB>(sm_w, sm_idx, sm_win + sub * 16u, (uint32_t)a.WW * 64u, grp, side, n_live, res);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       if (qm[j] >= 0) {
