@@ -355,8 +355,8 @@ def main():
     #     CUDA graph and timed with CUDA events on the launching stream: no host gaps, no L2 reuse.
     records, calls = {}, {}
     op_names = ('bev_sample', 'img_sample', 'bev_sample_win', 'img_sample_win', 'bev_sample_win32', 'img_sample_win32',
-                'linear_tf32', 'linear_f16', 'linear_tf32x3', 'linear_f16x3', 'linear_tf32x3_scatter', 'linear_simt', 'add_layernorm',
-                'value_to_half', 'flatten_feats', 'cnw_fuse', 'build_hits', 'hit_order', 'project_points', 'broadcast_rows')
+                'linear_tf32', 'linear_f16', 'linear_tf32x3', 'linear_f16x3', 'linear_f16x3_dyn', 'linear_tf32x3_scatter', 'linear_simt',
+                'add_layernorm', 'value_to_half', 'flatten_feats', 'flatten_feats_max', 'cnw_fuse', 'build_hits', 'hit_order', 'project_points', 'broadcast_rows')
     used = set()
     real = {n: getattr(ops, n) for n in op_names}
 
