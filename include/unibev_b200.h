@@ -110,6 +110,22 @@ int ub_img_sample_fwd(const float* value, const float* qproj, const float* ref_c
                       float* out, int B, int N, int bev_h, int bev_w, int fH, int fW, int H, int Dh, int P,
                       int D, int ld, int off_col, int logit_col, ub_stream_t stream);
 
+/* ---- [R4]/[R3] backward twins of the two kernels above (training step, BASELINE configs[4]) ----------
+ * Replace ms_deform_attn_backward + the autograd of the softmax / offset normalisation / reference-point add
+ * around it (spatial_cross_attention_img.py:390-419, spatial_cross_attention_pts.py:396-426) and, in camera mode,
+ * of the per-camera rebatch / scatter / count division (spatial_cross_attention_img.py:141-212).
+ * grad_out (B, Nq, H*Dh).  grad_value: same shape as value, ZERO-FILLED by the caller (red.global.add).
+ * grad_qproj (B, Nq, ld): gradient with respect to the RAW offset / logit columns (softmax backward folded in);
+ * only the columns [off_col, off_col + 2 H P) and [logit_col, logit_col + H P) of each row are written.
+ * Dh = 4 x a power of two <= 128, P <= 16; other shapes return UB_EUNSUPPORTED. */
+int ub_bev_sample_bwd(const float* value, const float* qproj, const float* grad_out, float* grad_value,
+                      float* grad_qproj, int B, int bev_h, int bev_w, int fH, int fW, int H, int Dh, int P, int ld,
+                      int off_col, int logit_col, ub_stream_t stream);
+int ub_img_sample_bwd(const float* value, const float* qproj, const float* ref_cam, const uint8_t* mask,
+                      const float* grad_out, float* grad_value, float* grad_qproj, int B, int N, int bev_h, int bev_w,
+                      int fH, int fW, int H, int Dh, int P, int D, int ld, int off_col, int logit_col,
+                      ub_stream_t stream);
+
 /* ---- [R4]/[R3] window-staged fast path (fp16-staged values, fp32 accumulation) ------------------------
  * Same arithmetic as ub_bev_sample_fwd / ub_img_sample_fwd, but the value map is read from fp16 head-major
  * planes staged in shared memory by TMA, and the bilinear x attention weights are rounded to fp16 before the

@@ -26,6 +26,8 @@ PROTOTYPES = {
     'ub_project_points': ([_p, _p, _p, _f, _f, _p, _p] + [_i] * 5 + [_p], _i),
     'ub_bev_sample_fwd': ([_p] * 3 + [_i] * 11 + [_p], _i),
     'ub_img_sample_fwd': ([_p] * 5 + [_i] * 13 + [_p], _i),
+    'ub_bev_sample_bwd': ([_p] * 5 + [_i] * 11 + [_p], _i),
+    'ub_img_sample_bwd': ([_p] * 7 + [_i] * 13 + [_p], _i),
     'ub_value_to_half': ([_p, _p] + [_i] * 4 + [_p], _i),
     'ub_bev_sample_win_fwd': ([_p] * 3 + [_i] * 12 + [_p, _i, _p], _i),
     'ub_bev_sample_win32_fwd': ([_p] * 3 + [_i] * 11 + [_p, _p], _i),

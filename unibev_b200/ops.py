@@ -132,6 +132,63 @@ def img_sample(value, qproj, ref_cam, mask, bev_h, bev_w, fH, fW, H, P, off_col,
     return out
 
 
+class BevSampleFunction(torch.autograd.Function):
+    """Autograd twin of ``bev_sample``: forward ``ub_bev_sample_fwd``, backward ``ub_bev_sample_bwd`` (gradients with
+    respect to the projected value rows and the RAW offset | logit rows; no loc / weight tensors in either direction).
+    ``FusedSample.bev(value, qproj, bev_h, bev_w, fH, fW, H, P, off_col, logit_col)``."""
+
+    @staticmethod
+    def forward(ctx, value, qproj, bev_h, bev_w, fH, fW, H, P, off_col, logit_col):
+        value, qproj = _need(value, 'value'), _need(qproj, 'qproj')
+        ctx.save_for_backward(value, qproj)
+        ctx.geo = (bev_h, bev_w, fH, fW, H, P, off_col, logit_col)
+        return bev_sample(value, qproj, bev_h, bev_w, fH, fW, H, P, off_col, logit_col)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        value, qproj = ctx.saved_tensors
+        bev_h, bev_w, fH, fW, H, P, off_col, logit_col = ctx.geo
+        go = _need(grad_out, 'grad_out')
+        B, _, C = value.shape
+        g_value = torch.zeros_like(value)
+        g_qproj = torch.empty_like(qproj) if qproj.shape[2] == 3 * H * P else torch.zeros_like(qproj)
+        _call('ub_bev_sample_bwd', value, _ptr(value), _ptr(qproj), _ptr(go), _ptr(g_value), _ptr(g_qproj), B, bev_h, bev_w,
+              fH, fW, H, C // H, P, qproj.shape[2], off_col, logit_col)
+        return (g_value, g_qproj) + (None,) * 8
+
+
+class ImgSampleFunction(torch.autograd.Function):
+    """Autograd twin of ``img_sample`` (camera cross-attention incl. the batch-0 hit quirk and the count division):
+    forward ``ub_img_sample_fwd``, backward ``ub_img_sample_bwd``."""
+
+    @staticmethod
+    def forward(ctx, value, qproj, ref_cam, mask, bev_h, bev_w, fH, fW, H, P, off_col, logit_col):
+        value, qproj, ref_cam = _need(value, 'value'), _need(qproj, 'qproj'), _need(ref_cam, 'ref_cam')
+        mask = _need(mask, 'mask', torch.uint8)
+        ctx.save_for_backward(value, qproj, ref_cam, mask)
+        ctx.geo = (bev_h, bev_w, fH, fW, H, P, off_col, logit_col)
+        return img_sample(value, qproj, ref_cam, mask, bev_h, bev_w, fH, fW, H, P, off_col, logit_col)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        value, qproj, ref_cam, mask = ctx.saved_tensors
+        bev_h, bev_w, fH, fW, H, P, off_col, logit_col = ctx.geo
+        go = _need(grad_out, 'grad_out')
+        B, N, _, C = value.shape
+        g_value = torch.zeros_like(value)
+        g_qproj = torch.empty_like(qproj) if qproj.shape[2] == 3 * H * P else torch.zeros_like(qproj)
+        _call('ub_img_sample_bwd', value, _ptr(value), _ptr(qproj), _ptr(ref_cam), _ptr(mask), _ptr(go), _ptr(g_value),
+              _ptr(g_qproj), B, N, bev_h, bev_w, fH, fW, H, C // H, P, ref_cam.shape[3], qproj.shape[2], off_col, logit_col)
+        return (g_value, g_qproj) + (None,) * 10
+
+
+def fused_sample_supported(Dh, P):
+    """Shapes ``ub_bev_sample_bwd`` / ``ub_img_sample_bwd`` (and the generic forward kernels) cover."""
+    return Dh % 4 == 0 and ((Dh // 4) & (Dh // 4 - 1)) == 0 and Dh <= 128 and P <= 16
+
+
 def value_to_half(value, G, Nv, H, out=None):
     """value (G*Nv, C) fp32 token-major -> (G, H, Nv, C // H) fp16 head-major planes for the window kernels."""
     value = _need(value, 'value')

@@ -17,8 +17,17 @@ import warnings
 import torch
 import torch.nn as nn
 
-from ..ops import MultiScaleDeformableAttnFunction
+import torch.nn.functional as F
+
+from ..ops import (BevSampleFunction, ImgSampleFunction, MultiScaleDeformableAttnFunction, fused_sample_supported)
 from ..registry import ATTENTION, HAVE_MMCV, build_attention
+
+# Module (autograd) path: when the caller is one of this package's encoders -- which pass the BEV grid shape
+# (``ub_bev_grid``) and, for the cameras, the raw output of ``ub_project_points`` (``ub_cam``) down to the attentions -- the
+# softmax / offset normalisation / reference-point add / (camera) rebatch-scatter-count glue and mmcv's op are replaced by
+# ONE fused kernel per direction (``ub_bev_sample_fwd/bwd``, ``ub_img_sample_fwd/bwd``) that reads the raw linear outputs.
+# UB_FUSED_TRAIN=0 (or setting this flag to False) keeps the op-level path (``ub_msda_fwd/bwd`` + torch glue).
+FUSED_TRAIN_SAMPLING = os.environ.get('UB_FUSED_TRAIN', '1') == '1'
 
 
 def _xavier_uniform(linear, bias=0.):
@@ -74,6 +83,16 @@ class _DeformAttnBase(nn.Module):
             _xavier_uniform(self.output_proj)
         self._is_init = True
 
+    def _raw_rows(self, query):
+        """(B, Nq, 3 H L P): raw sampling offsets (H, L, P, 2) then raw attention logits (H, L, P), one GEMM."""
+        w = torch.cat((self.sampling_offsets.weight, self.attention_weights.weight), 0)
+        b = torch.cat((self.sampling_offsets.bias, self.attention_weights.bias), 0)
+        return F.linear(query, w, b)
+
+    def _fused_ok(self, key_padding_mask):
+        return (FUSED_TRAIN_SAMPLING and self.num_levels == 1 and key_padding_mask is None
+                and fused_sample_supported(self.embed_dims // self.num_heads, self.num_points))
+
     def _project(self, query, value, key_padding_mask):
         bs, nq, _ = query.shape
         _, nv, _ = value.shape
@@ -113,6 +132,17 @@ class MultiScaleDeformableAttention(_DeformAttnBase):
             query = query + query_pos
         if not self.batch_first:
             query, value = query.permute(1, 0, 2), value.permute(1, 0, 2)
+        grid = kwargs.get('ub_bev_grid')
+        if (grid is not None and reference_points.shape[-1] == 2 and value.shape[1] == grid[0] * grid[1]
+                and query.shape[1] == grid[0] * grid[1] and self._fused_ok(key_padding_mask)):
+            # BEV self-attention over the query grid itself: reference points are the cell centres the kernel generates
+            H, P = self.num_heads, self.num_points
+            out = BevSampleFunction.apply(self.value_proj(value), self._raw_rows(query), grid[0], grid[1], grid[0], grid[1],
+                                          H, P, 0, 2 * H * P)
+            out = self.output_proj(out)
+            if not self.batch_first:
+                out = out.permute(1, 0, 2)
+            return self.dropout(out) + identity
         assert int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum()) == value.shape[1]
         v, off, aw = self._project(query, value, key_padding_mask)
         if reference_points.shape[-1] == 2:
@@ -149,6 +179,14 @@ class _MSDeformableAttention3D(_DeformAttnBase):
         if not self.batch_first:
             query, value = query.permute(1, 0, 2), value.permute(1, 0, 2)
         bs, nq, _ = query.shape
+        grid, fhw = kwargs.get('ub_bev_grid'), kwargs.get('ub_value_hw')
+        if (grid is not None and fhw is not None and nq == grid[0] * grid[1] and value.shape[1] == fhw[0] * fhw[1]
+                and reference_points.shape[-1] == 2 and self._fused_ok(key_padding_mask)):
+            # LiDAR cross-attention: every pillar anchor projects to its cell centre, which the kernel generates
+            H, P = self.num_heads, self.num_points
+            out = BevSampleFunction.apply(self.value_proj(value), self._raw_rows(query), grid[0], grid[1], fhw[0], fhw[1],
+                                          H, P, 0, 2 * H * P)
+            return out if self.batch_first else out.permute(1, 0, 2)
         assert int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum()) == value.shape[1]
         v, off, aw = self._project(query, value, key_padding_mask)
         if reference_points.shape[-1] != 2:
@@ -214,6 +252,17 @@ class SpatialCrossAttentionImg(nn.Module):
             query = query + query_pos
         B, Nq, C = query.shape
         N, D = reference_points_cam.size(0), reference_points_cam.size(3)
+        cam, grid, fhw = kwargs.get('ub_cam'), kwargs.get('ub_bev_grid'), kwargs.get('ub_value_hw')
+        da = self.deformable_attention
+        if (cam is not None and grid is not None and fhw is not None and Nq == grid[0] * grid[1]
+                and value.shape[1] == fhw[0] * fhw[1] and da.batch_first and da.num_points % D == 0
+                and da._fused_ok(key_padding_mask)):
+            # one fused kernel per direction instead of rebatch -> inner attention -> scatter -> count division
+            H, P = da.num_heads, da.num_points
+            v = da.value_proj(value.permute(2, 0, 1, 3))                # (B, N, hw, C)
+            slots = ImgSampleFunction.apply(v, da._raw_rows(query), cam[0], cam[1], grid[0], grid[1], fhw[0], fhw[1],
+                                            H, P, 0, 2 * H * P)
+            return self.dropout(self.output_proj(slots)) + inp_residual
         hit0 = bev_mask[:, 0].any(-1)                                  # (N, Nq)
         lens = hit0.sum(1)
         max_len = int(lens.max())                                      # one host sync (training path only)
@@ -273,6 +322,7 @@ class SpatialCrossAttentionPts(nn.Module):
         value = value.permute(1, 0, 2)
         out = self.deformable_attention(query=query, key=value, value=value,
                                         reference_points=reference_points_lidar.permute(1, 2, 0, 3),
-                                        spatial_shapes=spatial_shapes, level_start_index=level_start_index)
+                                        spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                                        ub_bev_grid=kwargs.get('ub_bev_grid'), ub_value_hw=kwargs.get('ub_value_hw'))
         out = self.output_proj(out.view(B, -1, C))
         return self.dropout(out) + inp_residual

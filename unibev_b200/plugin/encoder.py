@@ -208,6 +208,13 @@ class ImgEncoder(_Encoder):
         """-> reference_points_cam (num_cam, B, Nq, D, 2), bev_mask (num_cam, B, Nq, D) bool, computed by
         ``ub_project_points`` from the cell grid directly (``reference_points`` is only read for its shape;
         it must be the regular pillar grid of ``get_reference_points``)."""
+        ref, mask = self._project_raw(reference_points, pc_range, img_metas, bev_hw)
+        D = reference_points.shape[1]
+        bits = (mask[..., None] >> torch.arange(D, device=mask.device, dtype=torch.uint8)) & 1
+        return ref.permute(2, 0, 1, 3, 4), bits.bool().permute(2, 0, 1, 3)
+
+    def _project_raw(self, reference_points, pc_range, img_metas, bev_hw=None):
+        """``ub_project_points`` output as the fused kernels take it: ref (B, Nq, N, D, 2), mask (B, Nq, N) uint8 bits."""
         B, D, Nq, _ = reference_points.shape
         l2i = np.asarray([m['lidar2img'] for m in img_metas], dtype=np.float32)
         l2i = torch.from_numpy(l2i).to(reference_points.device)
@@ -217,9 +224,7 @@ class ImgEncoder(_Encoder):
         H, W = bev_hw
         zs = anchor_heights(pc_range[5] - pc_range[2], D).tolist()
         ih, iw = img_metas[0]['img_shape'][0][0], img_metas[0]['img_shape'][0][1]
-        ref, mask = ops.project_points(l2i, zs, pc_range, ih, iw, H, W)       # (B,Nq,N,D,2), (B,Nq,N) bits
-        bits = (mask[..., None] >> torch.arange(D, device=mask.device, dtype=torch.uint8)) & 1
-        return ref.permute(2, 0, 1, 3, 4), bits.bool().permute(2, 0, 1, 3)
+        return ops.project_points(l2i, zs, pc_range, ih, iw, H, W)             # (B,Nq,N,D,2), (B,Nq,N) bits
 
     def forward(self, bev_query, key, value, *args, bev_h=None, bev_w=None, bev_pos=None, spatial_shapes=None,
                 level_start_index=None, valid_ratios=None, **kwargs):
@@ -228,13 +233,18 @@ class ImgEncoder(_Encoder):
         ref_3d = self.get_reference_points(bev_h, bev_w, self.pc_range[5] - self.pc_range[2],
                                            self.num_points_in_pillar, dim='3d', bs=bs, device=dev, dtype=dt)
         ref_2d = self.get_reference_points(bev_h, bev_w, dim='2d', bs=bs, device=dev, dtype=dt)
-        ref_cam, bev_mask = self.point_sampling(ref_3d, self.pc_range, kwargs['img_metas'], bev_hw=(bev_h, bev_w))
+        raw_ref, raw_mask = self._project_raw(ref_3d, self.pc_range, kwargs['img_metas'], (bev_h, bev_w))
+        D = self.num_points_in_pillar
+        bits = (raw_mask[..., None] >> torch.arange(D, device=raw_mask.device, dtype=torch.uint8)) & 1
+        ref_cam, bev_mask = raw_ref.permute(2, 0, 1, 3, 4), bits.bool().permute(2, 0, 1, 3)     # == point_sampling(...)
         bev_query = bev_query.permute(1, 0, 2)
         if bev_pos is not None:
             bev_pos = bev_pos.permute(1, 0, 2)
         return self._run_layers(bev_query, key, value, args, kwargs, bev_pos=bev_pos, ref_2d=ref_2d, ref_3d=ref_3d,
                                 bev_h=bev_h, bev_w=bev_w, spatial_shapes=spatial_shapes,
-                                level_start_index=level_start_index, reference_points_cam=ref_cam, bev_mask=bev_mask)
+                                level_start_index=level_start_index, reference_points_cam=ref_cam, bev_mask=bev_mask,
+                                # for the fused sampling kernels of the module path (plugin/attention.py)
+                                ub_bev_grid=(bev_h, bev_w), ub_cam=(raw_ref, raw_mask))
 
 
 @TRANSFORMER_LAYER_SEQUENCE.register_module()
@@ -263,4 +273,5 @@ class PtsEncoder(_Encoder):
             bev_pos = bev_pos.permute(1, 0, 2)
         return self._run_layers(bev_query, key, value, args, kwargs, bev_pos=bev_pos, ref_2d=ref_2d, ref_3d=ref_3d,
                                 bev_h=bev_h, bev_w=bev_w, spatial_shapes=spatial_shapes,
-                                level_start_index=level_start_index, reference_points_lidar=ref_lidar)
+                                level_start_index=level_start_index, reference_points_lidar=ref_lidar,
+                                ub_bev_grid=(bev_h, bev_w))

@@ -228,12 +228,14 @@ class UniBEVTransformer(nn.Module):
         img = pts = None
         if img_mlvl_feats is not None:
             flat, shapes, start = self._pre_process_img_feats(img_mlvl_feats, q_img)
+            hw = tuple(img_mlvl_feats[0].shape[-2:]) if len(img_mlvl_feats) == 1 else None   # (one level: fused sampling)
             img = self.img_bev_encoder(q_img, flat, flat, bev_h=bev_h, bev_w=bev_w, bev_pos=bev_pos,
-                                       spatial_shapes=shapes, level_start_index=start, **kwargs)
+                                       spatial_shapes=shapes, level_start_index=start, ub_value_hw=hw, **kwargs)
         if pts_mlvl_feats is not None:
             flat, shapes, start = self._pre_process_pts_feats(pts_mlvl_feats, q_pts)
             pts = self.pts_bev_encoder(q_pts, flat, flat, bev_h=bev_h, bev_w=bev_w, bev_pos=bev_pos,
-                                       spatial_shapes=shapes, level_start_index=start, **kwargs)
+                                       spatial_shapes=shapes, level_start_index=start,
+                                       ub_value_hw=tuple(pts_mlvl_feats[0].shape[-2:]), **kwargs)
         return img, pts
 
     def _fuse_modules(self, img, pts):
