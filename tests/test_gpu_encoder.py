@@ -128,8 +128,14 @@ def test_fused_weights_follow_parameter_updates():
         torch.testing.assert_close(run(), first, rtol=0, atol=1e-6)
 
 
-def test_module_path_backward_matches_oracle_autograd():
-    """Training path: gradients through ub_msda_bwd vs autograd through the CPU oracle."""
+@pytest.mark.parametrize('fused_sampling', [True, False])
+def test_module_path_backward_matches_oracle_autograd(fused_sampling, monkeypatch):
+    """Training path: gradients through the fused sampling twins (ub_bev/img_sample_fwd + _bwd: raw offset | logit rows in,
+    their gradients out) and through the op-level path (ub_msda_fwd / ub_msda_bwd + torch glue) vs autograd through the
+    CPU oracle."""
+    from unibev_b200 import _cabi
+    from unibev_b200.plugin import attention
+    monkeypatch.setattr(attention, 'FUSED_TRAIN_SAMPLING', fused_sampling)
     a, p = load_golden('encoder_half_lc_cnw_linear')
     cfg, img, pts, q, bev_h, bev_w = encoder_half_inputs(a)
     m = _build(cfg, p).train()

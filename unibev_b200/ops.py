@@ -185,8 +185,8 @@ class ImgSampleFunction(torch.autograd.Function):
 
 
 def fused_sample_supported(Dh, P):
-    """Shapes ``ub_bev_sample_bwd`` / ``ub_img_sample_bwd`` (and the generic forward kernels) cover."""
-    return Dh % 4 == 0 and ((Dh // 4) & (Dh // 4 - 1)) == 0 and Dh <= 128 and P <= 16
+    """Shapes the generic fused sampling kernels cover in both directions (``ub_bev/img_sample_fwd`` + ``_bwd``)."""
+    return Dh in (8, 16, 32, 64) and 0 < P <= 16
 
 
 def value_to_half(value, G, Nv, H, out=None):
