@@ -40,3 +40,56 @@ def test_train_step_updates_parameters_and_matches_plain_autograd():
     assert moved > 30
     loss1 = float(train_step(model, emb, inp, opt, buckets))
     assert np.isfinite(loss0) and np.isfinite(loss1) and loss1 < loss0
+
+
+def test_full_size_cat128_gradients_vs_oracle_autograd():
+    """BASELINE configs[4] at full size (200 x 200 BEV queries, 6 x 29 x 50 camera tokens, 180 x 180 LiDAR map, 3 layers per
+    modality, 'cat' fusion of two 128-channel maps; dropout and modality dropout off so both sides are deterministic):
+    forward + backward through the module path with the fused sampling twins (ub_bev/img_sample_fwd + _bwd) against
+    autograd through the CPU oracle -- every parameter gradient, the query-table gradient and the feature gradients."""
+    import time
+    from oracle import unibev_encoder as oe
+    from unibev_b200 import _cabi, synth
+    from unibev_b200.plugin import attention
+    assert attention.FUSED_TRAIN_SAMPLING
+    wl = 'unibev_nus_LC_cat_128'
+    model, cfg = synth.build_model(wl, drop_modality=None, dropout=0.0)
+    model = model.cuda().train()
+    inp = synth.make_inputs(wl, batch=1, seed=3)
+    img = [t.cuda().requires_grad_() for t in inp['img_feats']]
+    pts = [t.cuda().requires_grad_() for t in inp['pts_feats']]
+    emb = inp['bev_queries'].cuda().requires_grad_()
+    _cabi.reset_launch_count()
+    out = model.encode(img, pts, emb, inp['bev_h'], inp['bev_w'], bev_pos=inp['bev_pos'].cuda(), img_metas=inp['img_metas'])
+    assert out.shape == (1, 40000, 256)
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
+    out.backward(go.cuda())
+    assert _cabi.launch_count() >= 2 * 9 and _cabi.unsupported_count() == 0      # 9 fused samplings, forward and backward
+
+    p = {k: v.detach().cpu().clone().requires_grad_() for k, v in model.state_dict().items()}
+    img_c = [t.detach().cpu().clone().requires_grad_() for t in img]
+    pts_c = [t.detach().cpu().clone().requires_grad_() for t in pts]
+    emb_c = emb.detach().cpu().clone().requires_grad_()
+    t0 = time.time()
+    want = oe.encoder_half(p, cfg, img_c, pts_c, emb_c, inp['bev_h'], inp['bev_w'], bev_pos=inp['bev_pos'],
+                           img_metas=inp['img_metas'])
+    want.backward(go)
+    print(f'\n[{wl} full size] oracle forward + backward {time.time() - t0:.1f}s')
+    torch.testing.assert_close(out.detach().cpu(), want.detach(), rtol=1e-3, atol=1e-4)
+
+    def check(name, got, ref):
+        scale = float(ref.abs().max()) + 1e-9
+        err = float((got.cpu() - ref).abs().max())
+        assert err <= 2e-3 * scale + 1e-7, (name, err, scale)
+    checked = 0
+    for name, prm in model.named_parameters():
+        ref = p[name].grad
+        if prm.grad is None:
+            assert ref is None or float(ref.abs().max()) == 0.0, name
+            continue
+        check(name, prm.grad, ref)
+        checked += 1
+    assert checked > 90
+    check('bev_queries', emb.grad, emb_c.grad)
+    check('img_feats', img[0].grad, img_c[0].grad)
+    check('pts_feats', pts[0].grad, pts_c[0].grad)
