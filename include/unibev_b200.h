@@ -263,6 +263,15 @@ int ub_split_tf32(const float* w, float* hi, float* lo, int64_t n, ub_stream_t s
  * bias (C) and residual (rows, C) may be NULL.  C % 4 == 0, C <= 1024.  out may alias x. */
 int ub_add_layernorm(const float* x, const float* bias, const float* residual, const float* gamma,
                      const float* beta, float* out, int64_t rows, int C, float eps, ub_stream_t stream);
+/* ---- training step: streaming reductions of the backward pass (BASELINE configs[4]) ------------------
+ * ub_colsum: out (N) += column sums of x (M, N): the bias gradient of a projection (autograd of the nn.Linear layers,
+ * spatial_cross_attention_img.py:59,285-289).  out is ACCUMULATED into (zero it first).  N % 4 == 0, N <= 1024.
+ * ub_layernorm_bwd: backward of y = LayerNorm(x) * gamma + beta over the last dim C (the 'norm' steps,
+ * encoder_unibev_detr_img.py:434-436,476-479): dx (rows, C) written; dgamma (C), dbeta (C) ACCUMULATED into (zero them
+ * first).  Row statistics are recomputed from x.  C % 4 == 0, C <= 1024. */
+int ub_colsum(const float* x, float* out, int64_t M, int N, ub_stream_t stream);
+int ub_layernorm_bwd(const float* x, const float* dy, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                     int64_t rows, int C, float eps, ub_stream_t stream);
 /* The same, additionally writing an fp16 copy `out16` (rows, C) of the result (may be NULL). */
 int ub_add_layernorm16(const float* x, const float* bias, const float* residual, const float* gamma,
                        const float* beta, float* out, void* out16, int64_t rows, int C, float eps, ub_stream_t stream);

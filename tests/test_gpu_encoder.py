@@ -133,9 +133,10 @@ def test_module_path_backward_matches_oracle_autograd(fused_sampling, monkeypatc
     """Training path: gradients through the fused sampling twins (ub_bev/img_sample_fwd + _bwd: raw offset | logit rows in,
     their gradients out) and through the op-level path (ub_msda_fwd / ub_msda_bwd + torch glue) vs autograd through the
     CPU oracle."""
-    from unibev_b200 import _cabi
+    from unibev_b200 import ops
     from unibev_b200.plugin import attention
     monkeypatch.setattr(attention, 'FUSED_TRAIN_SAMPLING', fused_sampling)
+    monkeypatch.setattr(ops, 'TRAIN_KERNELS', fused_sampling)     # (False: plain torch modules + ub_msda_fwd / ub_msda_bwd)
     a, p = load_golden('encoder_half_lc_cnw_linear')
     cfg, img, pts, q, bev_h, bev_w = encoder_half_inputs(a)
     m = _build(cfg, p).train()

@@ -5,6 +5,7 @@ arithmetic happens in libunibev_b200.so.  Every op requires CUDA fp32 tensors an
 raises otherwise -- there is no CPU path.
 """
 import ctypes
+import os
 
 import torch
 
@@ -634,6 +635,110 @@ def add_layernorm(x, gamma, beta, bias=None, residual=None, eps=1e-5, out=None, 
     _call('ub_add_layernorm', x, _ptr(x), _ptr(bias), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(out),
                                              rows, C, float(eps))
     return out
+
+
+def colsum(x, out=None):
+    """x (..., N) -> (N) column sums over all leading dims (``ub_colsum``): the bias gradient of a projection."""
+    x = _need(x, 'x')
+    N = x.shape[-1]
+    if out is None:
+        out = torch.zeros(N, device=x.device, dtype=torch.float32)
+    _call('ub_colsum', x, _ptr(x), _ptr(out), x.numel() // N, N)
+    return out
+
+
+def train_ops_supported(C):
+    """Last-dim sizes ``ub_colsum`` / ``ub_layernorm_bwd`` / ``ub_add_layernorm`` cover."""
+    return C % 4 == 0 and 0 < C <= 1024
+
+
+def _wgrad(g2, x2):
+    """g2 (M, N)^T @ x2 (M, K) -> (N, K): the weight gradient of a projection.  M is the number of BEV queries / tokens
+    (tens of thousands), N and K a few hundred: one skinny product with a very long reduction, for which cuBLAS picks a
+    single-wave kernel (72 us at M = 80 000, N = K = 128).  Splitting the reduction into S batches (one bmm, S x N x K partial
+    sums, one small sum) fills the GPU: ~3x faster."""
+    M = g2.shape[0]
+    for S in (64, 50, 40, 32, 25, 20, 16, 10, 8):
+        if M % S == 0 and M // S >= 512:
+            part = torch.bmm(g2.view(S, M // S, -1).transpose(1, 2), x2.reshape(S, M // S, -1))
+            return part.sum(0)
+    return g2.t() @ x2
+
+
+class LinearFunction(torch.autograd.Function):
+    """y = x W^T + b with the library's column-sum kernel for the bias gradient (torch's generic column reduction is the
+    single largest item of the training step's backward: ~50 us per projection against ~10 us here); the matrix products
+    stay with cuBLAS (TF32 when ``torch.backends.cuda.matmul.allow_tf32`` is set, as the reference's stack did)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        x2 = x.reshape(-1, x.shape[-1])
+        y = x.new_empty(*x.shape[:-1], weight.shape[0])      # (returned as is, not as a view: callers may apply in-place ReLU)
+        if bias is not None:
+            torch.addmm(bias, x2, weight.t(), out=y.view(-1, weight.shape[0]))
+        else:
+            torch.mm(x2, weight.t(), out=y.view(-1, weight.shape[0]))
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1])
+        g2 = g2 if g2.is_contiguous() else g2.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = (g2 @ weight).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            gw = _wgrad(g2, x.reshape(-1, x.shape[-1]))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = colsum(g2)
+        return gx, gw, gb
+
+
+class LayerNormFunction(torch.autograd.Function):
+    """y = LayerNorm(x) * gamma + beta: forward ``ub_add_layernorm``, backward ``ub_layernorm_bwd`` (one pass each)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x = _need(x, 'x')
+        ctx.save_for_backward(x, gamma)
+        ctx.eps = float(eps)
+        return add_layernorm(x, gamma.detach(), beta.detach(), eps=eps)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, gamma = ctx.saved_tensors
+        gy = _need(gy, 'grad_out')
+        C = x.shape[-1]
+        gx = torch.empty_like(x)
+        gg = torch.zeros(2, C, device=x.device, dtype=torch.float32)
+        _call('ub_layernorm_bwd', x, _ptr(x), _ptr(gy), _ptr(_need(gamma.detach(), 'gamma')), _ptr(gx), _ptr(gg[0]), _ptr(gg[1]),
+              x.numel() // C, C, ctx.eps)
+        return gx, gg[0], gg[1], None
+
+
+# UB_FUSED_TRAIN=0 keeps the module (autograd) path on plain torch modules + the op-level ub_msda_fwd / ub_msda_bwd
+TRAIN_KERNELS = os.environ.get('UB_FUSED_TRAIN', '1') == '1'
+
+
+def linear_train(module, x):
+    """``nn.Linear`` forward of the module (autograd) path: ``LinearFunction`` for fp32 CUDA activations, else the module."""
+    if (TRAIN_KERNELS and x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled() and module.bias is not None
+            and train_ops_supported(module.out_features)):
+        return LinearFunction.apply(x, module.weight, module.bias)
+    return module(x)
+
+
+def layer_norm_train(module, x):
+    """``nn.LayerNorm`` forward of the module (autograd) path through the library's kernels where the shape is covered."""
+    if (TRAIN_KERNELS and x.is_cuda and x.dtype == torch.float32 and module.elementwise_affine and len(module.normalized_shape) == 1
+            and train_ops_supported(x.shape[-1])):
+        return LayerNormFunction.apply(x, module.weight, module.bias, module.eps)
+    return module(x)
 
 
 def cnw_fuse(img, pts, w_img, w_pts, mode, c_flag, l_flag, s_img=None, s_pts=None, modal_embed=None):

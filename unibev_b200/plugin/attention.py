@@ -19,7 +19,9 @@ import torch.nn as nn
 
 import torch.nn.functional as F
 
-from ..ops import (BevSampleFunction, ImgSampleFunction, MultiScaleDeformableAttnFunction, fused_sample_supported)
+from ..ops import (BevSampleFunction, ImgSampleFunction, LinearFunction, MultiScaleDeformableAttnFunction,
+                   fused_sample_supported, linear_train)
+from .. import ops as _ops
 from ..registry import ATTENTION, HAVE_MMCV, build_attention
 
 # Module (autograd) path: when the caller is one of this package's encoders -- which pass the BEV grid shape
@@ -87,6 +89,8 @@ class _DeformAttnBase(nn.Module):
         """(B, Nq, 3 H L P): raw sampling offsets (H, L, P, 2) then raw attention logits (H, L, P), one GEMM."""
         w = torch.cat((self.sampling_offsets.weight, self.attention_weights.weight), 0)
         b = torch.cat((self.sampling_offsets.bias, self.attention_weights.bias), 0)
+        if _ops.TRAIN_KERNELS and query.is_cuda and query.dtype == torch.float32 and torch.is_grad_enabled():
+            return LinearFunction.apply(query, w, b)
         return F.linear(query, w, b)
 
     def _fused_ok(self, key_padding_mask):
@@ -137,9 +141,9 @@ class MultiScaleDeformableAttention(_DeformAttnBase):
                 and query.shape[1] == grid[0] * grid[1] and self._fused_ok(key_padding_mask)):
             # BEV self-attention over the query grid itself: reference points are the cell centres the kernel generates
             H, P = self.num_heads, self.num_points
-            out = BevSampleFunction.apply(self.value_proj(value), self._raw_rows(query), grid[0], grid[1], grid[0], grid[1],
-                                          H, P, 0, 2 * H * P)
-            out = self.output_proj(out)
+            out = BevSampleFunction.apply(linear_train(self.value_proj, value), self._raw_rows(query), grid[0], grid[1],
+                                          grid[0], grid[1], H, P, 0, 2 * H * P)
+            out = linear_train(self.output_proj, out)
             if not self.batch_first:
                 out = out.permute(1, 0, 2)
             return self.dropout(out) + identity
@@ -184,8 +188,8 @@ class _MSDeformableAttention3D(_DeformAttnBase):
                 and reference_points.shape[-1] == 2 and self._fused_ok(key_padding_mask)):
             # LiDAR cross-attention: every pillar anchor projects to its cell centre, which the kernel generates
             H, P = self.num_heads, self.num_points
-            out = BevSampleFunction.apply(self.value_proj(value), self._raw_rows(query), grid[0], grid[1], fhw[0], fhw[1],
-                                          H, P, 0, 2 * H * P)
+            out = BevSampleFunction.apply(linear_train(self.value_proj, value), self._raw_rows(query), grid[0], grid[1],
+                                          fhw[0], fhw[1], H, P, 0, 2 * H * P)
             return out if self.batch_first else out.permute(1, 0, 2)
         assert int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum()) == value.shape[1]
         v, off, aw = self._project(query, value, key_padding_mask)
@@ -259,10 +263,10 @@ class SpatialCrossAttentionImg(nn.Module):
                 and da._fused_ok(key_padding_mask)):
             # one fused kernel per direction instead of rebatch -> inner attention -> scatter -> count division
             H, P = da.num_heads, da.num_points
-            v = da.value_proj(value.permute(2, 0, 1, 3))                # (B, N, hw, C)
+            v = linear_train(da.value_proj, value.permute(2, 0, 1, 3))   # (B, N, hw, C)
             slots = ImgSampleFunction.apply(v, da._raw_rows(query), cam[0], cam[1], grid[0], grid[1], fhw[0], fhw[1],
                                             H, P, 0, 2 * H * P)
-            return self.dropout(self.output_proj(slots)) + inp_residual
+            return self.dropout(linear_train(self.output_proj, slots)) + inp_residual
         hit0 = bev_mask[:, 0].any(-1)                                  # (N, Nq)
         lens = hit0.sum(1)
         max_len = int(lens.max())                                      # one host sync (training path only)
@@ -324,5 +328,5 @@ class SpatialCrossAttentionPts(nn.Module):
                                         reference_points=reference_points_lidar.permute(1, 2, 0, 3),
                                         spatial_shapes=spatial_shapes, level_start_index=level_start_index,
                                         ub_bev_grid=kwargs.get('ub_bev_grid'), ub_value_hw=kwargs.get('ub_value_hw'))
-        out = self.output_proj(out.view(B, -1, C))
+        out = linear_train(self.output_proj, out.view(B, -1, C))
         return self.dropout(out) + inp_residual

@@ -42,7 +42,8 @@ class FFN(nn.Module):
         self.dropout_layer = nn.Identity()
 
     def forward(self, x, identity=None):
-        out = self.layers(x)
+        (lin1, act, drop1), lin2, drop2 = self.layers[0], self.layers[1], self.layers[2]
+        out = drop2(ops.linear_train(lin2, drop1(act(ops.linear_train(lin1, x)))))       # == self.layers(x)
         if not self.add_identity:
             return self.dropout_layer(out)
         return (x if identity is None else identity) + self.dropout_layer(out)
@@ -118,7 +119,7 @@ class _EncoderLayer(nn.Module):
                 attn_i += 1
                 identity = query
             elif op == 'norm':
-                query = self.norms[norm_i](query)
+                query = ops.layer_norm_train(self.norms[norm_i], query)
                 norm_i += 1
             elif op == 'cross_attn':
                 qp, kp = (bev_pos, bev_pos) if (modality == 'img' and attn_i == 0) else (query_pos, key_pos)
