@@ -50,6 +50,8 @@ def parse():
                     help='infer (default): BASELINE.json metric, configs[2]/[3].  train: configs[4], the data-parallel '
                          'training step of unibev_nus_LC_cat_128 (2 samples per GPU, NCCL gradient all-reduce, AdamW)')
     ap.add_argument('--bucket-mb', type=float, default=8.0, help='train mode: gradient bucket size')
+    ap.add_argument('--train-exchange', default='in_graph', choices=['in_graph', 'after'],
+                    help='train mode with CUDA graphs: all-reduces captured with the backward pass (overlapped) or run after the graph')
     ap.add_argument('--batch', type=int, default=4, help='frames per GPU per step (BASELINE configs[3]: 32 frames over 8 GPUs)')
     ap.add_argument('--no-graphs', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'fp16'],
@@ -510,7 +512,7 @@ def train_main(args, rank, world, local):
     import torch
     import torch.distributed as dist
     from unibev_b200 import _cabi, synth
-    from unibev_b200.train import GradBuckets, train_step
+    from unibev_b200.train import GradBuckets, GraphedTrainStep, train_step
     wl = 'unibev_nus_LC_cat_128'
     B = 2 if args.batch == 4 else args.batch            # (--batch defaults to the inference value)
     torch.cuda.set_device(local)
@@ -527,8 +529,11 @@ def train_main(args, rank, world, local):
     g = torch.Generator().manual_seed(7)
     bev_embedding = torch.nn.Parameter(torch.randn(host[0]['bev_queries'].shape, generator=g).to(dev))
     params = list(model.parameters()) + [bev_embedding]
-    opt = torch.optim.AdamW(params, lr=2e-4, weight_decay=0.01, fused=True)     # one multi-tensor kernel per step
+    use_graphs = not args.no_graphs
+    opt = torch.optim.AdamW(params, lr=2e-4, weight_decay=0.01, fused=True, capturable=use_graphs)
     buckets = GradBuckets(params, bucket_bytes=int(args.bucket_mb * (1 << 20)), uniform_usage=True)   # ranks seeded alike
+    graphed = (GraphedTrainStep(model, bev_embedding, opt, buckets, dev_sets[0], exchange=args.train_exchange)
+               if use_graphs else None)
 
     def barrier():
         if world > 1:
@@ -541,13 +546,15 @@ def train_main(args, rank, world, local):
         e0.record()
         loss_sum = 0.0
         for i in range(steps):
-            if from_host:
+            if from_host and graphed is not None:
+                inp = host[i % N_INPUT_SETS]                 # pinned host tensors: staged into the graph's static buffers
+            elif from_host:
                 h = host[i % N_INPUT_SETS]
                 inp = dict(h, img_feats=[h['img_feats'][0].to(dev, non_blocking=True)],
                            pts_feats=[h['pts_feats'][0].to(dev, non_blocking=True)], bev_pos=h['bev_pos'].to(dev, non_blocking=True))
             else:
                 inp = dev_sets[i % N_INPUT_SETS]
-            loss = train_step(model, bev_embedding, inp, opt, buckets)
+            loss = graphed(inp) if graphed is not None else train_step(model, bev_embedding, inp, opt, buckets)
             if from_host:
                 loss_sum += float(loss)                    # D2H read of the step's result
         e1.record()
@@ -557,12 +564,15 @@ def train_main(args, rank, world, local):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         barrier()
         return float(ms.item()), float(loss)
+    if graphed is not None:
+        graphed.capture_all(dev_sets[0])
     run(max(args.warmup, 3), False)
     _cabi.reset_launch_count()
+    n0 = graphed.replayed_launches if graphed is not None else 0
     clk = ClockSampler(local)
     clk.__enter__()
     ms, loss = run(args.steps, False)
-    launches = _cabi.launch_count()
+    launches = (graphed.replayed_launches - n0) if graphed is not None else _cabi.launch_count()
     run(2, True)
     e2e_ms, _ = run(args.steps, True)
     clk.__exit__(None, None, None)
@@ -585,7 +595,9 @@ def train_main(args, rank, world, local):
                                    'fused_bev_embed), AdamW',
                        'collective': f'nccl all_reduce, {buckets.nbytes() / 1e6:.1f} MB per step in {len(buckets.buckets)} buckets, '
                                      'overlapped with backward' if world > 1 else 'none (1 GPU)',
-                       'params_in_sync_across_ranks': in_sync, 'loss': loss},
+                       'params_in_sync_across_ranks': in_sync, 'loss': loss,
+                       'cuda_graphs': (f'one graph per modality-dropout flag pair ({graphed.captures} captured), gradient exchange '
+                                       f'{args.train_exchange}') if graphed is not None else False},
             'e2e': {'value': world * B * args.steps / (e2e_ms / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / args.steps},
             'gpu_launches': launches, 'clocks': clk.summary(), 'roofline': None, 'cpu_baseline': None}), flush=True)

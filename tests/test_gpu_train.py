@@ -110,3 +110,45 @@ def test_full_size_cat128_gradients_vs_oracle_autograd():
     worst.sort(reverse=True)
     print('largest relative L2 gradient errors (rel L2, max entry / max):', [(n, f'{a:.1e}', f'{b:.1e}') for a, b, n in worst[:5]],
           'median rel L2 %.1e' % worst[len(worst) // 2][0])
+
+
+def test_graphed_train_step_matches_eager():
+    """GraphedTrainStep (one CUDA graph per modality-dropout flag pair: forward, backward, optimizer) follows the eager
+    train_step update for update: same host flag stream, same losses, same parameters after six steps."""
+    import copy
+    from unibev_b200 import synth
+    from unibev_b200.train import GradBuckets, GraphedTrainStep, train_step
+    wl = 'unibev_nus_LC_cat_128'
+    model_a, _ = synth.build_model(wl, num_layers=1, drop_modality=0.5, dropout=0.0)
+    model_a = model_a.cuda().train()
+    model_b = copy.deepcopy(model_a)
+    sets = [synth.make_inputs(wl, batch=1, bev_hw=(24, 24), seed=10 + i, device='cuda') for i in range(3)]
+    emb_a = torch.nn.Parameter(sets[0]['bev_queries'].clone())
+    emb_b = torch.nn.Parameter(sets[0]['bev_queries'].clone())
+
+    def make_opt(model, emb):
+        params = list(model.parameters()) + [emb]
+        # (SGD: its update is linear in the gradient, so the ~1e-6 run-to-run differences of red.add sums stay ~1e-6)
+        return params, torch.optim.SGD(params, lr=0.02, momentum=0.9, weight_decay=0.01)
+    params_a, opt_a = make_opt(model_a, emb_a)
+    params_b, opt_b = make_opt(model_b, emb_b)
+    buckets_a, buckets_b = GradBuckets(params_a), GradBuckets(params_b)
+
+    np.random.seed(5)
+    losses_a, flags_a = [], []
+    for i in range(6):
+        losses_a.append(float(train_step(model_a, emb_a, sets[i % 3], opt_a, buckets_a)))
+        flags_a.append((model_a.c_flag, model_a.l_flag))
+    assert len(set(flags_a)) > 1                              # the flag stream really switches graphs
+
+    np.random.seed(5)
+    step = GraphedTrainStep(model_b, emb_b, opt_b, buckets_b, sets[0])
+    losses_b, flags_b = [], []
+    for i in range(6):
+        losses_b.append(float(step(sets[i % 3])))
+        flags_b.append((model_b.c_flag, model_b.l_flag))
+    assert flags_b == flags_a and step.captures == len(set(flags_a))
+    np.testing.assert_allclose(losses_b, losses_a, rtol=2e-4)
+    for (name, pa), pb in zip(model_a.named_parameters(), model_b.parameters()):
+        torch.testing.assert_close(pb, pa, rtol=1e-3, atol=2e-5, msg=lambda m: f'{name}: {m}')
+    torch.testing.assert_close(emb_b, emb_a, rtol=1e-3, atol=2e-5)

@@ -29,6 +29,20 @@ def _call(fn, t, *args):
             _cabi.check(getattr(_cabi.lib(), fn)(*args, _stream()), fn)
 
 
+_CONST = {}
+
+
+def const_tensor(values, dtype, device):
+    """A small constant tensor (shape lists, start indexes) built ONCE per (values, dtype, device): creating it from a
+    Python list is a pageable host -> device copy, which stalls the stream and is not allowed while a CUDA graph is being
+    captured (``unibev_b200.train.GraphedTrainStep``).  Callers must not write to the result."""
+    key = (repr(values), dtype, str(device))
+    t = _CONST.get(key)
+    if t is None:
+        t = _CONST[key] = torch.tensor(values, dtype=dtype, device=device)
+    return t
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 

@@ -114,8 +114,8 @@ class _EncoderLayer(nn.Module):
             if op == 'self_attn':
                 query = self.attentions[attn_i](
                     query, query, query, identity if self.pre_norm else None, query_pos=bev_pos, key_pos=bev_pos,
-                    reference_points=ref_2d, spatial_shapes=torch.tensor([[bev_h, bev_w]], device=query.device),
-                    level_start_index=torch.tensor([0], device=query.device), **kwargs)
+                    reference_points=ref_2d, spatial_shapes=ops.const_tensor([[bev_h, bev_w]], torch.long, query.device),
+                    level_start_index=ops.const_tensor([0], torch.long, query.device), **kwargs)
                 attn_i += 1
                 identity = query
             elif op == 'norm':
@@ -189,6 +189,17 @@ class _Encoder(nn.Module):
         ref = torch.stack((gx[None].expand(D, -1), gy[None].expand(D, -1), zs[:, None].expand(-1, H * W)), -1)
         return ref[None].repeat(bs, 1, 1, 1)
 
+    def _grids(self, bev_h, bev_w, Z, D, bs, device, dtype):
+        """(ref_3d, ref_2d) of ``get_reference_points``: constants of the grid, built once per shape and device (they cost a
+        dozen small kernels and one host -> device copy per forward otherwise)."""
+        key = (bev_h, bev_w, float(Z), D, bs, str(device), dtype)
+        cache = self.__dict__.setdefault('_grid_cache', {})
+        if key not in cache:
+            cache.clear()
+            cache[key] = (self.get_reference_points(bev_h, bev_w, Z, D, dim='3d', bs=bs, device=device, dtype=dtype),
+                          self.get_reference_points(bev_h, bev_w, dim='2d', bs=bs, device=device, dtype=dtype))
+        return cache[key]
+
     def _run_layers(self, bev_query, key, value, args, kwargs, **layer_kw):
         output, inter = bev_query, []
         for layer in self.layers:
@@ -214,27 +225,31 @@ class ImgEncoder(_Encoder):
         bits = (mask[..., None] >> torch.arange(D, device=mask.device, dtype=torch.uint8)) & 1
         return ref.permute(2, 0, 1, 3, 4), bits.bool().permute(2, 0, 1, 3)
 
-    def _project_raw(self, reference_points, pc_range, img_metas, bev_hw=None):
+    def _project_raw(self, reference_points, pc_range, img_metas, bev_hw=None, lidar2img=None, img_shape=None):
         """``ub_project_points`` output as the fused kernels take it: ref (B, Nq, N, D, 2), mask (B, Nq, N) uint8 bits."""
         B, D, Nq, _ = reference_points.shape
-        l2i = np.asarray([m['lidar2img'] for m in img_metas], dtype=np.float32)
-        l2i = torch.from_numpy(l2i).to(reference_points.device)
+        if lidar2img is not None:
+            l2i = lidar2img
+        else:
+            l2i = np.asarray([m['lidar2img'] for m in img_metas], dtype=np.float32)
+            l2i = torch.from_numpy(l2i).to(reference_points.device)
         if bev_hw is None:      # the reference signature carries no grid shape: recover W from the first grid row
             W = int((reference_points[0, 0, :, 1] == reference_points[0, 0, 0, 1]).sum())
             bev_hw = (Nq // W, W)
         H, W = bev_hw
         zs = anchor_heights(pc_range[5] - pc_range[2], D).tolist()
-        ih, iw = img_metas[0]['img_shape'][0][0], img_metas[0]['img_shape'][0][1]
+        ih, iw = img_shape if img_shape is not None else img_metas[0]['img_shape'][0][:2]
         return ops.project_points(l2i, zs, pc_range, ih, iw, H, W)             # (B,Nq,N,D,2), (B,Nq,N) bits
 
     def forward(self, bev_query, key, value, *args, bev_h=None, bev_w=None, bev_pos=None, spatial_shapes=None,
                 level_start_index=None, valid_ratios=None, **kwargs):
         """bev_query (Nq, B, C); key/value (num_cam, sum(hw), B, C) -> (B, Nq, C)."""
         bs, dev, dt = bev_query.size(1), bev_query.device, bev_query.dtype
-        ref_3d = self.get_reference_points(bev_h, bev_w, self.pc_range[5] - self.pc_range[2],
-                                           self.num_points_in_pillar, dim='3d', bs=bs, device=dev, dtype=dt)
-        ref_2d = self.get_reference_points(bev_h, bev_w, dim='2d', bs=bs, device=dev, dtype=dt)
-        raw_ref, raw_mask = self._project_raw(ref_3d, self.pc_range, kwargs['img_metas'], (bev_h, bev_w))
+        ref_3d, ref_2d = self._grids(bev_h, bev_w, self.pc_range[5] - self.pc_range[2], self.num_points_in_pillar, bs, dev, dt)
+        # ``lidar2img`` (B, N, 4, 4) fp32 on the device + ``img_shape`` (h, w) replace the per-forward host -> device copy of
+        # img_metas[i]['lidar2img'] (encoder_unibev_detr_img.py:115-124) when the caller stages calibration itself
+        raw_ref, raw_mask = self._project_raw(ref_3d, self.pc_range, kwargs.get('img_metas'), (bev_h, bev_w),
+                                              kwargs.get('lidar2img'), kwargs.get('img_shape'))
         D = self.num_points_in_pillar
         bits = (raw_mask[..., None] >> torch.arange(D, device=raw_mask.device, dtype=torch.uint8)) & 1
         ref_cam, bev_mask = raw_ref.permute(2, 0, 1, 3, 4), bits.bool().permute(2, 0, 1, 3)     # == point_sampling(...)
@@ -265,9 +280,8 @@ class PtsEncoder(_Encoder):
                 level_start_index=None, valid_ratios=None, prev_bev=None, shift=0., **kwargs):
         """bev_query (Nq, B, C); key/value (sum(hw), B, C) -> (B, Nq, C)."""
         bs, dev, dt = bev_query.size(1), bev_query.device, bev_query.dtype
-        ref_3d = self.get_reference_points(bev_h, bev_w, self.pc_range[5] - self.pc_range[2],
-                                           self.num_points_in_pillar_lidar, dim='3d', bs=bs, device=dev, dtype=dt)
-        ref_2d = self.get_reference_points(bev_h, bev_w, dim='2d', bs=bs, device=dev, dtype=dt)
+        ref_3d, ref_2d = self._grids(bev_h, bev_w, self.pc_range[5] - self.pc_range[2], self.num_points_in_pillar_lidar, bs,
+                                     dev, dt)
         ref_lidar, _ = self.point_sampling(ref_3d)
         bev_query = bev_query.permute(1, 0, 2)
         if bev_pos is not None:

@@ -199,9 +199,11 @@ class UniBEVTransformer(nn.Module):
             flat.append(tok.view(bs, n, h * w, c).permute(1, 2, 0, 3))       # (n, hw, bs, c)
             shapes.append((h, w))
         flat = torch.cat(flat, 1)
-        shapes = torch.as_tensor(shapes, dtype=torch.long, device=flat.device)
-        start = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
-        return flat, shapes, start
+        starts = [0]
+        for h, w in shapes[:-1]:
+            starts.append(starts[-1] + h * w)
+        return (flat, ops.const_tensor([list(hw) for hw in shapes], torch.long, flat.device),
+                ops.const_tensor(starts, torch.long, flat.device))
 
     def _pre_process_pts_feats(self, mlvl_pts_feats, bev_queries):
         if len(mlvl_pts_feats) != 1:
@@ -213,8 +215,8 @@ class UniBEVTransformer(nn.Module):
             tok = feat.flatten(2).permute(0, 2, 1) + self.pts_level_embeds[0]
         else:
             tok = ops.flatten_feats(feat, None, self.pts_level_embeds[0])
-        shapes = torch.as_tensor([(h, w)], dtype=torch.long, device=feat.device)
-        return tok.permute(1, 0, 2), shapes, shapes.new_zeros((1,))
+        return (tok.permute(1, 0, 2), ops.const_tensor([[h, w]], torch.long, feat.device),
+                ops.const_tensor([0], torch.long, feat.device))
 
     def _encode_modules(self, img_mlvl_feats, pts_mlvl_feats, bev_queries, bev_h, bev_w, bev_pos, **kwargs):
         bs = (img_mlvl_feats or pts_mlvl_feats)[0].size(0)
@@ -347,6 +349,6 @@ class UniBEVTransformer(nn.Module):
         inter_states, inter_references = self.decoder(
             query=query.permute(1, 0, 2), key=None, value=fused, query_pos=query_pos.permute(1, 0, 2),
             reference_points=reference_points, reg_branches=reg_branches, cls_branches=cls_branches,
-            spatial_shapes=torch.tensor([[bev_h, bev_w]], device=query.device),
-            level_start_index=torch.tensor([0], device=query.device), **kwargs)
+            spatial_shapes=ops.const_tensor([[bev_h, bev_w]], torch.long, query.device),
+            level_start_index=ops.const_tensor([0], torch.long, query.device), **kwargs)
         return fused, inter_states, init_reference_out, inter_references
