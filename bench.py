@@ -50,8 +50,8 @@ def parse():
                     help='infer (default): BASELINE.json metric, configs[2]/[3].  train: configs[4], the data-parallel '
                          'training step of unibev_nus_LC_cat_128 (2 samples per GPU, NCCL gradient all-reduce, AdamW)')
     ap.add_argument('--bucket-mb', type=float, default=8.0, help='train mode: gradient bucket size')
-    ap.add_argument('--train-exchange', default='in_graph', choices=['in_graph', 'after'],
-                    help='train mode with CUDA graphs: all-reduces captured with the backward pass (overlapped) or run after the graph')
+    ap.add_argument('--train-exchange', default='auto', choices=['auto', 'in_graph', 'after'],
+                    help='train mode with CUDA graphs: optimizer step inside the graph (1 GPU) or gradient exchange + optimizer after it')
     ap.add_argument('--batch', type=int, default=4, help='frames per GPU per step (BASELINE configs[3]: 32 frames over 8 GPUs)')
     ap.add_argument('--no-graphs', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'fp16'],
@@ -593,11 +593,12 @@ def train_main(args, rank, world, local):
                      'ub_layernorm / ub_layernorm_bwd, ub_colsum)', 'data': 'synthetic',
             'config': {'workload': f'{wl} training step, {B} samples per GPU, {world} GPU(s), synthetic loss (mean square of '
                                    'fused_bev_embed), AdamW',
-                       'collective': f'nccl all_reduce, {buckets.nbytes() / 1e6:.1f} MB per step in {len(buckets.buckets)} buckets, '
-                                     'overlapped with backward' if world > 1 else 'none (1 GPU)',
+                       'collective': (f'nccl all_reduce, {buckets.nbytes() / 1e6:.1f} MB per step in {len(buckets.buckets)} buckets, ' +
+                                      ('after the backward graph' if graphed is not None else 'overlapped with backward'))
+                       if world > 1 else 'none (1 GPU)',
                        'params_in_sync_across_ranks': in_sync, 'loss': loss,
                        'cuda_graphs': (f'one graph per modality-dropout flag pair ({graphed.captures} captured), gradient exchange '
-                                       f'{args.train_exchange}') if graphed is not None else False},
+                                       f'{graphed.exchange}') if graphed is not None else False},
             'e2e': {'value': world * B * args.steps / (e2e_ms / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / args.steps},
             'gpu_launches': launches, 'clocks': clk.summary(), 'roofline': None, 'cpu_baseline': None}), flush=True)

@@ -251,6 +251,18 @@ for step in range(2):
         else:
             assert p.grad.data_ptr() == flat_ptrs[p]           # still the bucket slot: no copy back
             torch.testing.assert_close(p.grad, wg, rtol=1e-6, atol=1e-7)
+# recorded pass (GraphedTrainStep, exchange='after'): the hooks put nothing on the wire, the book-keeping is dropped, and
+# exchange_all() averages the bucket buffers -- which ARE the gradients -- in place
+buckets.prepare()
+buckets.defer_launch = True
+loss_of(r, with_unused=(r == 0)).backward()
+buckets.defer_launch = False
+assert buckets._next == 0 and not buckets._works
+buckets.reset_pass()
+buckets.exchange_all()
+want = torch.autograd.grad(sum(loss_of(k, with_unused=(k == 0)) for k in range(w)) / w, params, allow_unused=True)
+for p, wg in zip(params, want):
+    torch.testing.assert_close(p.grad, wg if wg is not None else torch.zeros_like(p), rtol=1e-6, atol=1e-7)
 # uniform_usage=True (ranks seeded alike, every rank touches the same parameters): no flag exchange, same result
 ub = GradBuckets(list(net.parameters()) + list(never.parameters()), bucket_bytes=64, uniform_usage=True)
 buckets.remove()

@@ -53,6 +53,7 @@ class GradBuckets:
         self._next = 0             # next bucket to hand to the collective
         self._works = []
         self._stream = torch.cuda.Stream() if self.params and self.params[0].is_cuda else None
+        self.defer_launch = False      # True: the hooks only book-keep, nothing goes on the wire before finish() / exchange_all()
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
         # NCCL averages inside the collective; gloo has no AVG: sum, then one scale per bucket
         self._avg = (self.world > 1 and dist.get_backend(group) == 'nccl')
@@ -109,7 +110,7 @@ class GradBuckets:
         self._pending[bi] -= 1
         # collectives must be issued in the same order on every rank: bucket order, each as soon as it and all
         # earlier buckets are complete (a bucket of parameters this rank never touches waits for finish())
-        while self._next < len(self.buckets) and self._pending[self._next] == 0:
+        while not self.defer_launch and self._next < len(self.buckets) and self._pending[self._next] == 0:
             self._launch(self._next)
             self._next += 1
 
@@ -169,6 +170,26 @@ class GradBuckets:
         self._seen.clear()
         self._pending = [len(items) for _, items in self.buckets]
 
+    def reset_pass(self):
+        """Forget the current backward pass's book-keeping without exchanging anything (after a pass that was only recorded:
+        ``GraphedTrainStep`` with ``exchange='after'``)."""
+        self._works.clear()
+        self._seen.clear()
+        self._pending = [len(items) for _, items in self.buckets]
+        self._next = 0
+
+    def exchange_all(self):
+        """All-reduce (average) every bucket in place, on the current stream, in bucket order.  For gradients that already
+        live in the buckets (``prepare()``'s views) and a parameter set that is the same on every rank and step -- the
+        replayed-graph step: no hooks ran, so there is no per-pass book-keeping to consult."""
+        if self.world == 1:
+            return
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        for flat, _ in self.buckets:
+            dist.all_reduce(flat, op=op, group=self.group)
+            if not self._avg:
+                flat.mul_(1.0 / self.world)
+
     def nbytes(self):
         return sum(flat.numel() * 4 for flat, _ in self.buckets)
 
@@ -203,9 +224,11 @@ class GraphedTrainStep:
     * The modality-dropout flags (transformer_fusion.py:227-228, 474-477) are drawn on the host exactly as the eager step
       draws them (same ``np.random`` stream); they only change two multipliers of the fusion, so there is one graph per
       flag pair, captured the first time the pair comes up (at most three).
-    * ``exchange='in_graph'``: the bucketed all-reduces are captured with the backward pass, on the side stream, so they
-      overlap it exactly as in the eager step; ``'after'``: the graph ends after backward, the buckets are all-reduced and
-      the optimizer stepped eagerly (3-4 launches) -- the fallback should a NCCL build refuse capture.
+    * ``exchange='in_graph'`` (one process): forward, backward and the optimizer step are one graph.  ``'after'`` (several
+      ranks): the graph ends after backward -- gradients have been accumulated straight into the bucket buffers -- then
+      the buckets are all-reduced in place (2-3 NCCL calls, ~25 MB: ~0.2 ms over NVLink, not overlapped) and the optimizer
+      steps eagerly (one fused kernel).  ``'auto'`` picks by world size.  (Capturing the NCCL calls inside the graph hung
+      on the 2-GPU box of this pod, so the exchange stays outside.)
     * The optimizer must be graph-capturable (``torch.optim.AdamW(..., fused=True, capturable=True)``).
     * Capturing a flag pair rehearses the step ``warmup`` times first (allocator pools, optimizer state, communicators);
       parameters and optimizer state are restored afterwards, so the sequence of updates is the eager one (dropout masks
@@ -214,9 +237,14 @@ class GraphedTrainStep:
     Everything inside is the module path of the plugin: no tensor is created from host data and nothing synchronises while
     capturing (constant tensors come from ``ops.const_tensor`` / the encoders' grid cache, calibration from ``lidar2img``)."""
 
-    def __init__(self, model, bev_embedding, optimizer, buckets, example, loss_fn=None, exchange='in_graph', warmup=3):
-        if exchange not in ('in_graph', 'after'):
-            raise ValueError("exchange must be 'in_graph' or 'after'")
+    def __init__(self, model, bev_embedding, optimizer, buckets, example, loss_fn=None, exchange='auto', warmup=3):
+        if exchange not in ('auto', 'in_graph', 'after'):
+            raise ValueError("exchange must be 'auto', 'in_graph' or 'after'")
+        if exchange == 'auto':        # one process: nothing to exchange, the optimizer step joins the graph
+            exchange = 'in_graph' if buckets.world == 1 else 'after'
+        if exchange == 'in_graph' and buckets.world > 1:
+            raise ValueError("exchange='in_graph' is for single-process runs; with several ranks the NCCL all-reduces run "
+                             "after the graph (exchange='after')")
         self.model, self.emb, self.opt, self.buckets = model, bev_embedding, optimizer, buckets
         self.loss_fn, self.exchange, self.warmup = loss_fn, exchange, warmup
         dev = bev_embedding.device
@@ -284,12 +312,18 @@ class GraphedTrainStep:
         g = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
         n0 = _cabi.launch_count()
-        with torch.cuda.graph(g):
-            self.buckets.prepare()
-            loss = self._forward_backward(flags)
-            if self.exchange == 'in_graph':
-                self.buckets.finish()
-                self.opt.step()
+        self.buckets.defer_launch = self.exchange == 'after'
+        try:
+            with torch.cuda.graph(g):
+                self.buckets.prepare()
+                loss = self._forward_backward(flags)
+                if self.exchange == 'in_graph':
+                    self.buckets.finish()
+                    self.opt.step()
+        finally:
+            self.buckets.defer_launch = False
+        if self.exchange == 'after':
+            self.buckets.reset_pass()
         self.launches[flags] = _cabi.launch_count() - n0
         np.random.set_state(rng)
         self.captures += 1
@@ -337,6 +371,6 @@ class GraphedTrainStep:
         g.replay()
         self.replayed_launches += self.launches[flags]
         if self.exchange == 'after':
-            self.buckets.finish()
+            self.buckets.exchange_all()
             self.opt.step()
         return loss
