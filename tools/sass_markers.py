@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MARKERS = ['UTCHMMA', 'UTCQMMA', 'UTCOMMA', 'UTCCP', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTMAPF', 'UBLKCP', 'UTMAREDG',
-           'SYNCS', 'LDG.E.256', 'STG.E.256', 'RED.E', 'HMMA', 'FFMA']
+           'SYNCS', 'LDG.E.256', 'STG.E.256', 'REDG.E', 'HMMA', 'FFMA']
 
 
 def main():
