@@ -218,7 +218,7 @@ def test_batch_items_are_independent_at_full_size():
     torch.testing.assert_close(both[1:2], one, rtol=1e-5, atol=1e-5)
 
 
-def test_fp16x3_bounds_hold_and_path_is_taken():
+def test_fp16x3_bounds_hold_and_path_is_taken(monkeypatch):
     """The fp16 x3 projections of the default class run only on operands with a proven bound: (1) the bounds derived from
     the weights really dominate the activations they describe (hooks on the module path), (2) the fused pipeline takes the
     fp16 x3 path for them (launch counter of a UB_F16X3=0 run differs only in kernel flavour, results agree to fp32 noise)."""
@@ -248,7 +248,9 @@ def test_fp16x3_bounds_hold_and_path_is_taken():
             layer.ffns[0].layers[1].register_forward_hook(hook((enc, i, 'hid')))
             layer.attentions[0].output_proj.register_forward_hook(hook((enc, i, 'sa_s')))
             x_bound = bd['out']
-    model.train()                           # module path (torch linears: the hooks fire); dropout is irrelevant to magnitudes
+    from unibev_b200.plugin import attention
+    monkeypatch.setattr(attention, 'FUSED_TRAIN_SAMPLING', False)      # every nn.Linear is called as a module: the hooks fire
+    model.train()                           # module path; dropout is irrelevant to magnitudes
     model.drop_modality = None
     with torch.no_grad():
         model.encode(_cuda(inp['img_feats']), _cuda(inp['pts_feats']), inp['bev_queries'].cuda(), 40, 40,
