@@ -63,6 +63,7 @@ PROTOTYPES = {
 _PRIVATE = {
     'ub_set_tuning': ([_i] * 3, _i),
     'ub_set_window_halo': ([_i], _i),
+    'ub_set_bev_win32_buffers': ([_i], _i),
     'ub_set_gemm_cluster': ([_i], _i),
     'ub_set_gemm_x3': ([_i] * 4, _i),
     'ub_set_gemm_x3_pair': ([_i], _i),
@@ -101,6 +102,8 @@ def lib():
                         ('UB_IMG_VECREF', 'ub_set_img_vec_ref'), ('UB_PDL', 'ub_set_pdl')):
             if env in os.environ:
                 getattr(handle, fn)(int(os.environ[env]))
+        if 'UB_WIN32_BUFFERS' in os.environ:
+            handle.ub_set_bev_win32_buffers(int(os.environ['UB_WIN32_BUFFERS']))
         if 'UB_X3_PREFETCH' in os.environ:
             handle.ub_set_gemm_x3_prefetch(int(os.environ['UB_X3_PREFETCH']))
         if 'UB_X3_PAIR' in os.environ:

@@ -180,6 +180,7 @@ struct BevWin32Args {
   int WW, WH, R;
   int off_col, logit_col;
   float sx, sy;
+  int NB;                 // window buffers: 2, or 3 where shared memory allows (hides the window's load latency)
 };
 
 template <int PP>
@@ -187,7 +188,7 @@ struct BevSmem32 {
   static constexpr int slice_off_bytes = kWarpItems * PP * 8, slice_lg_bytes = kWarpItems * PP * 4;
   static constexpr int slice_bytes = slice_off_bytes + slice_lg_bytes;      // one query row of the offset|logit tile
   static constexpr int warp_bytes = slice_bytes + ((Desc32<PP>::bytes + 127) & ~127);
-  static size_t total(int win_bytes) { return (size_t)2 * win_bytes + (size_t)kWorkerWarps * warp_bytes; }
+  static size_t total(int win_bytes, int nb = 2) { return (size_t)nb * win_bytes + (size_t)kWorkerWarps * warp_bytes; }
 };
 
 // Worker warp w owns query row ty0 + w of the unit's 16 x 16 tile.  Its loop per unit k:
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kBevThreads, 1)
   using S = BevSmem32<PP>;
   using D = Desc32<PP>;
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t s_full[2], s_empty[2], s_unit[4], s_qp[kWorkerWarps];
+  __shared__ __align__(8) uint64_t s_full[3], s_empty[3], s_unit[4], s_qp[kWorkerWarps];
   __shared__ UnitInfo s_ring[4];
 
   const int win_bytes = (a.WW * a.WH * 64 + 127) & ~127;
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(kBevThreads, 1)
   const int Nq = a.bev_h * a.bev_w, C = a.H * 32;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&s_full[i]), 1), mbar_init(smem_u32(&s_empty[i]), kWorkerWarps);
+    for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&s_full[i]), 1), mbar_init(smem_u32(&s_empty[i]), kWorkerWarps);
     for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s_unit[i]), 1);
     for (int i = 0; i < kWorkerWarps; ++i) mbar_init(smem_u32(&s_qp[i]), 1);
     mbar_init_fence();
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(kBevThreads, 1)
     if (lane != 0) return;
     tma_prefetch_desc(&map_val);
     const int n_tiles = a.tiles_x * a.tiles_y;
+    int sched_buf = 0, sched_use = 0;
     for (int k = 0;; ++k) {
       const int u = atomicAdd(&a.counters[0], 1);
       UnitInfo w;
@@ -245,12 +247,15 @@ __global__ void __launch_bounds__(kBevThreads, 1)
       s_ring[k & 3] = w;
       mbar_arrive(smem_u32(&s_unit[k & 3]));
       if (w.u < 0) break;
+      // half-head window i = 2 k + s of the CTA's stream goes to buffer i % NB; its n-th use (n = i / NB) waits for the
+      // workers' release of use n - 1
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
-        if (k >= 1) mbar_wait(smem_u32(&s_empty[s]), (uint32_t)((k - 1) & 1));
-        const uint32_t bar = smem_u32(&s_full[s]);
+        if (sched_use > 0) mbar_wait(smem_u32(&s_empty[sched_buf]), (uint32_t)((sched_use - 1) & 1));
+        const uint32_t bar = smem_u32(&s_full[sched_buf]);
         mbar_arrive_expect_tx(bar, (uint32_t)(a.WW * a.WH * 64));
-        tma_load_4d(sm_win + (uint32_t)s * win_bytes, &map_val, bar, 0, w.wx0, w.wy0, (w.b * a.H + w.h) * 2 + s);
+        tma_load_4d(sm_win + (uint32_t)sched_buf * win_bytes, &map_val, bar, 0, w.wx0, w.wy0, (w.b * a.H + w.h) * 2 + s);
+        if (++sched_buf == a.NB) sched_buf = 0, ++sched_use;
       }
     }
     // the last CTA to leave re-arms the unit counter for the next launch
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(kBevThreads, 1)
   }
 
   // ---------------- worker warps
-  const uint32_t sm_slice = sm_win + 2u * win_bytes + (uint32_t)warp * S::warp_bytes;  // {offsets, logits}
+  const uint32_t sm_slice = sm_win + (uint32_t)a.NB * win_bytes + (uint32_t)warp * S::warp_bytes;  // {offsets, logits}
   const uint32_t sm_w = sm_slice + S::slice_bytes, sm_idx = sm_w + D::w_bytes;
   const uint32_t bar_qp = smem_u32(&s_qp[warp]);
   const uint32_t bar_unit = smem_u32(&s_unit[0]), bar_full = smem_u32(&s_full[0]), bar_empty = smem_u32(&s_empty[0]);
@@ -282,6 +287,7 @@ __global__ void __launch_bounds__(kBevThreads, 1)
   mbar_wait(bar_unit, 0u);
   UnitInfo w = s_ring[0];
   if (w.u >= 0 && lane == 0) issue_slice(w);
+  int w_buf = 0, w_use = 0;   // buffer and use count of the next half-head window of this CTA's stream
 
   for (int k = 0; w.u >= 0; ++k) {
     const int qy = w.ty0 + warp;
@@ -379,17 +385,20 @@ __global__ void __launch_bounds__(kBevThreads, 1)
 
     // ---- P2: the two half-head windows of the unit
     float4 r0[4], r1[4];
-    const uint32_t ph = (uint32_t)(k & 1);
     // real items of this warp's query row: none below the grid, 16 or fewer in the last tile column
     const int n_live = row_ok ? min(kWarpItems, a.bev_w - w.tx0) : 0;
-    mbar_wait(bar_full, ph);
-    gather_warp32<PP, ROWB>(sm_w, sm_idx, sm_win + sub * 16u, (uint32_t)a.WW * 64u, grp, side, n_live, r0);
+    mbar_wait(bar_full + 8u * (uint32_t)w_buf, (uint32_t)(w_use & 1));
+    gather_warp32<PP, ROWB>(sm_w, sm_idx, sm_win + (uint32_t)w_buf * win_bytes + sub * 16u, (uint32_t)a.WW * 64u, grp, side, n_live,
+                            r0);
     __syncwarp();   // every lane is done with window 0
-    if (lane == 0) mbar_arrive(bar_empty);
-    mbar_wait(bar_full + 8u, ph);
-    gather_warp32<PP, ROWB>(sm_w, sm_idx, sm_win + (uint32_t)win_bytes + sub * 16u, (uint32_t)a.WW * 64u, grp, side, n_live, r1);
+    if (lane == 0) mbar_arrive(bar_empty + 8u * (uint32_t)w_buf);
+    if (++w_buf == a.NB) w_buf = 0, ++w_use;
+    mbar_wait(bar_full + 8u * (uint32_t)w_buf, (uint32_t)(w_use & 1));
+    gather_warp32<PP, ROWB>(sm_w, sm_idx, sm_win + (uint32_t)w_buf * win_bytes + sub * 16u, (uint32_t)a.WW * 64u, grp, side, n_live,
+                            r1);
     __syncwarp();   // ... and with window 1 and the descriptors
-    if (lane == 0) mbar_arrive(bar_empty + 8u);
+    if (lane == 0) mbar_arrive(bar_empty + 8u * (uint32_t)w_buf);
+    if (++w_buf == a.NB) w_buf = 0, ++w_use;
     // rows: lanes of pixel side 0 write the first half-head's channels, side 1 the second's: 128 B per item and store
     if (row_ok) {
       const int64_t out0 = ((int64_t)w.b * Nq + qy * a.bev_w + w.tx0) * C + w.h * 32 + side * 16 + cq * 4;
@@ -423,6 +432,8 @@ static int launch_bev_win32_v(BevWin32Args& a, const CUtensorMap& mv, const CUte
   return check_launch(fn);
 }
 
+static int g_bev_win32_buffers = 0;   // A/B knob (tools): 0 = as many as fit (up to 3), 2 = always two
+
 template <int PP>
 static int launch_bev_win32(BevWin32Args& a, const float* planes, const float* qproj, int ld, cudaStream_t s) {
   const char* fn = "ub_bev_sample_win32_fwd";
@@ -440,10 +451,17 @@ static int launch_bev_win32(BevWin32Args& a, const float* planes, const float* q
       a.WW = keep;
   }
   while (smem_for() > kSmemBudget && a.R > 1) --a.R, a.WW -= 2, a.WH -= 2;
-  const size_t smem = smem_for();
+  size_t smem = smem_for();
   if (smem > kSmemBudget) {
     set_error("%s: window %d x %d needs %zu bytes of shared memory", fn, a.WW, a.WH, smem);
     return ub::unsupported();
+  }
+  // a third window buffer where it fits (4 points: 28 x 28 windows): the next unit's first window then loads while both
+  // windows of the current unit are still in use
+  a.NB = 2;
+  if (g_bev_win32_buffers != 2 && BevSmem32<PP>::total((a.WW * a.WH * 64 + 127) & ~127, 3) <= kSmemBudget) {
+    a.NB = 3;
+    smem = BevSmem32<PP>::total((a.WW * a.WH * 64 + 127) & ~127, 3);
   }
   CUtensorMap mv, mo, ml;
   {
@@ -473,6 +491,12 @@ extern int g_bev_halo_shared();
 }  // namespace ub
 
 using namespace ub;
+
+extern "C" int ub_set_bev_win32_buffers(int n) {
+  UB_REQUIRE(n == 0 || n == 2, "ub_set_bev_win32_buffers: 0 (as many as fit) or 2");
+  ub::g_bev_win32_buffers = n;
+  return UB_OK;
+}
 
 extern "C" int ub_bev_sample_win32_fwd(const float* planes32, const float* qproj, float* out, int B, int bev_h, int bev_w,
                                        int fH, int fW, int H, int Dh, int P, int ld, int off_col, int logit_col,
