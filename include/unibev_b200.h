@@ -266,12 +266,13 @@ int ub_add_layernorm(const float* x, const float* bias, const float* residual, c
 /* ---- training step: streaming reductions of the backward pass (BASELINE configs[4]) ------------------
  * ub_colsum: out (N) += column sums of x (M, N): the bias gradient of a projection (autograd of the nn.Linear layers,
  * spatial_cross_attention_img.py:59,285-289).  out is ACCUMULATED into (zero it first).  N % 4 == 0, N <= 1024.
- * ub_layernorm_bwd: backward of y = LayerNorm(x) * gamma + beta over the last dim C (the 'norm' steps,
- * encoder_unibev_detr_img.py:434-436,476-479): dx (rows, C) written; dgamma (C), dbeta (C) ACCUMULATED into (zero them
- * first).  Row statistics are recomputed from x.  C % 4 == 0, C <= 1024. */
+ * ub_layernorm_bwd: backward of y = LayerNorm(x + residual) * gamma + beta over the last dim C (the 'norm' steps with the
+ * `dropout(out) + identity` that precedes them, encoder_unibev_detr_img.py:434-436,476-479; residual may be NULL): dx (rows, C)
+ * written -- the gradient of the sum, i.e. of x and of residual alike; dgamma (C), dbeta (C) ACCUMULATED into (zero them
+ * first).  Row statistics are recomputed from the inputs.  C % 4 == 0, C <= 1024. */
 int ub_colsum(const float* x, float* out, int64_t M, int N, ub_stream_t stream);
-int ub_layernorm_bwd(const float* x, const float* dy, const float* gamma, float* dx, float* dgamma, float* dbeta,
-                     int64_t rows, int C, float eps, ub_stream_t stream);
+int ub_layernorm_bwd(const float* x, const float* residual, const float* dy, const float* gamma, float* dx, float* dgamma,
+                     float* dbeta, int64_t rows, int C, float eps, ub_stream_t stream);
 /* The same, additionally writing an fp16 copy `out16` (rows, C) of the result (may be NULL). */
 int ub_add_layernorm16(const float* x, const float* bias, const float* residual, const float* gamma,
                        const float* beta, float* out, void* out16, int64_t rows, int C, float eps, ub_stream_t stream);

@@ -2,7 +2,7 @@
 // projections and the 'norm' steps of the encoder layers (encoder_unibev_detr_img.py:434-436,476-479).
 //
 //   ub_colsum          out[n] += sum_m x[m, n]                      bias gradient of a projection (M = B * 40 000 rows)
-//   ub_layernorm_bwd   dx, dgamma += , dbeta +=                     backward of y = LayerNorm(x) * gamma + beta
+//   ub_layernorm_bwd   dx, dgamma += , dbeta +=                     backward of y = LayerNorm(x [+ residual]) * gamma + beta
 //
 // Both are one pass over their inputs with 128-bit accesses (HBM-bound: 4 bytes per element read, LayerNorm 12 bytes per
 // element moved); per-block partial column sums are folded into the (pre-zeroed) outputs with red.global.add.
@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 // recomputed from x (a row lives in registers), so the forward pass saves nothing but its input.
 //   xhat = (x - mean) rstd;  g = gamma dy;  dx = rstd (g - mean(g) - xhat mean(g xhat));  dgamma += dy xhat;  dbeta += dy
 template <int NV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                            const float* __restrict__ dy,
                                                             const float* __restrict__ gamma, float* __restrict__ dx,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows,
                                                             int C, float eps) {
@@ -71,6 +72,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       v[k] = d[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < C) {
         v[k] = ld_stream4(x + r * C + c);
+        if (res) {   // the normalised row was x + residual (ub_add_layernorm): the same sum, in the same order
+          const float4 t = ld_stream4(res + r * C + c);
+          v[k].x += t.x, v[k].y += t.y, v[k].z += t.z, v[k].w += t.w;
+        }
         d[k] = ld_stream4(dy + r * C + c);
         sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
       }
@@ -164,10 +169,11 @@ extern "C" int ub_colsum(const float* x, float* out, int64_t M, int N, ub_stream
   return check_launch("ub_colsum");
 }
 
-extern "C" int ub_layernorm_bwd(const float* x, const float* dy, const float* gamma, float* dx, float* dgamma, float* dbeta,
-                                int64_t rows, int C, float eps, ub_stream_t stream) {
+extern "C" int ub_layernorm_bwd(const float* x, const float* residual, const float* dy, const float* gamma, float* dx,
+                                float* dgamma, float* dbeta, int64_t rows, int C, float eps, ub_stream_t stream) {
   UB_REQUIRE(x && dy && gamma && dx && dgamma && dbeta && rows > 0 && C > 0, "ub_layernorm_bwd: bad argument");
   UB_REQUIRE_ALIGNED16(x);
+  if (residual) UB_REQUIRE_ALIGNED16(residual);
   UB_REQUIRE_ALIGNED16(dy);
   UB_REQUIRE_ALIGNED16(dx);
   UB_REQUIRE_ALIGNED16(gamma);
@@ -183,7 +189,7 @@ extern "C" int ub_layernorm_bwd(const float* x, const float* dy, const float* ga
   if (blocks < 1) blocks = 1;
   const int nv = (C + 127) / 128;
   cudaStream_t s = (cudaStream_t)stream;
-#define UB_LNB(NV) layernorm_bwd_kernel<NV><<<(int)blocks, 256, 0, s>>>(x, dy, gamma, dx, dgamma, dbeta, rows, C, eps)
+#define UB_LNB(NV) layernorm_bwd_kernel<NV><<<(int)blocks, 256, 0, s>>>(x, residual, dy, gamma, dx, dgamma, dbeta, rows, C, eps)
   if (nv <= 1) UB_LNB(1);
   else if (nv <= 2) UB_LNB(2);
   else if (nv <= 4) UB_LNB(4);

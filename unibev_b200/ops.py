@@ -680,27 +680,33 @@ def _wgrad(g2, x2):
 
 
 class LinearFunction(torch.autograd.Function):
-    """y = x W^T + b with the library's column-sum kernel for the bias gradient (torch's generic column reduction is the
-    single largest item of the training step's backward: ~50 us per projection against ~10 us here); the matrix products
-    stay with cuBLAS (TF32 when ``torch.backends.cuda.matmul.allow_tf32`` is set, as the reference's stack did)."""
+    """y = [relu](x W^T + b) with the library's column-sum kernel for the bias gradient (torch's generic column reduction is
+    the single largest item of the training step's backward: ~50 us per projection against ~10 us here) and a
+    split-reduction weight gradient; the matrix products stay with cuBLAS (TF32 when
+    ``torch.backends.cuda.matmul.allow_tf32`` is set, as the reference's stack did; ReLU in its epilogue)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
+    def forward(ctx, x, weight, bias, relu=False):
         ctx.has_bias = bias is not None
+        ctx.relu = bool(relu) and bias is not None
         x2 = x.reshape(-1, x.shape[-1])
         y = x.new_empty(*x.shape[:-1], weight.shape[0])      # (returned as is, not as a view: callers may apply in-place ReLU)
-        if bias is not None:
+        if ctx.relu:
+            torch._addmm_activation(bias, x2, weight.t(), use_gelu=False, out=y.view(-1, weight.shape[0]))
+        elif bias is not None:
             torch.addmm(bias, x2, weight.t(), out=y.view(-1, weight.shape[0]))
         else:
             torch.mm(x2, weight.t(), out=y.view(-1, weight.shape[0]))
+        ctx.save_for_backward(x, weight, y if ctx.relu else None)
         return y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
-        x, weight = ctx.saved_tensors
+        x, weight, y = ctx.saved_tensors
         g2 = gy.reshape(-1, gy.shape[-1])
+        if ctx.relu:
+            g2 = torch.ops.aten.threshold_backward(g2, y.view(-1, y.shape[-1]), 0)
         g2 = g2 if g2.is_contiguous() else g2.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
@@ -709,50 +715,78 @@ class LinearFunction(torch.autograd.Function):
             gw = _wgrad(g2, x.reshape(-1, x.shape[-1]))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = colsum(g2)
-        return gx, gw, gb
+        return gx, gw, gb, None
 
 
 class LayerNormFunction(torch.autograd.Function):
-    """y = LayerNorm(x) * gamma + beta: forward ``ub_add_layernorm``, backward ``ub_layernorm_bwd`` (one pass each)."""
+    """y = LayerNorm(x [+ residual]) * gamma + beta: forward ``ub_add_layernorm``, backward ``ub_layernorm_bwd`` (one pass
+    each; the sum x + residual is never written: the backward pass rebuilds it from its two terms)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps):
+    def forward(ctx, x, residual, gamma, beta, eps):
         x = _need(x, 'x')
-        ctx.save_for_backward(x, gamma)
+        residual = _need(residual, 'residual') if residual is not None else None
+        ctx.save_for_backward(x, residual, gamma)
         ctx.eps = float(eps)
-        return add_layernorm(x, gamma.detach(), beta.detach(), eps=eps)
+        return add_layernorm(x, gamma.detach(), beta.detach(), residual=residual, eps=eps)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
-        x, gamma = ctx.saved_tensors
+        x, residual, gamma = ctx.saved_tensors
         gy = _need(gy, 'grad_out')
         C = x.shape[-1]
         gx = torch.empty_like(x)
         gg = torch.zeros(2, C, device=x.device, dtype=torch.float32)
-        _call('ub_layernorm_bwd', x, _ptr(x), _ptr(gy), _ptr(_need(gamma.detach(), 'gamma')), _ptr(gx), _ptr(gg[0]), _ptr(gg[1]),
-              x.numel() // C, C, ctx.eps)
-        return gx, gg[0], gg[1], None
+        _call('ub_layernorm_bwd', x, _ptr(x), _ptr(residual), _ptr(gy), _ptr(_need(gamma.detach(), 'gamma')), _ptr(gx), _ptr(gg[0]),
+              _ptr(gg[1]), x.numel() // C, C, ctx.eps)
+        return gx, (gx if residual is not None else None), gg[0], gg[1], None
 
 
 # UB_FUSED_TRAIN=0 keeps the module (autograd) path on plain torch modules + the op-level ub_msda_fwd / ub_msda_bwd
 TRAIN_KERNELS = os.environ.get('UB_FUSED_TRAIN', '1') == '1'
 
 
-def linear_train(module, x):
-    """``nn.Linear`` forward of the module (autograd) path: ``LinearFunction`` for fp32 CUDA activations, else the module."""
+def linear_train(module, x, relu=False):
+    """``nn.Linear`` (+ ReLU) forward of the module (autograd) path: ``LinearFunction`` for fp32 CUDA activations, else the
+    module."""
     if (TRAIN_KERNELS and x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled() and module.bias is not None
             and train_ops_supported(module.out_features)):
-        return LinearFunction.apply(x, module.weight, module.bias)
-    return module(x)
+        return LinearFunction.apply(x, module.weight, module.bias, relu)
+    return torch.relu(module(x)) if relu else module(x)
+
+
+class Deferred:
+    """``out + identity`` not yet added: what an attention / FFN of the module path hands to a 'norm' step that can fold
+    the addition into its kernel (``layer_norm_train``).  ``materialize()`` is the plain sum for every other consumer."""
+    __slots__ = ('out', 'identity')
+
+    def __init__(self, out, identity):
+        self.out, self.identity = out, identity
+
+    def materialize(self):
+        return self.out + self.identity
+
+
+def add_identity(out, identity, defer):
+    """``out + identity`` of the attentions / FFN (``dropout(x) + identity``), or the pair when the caller's next step is a
+    'norm' that adds while normalising."""
+    if (defer and TRAIN_KERNELS and out.is_cuda and out.dtype == torch.float32 and out.shape == identity.shape
+            and train_ops_supported(out.shape[-1])):
+        return Deferred(out, identity)
+    return out + identity
 
 
 def layer_norm_train(module, x):
-    """``nn.LayerNorm`` forward of the module (autograd) path through the library's kernels where the shape is covered."""
+    """``nn.LayerNorm`` forward of the module (autograd) path through the library's kernels where the shape is covered.
+    ``x`` may be a ``Deferred`` sum."""
+    residual = None
+    if isinstance(x, Deferred):
+        x, residual = x.out, x.identity
     if (TRAIN_KERNELS and x.is_cuda and x.dtype == torch.float32 and module.elementwise_affine and len(module.normalized_shape) == 1
             and train_ops_supported(x.shape[-1])):
-        return LayerNormFunction.apply(x, module.weight, module.bias, module.eps)
-    return module(x)
+        return LayerNormFunction.apply(x, residual, module.weight, module.bias, module.eps)
+    return module(x if residual is None else x + residual)
 
 
 def cnw_fuse(img, pts, w_img, w_pts, mode, c_flag, l_flag, s_img=None, s_pts=None, modal_embed=None):

@@ -41,12 +41,12 @@ class FFN(nn.Module):
             nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop))
         self.dropout_layer = nn.Identity()
 
-    def forward(self, x, identity=None):
-        (lin1, act, drop1), lin2, drop2 = self.layers[0], self.layers[1], self.layers[2]
-        out = drop2(ops.linear_train(lin2, drop1(act(ops.linear_train(lin1, x)))))       # == self.layers(x)
+    def forward(self, x, identity=None, defer=False):
+        (lin1, _relu, drop1), lin2, drop2 = self.layers[0], self.layers[1], self.layers[2]
+        out = drop2(ops.linear_train(lin2, drop1(ops.linear_train(lin1, x, relu=True))))   # == self.layers(x)
         if not self.add_identity:
             return self.dropout_layer(out)
-        return (x if identity is None else identity) + self.dropout_layer(out)
+        return ops.add_identity(self.dropout_layer(out), x if identity is None else identity, defer)
 
 
 if not _ffn_registered():
@@ -110,7 +110,15 @@ class _EncoderLayer(nn.Module):
         ``query_pos`` (None in the encoders)."""
         attn_i = norm_i = ffn_i = 0
         identity = query
-        for op in self.operation_order:
+        order = self.operation_order
+        for pos, op in enumerate(order):
+            # post-norm layers: an attention / FFN directly followed by a 'norm' hands over (out, identity) unadded and the
+            # norm kernel adds while normalising (ops.Deferred; only this package's modules are asked to)
+            defer = (not self.pre_norm) and pos + 1 < len(order) and order[pos + 1] == 'norm'
+            if defer:
+                kwargs = dict(kwargs, ub_defer_add=True)
+            else:
+                kwargs = {k: v for k, v in kwargs.items() if k != 'ub_defer_add'}
             if op == 'self_attn':
                 query = self.attentions[attn_i](
                     query, query, query, identity if self.pre_norm else None, query_pos=bev_pos, key_pos=bev_pos,
@@ -130,9 +138,13 @@ class _EncoderLayer(nn.Module):
                 attn_i += 1
                 identity = query
             elif op == 'ffn':
-                query = self.ffns[ffn_i](query, identity if self.pre_norm else None)
+                ffn = self.ffns[ffn_i]
+                if isinstance(ffn, FFN):
+                    query = ffn(query, identity if self.pre_norm else None, defer=defer)
+                else:
+                    query = ffn(query, identity if self.pre_norm else None)
                 ffn_i += 1
-        return query
+        return query.materialize() if isinstance(query, ops.Deferred) else query
 
 
 @TRANSFORMER_LAYER.register_module()
