@@ -271,6 +271,19 @@ int ub_add_layernorm(const float* x, const float* bias, const float* residual, c
  * written -- the gradient of the sum, i.e. of x and of residual alike; dgamma (C), dbeta (C) ACCUMULATED into (zero them
  * first).  Row statistics are recomputed from the inputs.  C % 4 == 0, C <= 1024. */
 int ub_colsum(const float* x, float* out, int64_t M, int N, ub_stream_t stream);
+/* y = LayerNorm(dropout(x, p) + residual) * gamma + beta in one pass per direction: the `self.dropout(out) + identity` of the
+ * attentions / FFN (spatial_cross_attention_img.py:215, mmcv FFN) and the 'norm' step that follows
+ * (encoder_unibev_detr_img.py:434-436,476-479).  mask (rows * C / 4 bytes): keep bits of every float4, written by _fwd, read
+ * by _bwd.  rng_state: two int64 on the device {seed, step}; the caller advances step once per training step and numbers the
+ * call sites of a step (call_site), so that no mask repeats.  The drop probability actually applied is round(p 65536) / 65536.
+ * _bwd: dx = gradient of x (through the mask), dresidual = gradient of the sum; dgamma / dbeta ACCUMULATED into. */
+int ub_dropout_add_layernorm_fwd(const float* x, const float* residual, const float* gamma, const float* beta, float* out,
+                                 uint8_t* mask, int64_t rows, int C, float eps, float p, const int64_t* rng_state,
+                                 int call_site, ub_stream_t stream);
+int ub_dropout_add_layernorm_bwd(const float* x, const float* residual, const uint8_t* mask, const float* dy,
+                                 const float* gamma, float* dx, float* dresidual, float* dgamma, float* dbeta, int64_t rows,
+                                 int C, float eps, float p, ub_stream_t stream);
+
 int ub_layernorm_bwd(const float* x, const float* residual, const float* dy, const float* gamma, float* dx, float* dgamma,
                      float* dbeta, int64_t rows, int C, float eps, ub_stream_t stream);
 /* The same, additionally writing an fp16 copy `out16` (rows, C) of the result (may be NULL). */

@@ -74,3 +74,55 @@ def test_linear_function_vs_torch(shape, N, relu):
     torch.testing.assert_close(got[0], xb.grad, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(got[1], lin.weight.grad, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(got[2], lin.bias.grad, rtol=1e-4, atol=1e-4)
+
+
+def _keep_from_mask(mask, shape):
+    bits = (mask[:, None] >> torch.arange(4, device=mask.device, dtype=torch.uint8)) & 1
+    return bits.reshape(shape).bool()
+
+
+@pytest.mark.parametrize('rows,C,p', [(4000, 128, 0.1), (513, 256, 0.25), (64, 96, 0.5), (20000, 128, 0.0)])
+def test_dropout_add_layernorm_function(rows, C, p):
+    """y = LayerNorm(dropout(x) + residual): the arithmetic in both directions against torch for the mask the kernel drew,
+    the keep rate of that mask, and that masks change with the step and the call site but not on their own."""
+    from unibev_b200 import ops
+    g = torch.Generator('cuda').manual_seed(rows + C)
+    x = torch.randn(rows, C, device='cuda', generator=g) * 1.5
+    res = torch.randn(rows, C, device='cuda', generator=g)
+    gamma = torch.randn(C, device='cuda', generator=g)
+    beta = torch.randn(C, device='cuda', generator=g)
+    go = torch.randn(rows, C, device='cuda', generator=g)
+    rng = ops.DropoutRNG.get(x.device)
+    rng.advance()
+    xa, ra, ga, ba = (t.clone().requires_grad_() for t in (x, res, gamma, beta))
+    ya = ops.DropoutAddLayerNormFunction.apply(xa, ra, ga, ba, 1e-5, p)
+    mask = ya.grad_fn.saved_tensors[3]
+    keep = _keep_from_mask(mask, (rows, C))
+    thr = round(p * 65536)
+    p_eff = thr / 65536
+    n = rows * C
+    assert abs(float(keep.float().mean()) - (1 - p_eff)) < 5 * (p_eff * (1 - p_eff) / n) ** 0.5 + 1e-12
+    if p > 0:       # neighbouring elements / rows are not correlated in any obvious way
+        k = keep.float() - (1 - p_eff)
+        assert abs(float((k[:, 1:] * k[:, :-1]).mean())) < 5 * p_eff * (1 - p_eff) / n ** 0.5
+        assert abs(float((k[1:] * k[:-1]).mean())) < 5 * p_eff * (1 - p_eff) / n ** 0.5
+    ya.backward(go)
+    xb, rb, gb, bb = (t.double().clone().requires_grad_() for t in (x, res, gamma, beta))
+    yb = F.layer_norm(xb * keep.double() / (1 - p_eff) + rb, (C,), gb, bb, 1e-5)
+    yb.backward(go.double())
+    torch.testing.assert_close(ya.detach().double(), yb.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(xa.grad.double(), xb.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(ra.grad.double(), rb.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(ga.grad.double(), gb.grad, rtol=1e-4, atol=1e-5 * rows ** 0.5)
+    torch.testing.assert_close(ba.grad.double(), bb.grad, rtol=1e-4, atol=1e-5 * rows ** 0.5)
+    if p > 0:
+        def draw():
+            return ops.DropoutAddLayerNormFunction.apply(x, res, gamma, beta, 1e-5, p)
+        rng.advance()
+        y1 = draw()                       # step s, call site 1
+        rng.site = 0
+        y1_again = draw()                 # the same (step, site): the same mask
+        y2 = draw()                       # call site 2
+        rng.advance()
+        y3 = draw()                       # step s + 1, call site 1
+        assert torch.equal(y1, y1_again) and not torch.equal(y1, y2) and not torch.equal(y1, y3)

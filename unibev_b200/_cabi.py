@@ -48,6 +48,8 @@ PROTOTYPES = {
     'ub_add_layernorm': ([_p] * 6 + [_i64, _i, _f, _p], _i),
     'ub_colsum': ([_p, _p, _i64, _i, _p], _i),
     'ub_layernorm_bwd': ([_p] * 7 + [_i64, _i, _f, _p], _i),
+    'ub_dropout_add_layernorm_fwd': ([_p] * 6 + [_i64, _i, _f, _f, _p, _i, _p], _i),
+    'ub_dropout_add_layernorm_bwd': ([_p] * 9 + [_i64, _i, _f, _f, _p], _i),
     'ub_add_layernorm16': ([_p] * 7 + [_i64, _i, _f, _p], _i),
     'ub_cnw_fuse': ([_p] * 8 + [_i64, _i, _i, _i, _i, _i, _p], _i),
     'ub_flatten_feats': ([_p, _p, _i, _p, _p, _i, _i, _i, _p], _i),

@@ -3,6 +3,10 @@
 //
 //   ub_colsum          out[n] += sum_m x[m, n]                      bias gradient of a projection (M = B * 40 000 rows)
 //   ub_layernorm_bwd   dx, dgamma += , dbeta +=                     backward of y = LayerNorm(x [+ residual]) * gamma + beta
+//   ub_dropout_add_layernorm_fwd / _bwd                             y = LayerNorm(dropout(x) + residual) * gamma + beta: the
+//                      `dropout(out) + identity` of an attention / FFN and the 'norm' step after it in ONE pass per direction
+//                      (three kernels and two extra round trips of the activation otherwise); the keep mask is drawn in
+//                      the kernel from a counter-based generator and kept as 4 bits per 16 bytes for the backward pass
 //
 // Both are one pass over their inputs with 128-bit accesses (HBM-bound: 4 bytes per element read, LayerNorm 12 bytes per
 // element moved); per-block partial column sums are folded into the (pre-zeroed) outputs with red.global.add.
@@ -43,6 +47,84 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   }
 }
 
+// Counter-based keep mask: one 64-bit mix (splitmix64 finaliser) of (key, float4 index) yields four 16-bit uniform
+// fields, one per element; element j is KEPT iff field j >= thr (thr = round(p 65536)).  key = mix(seed, step, call site):
+// the caller advances `step` once per training step and numbers the call sites, so no (step, site, element) repeats.
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t dropout_key(const int64_t* __restrict__ rng, int salt) {
+  const uint64_t seed = (uint64_t)__ldg(rng), step = (uint64_t)__ldg(rng + 1);
+  return mix64(seed ^ mix64(step * 0x9e3779b97f4a7c15ull + (uint64_t)(uint32_t)salt));
+}
+__device__ __forceinline__ unsigned keep_bits(uint64_t key, uint64_t idx4, unsigned thr) {
+  const uint64_t r = mix64(key + idx4 * 0x9e3779b97f4a7c15ull);
+  return ((unsigned)(r & 0xffffu) >= thr ? 1u : 0u) | ((unsigned)((r >> 16) & 0xffffu) >= thr ? 2u : 0u) |
+         ((unsigned)((r >> 32) & 0xffffu) >= thr ? 4u : 0u) | ((unsigned)(r >> 48) >= thr ? 8u : 0u);
+}
+
+// y = LayerNorm(keep * x * scale + res) * gamma + beta; mask[(r C + c) / 4] = keep bits of the float4 at (r, c)
+template <int NV>
+__global__ void __launch_bounds__(256) dropout_add_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                                    const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, float* __restrict__ out,
+                                                                    uint8_t* __restrict__ mask, int64_t rows, int C, float eps,
+                                                                    unsigned thr, float scale, const int64_t* __restrict__ rng,
+                                                                    int salt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float inv_c = 1.f / (float)C;
+  const uint64_t key = dropout_key(rng, salt);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+    float4 v[NV];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * 4;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < C) {
+        const int64_t i4 = (r * C + c) >> 2;
+        const unsigned kb = keep_bits(key, (uint64_t)i4, thr);
+        mask[i4] = (uint8_t)kb;
+        const float4 t = ld_stream4(x + r * C + c), q = ld_stream4(res + r * C + c);
+        v[k].x = ((kb & 1u) ? t.x * scale : 0.f) + q.x, v[k].y = ((kb & 2u) ? t.y * scale : 0.f) + q.y;
+        v[k].z = ((kb & 4u) ? t.z * scale : 0.f) + q.z, v[k].w = ((kb & 8u) ? t.w * scale : 0.f) + q.w;
+        sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * 4;
+      if (c < C) {
+        const float a = v[k].x - mean, b2 = v[k].y - mean, c2 = v[k].z - mean, d = v[k].w - mean;
+        sq += (a * a + b2 * b2) + (c2 * c2 + d * d);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * inv_c + eps);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (k * 32 + lane) * 4;
+      if (c < C) {
+        const float4 g = ldg4(gamma + c), bt = ldg4(beta + c);
+        float4 o;
+        o.x = (v[k].x - mean) * rstd * g.x + bt.x;
+        o.y = (v[k].y - mean) * rstd * g.y + bt.y;
+        o.z = (v[k].z - mean) * rstd * g.z + bt.z;
+        o.w = (v[k].w - mean) * rstd * g.w + bt.w;
+        st_stream4(out + r * C + c, o);
+      }
+    }
+  }
+}
+
 // One warp per row; lane i owns float4 chunks i, i + 32, ... (NV chunks per lane, C <= 128 NV).  Row statistics are
 // recomputed from x (a row lives in registers), so the forward pass saves nothing but its input.
 //   xhat = (x - mean) rstd;  g = gamma dy;  dx = rstd (g - mean(g) - xhat mean(g xhat));  dgamma += dy xhat;  dbeta += dy
@@ -51,7 +133,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const float* __restrict__ dy,
                                                             const float* __restrict__ gamma, float* __restrict__ dx,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows,
-                                                            int C, float eps) {
+                                                            int C, float eps, const uint8_t* __restrict__ mask, float scale,
+                                                            float* __restrict__ dx_drop) {
   __shared__ float4 s_red[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -65,13 +148,20 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; r < rows; r += warps) {
     float4 v[NV], d[NV];
+    unsigned kb[NV];
     float sum = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int c = (k * 32 + lane) * 4;
       v[k] = d[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      kb[k] = 15u;
       if (c < C) {
         v[k] = ld_stream4(x + r * C + c);
+        if (mask) {   // the normalised row was dropout(x) + residual with the saved keep bits
+          kb[k] = mask[(r * C + c) >> 2];
+          v[k].x = (kb[k] & 1u) ? v[k].x * scale : 0.f, v[k].y = (kb[k] & 2u) ? v[k].y * scale : 0.f;
+          v[k].z = (kb[k] & 4u) ? v[k].z * scale : 0.f, v[k].w = (kb[k] & 8u) ? v[k].w * scale : 0.f;
+        }
         if (res) {   // the normalised row was x + residual (ub_add_layernorm): the same sum, in the same order
           const float4 t = ld_stream4(res + r * C + c);
           v[k].x += t.x, v[k].y += t.y, v[k].z += t.z, v[k].w += t.w;
@@ -123,6 +213,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         o.z = rstd * (d[k].z - m1 - v[k].z * m2);
         o.w = rstd * (d[k].w - m1 - v[k].w * m2);
         st_stream4(dx + r * C + c, o);
+        if (dx_drop)   // gradient of the un-dropped x: the gradient of the sum through the keep mask
+          st_stream4(dx_drop + r * C + c, make_float4((kb[k] & 1u) ? o.x * scale : 0.f, (kb[k] & 2u) ? o.y * scale : 0.f,
+                                                       (kb[k] & 4u) ? o.z * scale : 0.f, (kb[k] & 8u) ? o.w * scale : 0.f));
       }
     }
   }
@@ -189,11 +282,75 @@ extern "C" int ub_layernorm_bwd(const float* x, const float* residual, const flo
   if (blocks < 1) blocks = 1;
   const int nv = (C + 127) / 128;
   cudaStream_t s = (cudaStream_t)stream;
-#define UB_LNB(NV) layernorm_bwd_kernel<NV><<<(int)blocks, 256, 0, s>>>(x, residual, dy, gamma, dx, dgamma, dbeta, rows, C, eps)
+#define UB_LNB(NV) layernorm_bwd_kernel<NV><<<(int)blocks, 256, 0, s>>>(x, residual, dy, gamma, dx, dgamma, dbeta, rows, C, eps, nullptr, 1.f, nullptr)
   if (nv <= 1) UB_LNB(1);
   else if (nv <= 2) UB_LNB(2);
   else if (nv <= 4) UB_LNB(4);
   else UB_LNB(8);
 #undef UB_LNB
   return check_launch("ub_layernorm_bwd");
+}
+
+static int check_dropout_ln(const char* fn, const void* x, const void* residual, int64_t rows, int C, float p) {
+  UB_REQUIRE(x && residual && rows > 0 && C > 0, "%s: bad argument", fn);
+  UB_REQUIRE(p >= 0.f && p < 1.f, "%s: drop probability %g outside [0, 1)", fn, p);
+  UB_REQUIRE_ALIGNED16(x);
+  UB_REQUIRE_ALIGNED16(residual);
+  if (C % 4 != 0 || C > 1024) {
+    set_error("%s: C = %d not covered (need C %% 4 == 0, C <= 1024)", fn, C);
+    return ub::unsupported();
+  }
+  return UB_OK;
+}
+
+extern "C" int ub_dropout_add_layernorm_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
+                                            float* out, uint8_t* mask, int64_t rows, int C, float eps, float p,
+                                            const int64_t* rng_state, int call_site, ub_stream_t stream) {
+  const char* fn = "ub_dropout_add_layernorm_fwd";
+  if (int rc = check_dropout_ln(fn, x, residual, rows, C, p)) return rc;
+  UB_REQUIRE(gamma && beta && out && mask && rng_state, "%s: null pointer", fn);
+  UB_REQUIRE_ALIGNED16(out);
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > (int64_t)sm_count() * 32) blocks = (int64_t)sm_count() * 32;
+  const unsigned thr = (unsigned)lrintf(p * 65536.f);
+  const float scale = 1.f / (1.f - (float)thr / 65536.f);      // of the probability actually applied
+  const int nv = (C + 127) / 128;
+  cudaStream_t s = (cudaStream_t)stream;
+#define UB_DLN(NV) \
+  dropout_add_layernorm_kernel<NV><<<(int)blocks, 256, 0, s>>>(x, residual, gamma, beta, out, mask, rows, C, eps, thr, scale, rng_state, call_site)
+  if (nv <= 1) UB_DLN(1);
+  else if (nv <= 2) UB_DLN(2);
+  else if (nv <= 4) UB_DLN(4);
+  else UB_DLN(8);
+#undef UB_DLN
+  return check_launch(fn);
+}
+
+extern "C" int ub_dropout_add_layernorm_bwd(const float* x, const float* residual, const uint8_t* mask, const float* dy,
+                                            const float* gamma, float* dx, float* dresidual, float* dgamma, float* dbeta,
+                                            int64_t rows, int C, float eps, float p, ub_stream_t stream) {
+  const char* fn = "ub_dropout_add_layernorm_bwd";
+  if (int rc = check_dropout_ln(fn, x, residual, rows, C, p)) return rc;
+  UB_REQUIRE(mask && dy && gamma && dx && dresidual && dgamma && dbeta, "%s: null pointer", fn);
+  UB_REQUIRE_ALIGNED16(dy);
+  UB_REQUIRE_ALIGNED16(dx);
+  UB_REQUIRE_ALIGNED16(dresidual);
+  UB_REQUIRE_ALIGNED16(gamma);
+  UB_REQUIRE_ALIGNED16(dgamma);
+  UB_REQUIRE_ALIGNED16(dbeta);
+  int64_t blocks = (rows + 31) / 32;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  const unsigned thr = (unsigned)lrintf(p * 65536.f);
+  const float scale = 1.f / (1.f - (float)thr / 65536.f);
+  const int nv = (C + 127) / 128;
+  cudaStream_t s = (cudaStream_t)stream;
+#define UB_DLNB(NV) \
+  layernorm_bwd_kernel<NV><<<(int)blocks, 256, 0, s>>>(x, residual, dy, gamma, dresidual, dgamma, dbeta, rows, C, eps, mask, scale, dx)
+  if (nv <= 1) UB_DLNB(1);
+  else if (nv <= 2) UB_DLNB(2);
+  else if (nv <= 4) UB_DLNB(4);
+  else UB_DLNB(8);
+#undef UB_DLNB
+  return check_launch(fn);
 }

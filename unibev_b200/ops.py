@@ -756,37 +756,105 @@ def linear_train(module, x, relu=False):
     return torch.relu(module(x)) if relu else module(x)
 
 
-class Deferred:
-    """``out + identity`` not yet added: what an attention / FFN of the module path hands to a 'norm' step that can fold
-    the addition into its kernel (``layer_norm_train``).  ``materialize()`` is the plain sum for every other consumer."""
-    __slots__ = ('out', 'identity')
+class DropoutRNG:
+    """Per-device state of the in-kernel dropout generator: a device tensor {seed, step} plus the host-side numbering of
+    the call sites of a step.  ``advance()`` (one tiny kernel: also recorded by CUDA-graph capture, so every replay moves on)
+    starts a new step; ``UniBEVTransformer.encode`` calls it at the top of every training-mode forward."""
+    _by_device = {}
 
-    def __init__(self, out, identity):
-        self.out, self.identity = out, identity
+    def __init__(self, device):
+        self.state = torch.tensor([torch.initial_seed() & 0x7fffffffffffffff, 0], dtype=torch.int64, device=device)
+        self._one = torch.tensor([0, 1], dtype=torch.int64, device=device)
+        self.site = 0
+
+    @classmethod
+    def get(cls, device):
+        key = str(device)
+        if key not in cls._by_device:
+            cls._by_device[key] = cls(device)
+        return cls._by_device[key]
+
+    def advance(self):
+        self.state.add_(self._one)
+        self.site = 0
+
+    def next_site(self):
+        self.site += 1
+        return self.site
+
+
+class DropoutAddLayerNormFunction(torch.autograd.Function):
+    """y = LayerNorm(dropout(x, p) + residual) * gamma + beta: ``ub_dropout_add_layernorm_fwd`` / ``_bwd``."""
+
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, eps, p):
+        x, residual = _need(x, 'x'), _need(residual, 'residual')
+        C = x.shape[-1]
+        rng = DropoutRNG.get(x.device)
+        mask = torch.empty(x.numel() // 4, dtype=torch.uint8, device=x.device)
+        out = torch.empty_like(x)
+        _call('ub_dropout_add_layernorm_fwd', x, _ptr(x), _ptr(residual), _ptr(_need(gamma.detach(), 'gamma')),
+              _ptr(_need(beta.detach(), 'beta')), _ptr(out), _ptr(mask), x.numel() // C, C, float(eps), float(p), _ptr(rng.state),
+              rng.next_site())
+        ctx.save_for_backward(x, residual, gamma, mask)
+        ctx.eps, ctx.p = float(eps), float(p)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, residual, gamma, mask = ctx.saved_tensors
+        gy = _need(gy, 'grad_out')
+        C = x.shape[-1]
+        gx, gr = torch.empty_like(x), torch.empty_like(x)
+        gg = torch.zeros(2, C, device=x.device, dtype=torch.float32)
+        _call('ub_dropout_add_layernorm_bwd', x, _ptr(x), _ptr(residual), _ptr(mask), _ptr(gy), _ptr(_need(gamma.detach(), 'gamma')),
+              _ptr(gx), _ptr(gr), _ptr(gg[0]), _ptr(gg[1]), x.numel() // C, C, ctx.eps, ctx.p)
+        return gx, gr, gg[0], gg[1], None, None
+
+
+class Deferred:
+    """``dropout(out) + identity`` not yet computed: what an attention / FFN of the module path hands to a 'norm' step that
+    folds dropout and addition into its kernel (``layer_norm_train``).  ``p`` = drop probability still to be applied to
+    ``out`` (0: none).  ``materialize()`` is the plain expression for every other consumer."""
+    __slots__ = ('out', 'identity', 'p')
+
+    def __init__(self, out, identity, p=0.0):
+        self.out, self.identity, self.p = out, identity, float(p)
 
     def materialize(self):
-        return self.out + self.identity
+        out = torch.nn.functional.dropout(self.out, self.p, True) if self.p > 0.0 else self.out
+        return out + self.identity
 
 
-def add_identity(out, identity, defer):
-    """``out + identity`` of the attentions / FFN (``dropout(x) + identity``), or the pair when the caller's next step is a
-    'norm' that adds while normalising."""
+def add_identity(out, identity, defer, dropout=None):
+    """``dropout(out) + identity`` of the attentions / FFN, or the unevaluated triple when the caller's next step is a
+    'norm' that drops and adds while normalising."""
     if (defer and TRAIN_KERNELS and out.is_cuda and out.dtype == torch.float32 and out.shape == identity.shape
             and train_ops_supported(out.shape[-1])):
-        return Deferred(out, identity)
-    return out + identity
+        p = dropout.p if (isinstance(dropout, torch.nn.Dropout) and dropout.training) else 0.0
+        if dropout is None or isinstance(dropout, (torch.nn.Dropout, torch.nn.Identity)):
+            return Deferred(out, identity, p)
+    return (dropout(out) if dropout is not None else out) + identity
 
 
 def layer_norm_train(module, x):
     """``nn.LayerNorm`` forward of the module (autograd) path through the library's kernels where the shape is covered.
-    ``x`` may be a ``Deferred`` sum."""
-    residual = None
+    ``x`` may be a ``Deferred`` dropout + sum."""
     if isinstance(x, Deferred):
-        x, residual = x.out, x.identity
+        ok = (TRAIN_KERNELS and module.elementwise_affine and len(module.normalized_shape) == 1
+              and train_ops_supported(x.out.shape[-1]))
+        if ok and x.p > 0.0:
+            return DropoutAddLayerNormFunction.apply(x.out, x.identity, module.weight, module.bias, module.eps, x.p)
+        if ok:
+            return LayerNormFunction.apply(x.out, x.identity, module.weight, module.bias, module.eps)
+        return module(x.materialize())
     if (TRAIN_KERNELS and x.is_cuda and x.dtype == torch.float32 and module.elementwise_affine and len(module.normalized_shape) == 1
             and train_ops_supported(x.shape[-1])):
-        return LayerNormFunction.apply(x, residual, module.weight, module.bias, module.eps)
-    return module(x if residual is None else x + residual)
+        return LayerNormFunction.apply(x, None, module.weight, module.bias, module.eps)
+    return module(x)
+
+
 
 
 def cnw_fuse(img, pts, w_img, w_pts, mode, c_flag, l_flag, s_img=None, s_pts=None, modal_embed=None):

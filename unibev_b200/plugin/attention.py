@@ -146,7 +146,7 @@ class MultiScaleDeformableAttention(_DeformAttnBase):
             out = linear_train(self.output_proj, out)
             if not self.batch_first:
                 out = out.permute(1, 0, 2)
-            return add_identity(self.dropout(out), identity, kwargs.get('ub_defer_add', False))
+            return add_identity(out, identity, kwargs.get('ub_defer_add', False), self.dropout)
         assert int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum()) == value.shape[1]
         v, off, aw = self._project(query, value, key_padding_mask)
         if reference_points.shape[-1] == 2:
@@ -266,8 +266,8 @@ class SpatialCrossAttentionImg(nn.Module):
             v = linear_train(da.value_proj, value.permute(2, 0, 1, 3))   # (B, N, hw, C)
             slots = ImgSampleFunction.apply(v, da._raw_rows(query), cam[0], cam[1], grid[0], grid[1], fhw[0], fhw[1],
                                             H, P, 0, 2 * H * P)
-            return add_identity(self.dropout(linear_train(self.output_proj, slots)), inp_residual,
-                                kwargs.get('ub_defer_add', False))
+            return add_identity(linear_train(self.output_proj, slots), inp_residual, kwargs.get('ub_defer_add', False),
+                                self.dropout)
         hit0 = bev_mask[:, 0].any(-1)                                  # (N, Nq)
         lens = hit0.sum(1)
         max_len = int(lens.max())                                      # one host sync (training path only)
@@ -330,4 +330,4 @@ class SpatialCrossAttentionPts(nn.Module):
                                         spatial_shapes=spatial_shapes, level_start_index=level_start_index,
                                         ub_bev_grid=kwargs.get('ub_bev_grid'), ub_value_hw=kwargs.get('ub_value_hw'))
         out = linear_train(self.output_proj, out.view(B, -1, C))
-        return add_identity(self.dropout(out), inp_residual, kwargs.get('ub_defer_add', False))
+        return add_identity(out, inp_residual, kwargs.get('ub_defer_add', False), self.dropout)

@@ -43,10 +43,12 @@ class FFN(nn.Module):
 
     def forward(self, x, identity=None, defer=False):
         (lin1, _relu, drop1), lin2, drop2 = self.layers[0], self.layers[1], self.layers[2]
-        out = drop2(ops.linear_train(lin2, drop1(ops.linear_train(lin1, x, relu=True))))   # == self.layers(x)
+        out = ops.linear_train(lin2, drop1(ops.linear_train(lin1, x, relu=True)))          # drop2(out) == self.layers(x)
         if not self.add_identity:
-            return self.dropout_layer(out)
-        return ops.add_identity(self.dropout_layer(out), x if identity is None else identity, defer)
+            return self.dropout_layer(drop2(out))
+        if isinstance(self.dropout_layer, nn.Identity):
+            return ops.add_identity(out, x if identity is None else identity, defer, drop2)
+        return ops.add_identity(self.dropout_layer(drop2(out)), x if identity is None else identity, defer)
 
 
 if not _ffn_registered():

@@ -320,6 +320,10 @@ class UniBEVTransformer(nn.Module):
                 self._fused, self._fused_key = FusedEncoder(self, self.fused_precision, **over), key
             return self._fused(img_mlvl_feats, pts_mlvl_feats, bev_queries, bev_h, bev_w, bev_pos,
                                kwargs.get('img_metas'), kwargs.get('lidar2img'), kwargs.get('img_shape'))
+        if self.training:       # a new step of the in-kernel dropout generator (fused dropout + add + LayerNorm)
+            ref = (img_mlvl_feats or pts_mlvl_feats)[0]
+            if ref.is_cuda:
+                ops.DropoutRNG.get(ref.device).advance()
         img, pts = self._encode_modules(img_mlvl_feats, pts_mlvl_feats, bev_queries, bev_h, bev_w, bev_pos, **kwargs)
         if grad:
             return self._fuse_modules(img, pts)
