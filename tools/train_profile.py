@@ -35,7 +35,7 @@ def main():
         torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / 3
     print('wall per step: %.1f ms' % (wall * 1e3))
-    print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=40, max_name_column_width=70))
+    print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=60, max_name_column_width=70))
 
 
 if __name__ == '__main__':

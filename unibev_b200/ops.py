@@ -756,6 +756,27 @@ def linear_train(module, x, relu=False):
     return torch.relu(module(x)) if relu else module(x)
 
 
+class AddRowVectorFunction(torch.autograd.Function):
+    """x (..., C) + v (C) with the library's column sum for the gradient of v (the level / camera embeddings added to every
+    token, transformer_fusion.py:241-253,266-270: torch reduces their gradient with its generic column reduction)."""
+
+    @staticmethod
+    def forward(ctx, x, v):
+        return x + v
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        gc = g if g.is_contiguous() else g.contiguous()
+        return g, (colsum(gc) if ctx.needs_input_grad[1] else None)
+
+
+def add_row_vector(x, v):
+    if TRAIN_KERNELS and x.is_cuda and x.dtype == torch.float32 and v.dim() == 1 and train_ops_supported(v.numel()):
+        return AddRowVectorFunction.apply(x, v)
+    return x + v
+
+
 class DropoutRNG:
     """Per-device state of the in-kernel dropout generator: a device tensor {seed, step} plus the host-side numbering of
     the call sites of a step.  ``advance()`` (one tiny kernel: also recorded by CUDA-graph capture, so every replay moves on)

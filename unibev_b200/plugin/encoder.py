@@ -267,7 +267,7 @@ class ImgEncoder(_Encoder):
         D = self.num_points_in_pillar
         bits = (raw_mask[..., None] >> torch.arange(D, device=raw_mask.device, dtype=torch.uint8)) & 1
         ref_cam, bev_mask = raw_ref.permute(2, 0, 1, 3, 4), bits.bool().permute(2, 0, 1, 3)     # == point_sampling(...)
-        bev_query = bev_query.permute(1, 0, 2)
+        bev_query = bev_query.permute(1, 0, 2).contiguous()      # (one copy here instead of one per consumer in layer 0)
         if bev_pos is not None:
             bev_pos = bev_pos.permute(1, 0, 2)
         return self._run_layers(bev_query, key, value, args, kwargs, bev_pos=bev_pos, ref_2d=ref_2d, ref_3d=ref_3d,
@@ -297,7 +297,7 @@ class PtsEncoder(_Encoder):
         ref_3d, ref_2d = self._grids(bev_h, bev_w, self.pc_range[5] - self.pc_range[2], self.num_points_in_pillar_lidar, bs,
                                      dev, dt)
         ref_lidar, _ = self.point_sampling(ref_3d)
-        bev_query = bev_query.permute(1, 0, 2)
+        bev_query = bev_query.permute(1, 0, 2).contiguous()      # (one copy here instead of one per consumer in layer 0)
         if bev_pos is not None:
             bev_pos = bev_pos.permute(1, 0, 2)
         return self._run_layers(bev_query, key, value, args, kwargs, bev_pos=bev_pos, ref_2d=ref_2d, ref_3d=ref_3d,

@@ -192,7 +192,7 @@ class UniBEVTransformer(nn.Module):
                 tok = feat.flatten(3).permute(0, 1, 3, 2).reshape(bs * n, h * w, c)
                 if self.use_cams_embeds:
                     tok = tok + self.cams_embeds.repeat(bs, 1)[:, None]
-                tok = tok + self.img_level_embeds[lvl]
+                tok = ops.add_row_vector(tok.contiguous(), self.img_level_embeds[lvl])   # token-major once, not per layer
             else:
                 tok = ops.flatten_feats(feat, self.cams_embeds if self.use_cams_embeds else None,
                                         self.img_level_embeds[lvl])
@@ -212,7 +212,8 @@ class UniBEVTransformer(nn.Module):
         feat = mlvl_pts_feats[0]
         bs, c, h, w = feat.shape
         if torch.is_grad_enabled():
-            tok = feat.flatten(2).permute(0, 2, 1) + self.pts_level_embeds[0]
+            # (the sum inherits the channel-major strides of `feat`: make it token-major once, not in every layer's value_proj)
+            tok = ops.add_row_vector(feat.flatten(2).permute(0, 2, 1).contiguous(), self.pts_level_embeds[0])
         else:
             tok = ops.flatten_feats(feat, None, self.pts_level_embeds[0])
         return (tok.permute(1, 0, 2), ops.const_tensor([[h, w]], torch.long, feat.device),
@@ -221,12 +222,15 @@ class UniBEVTransformer(nn.Module):
     def _encode_modules(self, img_mlvl_feats, pts_mlvl_feats, bev_queries, bev_h, bev_w, bev_pos, **kwargs):
         bs = (img_mlvl_feats or pts_mlvl_feats)[0].size(0)
         if bev_pos is not None:
-            bev_pos = bev_pos.flatten(2).permute(2, 0, 1)
+            # (Nq, bs, C) as the reference passes it, over token-major memory: the encoders' permute back to (bs, Nq, C) is
+            # then contiguous and `query + query_pos` reads rows instead of a transposed map in every layer
+            bev_pos = bev_pos.flatten(2).permute(0, 2, 1).contiguous().permute(1, 0, 2)
+        def rep(q):     # == q.unsqueeze(1).repeat(1, bs, 1) (transformer_fusion.py:493-498), over batch-major memory: the
+            return q.unsqueeze(0).repeat(bs, 1, 1).permute(1, 0, 2)     # encoders' permute back to (bs, Nq, C) is contiguous
         if self.dual_queries:
-            q_img = bev_queries[0].unsqueeze(1).repeat(1, bs, 1)
-            q_pts = bev_queries[1].unsqueeze(1).repeat(1, bs, 1)
+            q_img, q_pts = rep(bev_queries[0]), rep(bev_queries[1])
         else:
-            q_img = q_pts = bev_queries.unsqueeze(1).repeat(1, bs, 1)
+            q_img = q_pts = rep(bev_queries)
         img = pts = None
         if img_mlvl_feats is not None:
             flat, shapes, start = self._pre_process_img_feats(img_mlvl_feats, q_img)
