@@ -39,7 +39,7 @@ __device__ __forceinline__ void sample_bwd(const float* __restrict__ vbase, floa
   const int h0 = (int)hf, w0 = (int)wf;
   const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
   const bool top = h0 >= 0, bot = h0 + 1 <= fH - 1, left = w0 >= 0, right = w0 + 1 <= fW - 1;
-  const int64_t o00 = ((int64_t)h0 * fW + w0) * row, o10 = o00 + (int64_t)fW * row;
+  const int o00 = (h0 * fW + w0) * row, o10 = o00 + fW * row;   // (one map < 2^31 floats: checked on the host; 32-bit address math)
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 v1 = (top && left) ? ldg4(vbase + o00) : z4;
   const float4 v2 = (top && right) ? ldg4(vbase + o00 + row) : z4;
@@ -71,8 +71,12 @@ struct SampleBwdArgs {
 
 // CAM = false: BEV-grid mode (reference point = cell centre); CAM = true: camera mode (projected anchors, hit cameras of
 // batch item 0, divisor from the item's own visibility).  PP >= P: compile-time bound of the point loop.
+// Register diet (the kernel is latency-bound: four 128-bit loads and four reductions per sample and lane, nothing to hide
+// them behind but other warps): only the softmax weights and the attention-weight gradients of the P points stay in
+// registers across the point loop; offsets are read per point and the location gradients are folded across the group's
+// lanes and written as soon as the point is done (camera mode: cameras are the INNER loop for that reason).
 template <int LPG, int PP, bool CAM>
-__global__ void __launch_bounds__(256) sample_bwd_kernel(const SampleBwdArgs a) {
+__global__ void __launch_bounds__(256, CAM ? 3 : 4) sample_bwd_kernel(const SampleBwdArgs a) {
   constexpr int Dh = LPG * 4;
   const int lane = threadIdx.x % LPG;
   const int Nq = a.bev_h * a.bev_w, row = a.H * Dh, P = a.P;
@@ -88,15 +92,15 @@ __global__ void __launch_bounds__(256) sample_bwd_kernel(const SampleBwdArgs a) 
     const int64_t bq = item_c / a.H;
     const int b = (int)(bq / Nq), q = (int)(bq - (int64_t)b * Nq);
     const float* rowp = a.qproj + bq * a.ld;
+    const float* offp = rowp + a.off_col + h * P * 2;
+    float* grow = a.grad_qproj + bq * a.ld;
     float4 go = live ? ldg4(a.grad_out + bq * row + h * Dh + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     // softmax over the item's P logits (every lane of the group computes it: P <= 16 scalar loads served by one line)
-    float aw[PP], ox[PP], oy[PP];
+    float aw[PP], g_a[PP];
     float mx = -INFINITY;
 #pragma unroll
     for (int p = 0; p < PP; ++p) {
       aw[p] = p < P ? __ldg(rowp + a.logit_col + h * P + p) : -INFINITY;
-      ox[p] = p < P ? __ldg(rowp + a.off_col + (h * P + p) * 2) : 0.f;
-      oy[p] = p < P ? __ldg(rowp + a.off_col + (h * P + p) * 2 + 1) : 0.f;
       mx = fmaxf(mx, aw[p]);
     }
     float sum = 0.f;
@@ -107,69 +111,68 @@ __global__ void __launch_bounds__(256) sample_bwd_kernel(const SampleBwdArgs a) 
     }
     const float inv = 1.f / sum;
 #pragma unroll
-    for (int p = 0; p < PP; ++p) aw[p] *= inv;
+    for (int p = 0; p < PP; ++p) aw[p] *= inv, g_a[p] = 0.f;
 
-    float g_a[PP], g_x[PP], g_y[PP];
-#pragma unroll
-    for (int p = 0; p < PP; ++p) g_a[p] = g_x[p] = g_y[p] = 0.f;
-
-    if (!CAM) {
-      const float* vbase = a.value + (int64_t)b * map_floats + h * Dh + lane * 4;
-      float* gbase = a.grad_value + (int64_t)b * map_floats + h * Dh + lane * 4;
-      if (live) {
-#pragma unroll
-        for (int p = 0; p < PP; ++p)
-          if (p < P)
-            // pixel = ((q + .5) / bev + off / f) * f - .5  ==  (q + .5) * (f / bev) + off - .5   (as the forward kernel)
-            sample_bwd(vbase, gbase, a.fH, a.fW, row, fmaf((float)(q / a.bev_w) + 0.5f, a.sy, oy[p] - 0.5f),
-                       fmaf((float)(q % a.bev_w) + 0.5f, a.sx, ox[p] - 0.5f), aw[p], go, g_a[p], g_x[p], g_y[p]);
-      }
-    } else {
-      unsigned hit = 0u;
+    unsigned hit = 1u;           // BEV mode: one "camera"
+    if (CAM) {
+      hit = 0u;
       int count = 0;
       for (int n = 0; n < a.N; ++n) {
         hit |= (__ldg(a.mask + (int64_t)q * a.N + n) != 0 ? 1u : 0u) << n;          // batch item 0 decides who contributes
         count += __ldg(a.mask + bq * a.N + n) != 0 ? 1 : 0;                           // the item's own visibility divides
       }
-      const float ic = 1.f / (float)max(count, 1);
-      go = scale4g(ic, go);
-      if (!live) hit = 0u;
-      while (hit) {
-        const int n = __ffs(hit) - 1;
-        hit &= hit - 1;
-        const float* vbase = a.value + ((int64_t)b * a.N + n) * map_floats + h * Dh + lane * 4;
-        float* gbase = a.grad_value + ((int64_t)b * a.N + n) * map_floats + h * Dh + lane * 4;
-        const float2* rp = reinterpret_cast<const float2*>(a.ref_cam) + (bq * a.N + n) * a.D;
+      go = scale4g(1.f / (float)max(count, 1), go);
+    }
+    if (!live) hit = 0u;
+    const int64_t lane_off = h * Dh + lane * 4;
+
 #pragma unroll
-        for (int p = 0; p < PP; ++p)
-          if (p < P) {
-            const float2 r = __ldg(rp + (p % a.D));
-            sample_bwd(vbase, gbase, a.fH, a.fW, row, fmaf(r.y, (float)a.fH, oy[p] - 0.5f), fmaf(r.x, (float)a.fW, ox[p] - 0.5f),
-                       aw[p], go, g_a[p], g_x[p], g_y[p]);
+    for (int p = 0; p < PP; ++p) {
+      float g_x = 0.f, g_y = 0.f;
+      if (p < P) {
+        const float ox = __ldg(offp + 2 * p), oy = __ldg(offp + 2 * p + 1);
+        if (!CAM) {
+          if (hit) {
+            // pixel = ((q + .5) / bev + off / f) * f - .5  ==  (q + .5) * (f / bev) + off - .5   (as the forward kernel)
+            const int64_t base = (int64_t)b * map_floats + lane_off;
+            sample_bwd(a.value + base, a.grad_value + base, a.fH, a.fW, row, fmaf((float)(q / a.bev_w) + 0.5f, a.sy, oy - 0.5f),
+                       fmaf((float)(q % a.bev_w) + 0.5f, a.sx, ox - 0.5f), aw[p], go, g_a[p], g_x, g_y);
           }
+        } else {
+          unsigned m = hit;
+          while (m) {
+            const int n = __ffs(m) - 1;
+            m &= m - 1;
+            const int64_t base = ((int64_t)b * a.N + n) * map_floats + lane_off;
+            const float2 r = __ldg(reinterpret_cast<const float2*>(a.ref_cam) + (bq * a.N + n) * a.D + (p % a.D));
+            sample_bwd(a.value + base, a.grad_value + base, a.fH, a.fW, row, fmaf(r.y, (float)a.fH, oy - 0.5f),
+                       fmaf(r.x, (float)a.fW, ox - 0.5f), aw[p], go, g_a[p], g_x, g_y);
+          }
+        }
+      }
+      // fold the lanes' channel shares of this point's location gradient; one lane writes it
+#pragma unroll
+      for (int o = LPG / 2; o > 0; o >>= 1) {
+        g_x += __shfl_xor_sync(0xffffffffu, g_x, o);
+        g_y += __shfl_xor_sync(0xffffffffu, g_y, o);
+      }
+      if (live && p < P && lane == p % LPG) {
+        grow[a.off_col + (h * P + p) * 2] = g_x;
+        grow[a.off_col + (h * P + p) * 2 + 1] = g_y;
       }
     }
-    // fold the lanes' channel shares, softmax backward, one lane per point writes
+    // attention-weight gradients: fold, softmax backward, one lane per point writes
     float dot = 0.f;
 #pragma unroll
     for (int p = 0; p < PP; ++p) {
 #pragma unroll
-      for (int o = LPG / 2; o > 0; o >>= 1) {
-        g_a[p] += __shfl_xor_sync(0xffffffffu, g_a[p], o);
-        g_x[p] += __shfl_xor_sync(0xffffffffu, g_x[p], o);
-        g_y[p] += __shfl_xor_sync(0xffffffffu, g_y[p], o);
-      }
+      for (int o = LPG / 2; o > 0; o >>= 1) g_a[p] += __shfl_xor_sync(0xffffffffu, g_a[p], o);
       dot = fmaf(aw[p], g_a[p], dot);
     }
     if (live) {
-      float* grow = a.grad_qproj + bq * a.ld;
 #pragma unroll
       for (int p = 0; p < PP; ++p)
-        if (p < P && lane == p % LPG) {
-          grow[a.off_col + (h * P + p) * 2] = g_x[p];
-          grow[a.off_col + (h * P + p) * 2 + 1] = g_y[p];
-          grow[a.logit_col + h * P + p] = aw[p] * (g_a[p] - dot);
-        }
+        if (p < P && lane == p % LPG) grow[a.logit_col + h * P + p] = aw[p] * (g_a[p] - dot);
     }
   }
 }
